@@ -1,0 +1,251 @@
+"""Generate the golden fixtures in ``tests/golden`` from the REFERENCE'S OWN forward code.
+
+Runs only in the build container (needs the read-only reference tree at ``/root/reference``; it is
+executed through the import shim ``oracle/ref_shim.py`` because autograd/proxmin/astropy are absent).
+The fixtures are small ``.npz`` files that travel with the repo, so the GPU box never needs the
+reference tree.  Re-run with:  ``python tests/golden/make_golden.py``
+
+What is written (all values produced by reference code, float64 unless the reference says otherwise):
+
+* ``obs_render_loss.npz``  -- the scenario of the reference's ``tests/test_observation.py:12-47``.
+* ``hsc_cosmos_35.npz``    -- BASELINE config 1: data/hsc_cosmos_35.npz, 3 ``ExtendedSource`` initialised by the
+                             reference; inputs, initial parameters, boxes, diff kernel, model, render, logL,
+                             spectrum steps, the morphology constraint chain applied to perturbed images,
+                             and central finite differences of the reference forward for a few parameters.
+* ``point_extended.npz``   -- data/psf_unmatched_sim.npz: 2 ``PointSource`` + 2 ``ExtendedSource``; same contents,
+                             plus point-source morphology models at sub-pixel centres.
+* ``prox_chain.npz``       -- constraint-chain outputs (monotonic angle/flat/nearest x symmetric on/off) on seeded
+                             random 41x41 / 21x21 / 20x31 images.
+* ``monotonic_weights.npz``-- ``getRadialMonotonicWeights`` for several shapes / kinds / centres.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+
+REF_DATA = os.path.join(ref_shim.REFERENCE_ROOT, "data")
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **arrays)
+    print("wrote %s (%.1f kB)" % (name, os.path.getsize(path) / 1e3))
+
+
+def obs_render_loss(sc):
+    """tests/test_observation.py:12-47 through reference code."""
+    shape0, s0 = (3, 13, 13), 0.9
+    model_psf = sc.psf.GaussianPSF(s0, boxsize=shape0[1])
+    model_psf_image = model_psf.get_model()
+    shape = (3, 43, 43)
+    channels = list(range(shape[0]))
+    frame = sc.frame.Frame(shape, psf=model_psf, channels=channels)
+    origin = (0, shape[1] // 2 - shape0[1] // 2, shape[2] // 2 - shape0[2] // 2)
+    bbox = sc.bbox.Box(shape0, origin=origin)
+    model = np.zeros(shape)
+    box = np.stack([model_psf_image[0] for _ in range(shape[0])], axis=0)
+    bbox.insert_into(model, box)
+    sigmas = np.array([2.1, 1.1, 3.5])
+    psf = sc.psf.GaussianPSF(sigmas, boxsize=shape[1])
+    images = np.ones(shape)
+    obs = sc.observation.Observation(images, psf=psf, channels=channels)
+    obs.match(frame)
+    rendered = obs.render(model)
+    logL = obs.get_log_likelihood(model)
+    save("obs_render_loss.npz", model_sigma=s0, model_boxsize=shape0[1], obs_sigmas=sigmas, obs_boxsize=shape[1],
+         model=model, model_psf_image=np.asarray(model_psf_image), obs_psf_image=np.asarray(psf.get_model()),
+         diff_kernel=obs.renderer.diff_kernel.image, rendered=rendered, logL=logL, images=images)
+
+
+def _finite_diff(blend, obs, params, which, eps=1e-4):
+    """Central differences of the reference forward, evaluated with a float64 model frame (the float32
+    default frame makes the loss too noisy to difference).  The loss is quadratic in any single sed or
+    morphology element, so the central difference is exact up to rounding; for centres it is O(eps^2)."""
+    frame = blend.frame
+    keep = frame.dtype
+    frame.dtype = np.float64
+    out = []
+    try:
+        for (pi, idx) in which:
+            p = params[pi]
+            old = p[idx].copy() if hasattr(p[idx], "copy") else p[idx]
+            vals, xs = [], []
+            for sgn in (+1, -1):
+                p[idx] = old + sgn * eps
+                xs.append(float(p[idx]))
+                model = blend.get_model()
+                vals.append(-obs.get_log_likelihood(model))
+            p[idx] = old
+            out.append((vals[0] - vals[1]) / (xs[0] - xs[1]))
+    finally:
+        frame.dtype = keep
+    return np.array(out)
+
+
+def _scene_dump(sc, prefix, frame, obs, sources, extra):
+    blend = sc.blend.Blend(sources, obs)
+    model = blend.get_model()
+    rendered = obs.render(model)
+    logL = obs.get_log_likelihood(model)
+    out = dict(extra)
+    out.update(model=model, rendered=rendered, logL=logL, log_norm=obs.log_norm,
+               diff_kernel=obs.renderer.diff_kernel.image,
+               noise_rms_band=np.array(np.mean(obs.noise_rms, axis=(1, 2))), n_sources=len(sources))
+    for k, src in enumerate(sources):
+        ps = src.parameters
+        out["src%d_kind" % k] = type(src).__name__
+        out["src%d_origin" % k] = np.array(src.bbox.origin)
+        out["src%d_shape" % k] = np.array(src.bbox.shape)
+        for p in ps:
+            out["src%d_%s" % (k, p.name)] = np.asarray(p)
+            st = p.step(p, it=0) if callable(p.step) else p.step
+            out["src%d_%s_step" % (k, p.name)] = np.asarray(st, dtype=np.float64)
+        out["src%d_model" % k] = np.asarray(src.get_model())
+    return blend, out
+
+
+def hsc_cosmos_35(sc):
+    d = np.load(os.path.join(REF_DATA, "hsc_cosmos_35.npz"))
+    images, variance, psfs = d["images"], d["variance"], d["psfs"]
+    weights = 1 / variance
+    channels = [str(f) for f in d["filters"]]
+    centers = [(float(s["y"]), float(s["x"])) for s in d["catalog"]][:3]
+    model_psf = sc.psf.GaussianPSF(sigma=(0.8,) * len(channels))
+    frame = sc.frame.Frame(images.shape, psf=model_psf, channels=channels)
+    obs = sc.observation.Observation(images, psf=sc.psf.ImagePSF(psfs.copy()), weights=weights, channels=channels)
+    obs.match(frame)
+    sources = [sc.source.ExtendedSource(frame, c, obs, resizing=False) for c in centers]
+    blend, out = _scene_dump(sc, "hsc", frame, obs, sources,
+                             dict(images=images, weights=weights.astype(np.float32), psfs=psfs,
+                                  model_sigma=0.8, centers=np.array(centers)))
+    params = blend.parameters
+    # promote the float32 spectra to float64 for the finite differences only
+    which = [(0, 2), (1, (20, 20)), (1, (5, 30)), (3, 0), (4, (30, 30)), (6, 4), (7, (20, 18)), (7, (0, 0))]
+    fd = []
+    for pi, idx in which:
+        p = params[pi]
+        eps = 1e-2 * max(abs(float(p[idx])), 1e-2) if p.dtype == np.float32 else 1e-4
+        fd.append(_finite_diff(blend, obs, params, [(pi, idx)], eps=eps)[0])
+    out["fd_which"] = np.array([(pi,) + (tuple(np.atleast_1d(idx)) + (-1,))[:2] for pi, idx in which])
+    out["fd_grad"] = np.array(fd)
+    # the constraint chain on perturbed morphologies (one prox application each)
+    rng = np.random.default_rng(35)
+    for k, src in enumerate(sources):
+        img = np.asarray(params[3 * k + 1]).copy()
+        pert = np.maximum(img + 0.05 * rng.standard_normal(img.shape), 0)
+        out["src%d_perturbed" % k] = pert.copy()
+        out["src%d_chain" % k] = np.asarray(params[3 * k + 1].constraint(pert.copy(), 0))
+    save("hsc_cosmos_35.npz", **out)
+
+
+def point_extended(sc):
+    d = np.load(os.path.join(REF_DATA, "psf_unmatched_sim.npz"), allow_pickle=True)
+    images, psfs = d["images"], d["psfs"]
+    channels = [str(f) for f in d["filters"]]
+    cat = d["catalog"]
+    _, first = np.unique(cat["index"], return_index=True)
+    cat = cat[np.sort(first)]
+    rng = np.random.default_rng(7)
+    weights = (1.0 / (0.05 + 0.02 * rng.random(images.shape))).astype(np.float32)
+    weights[:, :3, :5] = 0  # a masked corner: exercises log_norm / noise_rms masking
+    model_psf = sc.psf.GaussianPSF(sigma=(0.8,) * len(channels))
+    frame = sc.frame.Frame(images.shape, psf=model_psf, channels=channels)
+    obs = sc.observation.Observation(images, psf=sc.psf.ImagePSF(psfs.astype(np.float64)), weights=weights,
+                                     channels=channels)
+    obs.match(frame)
+    sources, kinds, centers = [], [], []
+    for row in cat:
+        c = (float(row["y"]) + 0.23, float(row["x"]) - 0.31)
+        if row["is_star"] and kinds.count("P") < 2:
+            sources.append(sc.source.PointSource(frame, c, obs))
+            kinds.append("P")
+            centers.append(c)
+        elif (not row["is_star"]) and kinds.count("E") < 2:
+            sources.append(sc.source.ExtendedSource(frame, c, obs, resizing=False))
+            kinds.append("E")
+            centers.append(c)
+    blend, out = _scene_dump(sc, "pe", frame, obs, sources,
+                             dict(images=images, weights=weights, psfs=psfs.astype(np.float64), model_sigma=0.8,
+                                  centers=np.array(centers), kinds=np.array(kinds)))
+    params = blend.parameters
+    names = [p.name for p in params]
+    which = []
+    for pi, n in enumerate(names):
+        if n == "center":
+            which += [(pi, 0), (pi, 1)]
+        elif n == "spectrum":
+            which += [(pi, 1)]
+    fd = []
+    for pi, idx in which:
+        p = params[pi]
+        eps = 1e-2 * max(abs(float(p[idx])), 1e-2) if p.dtype == np.float32 else 1e-4
+        fd.append(_finite_diff(blend, obs, params, [(pi, idx)], eps=eps)[0])
+    out["fd_which"] = np.array(which)
+    out["fd_grad"] = np.array(fd)
+    out["param_names"] = np.array(names)
+    # point-source morphology at a few sub-pixel centres (reference PointSourceMorphology.get_model)
+    k = kinds.index("P")
+    morph = sources[k].children[1]
+    cen = np.asarray(morph.center).copy()
+    offs = np.array([[0.0, 0.0], [0.3, -0.2], [-0.49, 0.49], [0.11, 0.07]])
+    out["ps_index"] = k
+    out["ps_offsets"] = offs
+    out["ps_models"] = np.stack([np.asarray(morph.get_model(sc.parameter.Parameter(cen + o, name="center")))
+                                 for o in offs])
+    save("point_extended.npz", **out)
+
+
+def prox_chain(sc):
+    rng = np.random.default_rng(2024)
+    out = {}
+    n = 0
+    for shape in [(41, 41), (21, 21), (20, 31)]:
+        yy, xx = np.meshgrid(np.arange(shape[0]) - shape[0] // 2, np.arange(shape[1]) - shape[1] // 2, indexing="ij")
+        base = np.exp(-np.hypot(yy, xx) / 4.0)
+        for kind in ("angle", "flat", "nearest"):
+            for sym in (False, True):
+                for min_grad in (0.0, 0.1):
+                    X = base + 0.1 * rng.standard_normal(shape)
+                    cons = [sc.constraint.MonotonicityConstraint(neighbor_weight=kind, min_gradient=min_grad)]
+                    if sym:
+                        cons.append(sc.constraint.SymmetryConstraint())
+                    cons += [sc.constraint.PositivityConstraint(), sc.constraint.CenterOnConstraint(),
+                             sc.constraint.NormalizationConstraint("max")]
+                    chain = sc.constraint.ConstraintChain(*cons)
+                    out["in%d" % n] = X.copy()
+                    out["out%d" % n] = np.asarray(chain(X.copy(), 0))
+                    out["cfg%d" % n] = np.array([kind, str(int(sym)), str(min_grad)])
+                    n += 1
+    out["n"] = n
+    save("prox_chain.npz", **out)
+
+
+def monotonic_weights(sc):
+    out = {}
+    n = 0
+    for shape in [(5, 5), (7, 9), (10, 8), (21, 21), (6, 6)]:
+        for kind in ("flat", "angle", "nearest"):
+            for center in (None, (shape[0] // 2, shape[1] // 2), (1, 2)):
+                w = sc.operator.getRadialMonotonicWeights(shape, neighbor_weight=kind, center=center)
+                out["w%d" % n] = w
+                out["cfg%d" % n] = np.array([shape[0], shape[1], -1 if center is None else center[0],
+                                             -1 if center is None else center[1]])
+                out["kind%d" % n] = np.array(kind)
+                n += 1
+    out["n"] = n
+    save("monotonic_weights.npz", **out)
+
+
+if __name__ == "__main__":
+    sc = ref_shim.install()
+    obs_render_loss(sc)
+    hsc_cosmos_35(sc)
+    point_extended(sc)
+    prox_chain(sc)
+    monotonic_weights(sc)
