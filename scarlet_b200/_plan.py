@@ -1,0 +1,383 @@
+"""Host "compiler": walks Blend objects and emits the flat batch descriptor the CUDA plan consumes; moves
+parameters / optimiser state between the host ``Parameter`` objects and the device.
+
+This is the seam the reference fills with closures handed to ``proxmin.adaprox`` (scarlet/blend.py:103-180).
+Anything the device cannot express (unknown Constraint / Renderer / Morphology classes, priors, callable steps
+other than ``relative_step``) raises here -- there is no host fallback.
+"""
+import ctypes
+from functools import partial
+
+import numpy as np
+import numpy.ma as ma
+
+from . import _native as nat
+from .component import CombinedComponent, FactorizedComponent
+from .constraint import MonoTables, chain_desc, constraint_ops
+from .morphology import ImageMorphology, PointSourceMorphology
+from .parameter import relative_step
+from .psf import GaussianPSF
+from .renderer import ConvolutionRenderer, NullRenderer
+from .spectrum import TabulatedSpectrum
+
+
+def leaf_components(sources):
+    """Depth-first list of FactorizedComponents (the order of ``Blend.parameters``, model.py:51-54)."""
+    out = []
+    for s in sources:
+        if isinstance(s, FactorizedComponent):
+            out.append(s)
+        elif isinstance(s, CombinedComponent):
+            if getattr(s, "operation", "add") != "add":
+                raise TypeError("CombinedComponent(operation=%r) is not on the device path" % s.operation)
+            out += leaf_components(s.children)
+        else:
+            raise TypeError("source of type %s is not on the device path (FactorizedComponent / CombinedComponent "
+                            "of FactorizedComponents only)" % type(s).__name__)
+    return out
+
+
+def _step_of_spectrum(p, C):
+    """-> (factor, min_step[C]); factor < 0 encodes a constant scalar step."""
+    st = p.step
+    if isinstance(st, partial) and st.func is relative_step and not st.args:
+        kw = dict(st.keywords)
+        factor = float(kw.pop("factor", 0.1))
+        minimum = kw.pop("minimum", 0)
+        if kw.pop("axis", None) is not None or kw:
+            raise TypeError("relative_step with axis/extra keywords is not on the device path")
+        mn = np.array(ma.filled(ma.asarray(minimum, dtype=np.float64), np.inf), dtype=np.float64)
+        return factor, np.broadcast_to(mn, (C,)).copy()
+    if st is relative_step:
+        return 0.1, np.zeros(C)
+    if callable(st):
+        raise TypeError("callable step %r of parameter '%s' has no device equivalent (only relative_step)" % (st, p.name))
+    return -1.0, np.full(C, float(st))
+
+
+def _const_step(p):
+    if callable(p.step):
+        raise TypeError("parameter '%s': only constant steps are supported on the device for this parameter kind "
+                        "(got %r)" % (p.name, p.step))
+    return float(p.step)
+
+
+class DevicePlan:
+    """One CUDA plan for a batch of structurally identical scenes (same frame / observation shapes)."""
+
+    def __init__(self, blends, precision=32, device=None):
+        self.blends = list(blends)
+        self.precision = int(precision)
+        self.device = nat.default_device() if device is None else int(device)
+        self._handle = None
+        self._keep = []  # host arrays referenced by the descriptor until sb_plan_create returns
+        b0 = self.blends[0]
+        self.frame_shape = tuple(b0.frame.shape)
+        C, Ny, Nx = self.frame_shape
+        if C > nat.SB_MAX_CHANNELS:
+            raise ValueError("at most %d channels" % nat.SB_MAX_CHANNELS)
+        self.S = len(self.blends)
+
+        desc = nat.sb_batch_desc()
+        desc.precision, desc.n_scenes, desc.C, desc.Ny, desc.Nx = self.precision, self.S, C, Ny, Nx
+
+        # ---- observations ------------------------------------------------------------------------
+        n_obs = len(b0.observations)
+        if not 1 <= n_obs <= nat.SB_MAX_OBS:
+            raise ValueError("between 1 and %d observations per scene" % nat.SB_MAX_OBS)
+        desc.n_obs = n_obs
+        self.obs_meta = []
+        for o in range(n_obs):
+            metas = [self._obs_meta(b, o) for b in self.blends]
+            m0 = metas[0]
+            for m in metas[1:]:
+                if (m["kind"], m["shape"], m["chan_off"], m["origin"], m["fshape"]) != \
+                        (m0["kind"], m0["shape"], m0["chan_off"], m0["origin"], m0["fshape"]):
+                    raise ValueError("all scenes of a batch need identically shaped observations")
+            shared = all(m["khat"] is m0["khat"] for m in metas)
+            desc.obs[o] = nat.sb_obs_desc(m0["kind"], m0["shape"][0], m0["shape"][1], m0["shape"][2], m0["chan_off"],
+                                          m0["origin"][0], m0["origin"][1], m0["fshape"][0], m0["fshape"][1], int(shared))
+            self.obs_meta.append(dict(metas=metas, shared=shared))
+
+        # ---- sources -----------------------------------------------------------------------------
+        tables = MonoTables()
+        chains, chain_keys = [], {}
+
+        def chain_index(constraint, shape):
+            if constraint is None:
+                return -1
+            ops, repeat = constraint_ops(constraint, shape, tables)
+            key = (tuple(ops), repeat)
+            if key not in chain_keys:
+                chain_keys[key] = len(chains)
+                chains.append(chain_desc(ops, repeat))
+            return chain_keys[key]
+
+        self.slots = []  # per leaf component: dict(kind, spectrum, image|center, shift)
+        starts = [0]
+        psf_box, psf_sigma = 0, np.zeros(nat.SB_MAX_CHANNELS)
+        src_descs = []
+        for b in self.blends:
+            if tuple(b.frame.shape) != self.frame_shape:
+                raise ValueError("all scenes of a batch need the same model frame shape")
+            for comp in leaf_components(b.sources):
+                spec, morph = comp.children[0], comp.children[1]
+                if not isinstance(spec, TabulatedSpectrum):
+                    raise TypeError("spectrum model %s is not on the device path" % type(spec).__name__)
+                sp = spec.parameters[0]
+                if sp.shape != (C,) or spec.bbox.origin != (0,):
+                    raise NotImplementedError("spectra must cover all model channels")
+                for p in comp.parameters:
+                    if p.prior is not None:
+                        raise NotImplementedError("priors are not supported on the device path (parameter '%s')" % p.name)
+                d = nat.sb_source_desc()
+                factor, mn = _step_of_spectrum(sp, C)
+                d.sed_step_factor = factor
+                for c in range(C):
+                    d.sed_step_min[c] = mn[c]
+                d.sed_chain = chain_index(sp.constraint, (1, C))
+                d.sed_is_f32 = int(sp.dtype == np.float32)
+                d.sed_fixed = int(bool(sp.fixed))
+                slot = dict(spectrum=sp, comp=comp)
+                if isinstance(morph, PointSourceMorphology):
+                    psf = morph.psf
+                    if not isinstance(psf, GaussianPSF) or not psf.integrate:
+                        raise TypeError("PointSourceMorphology needs a pixel-integrated GaussianPSF model PSF on the device path")
+                    sig = np.asarray(psf.sigma, dtype=np.float64)
+                    sig = np.full(C, sig[0]) if sig.size == 1 else sig
+                    if sig.size != C:
+                        raise ValueError("model PSF sigma must have one entry per channel")
+                    bs = psf.bbox.shape[1]
+                    if psf_box and (psf_box != bs or not np.array_equal(psf_sigma[:C], sig)):
+                        raise ValueError("all point sources of a batch must share the model PSF")
+                    psf_box, psf_sigma[:C] = bs, sig
+                    cen = morph.parameters[0]
+                    d.kind, d.By, d.Bx = 1, bs, bs
+                    d.oy, d.ox = morph.bbox.origin[-2], morph.bbox.origin[-1]
+                    d.chain = -1
+                    if cen.constraint is not None:
+                        raise TypeError("constraints on point-source centres are not on the device path")
+                    d.morph_step = _const_step(cen)
+                    d.morph_fixed = int(bool(cen.fixed))
+                    slot.update(kind=1, center=cen)
+                elif isinstance(morph, ImageMorphology):
+                    if morph.shifting:
+                        raise NotImplementedError("shifting=True is a 'next' row (SURVEY f-3)")
+                    img = morph.parameters[0]
+                    d.kind, d.By, d.Bx = 0, img.shape[0], img.shape[1]
+                    d.oy, d.ox = morph.bbox.origin[-2], morph.bbox.origin[-1]
+                    d.chain = chain_index(img.constraint, img.shape)
+                    d.morph_step = _const_step(img)
+                    d.morph_fixed = int(bool(img.fixed))
+                    slot.update(kind=0, image=img, shift=morph.parameters[1] if len(morph.parameters) > 1 else None)
+                else:
+                    raise TypeError("morphology model %s is not on the device path" % type(morph).__name__)
+                src_descs.append(d)
+                self.slots.append(slot)
+            starts.append(len(src_descs))
+        self.n_src = len(src_descs)
+        self.C = C
+        self.ext = [s for s in self.slots if s["kind"] == 0]
+        self.pts = [s for s in self.slots if s["kind"] == 1]
+        self.morph_sizes = [s["image"].size for s in self.ext]
+        self.morph_offsets = np.concatenate([[0], np.cumsum(self.morph_sizes)]).astype(np.int64)
+        self.n_morph = int(self.morph_offsets[-1])
+
+        src_arr = (nat.sb_source_desc * max(self.n_src, 1))(*src_descs)
+        chain_arr = (nat.sb_chain_desc * max(len(chains), 1))(*chains)
+        mono_arr = tables.descs()
+        start_arr = np.asarray(starts, dtype=np.int32)
+        desc.n_sources, desc.n_chains, desc.n_mono = self.n_src, len(chains), len(tables.tables)
+        desc.psf_boxsize = psf_box
+        for c in range(nat.SB_MAX_CHANNELS):
+            desc.psf_sigma[c] = psf_sigma[c]
+        desc.scene_src_start = nat.ptr(start_arr)
+        desc.sources = ctypes.addressof(src_arr)
+        desc.chains = ctypes.addressof(chain_arr)
+        desc.mono = ctypes.addressof(mono_arr)
+        self._keep = [src_arr, chain_arr, mono_arr, start_arr, tables]
+        handle = ctypes.c_void_p()
+        nat.check(nat.lib().sb_plan_create(ctypes.byref(desc), self.device, ctypes.byref(handle)))
+        self._handle = handle
+        self.upload_observations()
+
+    # -------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _obs_meta(blend, o):
+        obs = blend.observations[o]
+        r = getattr(obs, "renderer", None)
+        if r is None:
+            raise RuntimeError("observation %d is not matched to the model frame (call obs.match(frame))" % o)
+        if type(r) is ConvolutionRenderer:
+            fshape, khat = r.kernel_transform()
+            kind = 0
+        elif type(r) is NullRenderer:
+            fshape, khat, kind = (blend.frame.shape[1], blend.frame.shape[2]), None, 1
+        else:
+            raise TypeError("renderer %s is not on the device path (ConvolutionRenderer / NullRenderer)" % type(r).__name__)
+        if r.parameters:
+            raise NotImplementedError("parameterised renderers (psf_shift) are not on the device path")
+        return dict(kind=kind, shape=tuple(obs.data.shape), chan_off=r.channel_offset, origin=tuple(r.origin),
+                    fshape=tuple(int(f) for f in fshape), khat=khat, obs=obs, renderer=r)
+
+    def upload_observations(self):
+        C, Ny, Nx = self.frame_shape
+        for o, om in enumerate(self.obs_meta):
+            metas = om["metas"]
+            data = np.ascontiguousarray(np.stack([np.asarray(m["obs"].data, dtype=np.float32) for m in metas]))
+            weights = np.ascontiguousarray(np.stack([np.asarray(m["obs"].weights, dtype=np.float32) for m in metas]))
+            khat = None
+            if metas[0]["kind"] == 0:
+                ks = [metas[0]["khat"]] if om["shared"] else [m["khat"] for m in metas]
+                khat = np.ascontiguousarray(np.stack(ks), dtype=np.complex128)
+            consts = []
+            for m in metas:
+                obs, (oy, ox) = m["obs"], m["origin"]
+                H, W = obs.data.shape[1:]
+                outside = np.ones((H, W), dtype=bool)
+                y0, y1, x0, x1 = max(0, -oy), min(H, Ny - oy), max(0, -ox), min(W, Nx - ox)
+                if y1 > y0 and x1 > x0:
+                    outside[y0:y1, x0:x1] = False
+                extra = 0.0
+                if outside.any():
+                    w = np.asarray(obs.weights, dtype=np.float64)[:, outside]
+                    dd = np.asarray(obs.data, dtype=np.float64)[:, outside]
+                    extra = 0.5 * float((w * dd * dd).sum())
+                consts.append(float(obs.log_norm) + extra)
+            consts = np.asarray(consts, dtype=np.float64)
+            nat.check(nat.lib().sb_plan_upload_observation(self._handle, o, nat.ptr(data), nat.ptr(weights),
+                                                           nat.ptr(khat.view(np.float64)) if khat is not None else None,
+                                                           nat.ptr(consts)))
+
+    # -------------------------------------------------------------------------------------------------
+    def _pack(self, which):
+        """Host Parameters -> packed float64 arrays (which: 0 value, 1 m, 2 v, 3 vhat)."""
+        attr = (None, "m", "v", "vhat")[which]
+
+        def get(p):
+            a = p._data if attr is None else getattr(p, attr)
+            return np.zeros(p.shape) if a is None else np.asarray(a, dtype=np.float64)
+
+        sed = np.zeros((max(self.n_src, 1), self.C))
+        for k, s in enumerate(self.slots):
+            sed[k] = get(s["spectrum"])
+        morph = np.zeros(max(self.n_morph, 1))
+        for s, a, b in zip(self.ext, self.morph_offsets[:-1], self.morph_offsets[1:]):
+            morph[a:b] = get(s["image"]).reshape(-1)
+        cen = np.zeros((max(len(self.pts), 1), 2))
+        for i, s in enumerate(self.pts):
+            cen[i] = get(s["center"])
+        return sed, morph, cen
+
+    def upload_parameters(self, state=True):
+        for which in ((0, 1, 2, 3) if state else (0,)):
+            sed, morph, cen = self._pack(which)
+            nat.check(nat.lib().sb_plan_upload_params(self._handle, which, nat.ptr(sed), nat.ptr(morph), nat.ptr(cen)))
+
+    def download_parameters(self, state=True):
+        """Device -> the same host Parameter objects, in place (values keep their dtype; m/v/vhat float64)."""
+        for which in ((0, 1, 2, 3) if state else (0,)):
+            sed = np.zeros((max(self.n_src, 1), self.C))
+            morph = np.zeros(max(self.n_morph, 1))
+            cen = np.zeros((max(len(self.pts), 1), 2))
+            nat.check(nat.lib().sb_plan_download_params(self._handle, which, nat.ptr(sed), nat.ptr(morph), nat.ptr(cen)))
+            attr = (None, "m", "v", "vhat")[which]
+
+            def put(p, val):
+                if attr is None:
+                    p._data[...] = val.reshape(p.shape)
+                else:
+                    setattr(p, attr, np.array(val, dtype=np.float64).reshape(p.shape))
+
+            for k, s in enumerate(self.slots):
+                put(s["spectrum"], sed[k])
+            for s, a, b in zip(self.ext, self.morph_offsets[:-1], self.morph_offsets[1:]):
+                put(s["image"], morph[a:b])
+                sh = s.get("shift")
+                if sh is not None and attr is not None and getattr(sh, attr) is None:
+                    setattr(sh, attr, np.zeros(sh.shape))  # free but unused parameter: zero gradient forever
+            for i, s in enumerate(self.pts):
+                put(s["center"], cen[i])
+        if state:
+            for s in self.slots:
+                for key in ("spectrum", "image", "center", "shift"):
+                    p = s.get(key)
+                    if p is not None and p.v is not None:
+                        p.std = 1 / np.sqrt(ma.masked_equal(p.v, 0))
+
+    # -------------------------------------------------------------------------------------------------
+    def evaluate(self, obs=0, want=("model", "rendered", "loss", "grads")):
+        """One forward + backward at the device's current parameters (no update)."""
+        C, Ny, Nx = self.frame_shape
+        m0 = self.obs_meta[obs]["metas"][0]
+        out = {}
+        model = np.zeros((self.S, C, Ny, Nx)) if "model" in want else None
+        rendered = np.zeros((self.S,) + m0["shape"]) if "rendered" in want else None
+        loss = np.zeros(self.S) if "loss" in want else None
+        g_sed = g_morph = g_cen = None
+        if "grads" in want:
+            g_sed = np.zeros((max(self.n_src, 1), self.C))
+            g_morph = np.zeros(max(self.n_morph, 1))
+            g_cen = np.zeros((max(len(self.pts), 1), 2))
+        nat.check(nat.lib().sb_plan_evaluate(self._handle, obs, nat.ptr(model), nat.ptr(rendered), nat.ptr(loss),
+                                             nat.ptr(g_sed), nat.ptr(g_morph), nat.ptr(g_cen)))
+        out.update(model=model, rendered=rendered, loss=loss)
+        if "grads" in want:
+            out["g_sed"] = g_sed[:self.n_src]
+            out["g_morph"] = [g_morph[a:b].reshape(s["image"].shape)
+                              for s, a, b in zip(self.ext, self.morph_offsets[:-1], self.morph_offsets[1:])]
+            out["g_center"] = g_cen[:len(self.pts)]
+        return out
+
+    def fit(self, opts):
+        n_iter = np.zeros(self.S, dtype=np.int32)
+        status = np.zeros(self.S, dtype=np.int32)
+        loss = np.zeros((self.S, max(opts.max_iter, 1)))
+        nat.check(nat.lib().sb_plan_fit(self._handle, ctypes.byref(opts), nat.ptr(n_iter), nat.ptr(loss), nat.ptr(status)))
+        return n_iter, loss, status
+
+    def fit_enqueue(self, opts, n_iterations):
+        nat.check(nat.lib().sb_plan_fit_enqueue(self._handle, ctypes.byref(opts), int(n_iterations)))
+
+    def sync(self):
+        nat.check(nat.lib().sb_plan_sync(self._handle))
+
+    def timer_start(self):
+        nat.check(nat.lib().sb_plan_timer_start(self._handle))
+
+    def timer_stop(self):
+        ms = ctypes.c_float()
+        nat.check(nat.lib().sb_plan_timer_stop(self._handle, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def profile(self, opts, n_iterations):
+        ms = np.zeros(nat.SB_N_STAGES, dtype=np.float32)
+        nat.check(nat.lib().sb_plan_profile_iterations(self._handle, ctypes.byref(opts), int(n_iterations), nat.ptr(ms)))
+        names = [nat.lib().sb_stage_name(i).decode() for i in range(nat.SB_N_STAGES)]
+        return dict(zip(names, (ms / max(n_iterations, 1)).tolist()))
+
+    @property
+    def kernel_launches(self):
+        return int(nat.lib().sb_plan_kernel_launches(self._handle))
+
+    @property
+    def device_bytes(self):
+        return int(nat.lib().sb_plan_device_bytes(self._handle))
+
+    def device_params(self):
+        sed, morph = ctypes.c_void_p(), ctypes.c_void_p()
+        n_sed, n_morph, eb = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
+        nat.check(nat.lib().sb_plan_device_params(self._handle, ctypes.byref(sed), ctypes.byref(n_sed), ctypes.byref(morph),
+                                                  ctypes.byref(n_morph), ctypes.byref(eb)))
+        return dict(sed=sed.value, n_sed=n_sed.value, morph=morph.value, n_morph=n_morph.value, elem_bytes=eb.value)
+
+    def close(self):
+        if self._handle is not None:
+            nat.lib().sb_plan_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

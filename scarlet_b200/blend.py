@@ -1,0 +1,132 @@
+"""The blended scene and its fitting loop.  Mirrors scarlet/blend.py (``Blend`` 49-308).
+
+``Blend.fit`` keeps the reference's signature, return value and side effects (parameters updated in place,
+``m/v/vhat/std`` filled, ``blend.loss`` extended by one entry per gradient evaluation) but the loop itself --
+render, PSF convolution, residual, gradients, AMSGrad step, constraint projections, stop rule -- runs on the
+GPU as a CUDA graph per iteration (csrc/).  ``BlendBatch`` fits many independent scenes in one plan: the
+data-parallel axis the reference leaves to a user-level loop (testing/api.py:216-226).
+"""
+import logging
+
+import numpy as np
+
+from . import _native as nat
+from ._plan import DevicePlan
+from .component import CombinedComponent
+
+logger = logging.getLogger("scarlet_b200.blend")
+
+
+def _fit_options(max_iter, e_rel, min_iter, noise_factor, alg_kwargs, check_every):
+    if noise_factor:
+        raise NotImplementedError("noise_factor > 0 (host RNG noise injection) is outside the device path")
+    kw = dict(alg_kwargs)
+    scheme = kw.pop("scheme", "amsgrad")
+    if scheme != "amsgrad":
+        raise NotImplementedError("only scheme='amsgrad' (the reference default, blend.py:144) is implemented")
+    if kw.pop("callback", None) is not None:
+        raise NotImplementedError("per-iteration host callbacks would serialise the device loop; not supported")
+    prox_max_iter = kw.pop("prox_max_iter", 10)
+    b1, b2, eps = kw.pop("b1", 0.9), kw.pop("b2", 0.999), kw.pop("eps", 1e-8)
+    kw.pop("p", None)
+    if np.ndim(b1) != 0:
+        raise NotImplementedError("per-iteration b1 schedules are not supported")
+    fixed = bool(kw.pop("fixed_iterations", False))
+    if kw:
+        raise TypeError("unsupported optimiser keywords: %s" % sorted(kw))
+    return nat.fit_opts(max_iter=max_iter, e_rel=e_rel, min_iter=min_iter, prox_max_iter=prox_max_iter,
+                        check_every=check_every, fixed_iterations=fixed, b1=b1, b2=b2, eps=eps)
+
+
+class Blend(CombinedComponent):
+    def __init__(self, sources, observations, precision=32, device=None):
+        self.sources = sources if hasattr(sources, "__iter__") else (sources,)
+        self.observations = observations if hasattr(observations, "__iter__") else (observations,)
+        super().__init__(list(self.sources))
+        self.loss = []
+        self._precision = precision
+        self._device = device
+        self._plan = None
+        self._plan_key = None
+
+    # -- device plan ----------------------------------------------------------------------------------
+    def _structure_key(self):
+        return tuple((id(p), p.shape) for p in self.parameters) + tuple(id(getattr(o, "renderer", None)) for o in self.observations)
+
+    def _get_plan(self):
+        key = self._structure_key()
+        if self._plan is None or key != self._plan_key:
+            if self._plan is not None:
+                self._plan.close()
+            self._plan = DevicePlan([self], precision=self._precision, device=self._device)
+            self._plan_key = key
+        return self._plan
+
+    # -- the fitting loop -----------------------------------------------------------------------------
+    def fit(self, max_iter=200, e_rel=1e-3, min_iter=1, noise_factor=0, **alg_kwargs):
+        """Fit the model of every source to the data.  Returns ``(len(self.log_likelihood), logL)``."""
+        check_every = int(alg_kwargs.pop("check_every", 10))
+        opts = _fit_options(max_iter, e_rel, min_iter, noise_factor, alg_kwargs, check_every)
+        for src in self.sources:
+            src.check_parameters()
+        if max_iter <= 0:
+            return len(self.loss), (-self.loss[-1] if self.loss else None)
+        plan = self._get_plan()
+        plan.upload_parameters(state=True)
+        n_iter, loss, status = plan.fit(opts)
+        plan.download_parameters(state=True)
+        n = int(n_iter[0])
+        self.loss.extend(float(x) for x in loss[0, :n])
+        if status[0] == nat.SB_ERR_NONFINITE:
+            for src in self.sources:
+                src.check_parameters()  # raises ArithmeticError naming the parameter (model.py:153-165)
+            raise ArithmeticError("a parameter became non-finite during the fit")
+        logger.info("scarlet ran for {0} iterations to logL = {1}".format(len(self.loss), -self.loss[-1]))
+        return len(self.loss), -self.loss[-1]
+
+    # -- forward --------------------------------------------------------------------------------------
+    def get_model(self, *parameters, frame=None):
+        """Model of the entire blend in the model frame, rendered on the device."""
+        if parameters:
+            raise NotImplementedError("explicit parameter tuples (autograd tracing) do not exist on the device path")
+        plan = self._get_plan()
+        plan.upload_parameters(state=False)
+        model = plan.evaluate(want=("model",))["model"][0].astype(self.frame.dtype)
+        if frame is not None and frame is not self.frame and frame.bbox != self.frame.bbox:
+            from .bbox import overlapped_slices
+            out = np.zeros(frame.shape, dtype=frame.dtype)
+            fs, ms = overlapped_slices(frame.bbox, self.frame.bbox)
+            out[fs] = model[ms]
+            return out
+        return model
+
+    @property
+    def log_likelihood(self):
+        return -np.array(self.loss)
+
+    @property
+    def bbox(self):
+        return self.frame.bbox
+
+
+class BlendBatch:
+    """Many independent, structurally identical scenes fitted together on one GPU."""
+
+    def __init__(self, blends, precision=32, device=None):
+        self.blends = list(blends)
+        self.plan = DevicePlan(self.blends, precision=precision, device=device)
+
+    def fit(self, max_iter=200, e_rel=1e-3, min_iter=1, noise_factor=0, **alg_kwargs):
+        check_every = int(alg_kwargs.pop("check_every", 10))
+        opts = _fit_options(max_iter, e_rel, min_iter, noise_factor, alg_kwargs, check_every)
+        self.plan.upload_parameters(state=True)
+        n_iter, loss, status = self.plan.fit(opts)
+        self.plan.download_parameters(state=True)
+        results = []
+        for s, b in enumerate(self.blends):
+            n = int(n_iter[s])
+            b.loss.extend(float(x) for x in loss[s, :n])
+            if status[s] == nat.SB_ERR_NONFINITE:
+                raise ArithmeticError("scene %d: a parameter became non-finite during the fit" % s)
+            results.append((len(b.loss), -b.loss[-1]))
+        return results

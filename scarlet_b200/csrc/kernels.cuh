@@ -1,0 +1,739 @@
+// Device kernels of the scarlet_b200 fitting path (sm_100a).  Templated on the real type T (float = product
+// path, double = high-precision twin used to separate algorithmic from rounding differences in the parity tests).
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+// ======================================================================================================
+// radial monotonicity: wavefront sweep
+// reference: scarlet/operators_pybind11.cc:14-36 (sequential sweep in distance order).  A pixel only reads
+// neighbours that are STRICTLY closer to the centre (operator.py:612-614), so pixels fall into dependency
+// levels; all pixels of a level are independent.  Per pixel the arithmetic (sum over the positive-weight
+// neighbours in offset order, un-fused multiply/add, times (1-min_gradient), min) is the reference's, hence
+// the result is bit-identical to the sequential sweep.
+// ======================================================================================================
+template <typename T> struct __align__(16) W4 { T a, b, c, d; };
+
+template <typename T, int NB> struct MonoRec {
+    int pix;
+    uint2 nbr[NB / 4];
+    W4<T> w[NB / 4];
+};
+
+template <typename T, int NB>
+__device__ __forceinline__ void mono_load(MonoRec<T, NB> &r, const DevMono &mo, int j) {
+    r.pix = __ldg(mo.pix + j);
+    const uint2 *nbr = reinterpret_cast<const uint2 *>(mo.code);
+    const W4<T> *w = reinterpret_cast<const W4<T> *>(mo.w);
+#pragma unroll
+    for (int g = 0; g < NB / 4; ++g) {
+        r.nbr[g] = nbr[(size_t)g * mo.n_tasks + j];
+        r.w[g] = w[(size_t)g * mo.n_tasks + j];
+    }
+}
+
+template <typename T, int NB>
+__device__ __forceinline__ void mono_apply(T *img, const MonoRec<T, NB> &r, T keep) {
+    T ref = T(0);
+#pragma unroll
+    for (int g = 0; g < NB / 4; ++g) {
+        const unsigned n0 = r.nbr[g].x & 0xffffu, n1 = r.nbr[g].x >> 16, n2 = r.nbr[g].y & 0xffffu, n3 = r.nbr[g].y >> 16;
+        if (n0 != 0xffffu) ref = add_rn(ref, mul_rn(img[n0], r.w[g].a));
+        if (n1 != 0xffffu) ref = add_rn(ref, mul_rn(img[n1], r.w[g].b));
+        if (n2 != 0xffffu) ref = add_rn(ref, mul_rn(img[n2], r.w[g].c));
+        if (n3 != 0xffffu) ref = add_rn(ref, mul_rn(img[n3], r.w[g].d));
+    }
+    const T cap = mul_rn(ref, keep);
+    if (cap < img[r.pix]) img[r.pix] = cap;
+}
+
+// img lives in shared memory; every thread of the block calls this; ends with a block barrier.
+template <typename T, int NB> __device__ void mono_sweep(T *img, const DevMono &mo, T min_gradient) {
+    const T keep = T(1) - min_gradient;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int *ls = mo.level_start;
+    MonoRec<T, NB> nxt;
+    int beg = __ldg(ls), end = __ldg(ls + 1);
+    bool have = beg + tid < end;
+    if (have) mono_load<T, NB>(nxt, mo, beg + tid);
+    for (int L = 0; L < mo.n_levels; ++L) {
+        const MonoRec<T, NB> cur = nxt;
+        const bool chave = have;
+        const int cbeg = beg, cend = end;
+        if (L + 1 < mo.n_levels) { // prefetch this thread's first task of the next level before the barrier
+            beg = cend;
+            end = __ldg(ls + L + 2);
+            have = beg + tid < end;
+            if (have) mono_load<T, NB>(nxt, mo, beg + tid);
+        }
+        if (chave) mono_apply<T, NB>(img, cur, keep);
+        for (int j = cbeg + tid + nt; j < cend; j += nt) { // levels wider than the block (rare)
+            MonoRec<T, NB> extra;
+            mono_load<T, NB>(extra, mo, j);
+            mono_apply<T, NB>(img, extra, keep);
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T> __device__ __forceinline__ void mono_sweep_any(T *img, const DevMono &mo, T min_gradient) {
+    if (mo.nb == 4)
+        mono_sweep<T, 4>(img, mo, min_gradient);
+    else
+        mono_sweep<T, 8>(img, mo, min_gradient);
+}
+
+// ======================================================================================================
+// ConstraintChain on one image in shared memory (constraint.py:58-114, 183-287; operator.py:274-293)
+// ======================================================================================================
+template <typename T>
+__device__ void apply_chain(T *a, int By, int Bx, const DevChain &ch, const DevMono *monos, double *red) {
+    const int n = By * Bx, tid = threadIdx.x, nt = blockDim.x;
+    for (int r = 0; r < ch.repeat; ++r) {
+        for (int o = 0; o < ch.n_ops; ++o) {
+            const sb_op op = ch.ops[o];
+            switch (op.code) {
+            case SB_OP_MONOTONIC:
+                mono_sweep_any<T>(a, monos[op.iarg], (T)op.farg);
+                break;
+            case SB_OP_SYMMETRY: { // blend with the 180-degree rotation; even axes are extended by one zero line
+                const T s = (T)op.farg, hs = (T)(0.5 * op.farg), om = (T)(1.0 - op.farg);
+                const int Hy = By + ((By & 1) == 0), Wx = Bx + ((Bx & 1) == 0);
+                for (int p = tid; p < n; p += nt) {
+                    const int y = p / Bx, x = p - y * Bx;
+                    const int yr = Hy - 1 - y, xr = Wx - 1 - x;
+                    if (yr >= By || xr >= Bx) {
+                        const T u = a[p];
+                        a[p] = hs * (u + T(0)) + om * u;
+                    } else {
+                        const int q = yr * Bx + xr;
+                        if (q > p) {
+                            const T u = a[p], v = a[q];
+                            a[p] = hs * (u + v) + om * u;
+                            a[q] = hs * (v + u) + om * v;
+                        } else if (q == p) {
+                            const T u = a[p];
+                            a[p] = hs * (u + u) + om * u;
+                        }
+                    }
+                }
+                (void)s;
+                __syncthreads();
+                break;
+            }
+            case SB_OP_POSITIVITY: {
+                const T zero = (T)op.farg;
+                for (int p = tid; p < n; p += nt) a[p] = a[p] > zero ? a[p] : zero; // np.maximum
+                __syncthreads();
+                break;
+            }
+            case SB_OP_CENTER_ON: {
+                if (tid == 0) {
+                    const int c = (By / 2) * Bx + Bx / 2;
+                    const T tiny = (T)op.farg;
+                    a[c] = a[c] > tiny ? a[c] : tiny;
+                }
+                __syncthreads();
+                break;
+            }
+            case SB_OP_NORMALIZE: {
+                double acc;
+                if (op.iarg == 1) {
+                    acc = -INFINITY;
+                    for (int p = tid; p < n; p += nt) acc = fmax(acc, (double)a[p]);
+                    acc = block_max(acc, red);
+                } else {
+                    acc = 0.0;
+                    for (int p = tid; p < n; p += nt) acc += (double)a[p];
+                    acc = block_sum(acc, red);
+                }
+                const T den = (T)acc;
+                for (int p = tid; p < n; p += nt) a[p] = a[p] / den;
+                __syncthreads();
+                break;
+            }
+            default:
+                break;
+            }
+        }
+    }
+}
+
+// element-wise subset of the chain for 1-D spectra, executed by ONE thread (C <= 16 values)
+__device__ inline void apply_chain_1d(double *a, int n, const DevChain &ch) {
+    for (int r = 0; r < ch.repeat; ++r)
+        for (int o = 0; o < ch.n_ops; ++o) {
+            const sb_op op = ch.ops[o];
+            if (op.code == SB_OP_POSITIVITY) {
+                for (int i = 0; i < n; ++i) a[i] = a[i] > op.farg ? a[i] : op.farg;
+            } else if (op.code == SB_OP_NORMALIZE) {
+                double acc = op.iarg == 1 ? -INFINITY : 0.0;
+                for (int i = 0; i < n; ++i) acc = op.iarg == 1 ? fmax(acc, a[i]) : acc + a[i];
+                for (int i = 0; i < n; ++i) a[i] /= acc;
+            }
+        }
+}
+
+// ======================================================================================================
+// K1  render: model[c,y,x] = sum_k sed_k[c] * morph_k[y-oy_k, x-ox_k]   (gather form, deterministic order)
+// reference: component.py:144-171 (outer product), blend.py:17-27, 200-244 (insertion in source order).
+// The model is written straight into the zero-padded real FFT grid of every observation (image at the grid
+// origin -- the reference's centring + ifftshift cancel against fftshift + centre-crop).
+// ======================================================================================================
+template <typename T> struct RenderArgs {
+    const DevSource *src;
+    const int *scene_src_start;
+    const double *sed; // [n_src][C]
+    const T *morph;
+    const T *pmorph;
+    int C, Ny, Nx, n_obs;
+    DevObs<T> obs[SB_MAX_OBS];
+    const int *done;
+    const int *it_ptr;
+    double *loss;            // [S][cap]
+    const double *loss_const; // [S]
+    int cap;
+    T *model_out; // optional [S][C][Ny][Nx]
+};
+
+template <typename T> __global__ void __launch_bounds__(256) k_render(const RenderArgs<T> a) {
+    const int s = blockIdx.z;
+    if (a.done[s]) return;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0)
+        a.loss[(size_t)s * a.cap + *a.it_ptr] = a.loss_const[s];
+    if (x >= a.Nx || y >= a.Ny) return;
+    T acc[SB_MAXC];
+#pragma unroll
+    for (int c = 0; c < SB_MAXC; ++c) acc[c] = T(0);
+    const int k0 = a.scene_src_start[s], k1 = a.scene_src_start[s + 1];
+    const int C = a.C;
+    for (int k = k0; k < k1; ++k) {
+        const DevSource &d = a.src[k];
+        const int by = y - d.oy, bx = x - d.ox;
+        if ((unsigned)by < (unsigned)d.By && (unsigned)bx < (unsigned)d.Bx) {
+            const double *sed = a.sed + (size_t)k * C;
+            if (d.kind == 0) {
+                const T mv = a.morph[d.morph_off + (size_t)by * d.Bx + bx];
+#pragma unroll
+                for (int c = 0; c < SB_MAXC; ++c)
+                    if (c < C) acc[c] += (T)sed[c] * mv;
+            } else {
+                const T *pm = a.pmorph + d.morph_off + (size_t)by * d.Bx + bx;
+                const int plane = d.By * d.Bx;
+#pragma unroll
+                for (int c = 0; c < SB_MAXC; ++c)
+                    if (c < C) acc[c] += (T)sed[c] * pm[(size_t)c * plane];
+            }
+        }
+    }
+    for (int o = 0; o < a.n_obs; ++o) {
+        const DevObs<T> &ob = a.obs[o];
+#pragma unroll
+        for (int c = 0; c < SB_MAXC; ++c) {
+            const int co = c - ob.chan_off;
+            if (c < C && co >= 0 && co < ob.C) ob.A[(((size_t)s * ob.C + co) * ob.Fy + y) * ob.Fx + x] = acc[c];
+        }
+    }
+    if (a.model_out) {
+#pragma unroll
+        for (int c = 0; c < SB_MAXC; ++c)
+            if (c < C) a.model_out[(((size_t)s * C + c) * a.Ny + y) * a.Nx + x] = acc[c];
+    }
+}
+
+// ======================================================================================================
+// K2  k-space product  X^ *= K^  (or conj K^ for the adjoint)      reference: fft.py:316-331, 385-396
+// ======================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_kmul(typename Cx<T>::type *__restrict__ X, const typename Cx<T>::type *__restrict__ K, long long per_scene,
+       long long total, int shared, int conj, const int *done) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long s = i / per_scene;
+        if (done && done[s]) continue;
+        const typename Cx<T>::type k = K[shared ? i - s * per_scene : i];
+        const typename Cx<T>::type v = X[i];
+        const T ki = conj ? -k.y : k.y;
+        typename Cx<T>::type r;
+        r.x = v.x * k.x - v.y * ki;
+        r.y = v.x * ki + v.y * k.x;
+        X[i] = r;
+    }
+}
+
+// ======================================================================================================
+// K3  residual + loss: r = w (render - data), written into the (zero-padded) gradient grid; loss partials
+// reference: observation.py:147-170, renderer.py:130-161 (match_shape and its VJP)
+// ======================================================================================================
+template <typename T> struct ResidualArgs {
+    DevObs<T> ob;
+    int Ny, Nx, cap;
+    const int *done;
+    const int *it_ptr;
+    double *loss;
+    T *rendered_out; // optional [S][C][H][W]
+};
+
+template <typename T> __global__ void __launch_bounds__(256) k_residual(const ResidualArgs<T> a) {
+    __shared__ double red[40];
+    const DevObs<T> &ob = a.ob;
+    const int sc = blockIdx.z; // scene * C + channel
+    const int s = sc / ob.C;
+    if (a.done[s]) return;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    double part = 0.0;
+    if (x < a.Nx && y < a.Ny) {
+        const int dy = y - ob.oy, dx = x - ob.ox;
+        T r = T(0);
+        if ((unsigned)dy < (unsigned)ob.H && (unsigned)dx < (unsigned)ob.W) {
+            const size_t di = ((size_t)sc * ob.H + dy) * ob.W + dx;
+            const T m = ob.B[((size_t)sc * ob.Fy + y) * ob.Fx + x];
+            const T w = ob.weights[di];
+            const T diff = m - ob.data[di];
+            r = w * diff;
+            part = (double)w * (double)diff * (double)diff;
+            if (a.rendered_out) a.rendered_out[di] = m;
+        }
+        ob.A[((size_t)sc * ob.Fy + y) * ob.Fx + x] = r;
+    }
+    // block reduction (blockDim = 32x8 -> linear thread id)
+    const int lin = threadIdx.y * 32 + threadIdx.x;
+    part = warp_sum(part);
+    if ((lin & 31) == 0) red[lin >> 5] = part;
+    __syncthreads();
+    if (lin < 32) {
+        part = lin < 8 ? red[lin] : 0.0;
+        part = warp_sum(part);
+        if (lin == 0 && part != 0.0) atomicAdd(a.loss + (size_t)s * a.cap + *a.it_ptr, 0.5 * part);
+    }
+}
+
+// ======================================================================================================
+// pixel-integrated Gaussian (psf.py:129-142) and its derivative
+// ======================================================================================================
+__device__ __forceinline__ double gauss_int(double x, double sigma) {
+    const double s2 = sqrt(2.0) * sigma;
+    return sqrt(M_PI / 2) * sigma * (1 - erfc((0.5 - x) / s2) + 1 - erfc((2 * x + 1) / (2 * s2)));
+}
+__device__ __forceinline__ double gauss_int_deriv(double x, double sigma) {
+    return exp(-((x + 0.5) * (x + 0.5)) / (2 * sigma * sigma)) - exp(-((x - 0.5) * (x - 0.5)) / (2 * sigma * sigma));
+}
+
+// numpy's float mean for short vectors (pairwise_sum: n < 8 sequential; else 8 accumulators), parameter.py:126-129
+template <typename TS> __device__ inline TS numpy_mean(const double *x, int n) {
+    TS res;
+    if (n < 8) {
+        res = TS(0);
+        for (int i = 0; i < n; ++i) res += (TS)x[i];
+    } else {
+        TS r[8];
+        for (int j = 0; j < 8; ++j) r[j] = (TS)x[j];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += (TS)x[i + j];
+        res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += (TS)x[i];
+    }
+    return res / (TS)n;
+}
+
+// ======================================================================================================
+// K4/K5  per-source backward + AMSGrad adaprox update + constraint projections
+// reference: gradients = what autograd.grad yields at blend.py:118 (explicit forms lite/models.py:206-216);
+// update = proxmin.adaprox(scheme="amsgrad", prox_max_iter) as called at blend.py:165-180 (structure mirrored
+// in-tree at lite/parameters.py:274-305); step sizes blend.py:135-138, parameter.py:126-129.
+// ======================================================================================================
+template <typename T> struct UpdateArgs {
+    const DevSource *src;
+    int C, Ny, Nx, n_obs;
+    DevObs<T> obs[SB_MAX_OBS];
+    double *sed, *sed_m, *sed_v, *sed_vhat;
+    T *morph, *morph_m, *morph_v, *morph_vhat;
+    double *center, *cen_m, *cen_v, *cen_vhat;
+    T *pmorph;
+    const DevChain *chains;
+    const DevMono *monos;
+    const int *it_ptr;
+    const int *done;
+    int *status;
+    FitScalars fs;
+    int psf_b;
+    double psf_sigma[SB_MAXC];
+    int npix_max; // shared-memory array length
+    int mode;     // 0 = update, 1 = gradients only
+    double *g_sed, *g_morph, *g_center;
+};
+
+// gradient of the loss wrt the model at frame pixel (y,x), channel c: sum over the observations that see c
+template <typename T>
+__device__ __forceinline__ double grad_at(const UpdateArgs<T> &a, int s, int c, int y, int x) {
+    double g = 0.0;
+    for (int o = 0; o < a.n_obs; ++o) {
+        const DevObs<T> &ob = a.obs[o];
+        const int co = c - ob.chan_off;
+        if (co >= 0 && co < ob.C) g += (double)ob.B[(((size_t)s * ob.C + co) * ob.Fy + y) * ob.Fx + x];
+    }
+    return g;
+}
+
+// AMSGrad moments (Reddi, Kale & Kumar 2018, no bias correction) -- proxmin's _amsgrad_phi_psi as restated
+// in oracle/scarlet_oracle.py:amsgrad_phi_psi.  Returns psi; m, v, vhat updated in place.
+__device__ __forceinline__ double amsgrad(double g, double &m, double &v, double &vhat, int it, const FitScalars &fs) {
+    m = (1 - fs.b1) * g + fs.b1 * m;
+    v = (1 - fs.b2) * (g * g) + fs.b2 * v;
+    vhat = (it == 0 && fs.overwrite_vhat_at_it0) ? v : fmax(vhat, v);
+    return sqrt(fs.eps > 0 ? fmax(vhat, fs.eps) : vhat);
+}
+
+// spectrum update, executed by one thread.  g: gradient [C].
+template <typename T>
+__device__ void sed_update(const UpdateArgs<T> &a, const DevSource &d, int k, const double *g, int it) {
+    const int C = a.C;
+    double *x = a.sed + (size_t)k * C, *m = a.sed_m + (size_t)k * C, *v = a.sed_v + (size_t)k * C,
+           *vh = a.sed_vhat + (size_t)k * C;
+    double alpha[SB_MAXC], psi[SB_MAXC], xn[SB_MAXC], z[SB_MAXC], zn[SB_MAXC];
+    double rel = 0.0;
+    if (d.sed_step_factor >= 0) {
+        if (d.sed_is_f32)
+            rel = (double)((float)d.sed_step_factor * numpy_mean<float>(x, C));
+        else
+            rel = d.sed_step_factor * numpy_mean<double>(x, C);
+    }
+    double psimax = 0.0;
+    for (int c = 0; c < C; ++c) {
+        alpha[c] = d.sed_step_factor >= 0 ? fmax(d.sed_step_min[c], rel) : d.sed_step_min[0];
+        double mm = m[c], vv = v[c], vvh = vh[c];
+        psi[c] = amsgrad(g[c], mm, vv, vvh, it, a.fs);
+        m[c] = mm, v[c] = vv, vh[c] = vvh;
+        xn[c] = x[c] - alpha[c] * mm / psi[c];
+        if (d.sed_is_f32) xn[c] = (double)(float)xn[c];
+        psimax = fmax(psimax, psi[c]);
+    }
+    if (d.sed_chain >= 0) {
+        const DevChain &ch = a.chains[d.sed_chain];
+        for (int c = 0; c < C; ++c) z[c] = xn[c];
+        for (int sub = 0; sub < a.fs.prox_max_iter; ++sub) {
+            for (int c = 0; c < C; ++c) {
+                const double gamma = alpha[c] / psimax;
+                zn[c] = z[c] - gamma / alpha[c] * psi[c] * (z[c] - xn[c]);
+            }
+            apply_chain_1d(zn, C, ch);
+            double dd = 0.0, nn = 0.0;
+            for (int c = 0; c < C; ++c) {
+                dd += (zn[c] - z[c]) * (zn[c] - z[c]);
+                nn += z[c] * z[c];
+                z[c] = zn[c];
+            }
+            if (dd <= a.fs.e_rel * a.fs.e_rel * nn) break;
+        }
+        for (int c = 0; c < C; ++c) xn[c] = d.sed_is_f32 ? (double)(float)z[c] : z[c];
+    }
+    bool bad = false;
+    for (int c = 0; c < C; ++c) {
+        x[c] = xn[c];
+        bad |= !isfinite(xn[c]);
+    }
+    if (bad) atomicExch(a.status + d.scene, SB_ERR_NONFINITE);
+}
+
+// normalised point-source morphology planes for the current centre (morphology.py:503-507, psf.py:103-127)
+// fy/fx: shared scratch of >= 16 doubles each.  Every thread of the block must call this.
+template <typename T>
+__device__ void point_planes(const UpdateArgs<T> &a, const DevSource &d, double cy, double cx, double *fy, double *fx) {
+    const int b = d.By, tid = threadIdx.x, nt = blockDim.x, C = a.C;
+    const double offy = cy - (d.oy + b / 2.0), offx = cx - (d.ox + b / 2.0);
+    T *pm = a.pmorph + d.morph_off;
+    for (int c = 0; c < C; ++c) {
+        const double sg = a.psf_sigma[c];
+        if (tid < b)
+            fy[tid] = gauss_int((double)(tid - b / 2) - offy, sg);
+        else if (tid < 2 * b)
+            fx[tid - b] = gauss_int((double)(tid - b - b / 2) - offx, sg);
+        __syncthreads();
+        double Sy = 0.0, Sx = 0.0;
+        for (int j = 0; j < b; ++j) Sy += fy[j], Sx += fx[j];
+        for (int p = tid; p < b * b; p += nt) {
+            const int by = p / b, bx = p - by * b;
+            pm[(size_t)c * b * b + p] = (T)((fy[by] * fx[bx]) / (Sy * Sx));
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T> __global__ void __launch_bounds__(128) k_point_morph(const UpdateArgs<T> a, int n_src) {
+    __shared__ double fy[16], fx[16];
+    const int k = blockIdx.x;
+    if (k >= n_src) return;
+    const DevSource &d = a.src[k];
+    if (d.kind != 1) return;
+    point_planes<T>(a, d, a.center[2 * d.point_idx], a.center[2 * d.point_idx + 1], fy, fx);
+}
+
+template <typename T> __device__ void update_point(const UpdateArgs<T> &a, const DevSource &d, int k, double *red) {
+    __shared__ double fy[16], fx[16], dfy[16], dfx[16], gsed[SB_MAXC];
+    const int b = d.By, tid = threadIdx.x, nt = blockDim.x, C = a.C, s = d.scene, it = *a.it_ptr;
+    double *cen = a.center + 2 * d.point_idx;
+    const double cy = cen[0], cx = cen[1];
+    const double offy = cy - (d.oy + b / 2.0), offx = cx - (d.ox + b / 2.0);
+    const double *sed = a.sed + (size_t)k * C;
+    double gc0 = 0.0, gc1 = 0.0;
+    for (int c = 0; c < C; ++c) {
+        const double sg = a.psf_sigma[c];
+        if (tid < b) {
+            const double X = (double)(tid - b / 2) - offy;
+            fy[tid] = gauss_int(X, sg);
+            dfy[tid] = -gauss_int_deriv(X, sg);
+        } else if (tid < 2 * b) {
+            const double X = (double)(tid - b - b / 2) - offx;
+            fx[tid - b] = gauss_int(X, sg);
+            dfx[tid - b] = -gauss_int_deriv(X, sg);
+        }
+        __syncthreads();
+        double Sy = 0.0, Sx = 0.0, Dy = 0.0, Dx = 0.0;
+        for (int j = 0; j < b; ++j) Sy += fy[j], Sx += fx[j], Dy += dfy[j], Dx += dfx[j];
+        double gs = 0.0;
+        const double sc = sed[c];
+        for (int p = tid; p < b * b; p += nt) {
+            const int by = p / b, bx = p - by * b, y = d.oy + by, x = d.ox + bx;
+            if ((unsigned)y < (unsigned)a.Ny && (unsigned)x < (unsigned)a.Nx) {
+                const double g = grad_at<T>(a, s, c, y, x);
+                const double ny = fy[by] / Sy, nx = fx[bx] / Sx;
+                const double dny = dfy[by] / Sy - fy[by] * Dy / (Sy * Sy), dnx = dfx[bx] / Sx - fx[bx] * Dx / (Sx * Sx);
+                gs += g * (ny * nx);
+                const double Gm = sc * g;
+                gc0 += Gm * (dny * nx);
+                gc1 += Gm * (ny * dnx);
+            }
+        }
+        gs = block_sum(gs, red);
+        if (tid == 0) gsed[c] = gs;
+        __syncthreads();
+    }
+    gc0 = block_sum(gc0, red);
+    gc1 = block_sum(gc1, red);
+    if (a.mode == 1) {
+        if (tid == 0) {
+            if (a.g_sed)
+                for (int c = 0; c < C; ++c) a.g_sed[(size_t)k * C + c] = gsed[c];
+            if (a.g_center) a.g_center[2 * d.point_idx] = gc0, a.g_center[2 * d.point_idx + 1] = gc1;
+        }
+        return;
+    }
+    if (tid == 0) {
+        if (!d.morph_fixed) {
+            const double g2[2] = {gc0, gc1};
+            double *m = a.cen_m + 2 * d.point_idx, *v = a.cen_v + 2 * d.point_idx, *vh = a.cen_vhat + 2 * d.point_idx;
+            for (int i = 0; i < 2; ++i) {
+                double mm = m[i], vv = v[i], vvh = vh[i];
+                const double psi = amsgrad(g2[i], mm, vv, vvh, it, a.fs);
+                m[i] = mm, v[i] = vv, vh[i] = vvh;
+                cen[i] = cen[i] - d.morph_step * mm / psi;
+                if (!isfinite(cen[i])) atomicExch(a.status + s, SB_ERR_NONFINITE);
+            }
+        }
+        if (!d.sed_fixed) sed_update<T>(a, d, k, gsed, it);
+    }
+    __syncthreads();
+    __threadfence_block();
+    point_planes<T>(a, d, cen[0], cen[1], fy, fx);
+}
+
+template <typename T> __device__ void update_extended(const UpdateArgs<T> &a, const DevSource &d, int k, unsigned char *smem) {
+    const int tid = threadIdx.x, nt = blockDim.x, C = a.C, s = d.scene, it = *a.it_ptr;
+    const int n = d.By * d.Bx, Bx = d.Bx;
+    T *xs = reinterpret_cast<T *>(smem);
+    T *z = xs + a.npix_max, *zn = z + a.npix_max, *ps = zn + a.npix_max;
+    double *red = reinterpret_cast<double *>(ps + a.npix_max);
+    double *gsum = red + 40;
+
+    double sedv[SB_MAXC], gs[SB_MAXC];
+#pragma unroll
+    for (int c = 0; c < SB_MAXC; ++c) {
+        sedv[c] = c < C ? a.sed[(size_t)k * C + c] : 0.0;
+        gs[c] = 0.0;
+    }
+    T *mp = a.morph + d.morph_off, *mm = a.morph_m + d.morph_off, *mv = a.morph_v + d.morph_off,
+      *mvh = a.morph_vhat + d.morph_off;
+    const double alpha = d.morph_step;
+    const bool upd = a.mode == 0 && !d.morph_fixed;
+    double pmax = 0.0;
+    for (int p = tid; p < n; p += nt) {
+        const int by = p / Bx, bx = p - by * Bx, y = d.oy + by, x = d.ox + bx;
+        const T mval = mp[p];
+        double gm = 0.0;
+        if ((unsigned)y < (unsigned)a.Ny && (unsigned)x < (unsigned)a.Nx) {
+#pragma unroll
+            for (int c = 0; c < SB_MAXC; ++c) {
+                if (c < C) {
+                    const double g = grad_at<T>(a, s, c, y, x);
+                    gm += sedv[c] * g;
+                    gs[c] += g * (double)mval;
+                }
+            }
+        }
+        if (upd) {
+            double m_ = (double)mm[p], v_ = (double)mv[p], vh_ = (double)mvh[p];
+            const double psi = amsgrad(gm, m_, v_, vh_, it, a.fs);
+            mm[p] = (T)m_, mv[p] = (T)v_, mvh[p] = (T)vh_;
+            xs[p] = (T)((double)mval - alpha * m_ / psi);
+            ps[p] = (T)psi;
+            pmax = fmax(pmax, psi);
+        } else {
+            xs[p] = mval;
+        }
+        if (a.mode == 1 && a.g_morph) a.g_morph[d.morph_off + p] = gm;
+    }
+    // spectrum gradient: block reduction per band (double)
+#pragma unroll
+    for (int c = 0; c < SB_MAXC; ++c) {
+        if (c < C) {
+            const double t = block_sum(gs[c], red);
+            if (tid == 0) gsum[c] = t;
+        }
+    }
+    __syncthreads();
+    if (a.mode == 1) {
+        if (tid == 0 && a.g_sed)
+            for (int c = 0; c < C; ++c) a.g_sed[(size_t)k * C + c] = gsum[c];
+        return;
+    }
+    if (upd) {
+        const double psimax = block_max(pmax, red);
+        if (d.chain >= 0) {
+            const DevChain &ch = a.chains[d.chain];
+            const double gamma = alpha / psimax;
+            const double fac = gamma / alpha;
+            for (int p = tid; p < n; p += nt) z[p] = xs[p];
+            for (int sub = 0; sub < a.fs.prox_max_iter; ++sub) {
+                for (int p = tid; p < n; p += nt) {
+                    const double zz = (double)z[p];
+                    zn[p] = (T)(zz - fac * (double)ps[p] * (zz - (double)xs[p]));
+                }
+                __syncthreads();
+                apply_chain<T>(zn, d.By, d.Bx, ch, a.monos, red);
+                double dd = 0.0, nn = 0.0;
+                for (int p = tid; p < n; p += nt) {
+                    const double zo = (double)z[p], zv = (double)zn[p];
+                    dd += (zv - zo) * (zv - zo);
+                    nn += zo * zo;
+                    z[p] = zn[p];
+                }
+                dd = block_sum(dd, red);
+                nn = block_sum(nn, red);
+                if (dd <= a.fs.e_rel * a.fs.e_rel * nn) break;
+            }
+            bool bad = false;
+            for (int p = tid; p < n; p += nt) {
+                const T r = z[p];
+                mp[p] = r;
+                bad |= !isfinite((double)r);
+            }
+            if (bad) atomicExch(a.status + s, SB_ERR_NONFINITE);
+        } else {
+            bool bad = false;
+            for (int p = tid; p < n; p += nt) {
+                const T r = xs[p];
+                mp[p] = r;
+                bad |= !isfinite((double)r);
+            }
+            if (bad) atomicExch(a.status + s, SB_ERR_NONFINITE);
+        }
+    }
+    if (tid == 0 && !d.sed_fixed) sed_update<T>(a, d, k, gsum, it);
+}
+
+template <typename T> __global__ void __launch_bounds__(128) k_update(const UpdateArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int k = blockIdx.x;
+    const DevSource &d = a.src[k];
+    if (a.done[d.scene]) return;
+    if (d.kind == 0) {
+        update_extended<T>(a, d, k, smem);
+    } else {
+        double *red = reinterpret_cast<double *>(smem);
+        update_point<T>(a, d, k, red);
+    }
+}
+
+// ======================================================================================================
+// K7  per-scene stop rule + iteration counter      reference: blend.py:276-302 (Blend._callback)
+// ======================================================================================================
+__global__ void __launch_bounds__(256)
+k_advance(int S, int cap, const double *loss, int *done, int *n_iter, int *it_ptr, int *n_active, const int *status,
+          FitScalars fs) {
+    __shared__ double red[40];
+    const int it = *it_ptr;
+    int active = 0;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        if (done[s]) continue;
+        n_iter[s] = it + 1;
+        bool stop = status[s] != 0;
+        if (!fs.fixed_iterations && it > 0 && it > fs.min_iter) {
+            const double l1 = loss[(size_t)s * cap + it], l0 = loss[(size_t)s * cap + it - 1];
+            if (fabs(l1 - l0) < fs.e_rel * fabs(l1)) stop = true;
+        }
+        if (stop)
+            done[s] = 1;
+        else
+            active++;
+    }
+    const double tot = block_sum((double)active, red);
+    if (threadIdx.x == 0) {
+        *n_active = (int)tot;
+        *it_ptr = it + 1;
+    }
+}
+
+// ======================================================================================================
+// single-operator kernels (test / plugin entry points)
+// ======================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(128) k_chain_only(T *img, int By, int Bx, const DevChain *ch, const DevMono *monos) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int n = By * Bx, npad = (n + 1) & ~1;
+    T *a = reinterpret_cast<T *>(smem);
+    double *red = reinterpret_cast<double *>(a + npad + (sizeof(T) == 4 ? (npad & 2) : 0));
+    T *g = img + (size_t)blockIdx.x * n;
+    for (int p = threadIdx.x; p < n; p += blockDim.x) a[p] = g[p];
+    __syncthreads();
+    apply_chain<T>(a, By, Bx, *ch, monos, red);
+    for (int p = threadIdx.x; p < n; p += blockDim.x) g[p] = a[p];
+}
+
+template <typename T> __global__ void k_cast_scale_cplx(const double2 *in, typename Cx<T>::type *out, long long n, double scale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        typename Cx<T>::type r;
+        r.x = (T)(in[i].x * scale);
+        r.y = (T)(in[i].y * scale);
+        out[i] = r;
+    }
+}
+template <typename TI, typename TO> __global__ void k_cast(const TI *in, TO *out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = (TO)in[i];
+}
+// copy the [0:Ny,0:Nx) corner of padded grids to a dense cube and back
+template <typename T> __global__ void k_crop(const T *grid, T *out, int n_img, int Fy, int Fx, int Ny, int Nx) {
+    const long long total = (long long)n_img * Ny * Nx;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = i % Nx;
+        const long long t = i / Nx;
+        const int y = t % Ny;
+        const long long im = t / Ny;
+        out[i] = grid[(im * Fy + y) * Fx + x];
+    }
+}
+template <typename T> __global__ void k_embed(const T *in, T *grid, int n_img, int Fy, int Fx, int Ny, int Nx) {
+    const long long total = (long long)n_img * Ny * Nx;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = i % Nx;
+        const long long t = i / Nx;
+        const int y = t % Ny;
+        const long long im = t / Ny;
+        grid[(im * Fy + y) * Fx + x] = in[i];
+    }
+}
+
+} // namespace sb

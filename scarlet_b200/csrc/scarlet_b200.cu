@@ -1,0 +1,1048 @@
+// scarlet_b200 -- host side of the CUDA library: plan (device memory, cuFFT plans, CUDA graph of one
+// proximal-gradient iteration) and the C ABI declared in include/scarlet_b200.h.
+//
+// The plan replaces the closures that scarlet's Blend.fit hands to proxmin.adaprox
+// (reference scarlet/blend.py:103-180): gradient of the loss, step sizes, proximal operators, callback.
+#include <stdarg.h>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+
+#include "kernels.cuh"
+
+namespace sb {
+
+thread_local std::string g_err;
+int set_err(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+static const char *kStageNames[SB_N_STAGES] = {"render",       "fft_fwd_model", "kmul",     "fft_inv_model", "residual_loss",
+                                               "fft_fwd_resid", "kmul_conj",     "fft_inv_grad", "source_update", "advance"};
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    int alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return SB_OK;
+        SB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+        return SB_OK;
+    }
+    int zero(cudaStream_t st) {
+        if (n) SB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), st));
+        return SB_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// ---- wavefront tables ---------------------------------------------------------------------------
+struct HostMono {
+    int n_pix = 0, n_tasks = 0, n_levels = 0, nb = 4;
+    int off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<int> pix, level_start;
+    std::vector<uint16_t> nbr; // [nb][n_tasks] (grouped by 4 below when uploaded)
+    std::vector<double> w;     // [nb][n_tasks]
+};
+
+// Turn the arguments of the reference's sequential sweep into a level schedule that is exact for ANY input
+// (read-after-write, write-after-write and write-after-read hazards between tasks are all honoured).
+template <typename T> static int build_mono(const sb_mono_desc &d, HostMono &h) {
+    if (d.n_pix <= 0 || d.n_pix >= 0xffff) return set_err(SB_ERR_ARG, "monotonic operator: n_pix=%d out of range", d.n_pix);
+    if (d.n_off <= 0 || d.n_off > 8) return set_err(SB_ERR_ARG, "monotonic operator: n_off=%d (max 8)", d.n_off);
+    if (!d.weights || !d.offsets || (d.n_idx > 0 && !d.dist_idx)) return set_err(SB_ERR_ARG, "monotonic operator: null table");
+    h.n_pix = d.n_pix;
+    h.n_tasks = d.n_idx;
+    for (int i = 0; i < d.n_off; ++i) h.off[i] = d.offsets[i];
+    std::vector<int> last_w(d.n_pix, 0), last_r(d.n_pix, 0), level(d.n_idx, 0), cnt(d.n_idx, 0);
+    std::vector<uint16_t> nb8((size_t)8 * d.n_idx, 0xffff);
+    std::vector<double> w8((size_t)8 * d.n_idx, 0.0);
+    int maxcnt = 0, maxlvl = 0;
+    for (int t = 0; t < d.n_idx; ++t) {
+        const int p = d.dist_idx[t];
+        if (p < 0 || p >= d.n_pix) return set_err(SB_ERR_ARG, "monotonic operator: dist_idx[%d]=%d out of range", t, p);
+        int lvl = std::max(last_w[p], last_r[p]);
+        int c = 0;
+        for (int i = 0; i < d.n_off; ++i) {
+            const T wt = (T)d.weights[(size_t)i * d.n_pix + p]; // the reference tests the weight in the image dtype
+            if (wt > 0) {
+                const int q = p + d.offsets[i];
+                if (q < 0 || q >= d.n_pix) return set_err(SB_ERR_ARG, "monotonic operator: neighbour of pixel %d outside the image", p);
+                lvl = std::max(lvl, last_w[q]);
+                nb8[(size_t)c * d.n_idx + t] = (uint16_t)q;
+                w8[(size_t)c * d.n_idx + t] = (double)wt;
+                ++c;
+            }
+        }
+        lvl += 1;
+        for (int i = 0; i < c; ++i) {
+            const int q = nb8[(size_t)i * d.n_idx + t];
+            last_r[q] = std::max(last_r[q], lvl);
+        }
+        last_w[p] = lvl;
+        level[t] = lvl;
+        cnt[t] = c;
+        maxcnt = std::max(maxcnt, c);
+        maxlvl = std::max(maxlvl, lvl);
+    }
+    h.nb = maxcnt <= 4 ? 4 : 8;
+    h.n_levels = maxlvl;
+    // stable counting sort by level
+    h.level_start.assign(maxlvl + 1, 0);
+    for (int t = 0; t < d.n_idx; ++t) h.level_start[level[t]]++; // level in 1..maxlvl -> slot level
+    {
+        int run = 0;
+        for (int l = 1; l <= maxlvl; ++l) {
+            const int c = h.level_start[l];
+            h.level_start[l - 1] = run;
+            run += c;
+        }
+        h.level_start[maxlvl] = run;
+    }
+    std::vector<int> cursor(h.level_start.begin(), h.level_start.end());
+    h.pix.assign(d.n_idx, 0);
+    h.nbr.assign((size_t)h.nb * d.n_idx, 0xffff);
+    h.w.assign((size_t)h.nb * d.n_idx, 0.0);
+    for (int t = 0; t < d.n_idx; ++t) {
+        const int j = cursor[level[t] - 1]++;
+        h.pix[j] = d.dist_idx[t];
+        for (int i = 0; i < cnt[t]; ++i) {
+            h.nbr[(size_t)i * d.n_idx + j] = nb8[(size_t)i * d.n_idx + t];
+            h.w[(size_t)i * d.n_idx + j] = w8[(size_t)i * d.n_idx + t];
+        }
+    }
+    return SB_OK;
+}
+
+template <typename T> struct MonoDevice {
+    DevBuf<int> pix, level_start;
+    DevBuf<uint2> nbr;
+    DevBuf<W4<T>> w;
+    DevMono dev;
+    int upload(const HostMono &h, cudaStream_t st) {
+        const int n = h.n_tasks, groups = h.nb / 4;
+        SB_TRY(pix.alloc(std::max(n, 1)));
+        SB_TRY(level_start.alloc(h.level_start.size() + 1));
+        SB_TRY(nbr.alloc((size_t)groups * std::max(n, 1)));
+        SB_TRY(w.alloc((size_t)groups * std::max(n, 1)));
+        std::vector<uint2> hn((size_t)groups * std::max(n, 1));
+        std::vector<W4<T>> hw((size_t)groups * std::max(n, 1));
+        for (int g = 0; g < groups; ++g)
+            for (int j = 0; j < n; ++j) {
+                const uint16_t *q = &h.nbr[0];
+                const size_t s0 = (size_t)(4 * g) * n + j, s1 = s0 + n, s2 = s1 + n, s3 = s2 + n;
+                uint2 u;
+                u.x = (unsigned)q[s0] | ((unsigned)q[s1] << 16);
+                u.y = (unsigned)q[s2] | ((unsigned)q[s3] << 16);
+                hn[(size_t)g * n + j] = u;
+                W4<T> ww;
+                ww.a = (T)h.w[s0], ww.b = (T)h.w[s1], ww.c = (T)h.w[s2], ww.d = (T)h.w[s3];
+                hw[(size_t)g * n + j] = ww;
+            }
+        if (n) {
+            SB_CUDA(cudaMemcpyAsync(pix.p, h.pix.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+            SB_CUDA(cudaMemcpyAsync(nbr.p, hn.data(), hn.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+            SB_CUDA(cudaMemcpyAsync(w.p, hw.data(), hw.size() * sizeof(W4<T>), cudaMemcpyHostToDevice, st));
+        }
+        SB_CUDA(cudaMemcpyAsync(level_start.p, h.level_start.data(), h.level_start.size() * sizeof(int),
+                                cudaMemcpyHostToDevice, st));
+        SB_CUDA(cudaStreamSynchronize(st)); // host staging vectors die here
+        dev.n_pix = h.n_pix, dev.n_tasks = n, dev.n_levels = h.n_levels, dev.nb = h.nb;
+        for (int i = 0; i < 8; ++i) dev.off[i] = h.off[i];
+        dev.pix = pix.p, dev.code = reinterpret_cast<const unsigned *>(nbr.p), dev.w = w.p, dev.level_start = level_start.p;
+        return SB_OK;
+    }
+};
+
+static int check_chain(const sb_chain_desc &c, int n_mono) {
+    if (c.n_ops < 0 || c.n_ops > SB_MAX_CHAIN_OPS || c.repeat < 1) return set_err(SB_ERR_ARG, "bad constraint chain");
+    for (int i = 0; i < c.n_ops; ++i) {
+        const sb_op &o = c.ops[i];
+        if (o.code < SB_OP_MONOTONIC || o.code > SB_OP_NORMALIZE) return set_err(SB_ERR_ARG, "unknown constraint op-code %d", o.code);
+        if (o.code == SB_OP_MONOTONIC && (o.iarg < 0 || o.iarg >= n_mono)) return set_err(SB_ERR_ARG, "monotonic table index %d out of range", o.iarg);
+    }
+    return SB_OK;
+}
+
+static inline int grid_for(long long n, int block = 256, int cap = 148 * 16) {
+    long long g = (n + block - 1) / block;
+    return (int)std::max<long long>(1, std::min<long long>(g, cap));
+}
+
+} // namespace sb
+
+using namespace sb;
+
+// =====================================================================================================
+// plan
+// =====================================================================================================
+struct sb_plan {
+    virtual ~sb_plan() {}
+    virtual int upload_observation(int obs, const float *data, const float *weights, const double *khat, const double *loss_const) = 0;
+    virtual int upload_params(int which, const double *sed, const double *morph, const double *center) = 0;
+    virtual int download_params(int which, double *sed, double *morph, double *center) = 0;
+    virtual int evaluate(int obs, double *model, double *rendered, double *loss, double *g_sed, double *g_morph, double *g_center) = 0;
+    virtual int fit(const sb_fit_opts *o, int32_t *n_iter, double *loss, int32_t *status) = 0;
+    virtual int fit_enqueue(const sb_fit_opts *o, int n) = 0;
+    virtual int profile(const sb_fit_opts *o, int n, float *stage_ms) = 0;
+    virtual int device_params(void **sed, int64_t *n_sed, void **morph, int64_t *n_morph, int *elem_bytes) = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t dev_bytes = 0;
+    int64_t launches = 0;
+};
+
+template <typename T> struct PlanT : sb_plan {
+    typedef typename Cx<T>::type cplx;
+    sb_batch_desc desc;
+    int S = 0, C = 0, n_src = 0, n_point = 0, npix_max = 0;
+    long long n_morph = 0, n_pmorph = 0;
+    std::vector<DevSource> h_src;
+    std::vector<int> h_start;
+    DevBuf<DevSource> d_src;
+    DevBuf<int> d_start, d_done, d_niter, d_status, d_it, d_nactive;
+    DevBuf<double> d_sed, d_sed_m, d_sed_v, d_sed_vhat, d_center, d_cen_m, d_cen_v, d_cen_vhat, d_loss, d_loss_const;
+    DevBuf<double> d_gsed, d_gcenter, d_gmorph, d_stage;
+    DevBuf<T> d_morph, d_morph_m, d_morph_v, d_morph_vhat, d_pmorph, d_model, d_rendered;
+    DevBuf<float> d_stage_f;
+    DevBuf<DevChain> d_chains;
+    DevBuf<DevMono> d_monos;
+    std::vector<std::unique_ptr<MonoDevice<T>>> monos;
+    struct Obs {
+        DevObs<T> dev;
+        DevBuf<T> A, B, data, weights;
+        DevBuf<cplx> Ahat, khat;
+        cufftHandle fwd = 0, inv = 0;
+        bool have_plans = false;
+        std::vector<double> loss_const;
+    };
+    std::vector<std::unique_ptr<Obs>> obs;
+    int loss_cap = 0;
+    int *h_nactive = nullptr; // pinned
+    cudaGraphExec_t graph = nullptr;
+    FitScalars graph_fs;
+    bool have_graph = false;
+    int kernels_per_iter = 0, ffts_per_iter = 0;
+
+    ~PlanT() override {
+        if (graph) cudaGraphExecDestroy(graph);
+        for (auto &o : obs)
+            if (o->have_plans) {
+                cufftDestroy(o->fwd);
+                cufftDestroy(o->inv);
+            }
+        if (h_nactive) cudaFreeHost(h_nactive);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    int64_t total_bytes() {
+        int64_t b = d_src.bytes() + d_sed.bytes() * 4 + d_center.bytes() * 4 + d_loss.bytes() + d_morph.bytes() * 4 + d_pmorph.bytes() +
+                    d_model.bytes() + d_rendered.bytes() + d_gmorph.bytes();
+        for (auto &o : obs) b += o->A.bytes() + o->B.bytes() + o->data.bytes() + o->weights.bytes() + o->Ahat.bytes() + o->khat.bytes();
+        return b;
+    }
+
+    int init(const sb_batch_desc *dsc, int dev) {
+        desc = *dsc;
+        device = dev;
+        S = desc.n_scenes, C = desc.C, n_src = desc.n_sources;
+        if (S <= 0 || C <= 0 || C > SB_MAXC || desc.Ny <= 0 || desc.Nx <= 0) return set_err(SB_ERR_ARG, "bad frame (S=%d C=%d Ny=%d Nx=%d)", S, C, desc.Ny, desc.Nx);
+        if (desc.n_obs <= 0 || desc.n_obs > SB_MAX_OBS) return set_err(SB_ERR_ARG, "n_obs=%d out of range", desc.n_obs);
+        if (n_src < 0 || !desc.scene_src_start || (n_src && !desc.sources)) return set_err(SB_ERR_ARG, "missing source tables");
+        SB_CUDA(cudaSetDevice(device));
+        SB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        SB_CUDA(cudaEventCreate(&ev0));
+        SB_CUDA(cudaEventCreate(&ev1));
+        SB_CUDA(cudaHostAlloc((void **)&h_nactive, sizeof(int), cudaHostAllocDefault));
+
+        // ---- constraint tables
+        for (int i = 0; i < desc.n_chains; ++i) SB_TRY(check_chain(desc.chains[i], desc.n_mono));
+        std::vector<DevMono> hm(std::max(desc.n_mono, 1));
+        for (int i = 0; i < desc.n_mono; ++i) {
+            HostMono h;
+            SB_TRY(build_mono<T>(desc.mono[i], h));
+            monos.emplace_back(new MonoDevice<T>());
+            SB_TRY(monos.back()->upload(h, stream));
+            hm[i] = monos.back()->dev;
+        }
+        SB_TRY(d_monos.alloc(hm.size()));
+        SB_CUDA(cudaMemcpy(d_monos.p, hm.data(), hm.size() * sizeof(DevMono), cudaMemcpyHostToDevice));
+        std::vector<DevChain> hc(std::max(desc.n_chains, 1));
+        for (int i = 0; i < desc.n_chains; ++i) {
+            hc[i].n_ops = desc.chains[i].n_ops, hc[i].repeat = desc.chains[i].repeat;
+            memcpy(hc[i].ops, desc.chains[i].ops, sizeof(hc[i].ops));
+        }
+        SB_TRY(d_chains.alloc(hc.size()));
+        SB_CUDA(cudaMemcpy(d_chains.p, hc.data(), hc.size() * sizeof(DevChain), cudaMemcpyHostToDevice));
+
+        // ---- sources
+        h_start.assign(desc.scene_src_start, desc.scene_src_start + S + 1);
+        if (h_start[0] != 0 || h_start[S] != n_src) return set_err(SB_ERR_ARG, "scene_src_start must run from 0 to n_sources");
+        h_src.resize(n_src);
+        const int b = desc.psf_boxsize;
+        for (int s = 0; s < S; ++s) {
+            if (h_start[s + 1] < h_start[s]) return set_err(SB_ERR_ARG, "scene_src_start not monotone");
+            for (int k = h_start[s]; k < h_start[s + 1]; ++k) {
+                const sb_source_desc &in = desc.sources[k];
+                DevSource &d = h_src[k];
+                memset(&d, 0, sizeof d);
+                d.kind = in.kind, d.By = in.By, d.Bx = in.Bx, d.oy = in.oy, d.ox = in.ox, d.chain = in.chain, d.sed_chain = in.sed_chain;
+                d.sed_is_f32 = in.sed_is_f32, d.morph_fixed = in.morph_fixed, d.sed_fixed = in.sed_fixed, d.scene = s;
+                d.morph_step = in.morph_step, d.sed_step_factor = in.sed_step_factor;
+                memcpy(d.sed_step_min, in.sed_step_min, sizeof d.sed_step_min);
+                if (d.By <= 0 || d.Bx <= 0 || (long long)d.By * d.Bx >= 0xffff) return set_err(SB_ERR_ARG, "source %d: bad box %dx%d", k, d.By, d.Bx);
+                if (d.chain >= desc.n_chains || d.sed_chain >= desc.n_chains) return set_err(SB_ERR_ARG, "source %d: chain index out of range", k);
+                if (d.sed_chain >= 0)
+                    for (int i = 0; i < desc.chains[d.sed_chain].n_ops; ++i) {
+                        const int code = desc.chains[d.sed_chain].ops[i].code;
+                        if (code != SB_OP_POSITIVITY && code != SB_OP_NORMALIZE)
+                            return set_err(SB_ERR_ARG, "source %d: spectrum constraint op-code %d is not supported on a 1-D parameter", k, code);
+                    }
+                if (d.kind == 0) {
+                    if (d.chain >= 0)
+                        for (int i = 0; i < desc.chains[d.chain].n_ops; ++i) {
+                            const sb_op &op = desc.chains[d.chain].ops[i];
+                            if (op.code == SB_OP_MONOTONIC && desc.mono[op.iarg].n_pix != d.By * d.Bx)
+                                return set_err(SB_ERR_ARG, "source %d: monotonic table size %d != box %dx%d", k, desc.mono[op.iarg].n_pix, d.By, d.Bx);
+                        }
+                    d.morph_off = n_morph;
+                    d.point_idx = -1;
+                    n_morph += (long long)d.By * d.Bx;
+                    npix_max = std::max(npix_max, d.By * d.Bx);
+                } else if (d.kind == 1) {
+                    if (b <= 0 || b > 15 || (b & 1) == 0) return set_err(SB_ERR_ARG, "point source needs an odd model-PSF box <= 15 (got %d)", b);
+                    if (d.By != b || d.Bx != b) return set_err(SB_ERR_ARG, "source %d: point-source box must equal the model PSF box", k);
+                    d.morph_off = n_pmorph;
+                    d.point_idx = n_point++;
+                    n_pmorph += (long long)C * b * b;
+                } else
+                    return set_err(SB_ERR_ARG, "source %d: unknown kind %d", k, d.kind);
+            }
+        }
+        npix_max = (npix_max + 3) & ~3;
+        SB_TRY(d_src.alloc(std::max(n_src, 1)));
+        SB_TRY(d_start.alloc(S + 1));
+        if (n_src) SB_CUDA(cudaMemcpy(d_src.p, h_src.data(), n_src * sizeof(DevSource), cudaMemcpyHostToDevice));
+        SB_CUDA(cudaMemcpy(d_start.p, h_start.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        const size_t nsed = (size_t)std::max(n_src, 1) * C, ncen = (size_t)std::max(n_point, 1) * 2;
+        DevBuf<double> *dz[] = {&d_sed, &d_sed_m, &d_sed_v, &d_sed_vhat, &d_gsed};
+        for (auto *bf : dz) {
+            SB_TRY(bf->alloc(nsed));
+            SB_TRY(bf->zero(stream));
+        }
+        DevBuf<double> *dc[] = {&d_center, &d_cen_m, &d_cen_v, &d_cen_vhat, &d_gcenter};
+        for (auto *bf : dc) {
+            SB_TRY(bf->alloc(ncen));
+            SB_TRY(bf->zero(stream));
+        }
+        DevBuf<T> *dm[] = {&d_morph, &d_morph_m, &d_morph_v, &d_morph_vhat};
+        for (auto *bf : dm) {
+            SB_TRY(bf->alloc(std::max<long long>(n_morph, 1)));
+            SB_TRY(bf->zero(stream));
+        }
+        SB_TRY(d_pmorph.alloc(std::max<long long>(n_pmorph, 1)));
+        SB_TRY(d_pmorph.zero(stream));
+        SB_TRY(d_done.alloc(S));
+        SB_TRY(d_niter.alloc(S));
+        SB_TRY(d_status.alloc(S));
+        SB_TRY(d_it.alloc(1));
+        SB_TRY(d_nactive.alloc(1));
+        SB_TRY(d_loss_const.alloc(S));
+        SB_TRY(d_loss_const.zero(stream));
+        SB_TRY(ensure_loss_cap(256));
+
+        // ---- observations
+        for (int o = 0; o < desc.n_obs; ++o) {
+            const sb_obs_desc &od = desc.obs[o];
+            obs.emplace_back(new Obs());
+            Obs &ob = *obs.back();
+            if (od.C <= 0 || od.chan_off < 0 || od.chan_off + od.C > C) return set_err(SB_ERR_ARG, "observation %d: channels outside the model frame", o);
+            if (od.kind != 0 && od.kind != 1) return set_err(SB_ERR_ARG, "observation %d: unsupported renderer kind %d", o, od.kind);
+            int Fy = od.Fy, Fx = od.Fx;
+            if (od.kind == 1) Fy = desc.Ny, Fx = desc.Nx;
+            if (Fy < desc.Ny || Fx < desc.Nx) return set_err(SB_ERR_ARG, "observation %d: FFT grid %dx%d smaller than the frame", o, Fy, Fx);
+            DevObs<T> &d = ob.dev;
+            d.kind = od.kind, d.C = od.C, d.H = od.H, d.W = od.W, d.chan_off = od.chan_off, d.oy = od.oy, d.ox = od.ox;
+            d.Fy = Fy, d.Fx = Fx, d.Fxc = Fx / 2 + 1, d.khat_shared = od.khat_shared;
+            const size_t ngrid = (size_t)S * od.C * Fy * Fx, ncplx = (size_t)S * od.C * Fy * d.Fxc, ndata = (size_t)S * od.C * od.H * od.W;
+            SB_TRY(ob.A.alloc(ngrid));
+            SB_TRY(ob.A.zero(stream));
+            SB_TRY(ob.data.alloc(ndata));
+            SB_TRY(ob.weights.alloc(ndata));
+            SB_TRY(ob.data.zero(stream));
+            SB_TRY(ob.weights.zero(stream));
+            ob.loss_const.assign(S, 0.0);
+            if (od.kind == 0) {
+                SB_TRY(ob.B.alloc(ngrid));
+                SB_TRY(ob.Ahat.alloc(ncplx));
+                SB_TRY(ob.khat.alloc(od.khat_shared ? (size_t)od.C * Fy * d.Fxc : ncplx));
+                SB_TRY(ob.khat.zero(stream));
+                int n[2] = {Fy, Fx};
+                SB_CUFFT(cufftPlanMany(&ob.fwd, 2, n, nullptr, 1, 0, nullptr, 1, 0, Cx<T>::r2c, S * od.C));
+                SB_CUFFT(cufftPlanMany(&ob.inv, 2, n, nullptr, 1, 0, nullptr, 1, 0, Cx<T>::c2r, S * od.C));
+                ob.have_plans = true;
+                SB_CUFFT(cufftSetStream(ob.fwd, stream));
+                SB_CUFFT(cufftSetStream(ob.inv, stream));
+                size_t ws = 0;
+                cufftGetSize(ob.fwd, &ws);
+                dev_bytes += (int64_t)ws;
+                cufftGetSize(ob.inv, &ws);
+                dev_bytes += (int64_t)ws;
+            }
+            d.A = ob.A.p, d.B = od.kind == 0 ? ob.B.p : ob.A.p, d.Ahat = ob.Ahat.p, d.khat = ob.khat.p;
+            d.data = ob.data.p, d.weights = ob.weights.p;
+        }
+        SB_TRY(d_stage.alloc(1));
+        // dynamic shared memory of the update kernel
+        const size_t smem = update_smem();
+        if (smem > 227 * 1024) return set_err(SB_ERR_ARG, "largest morphology box (%d px) does not fit in shared memory", npix_max);
+        SB_CUDA(cudaFuncSetAttribute(k_update<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_TRY(reset_counters());
+        SB_CUDA(cudaStreamSynchronize(stream));
+        dev_bytes += total_bytes();
+        return SB_OK;
+    }
+
+    size_t update_smem() const { return (size_t)4 * npix_max * sizeof(T) + (40 + SB_MAXC) * sizeof(double); }
+
+    int ensure_loss_cap(int cap) {
+        if (cap <= loss_cap) return SB_OK;
+        SB_CUDA(cudaStreamSynchronize(stream));
+        SB_TRY(d_loss.alloc((size_t)S * cap));
+        SB_TRY(d_loss.zero(stream));
+        loss_cap = cap;
+        have_graph = false; // cap is baked into kernel arguments
+        return SB_OK;
+    }
+
+    int reset_counters() {
+        SB_TRY(d_done.zero(stream));
+        SB_TRY(d_niter.zero(stream));
+        SB_TRY(d_status.zero(stream));
+        SB_TRY(d_it.zero(stream));
+        SB_CUDA(cudaMemcpyAsync(d_nactive.p, &S, sizeof(int), cudaMemcpyHostToDevice, stream));
+        return SB_OK;
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    int upload_observation(int o, const float *data, const float *weights, const double *khat, const double *loss_const) override {
+        if (o < 0 || o >= (int)obs.size()) return set_err(SB_ERR_ARG, "observation index %d out of range", o);
+        SB_CUDA(cudaSetDevice(device));
+        Obs &ob = *obs[o];
+        const size_t nd = ob.data.n;
+        DevBuf<float> stage;
+        if (sizeof(T) == 8 && (data || weights)) SB_TRY(stage.alloc(nd));
+        const float *srcs[2] = {data, weights};
+        T *dsts[2] = {ob.data.p, ob.weights.p};
+        for (int i = 0; i < 2; ++i) {
+            if (!srcs[i]) continue;
+            if (sizeof(T) == 4) {
+                SB_CUDA(cudaMemcpyAsync(dsts[i], srcs[i], nd * sizeof(float), cudaMemcpyHostToDevice, stream));
+            } else {
+                SB_CUDA(cudaMemcpyAsync(stage.p, srcs[i], nd * sizeof(float), cudaMemcpyHostToDevice, stream));
+                k_cast<float, T><<<grid_for(nd), 256, 0, stream>>>(stage.p, dsts[i], (long long)nd);
+                SB_CUDA(cudaGetLastError());
+            }
+        }
+        if (khat && ob.dev.kind == 0) {
+            DevBuf<double2> ks;
+            SB_TRY(ks.alloc(ob.khat.n));
+            SB_CUDA(cudaMemcpyAsync(ks.p, khat, ob.khat.n * sizeof(double2), cudaMemcpyHostToDevice, stream));
+            k_cast_scale_cplx<T><<<grid_for(ob.khat.n), 256, 0, stream>>>(ks.p, ob.khat.p, (long long)ob.khat.n,
+                                                                          1.0 / ((double)ob.dev.Fy * ob.dev.Fx));
+            SB_CUDA(cudaGetLastError());
+            SB_CUDA(cudaStreamSynchronize(stream));
+        }
+        if (loss_const) {
+            ob.loss_const.assign(loss_const, loss_const + S);
+            std::vector<double> tot(S, 0.0);
+            for (auto &q : obs)
+                for (int s = 0; s < S; ++s) tot[s] += q->loss_const[s];
+            SB_CUDA(cudaMemcpyAsync(d_loss_const.p, tot.data(), S * sizeof(double), cudaMemcpyHostToDevice, stream));
+        }
+        SB_CUDA(cudaStreamSynchronize(stream));
+        return SB_OK;
+    }
+
+    DevBuf<double> stage_d;
+    int upload_T(T *dst, const double *src, size_t n) {
+        if (!src || n == 0) return SB_OK;
+        if (sizeof(T) == 8) {
+            SB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        } else {
+            if (stage_d.n < n) SB_TRY(stage_d.alloc(n));
+            SB_CUDA(cudaMemcpyAsync(stage_d.p, src, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+            k_cast<double, T><<<grid_for(n), 256, 0, stream>>>(stage_d.p, dst, (long long)n);
+            SB_CUDA(cudaGetLastError());
+            SB_CUDA(cudaStreamSynchronize(stream));
+        }
+        return SB_OK;
+    }
+    int download_T(double *dst, const T *src, size_t n) {
+        if (!dst || n == 0) return SB_OK;
+        if (sizeof(T) == 8) {
+            SB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        } else {
+            if (stage_d.n < n) SB_TRY(stage_d.alloc(n));
+            k_cast<T, double><<<grid_for(n), 256, 0, stream>>>(src, stage_d.p, (long long)n);
+            SB_CUDA(cudaGetLastError());
+            SB_CUDA(cudaMemcpyAsync(dst, stage_d.p, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        }
+        SB_CUDA(cudaStreamSynchronize(stream));
+        return SB_OK;
+    }
+
+    int upload_params(int which, const double *sed, const double *morph, const double *center) override {
+        if (which < 0 || which > 3) return set_err(SB_ERR_ARG, "which=%d", which);
+        SB_CUDA(cudaSetDevice(device));
+        double *ds[4] = {d_sed.p, d_sed_m.p, d_sed_v.p, d_sed_vhat.p};
+        T *dm[4] = {d_morph.p, d_morph_m.p, d_morph_v.p, d_morph_vhat.p};
+        double *dc[4] = {d_center.p, d_cen_m.p, d_cen_v.p, d_cen_vhat.p};
+        if (sed && n_src) SB_CUDA(cudaMemcpyAsync(ds[which], sed, (size_t)n_src * C * sizeof(double), cudaMemcpyHostToDevice, stream));
+        SB_TRY(upload_T(dm[which], morph, (size_t)n_morph));
+        if (center && n_point) SB_CUDA(cudaMemcpyAsync(dc[which], center, (size_t)n_point * 2 * sizeof(double), cudaMemcpyHostToDevice, stream));
+        if (which == 0 && center && n_point) {
+            UpdateArgs<T> ua = update_args(0);
+            k_point_morph<T><<<n_src, 128, 0, stream>>>(ua, n_src);
+            SB_CUDA(cudaGetLastError());
+        }
+        SB_CUDA(cudaStreamSynchronize(stream));
+        return SB_OK;
+    }
+    int download_params(int which, double *sed, double *morph, double *center) override {
+        if (which < 0 || which > 3) return set_err(SB_ERR_ARG, "which=%d", which);
+        SB_CUDA(cudaSetDevice(device));
+        double *ds[4] = {d_sed.p, d_sed_m.p, d_sed_v.p, d_sed_vhat.p};
+        T *dm[4] = {d_morph.p, d_morph_m.p, d_morph_v.p, d_morph_vhat.p};
+        double *dc[4] = {d_center.p, d_cen_m.p, d_cen_v.p, d_cen_vhat.p};
+        if (sed && n_src) SB_CUDA(cudaMemcpyAsync(sed, ds[which], (size_t)n_src * C * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (center && n_point) SB_CUDA(cudaMemcpyAsync(center, dc[which], (size_t)n_point * 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        SB_TRY(download_T(morph, dm[which], (size_t)n_morph));
+        SB_CUDA(cudaStreamSynchronize(stream));
+        return SB_OK;
+    }
+    int device_params(void **sed, int64_t *n_sed, void **morph, int64_t *nm, int *elem_bytes) override {
+        if (sed) *sed = d_sed.p;
+        if (n_sed) *n_sed = (int64_t)n_src * C;
+        if (morph) *morph = d_morph.p;
+        if (nm) *nm = n_morph;
+        if (elem_bytes) *elem_bytes = (int)sizeof(T);
+        return SB_OK;
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    static FitScalars scalars(const sb_fit_opts *o) {
+        FitScalars f;
+        memset(&f, 0, sizeof f);
+        f.prox_max_iter = o->prox_max_iter, f.min_iter = o->min_iter, f.fixed_iterations = o->fixed_iterations;
+        f.overwrite_vhat_at_it0 = o->overwrite_vhat_at_it0;
+        f.e_rel = o->e_rel, f.b1 = o->b1, f.b2 = o->b2, f.eps = o->eps;
+        return f;
+    }
+    FitScalars cur_fs;
+
+    UpdateArgs<T> update_args(int mode) {
+        UpdateArgs<T> a;
+        memset(&a, 0, sizeof a);
+        a.src = d_src.p, a.C = C, a.Ny = desc.Ny, a.Nx = desc.Nx, a.n_obs = (int)obs.size();
+        for (size_t o = 0; o < obs.size(); ++o) a.obs[o] = obs[o]->dev;
+        a.sed = d_sed.p, a.sed_m = d_sed_m.p, a.sed_v = d_sed_v.p, a.sed_vhat = d_sed_vhat.p;
+        a.morph = d_morph.p, a.morph_m = d_morph_m.p, a.morph_v = d_morph_v.p, a.morph_vhat = d_morph_vhat.p;
+        a.center = d_center.p, a.cen_m = d_cen_m.p, a.cen_v = d_cen_v.p, a.cen_vhat = d_cen_vhat.p;
+        a.pmorph = d_pmorph.p, a.chains = d_chains.p, a.monos = d_monos.p;
+        a.it_ptr = d_it.p, a.done = d_done.p, a.status = d_status.p;
+        a.fs = cur_fs;
+        a.psf_b = desc.psf_boxsize;
+        memcpy(a.psf_sigma, desc.psf_sigma, sizeof a.psf_sigma);
+        a.npix_max = npix_max, a.mode = mode;
+        a.g_sed = d_gsed.p, a.g_morph = d_gmorph.p, a.g_center = d_gcenter.p;
+        return a;
+    }
+
+    struct StageTimer {
+        std::vector<cudaEvent_t> ev;
+        bool on = false;
+    };
+
+    // Enqueue one iteration.  mode 0 = full iteration, 1 = forward + gradients only (evaluate).
+    int enqueue_iteration(int mode, T *model_out, T *rendered_out, int rendered_obs, std::vector<cudaEvent_t> *marks) {
+        auto mark = [&](void) {
+            if (marks) {
+                cudaEvent_t e;
+                cudaEventCreate(&e);
+                cudaEventRecord(e, stream);
+                marks->push_back(e);
+            }
+        };
+        int nk = 0, nf = 0;
+        mark();
+        {
+            RenderArgs<T> ra;
+            memset(&ra, 0, sizeof ra);
+            ra.src = d_src.p, ra.scene_src_start = d_start.p, ra.sed = d_sed.p, ra.morph = d_morph.p, ra.pmorph = d_pmorph.p;
+            ra.C = C, ra.Ny = desc.Ny, ra.Nx = desc.Nx, ra.n_obs = (int)obs.size();
+            for (size_t o = 0; o < obs.size(); ++o) ra.obs[o] = obs[o]->dev;
+            ra.done = d_done.p, ra.it_ptr = d_it.p, ra.loss = d_loss.p, ra.loss_const = d_loss_const.p, ra.cap = loss_cap;
+            ra.model_out = model_out;
+            dim3 grid((desc.Nx + 31) / 32, (desc.Ny + 7) / 8, S), block(32, 8);
+            k_render<T><<<grid, block, 0, stream>>>(ra);
+            SB_CUDA(cudaGetLastError());
+            ++nk;
+        }
+        mark();
+        // stage order inside the marks: fwd, kmul, inv, residual, fwd, kmul*, inv (summed over observations)
+        for (size_t o = 0; o < obs.size(); ++o) {
+            Obs &ob = *obs[o];
+            const DevObs<T> &d = ob.dev;
+            const long long per_scene = (long long)d.C * d.Fy * d.Fxc, total = per_scene * S;
+            if (d.kind == 0) {
+                SB_CUFFT(Cx<T>::fwd(ob.fwd, (typename Cx<T>::real_t *)d.A, (typename Cx<T>::cplx_t *)d.Ahat));
+                ++nf;
+                mark();
+                k_kmul<T><<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(d.Ahat, d.khat, per_scene, total, d.khat_shared, 0, d_done.p);
+                SB_CUDA(cudaGetLastError());
+                ++nk;
+                mark();
+                SB_CUFFT(Cx<T>::inv(ob.inv, (typename Cx<T>::cplx_t *)d.Ahat, (typename Cx<T>::real_t *)d.B));
+                ++nf;
+                mark();
+            } else if (marks) {
+                mark(), mark(), mark();
+            }
+            {
+                ResidualArgs<T> ra;
+                memset(&ra, 0, sizeof ra);
+                ra.ob = d, ra.Ny = desc.Ny, ra.Nx = desc.Nx, ra.cap = loss_cap, ra.done = d_done.p, ra.it_ptr = d_it.p, ra.loss = d_loss.p;
+                ra.rendered_out = ((int)o == rendered_obs) ? rendered_out : nullptr;
+                dim3 grid((desc.Nx + 31) / 32, (desc.Ny + 7) / 8, S * d.C), block(32, 8);
+                k_residual<T><<<grid, block, 0, stream>>>(ra);
+                SB_CUDA(cudaGetLastError());
+                ++nk;
+            }
+            mark();
+            if (d.kind == 0) {
+                SB_CUFFT(Cx<T>::fwd(ob.fwd, (typename Cx<T>::real_t *)d.A, (typename Cx<T>::cplx_t *)d.Ahat));
+                ++nf;
+                mark();
+                k_kmul<T><<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(d.Ahat, d.khat, per_scene, total, d.khat_shared, 1, d_done.p);
+                SB_CUDA(cudaGetLastError());
+                ++nk;
+                mark();
+                SB_CUFFT(Cx<T>::inv(ob.inv, (typename Cx<T>::cplx_t *)d.Ahat, (typename Cx<T>::real_t *)d.B));
+                ++nf;
+                mark();
+            } else if (marks) {
+                mark(), mark(), mark();
+            }
+        }
+        if (n_src) {
+            UpdateArgs<T> ua = update_args(mode);
+            k_update<T><<<n_src, 128, update_smem(), stream>>>(ua);
+            SB_CUDA(cudaGetLastError());
+            ++nk;
+        }
+        mark();
+        if (mode == 0) {
+            k_advance<<<1, 256, 0, stream>>>(S, loss_cap, d_loss.p, d_done.p, d_niter.p, d_it.p, d_nactive.p, d_status.p, cur_fs);
+            SB_CUDA(cudaGetLastError());
+            ++nk;
+        }
+        mark();
+        kernels_per_iter = nk, ffts_per_iter = nf;
+        return SB_OK;
+    }
+
+    int ensure_graph(const sb_fit_opts *o) {
+        FitScalars f = scalars(o);
+        if (have_graph && memcmp(&f, &graph_fs, sizeof f) == 0) return SB_OK;
+        cur_fs = f;
+        if (graph) {
+            cudaGraphExecDestroy(graph);
+            graph = nullptr;
+        }
+        cudaGraph_t g = nullptr;
+        SB_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_iteration(0, nullptr, nullptr, -1, nullptr);
+        cudaError_t e = cudaStreamEndCapture(stream, &g);
+        if (rc != SB_OK) {
+            if (g) cudaGraphDestroy(g);
+            return rc;
+        }
+        if (e != cudaSuccess) return set_err(SB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return set_err(SB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+        graph_fs = f;
+        have_graph = true;
+        return SB_OK;
+    }
+
+    int check_opts(const sb_fit_opts *o) {
+        if (!o) return set_err(SB_ERR_ARG, "null fit options");
+        if (o->max_iter < 0 || o->prox_max_iter < 0 || o->check_every < 1) return set_err(SB_ERR_ARG, "bad fit options");
+        return SB_OK;
+    }
+
+    int fit_enqueue(const sb_fit_opts *o, int n) override {
+        SB_TRY(check_opts(o));
+        SB_CUDA(cudaSetDevice(device));
+        SB_TRY(ensure_loss_cap(std::max(n, 1)));
+        SB_TRY(ensure_graph(o));
+        SB_TRY(reset_counters());
+        for (int i = 0; i < n; ++i) SB_CUDA(cudaGraphLaunch(graph, stream));
+        launches += (int64_t)n * kernels_per_iter;
+        return SB_OK;
+    }
+
+    int fit(const sb_fit_opts *o, int32_t *n_iter, double *loss, int32_t *status) override {
+        SB_TRY(check_opts(o));
+        SB_CUDA(cudaSetDevice(device));
+        SB_TRY(ensure_loss_cap(std::max(o->max_iter, 1)));
+        SB_TRY(ensure_graph(o));
+        SB_TRY(reset_counters());
+        int done_iters = 0;
+        for (int it = 0; it < o->max_iter; ++it) {
+            SB_CUDA(cudaGraphLaunch(graph, stream));
+            ++done_iters;
+            if (!o->fixed_iterations && ((it + 1) % o->check_every == 0)) {
+                SB_CUDA(cudaMemcpyAsync(h_nactive, d_nactive.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                SB_CUDA(cudaStreamSynchronize(stream));
+                if (*h_nactive == 0) break;
+            }
+        }
+        launches += (int64_t)done_iters * kernels_per_iter;
+        if (n_iter) SB_CUDA(cudaMemcpyAsync(n_iter, d_niter.p, S * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        if (status) SB_CUDA(cudaMemcpyAsync(status, d_status.p, S * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        if (loss && o->max_iter > 0)
+            SB_CUDA(cudaMemcpy2DAsync(loss, (size_t)o->max_iter * sizeof(double), d_loss.p, (size_t)loss_cap * sizeof(double),
+                                      (size_t)o->max_iter * sizeof(double), S, cudaMemcpyDeviceToHost, stream));
+        SB_CUDA(cudaStreamSynchronize(stream));
+        return SB_OK;
+    }
+
+    int profile(const sb_fit_opts *o, int n, float *stage_ms) override {
+        SB_TRY(check_opts(o));
+        SB_CUDA(cudaSetDevice(device));
+        SB_TRY(ensure_loss_cap(std::max(n, 1)));
+        cur_fs = scalars(o);
+        have_graph = false;
+        SB_TRY(reset_counters());
+        for (int i = 0; i < SB_N_STAGES; ++i) stage_ms[i] = 0.f;
+        for (int i = 0; i < n; ++i) {
+            std::vector<cudaEvent_t> marks;
+            SB_TRY(enqueue_iteration(0, nullptr, nullptr, -1, &marks));
+            SB_CUDA(cudaStreamSynchronize(stream));
+            // marks: [start, after render, (7 per observation), after update, after advance]
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, marks[0], marks[1]);
+            stage_ms[0] += ms;
+            size_t idx = 1;
+            for (size_t ob = 0; ob < obs.size(); ++ob)
+                for (int st = 1; st <= 7; ++st) {
+                    cudaEventElapsedTime(&ms, marks[idx], marks[idx + 1]);
+                    stage_ms[st] += ms;
+                    ++idx;
+                }
+            cudaEventElapsedTime(&ms, marks[idx], marks[idx + 1]);
+            stage_ms[8] += ms;
+            cudaEventElapsedTime(&ms, marks[idx + 1], marks[idx + 2]);
+            stage_ms[9] += ms;
+            for (auto e : marks) cudaEventDestroy(e);
+        }
+        launches += (int64_t)n * kernels_per_iter;
+        return SB_OK;
+    }
+
+    int evaluate(int o, double *model, double *rendered, double *loss, double *g_sed, double *g_morph, double *g_center) override {
+        SB_CUDA(cudaSetDevice(device));
+        if (o < 0 || o >= (int)obs.size()) return set_err(SB_ERR_ARG, "observation index %d out of range", o);
+        SB_TRY(ensure_loss_cap(1));
+        SB_TRY(reset_counters());
+        const size_t nmodel = (size_t)S * C * desc.Ny * desc.Nx, nrend = obs[o]->data.n;
+        if (model && d_model.n < nmodel) SB_TRY(d_model.alloc(nmodel));
+        if (rendered) {
+            if (d_rendered.n < nrend) SB_TRY(d_rendered.alloc(nrend));
+            SB_CUDA(cudaMemsetAsync(d_rendered.p, 0, nrend * sizeof(T), stream));
+        }
+        if (g_morph && d_gmorph.n < (size_t)std::max<long long>(n_morph, 1)) SB_TRY(d_gmorph.alloc(std::max<long long>(n_morph, 1)));
+        T *keep_rendered = rendered ? d_rendered.p : nullptr;
+        double *keep_gm = d_gmorph.p;
+        if (!g_morph) d_gmorph.p = nullptr; // kernel skips the write
+        int rc = enqueue_iteration(1, model ? d_model.p : nullptr, keep_rendered, o, nullptr);
+        d_gmorph.p = keep_gm;
+        SB_TRY(rc);
+        launches += kernels_per_iter;
+        SB_TRY(download_T(model, d_model.p, model ? nmodel : 0));
+        SB_TRY(download_T(rendered, d_rendered.p, rendered ? nrend : 0));
+        if (loss) SB_CUDA(cudaMemcpy2DAsync(loss, sizeof(double), d_loss.p, (size_t)loss_cap * sizeof(double), sizeof(double), S, cudaMemcpyDeviceToHost, stream));
+        if (g_sed && n_src) SB_CUDA(cudaMemcpyAsync(g_sed, d_gsed.p, (size_t)n_src * C * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (g_center && n_point) SB_CUDA(cudaMemcpyAsync(g_center, d_gcenter.p, (size_t)n_point * 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (g_morph && n_morph) SB_CUDA(cudaMemcpyAsync(g_morph, d_gmorph.p, (size_t)n_morph * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        SB_CUDA(cudaStreamSynchronize(stream));
+        return SB_OK;
+    }
+};
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char *sb_last_error(void) { return g_err.c_str(); }
+const char *sb_version(void) { return "scarlet_b200 0.1 (sm_100a)"; }
+int sb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+const char *sb_stage_name(int s) { return (s >= 0 && s < SB_N_STAGES) ? kStageNames[s] : ""; }
+
+static int need_device(int device) {
+    int n = sb_device_count();
+    if (n <= 0) return set_err(SB_ERR_CUDA, "no CUDA device available: scarlet_b200 has no CPU fallback");
+    if (device < 0 || device >= n) return set_err(SB_ERR_ARG, "device %d out of range (have %d)", device, n);
+    return SB_OK;
+}
+
+int sb_plan_create(const sb_batch_desc *desc, int device, sb_plan **out) {
+    if (!desc || !out) return set_err(SB_ERR_ARG, "null argument");
+    *out = nullptr;
+    SB_TRY(need_device(device));
+    sb_plan *p = nullptr;
+    int rc;
+    if (desc->precision == 32) {
+        auto *q = new PlanT<float>();
+        rc = q->init(desc, device);
+        p = q;
+    } else if (desc->precision == 64) {
+        auto *q = new PlanT<double>();
+        rc = q->init(desc, device);
+        p = q;
+    } else
+        return set_err(SB_ERR_ARG, "precision must be 32 or 64");
+    if (rc != SB_OK) {
+        delete p;
+        return rc;
+    }
+    *out = p;
+    return SB_OK;
+}
+void sb_plan_destroy(sb_plan *plan) {
+    if (plan) {
+        cudaSetDevice(plan->device);
+        cudaStreamSynchronize(plan->stream);
+        delete plan;
+    }
+}
+int64_t sb_plan_device_bytes(const sb_plan *plan) { return plan ? plan->dev_bytes : 0; }
+int64_t sb_plan_kernel_launches(const sb_plan *plan) { return plan ? plan->launches : 0; }
+void *sb_plan_stream(sb_plan *plan) { return plan ? (void *)plan->stream : nullptr; }
+
+void *sb_host_alloc(int64_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void sb_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+#define PLAN_CALL(expr)                                   \
+    if (!plan) return set_err(SB_ERR_ARG, "null plan");   \
+    return plan->expr;
+
+int sb_plan_upload_observation(sb_plan *plan, int obs, const float *data, const float *weights, const double *khat, const double *loss_const) {
+    PLAN_CALL(upload_observation(obs, data, weights, khat, loss_const))
+}
+int sb_plan_upload_params(sb_plan *plan, int which, const double *sed, const double *morph, const double *center) {
+    PLAN_CALL(upload_params(which, sed, morph, center))
+}
+int sb_plan_download_params(sb_plan *plan, int which, double *sed, double *morph, double *center) {
+    PLAN_CALL(download_params(which, sed, morph, center))
+}
+int sb_plan_evaluate(sb_plan *plan, int obs, double *model, double *rendered, double *loss, double *g_sed, double *g_morph, double *g_center) {
+    PLAN_CALL(evaluate(obs, model, rendered, loss, g_sed, g_morph, g_center))
+}
+int sb_plan_fit(sb_plan *plan, const sb_fit_opts *opts, int32_t *n_iter_out, double *loss_out, int32_t *status_out) {
+    PLAN_CALL(fit(opts, n_iter_out, loss_out, status_out))
+}
+int sb_plan_fit_enqueue(sb_plan *plan, const sb_fit_opts *opts, int n_iterations) { PLAN_CALL(fit_enqueue(opts, n_iterations)) }
+int sb_plan_profile_iterations(sb_plan *plan, const sb_fit_opts *opts, int n_iterations, float *stage_ms) {
+    if (!stage_ms) return set_err(SB_ERR_ARG, "null stage_ms");
+    PLAN_CALL(profile(opts, n_iterations, stage_ms))
+}
+int sb_plan_device_params(sb_plan *plan, void **sed, int64_t *n_sed, void **morph, int64_t *n_morph, int *elem_bytes) {
+    PLAN_CALL(device_params(sed, n_sed, morph, n_morph, elem_bytes))
+}
+int sb_plan_sync(sb_plan *plan) {
+    if (!plan) return set_err(SB_ERR_ARG, "null plan");
+    SB_CUDA(cudaSetDevice(plan->device));
+    SB_CUDA(cudaStreamSynchronize(plan->stream));
+    return SB_OK;
+}
+int sb_plan_timer_start(sb_plan *plan) {
+    if (!plan) return set_err(SB_ERR_ARG, "null plan");
+    SB_CUDA(cudaEventRecord(plan->ev0, plan->stream));
+    return SB_OK;
+}
+int sb_plan_timer_stop(sb_plan *plan, float *ms) {
+    if (!plan || !ms) return set_err(SB_ERR_ARG, "null argument");
+    SB_CUDA(cudaEventRecord(plan->ev1, plan->stream));
+    SB_CUDA(cudaEventSynchronize(plan->ev1));
+    SB_CUDA(cudaEventElapsedTime(ms, plan->ev0, plan->ev1));
+    return SB_OK;
+}
+
+} // extern "C"
+
+// ---- single-operator entry points -------------------------------------------------------------------
+template <typename T>
+static int run_chain(T *img, int By, int Bx, int n_img, const sb_chain_desc *chain, const sb_mono_desc *mono, int n_mono, int device) {
+    if (!img || !chain || By <= 0 || Bx <= 0 || n_img <= 0) return set_err(SB_ERR_ARG, "bad argument");
+    SB_TRY(need_device(device));
+    SB_TRY(check_chain(*chain, n_mono));
+    SB_CUDA(cudaSetDevice(device));
+    const int n = By * Bx;
+    if (n >= 0xffff) return set_err(SB_ERR_ARG, "image too large (%d px)", n);
+    std::vector<std::unique_ptr<MonoDevice<T>>> monos;
+    std::vector<DevMono> hm(std::max(n_mono, 1));
+    for (int i = 0; i < n_mono; ++i) {
+        if (mono[i].n_pix != n) return set_err(SB_ERR_ARG, "monotonic table %d has %d pixels, image has %d", i, mono[i].n_pix, n);
+        HostMono h;
+        SB_TRY(build_mono<T>(mono[i], h));
+        monos.emplace_back(new MonoDevice<T>());
+        SB_TRY(monos.back()->upload(h, 0));
+        hm[i] = monos.back()->dev;
+    }
+    DevBuf<DevMono> dmo;
+    DevBuf<DevChain> dch;
+    DevBuf<T> dimg;
+    SB_TRY(dmo.alloc(hm.size()));
+    SB_TRY(dch.alloc(1));
+    SB_TRY(dimg.alloc((size_t)n * n_img));
+    DevChain hc;
+    hc.n_ops = chain->n_ops, hc.repeat = chain->repeat;
+    memcpy(hc.ops, chain->ops, sizeof hc.ops);
+    SB_CUDA(cudaMemcpy(dmo.p, hm.data(), hm.size() * sizeof(DevMono), cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(dch.p, &hc, sizeof hc, cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(dimg.p, img, (size_t)n * n_img * sizeof(T), cudaMemcpyHostToDevice));
+    const size_t smem = (size_t)(((n + 1) & ~1) + 2) * sizeof(T) + 48 * sizeof(double);
+    SB_CUDA(cudaFuncSetAttribute(k_chain_only<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_chain_only<T><<<n_img, 128, smem>>>(dimg.p, By, Bx, dch.p, dmo.p);
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaMemcpy(img, dimg.p, (size_t)n * n_img * sizeof(T), cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+
+template <typename T>
+static int run_monotonic(T *flat_img, const T *weights, const int32_t *offsets, int n_off, const int32_t *dist_idx, int n_idx,
+                         int n_pix, T min_gradient, int n_img, int device) {
+    if (!flat_img || !weights || !offsets || n_pix <= 0) return set_err(SB_ERR_ARG, "bad argument");
+    std::vector<double> w64((size_t)n_off * n_pix);
+    for (size_t i = 0; i < w64.size(); ++i) w64[i] = (double)weights[i];
+    sb_mono_desc md;
+    memset(&md, 0, sizeof md);
+    md.n_pix = n_pix, md.n_off = n_off, md.n_idx = n_idx, md.weights = w64.data(), md.offsets = offsets, md.dist_idx = dist_idx;
+    sb_chain_desc ch;
+    memset(&ch, 0, sizeof ch);
+    ch.n_ops = 1, ch.repeat = 1;
+    ch.ops[0].code = SB_OP_MONOTONIC, ch.ops[0].iarg = 0, ch.ops[0].farg = (double)min_gradient;
+    // the image is 1-D for this operator: treat it as a single row
+    return run_chain<T>(flat_img, 1, n_pix, n_img, &ch, &md, 1, device);
+}
+
+extern "C" {
+
+int sb_monotonic_f32(float *flat_img, const float *weights, const int32_t *offsets, int n_off, const int32_t *dist_idx, int n_idx,
+                     int n_pix, float min_gradient, int n_img, int device) {
+    return run_monotonic<float>(flat_img, weights, offsets, n_off, dist_idx, n_idx, n_pix, min_gradient, n_img, device);
+}
+int sb_monotonic_f64(double *flat_img, const double *weights, const int32_t *offsets, int n_off, const int32_t *dist_idx, int n_idx,
+                     int n_pix, double min_gradient, int n_img, int device) {
+    return run_monotonic<double>(flat_img, weights, offsets, n_off, dist_idx, n_idx, n_pix, min_gradient, n_img, device);
+}
+int sb_prox_chain_f32(float *img, int By, int Bx, int n_img, const sb_chain_desc *chain, const sb_mono_desc *mono, int n_mono, int device) {
+    return run_chain<float>(img, By, Bx, n_img, chain, mono, n_mono, device);
+}
+int sb_prox_chain_f64(double *img, int By, int Bx, int n_img, const sb_chain_desc *chain, const sb_mono_desc *mono, int n_mono, int device) {
+    return run_chain<double>(img, By, Bx, n_img, chain, mono, n_mono, device);
+}
+
+} // extern "C"
+
+template <typename T>
+static int run_convolve(const T *image, int C, int Ny, int Nx, const double *khat, int Fy, int Fx, int adjoint, T *out, int device) {
+    typedef typename Cx<T>::type cplx;
+    if (!image || !khat || !out || C <= 0 || Ny <= 0 || Nx <= 0 || Fy < Ny || Fx < Nx) return set_err(SB_ERR_ARG, "bad argument");
+    SB_TRY(need_device(device));
+    SB_CUDA(cudaSetDevice(device));
+    const int Fxc = Fx / 2 + 1;
+    const size_t nimg = (size_t)C * Ny * Nx, ngrid = (size_t)C * Fy * Fx, nc = (size_t)C * Fy * Fxc;
+    DevBuf<T> dimg, A, B;
+    DevBuf<cplx> Ahat, K;
+    DevBuf<double2> ks;
+    SB_TRY(dimg.alloc(nimg));
+    SB_TRY(A.alloc(ngrid));
+    SB_TRY(B.alloc(ngrid));
+    SB_TRY(Ahat.alloc(nc));
+    SB_TRY(K.alloc(nc));
+    SB_TRY(ks.alloc(nc));
+    SB_TRY(A.zero(0));
+    SB_CUDA(cudaMemcpy(dimg.p, image, nimg * sizeof(T), cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(ks.p, khat, nc * sizeof(double2), cudaMemcpyHostToDevice));
+    k_cast_scale_cplx<T><<<grid_for(nc), 256>>>(ks.p, K.p, (long long)nc, 1.0 / ((double)Fy * Fx));
+    k_embed<T><<<grid_for(nimg), 256>>>(dimg.p, A.p, C, Fy, Fx, Ny, Nx);
+    SB_CUDA(cudaGetLastError());
+    cufftHandle fwd = 0, inv = 0;
+    int n[2] = {Fy, Fx};
+    SB_CUFFT(cufftPlanMany(&fwd, 2, n, nullptr, 1, 0, nullptr, 1, 0, Cx<T>::r2c, C));
+    cufftResult r2 = cufftPlanMany(&inv, 2, n, nullptr, 1, 0, nullptr, 1, 0, Cx<T>::c2r, C);
+    if (r2 != CUFFT_SUCCESS) {
+        cufftDestroy(fwd);
+        return set_err(SB_ERR_CUFFT, "cufftPlanMany(c2r) -> %d", (int)r2);
+    }
+    cufftResult r = Cx<T>::fwd(fwd, (typename Cx<T>::real_t *)A.p, (typename Cx<T>::cplx_t *)Ahat.p);
+    if (r == CUFFT_SUCCESS) {
+        k_kmul<T><<<grid_for(nc), 256>>>(Ahat.p, K.p, (long long)nc, (long long)nc, 1, adjoint, nullptr);
+        r = Cx<T>::inv(inv, (typename Cx<T>::cplx_t *)Ahat.p, (typename Cx<T>::real_t *)B.p);
+    }
+    cufftDestroy(fwd);
+    cufftDestroy(inv);
+    if (r != CUFFT_SUCCESS) return set_err(SB_ERR_CUFFT, "cufft exec -> %d", (int)r);
+    k_crop<T><<<grid_for(nimg), 256>>>(B.p, dimg.p, C, Fy, Fx, Ny, Nx);
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaMemcpy(out, dimg.p, nimg * sizeof(T), cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+extern "C" {
+int sb_fft_convolve_f32(const float *image, int C, int Ny, int Nx, const double *khat, int Fy, int Fx, int adjoint, float *out, int device) {
+    return run_convolve<float>(image, C, Ny, Nx, khat, Fy, Fx, adjoint, out, device);
+}
+int sb_fft_convolve_f64(const double *image, int C, int Ny, int Nx, const double *khat, int Fy, int Fx, int adjoint, double *out, int device) {
+    return run_convolve<double>(image, C, Ny, Nx, khat, Fy, Fx, adjoint, out, device);
+}
+
+} // extern "C"

@@ -1,0 +1,122 @@
+"""Seeded synthetic multi-band scenes for the benchmark and the parity tests (pure NumPy/SciPy; no CUDA, no oracle).
+
+Follows the generator specified in SURVEY.md 8(d): model PSF GaussianPSF(0.8); observed PSFs either Gaussian
+(cfg2) or Moffat images (cfg3/cfg5); exponential elliptical galaxies with log-uniform amplitudes and Dirichlet
+colours; point sources at sub-pixel positions; unit-variance Gaussian noise (weights = 1); fixed B x B boxes,
+``resizing=False``, ``shifting=False``.  One documented deviation: the initial morphologies are the truth
+profiles with perturbed shape parameters (already monotonic / normalised) instead of "truth + noise pushed
+through the constraint chain", so that generating a scene needs neither the GPU nor the oracle.
+"""
+import numpy as np
+from scipy import signal
+
+CONFIGS = {
+    # name: frame, sources, observed PSF, constraints, default iteration count
+    "cfg2": dict(C=5, N=128, n_ext=10, n_pt=0, psf="gaussian", P=21, B=41, symmetric=False, iters=200, config_id=2),
+    "cfg3": dict(C=5, N=256, n_ext=20, n_pt=5, psf="moffat", P=41, B=41, symmetric=True, iters=100, config_id=3),
+    "cfg5": dict(C=5, N=128, n_ext=12, n_pt=0, psf="moffat", P=41, B=41, symmetric=False, iters=100, config_id=5),
+    "tiny": dict(C=3, N=40, n_ext=3, n_pt=1, psf="gaussian", P=15, B=15, symmetric=True, iters=30, config_id=9),
+}
+MODEL_SIGMA = 0.8
+
+
+def _moffat(P, fwhm, beta=2.5):
+    alpha = fwhm / (2 * np.sqrt(2 ** (1 / beta) - 1))
+    y, x = np.mgrid[:P, :P] - P // 2
+    img = (1 + (x * x + y * y) / alpha ** 2) ** (-beta)
+    return img / img.sum()
+
+
+def _profile(B, dy, dx, rs, q, theta):
+    y, x = np.mgrid[:B, :B] - B // 2
+    y = y - dy
+    x = x - dx
+    ct, st = np.cos(theta), np.sin(theta)
+    u = ct * x + st * y
+    v = (-st * x + ct * y) / q
+    img = np.exp(-np.sqrt(u * u + v * v) / rs)
+    return img / img.max()
+
+
+def make_scene(config="cfg2", scene_id=0, per_scene_psf=True):
+    """-> dict of plain arrays describing one scene (data, PSFs, truth and initial parameters)."""
+    cfg = dict(CONFIGS[config]) if isinstance(config, str) else dict(config)
+    rng = np.random.default_rng(1000 * cfg["config_id"] + scene_id)
+    C, N, B, P = cfg["C"], cfg["N"], cfg["B"], cfg["P"]
+    from . import fft as sfft
+    from .psf import GaussianPSF
+    model_psf = GaussianPSF(sigma=(MODEL_SIGMA,) * C)
+    jitter = rng.uniform(0.9, 1.1) if per_scene_psf else 1.0
+    if cfg["psf"] == "gaussian":
+        sig = np.linspace(1.2, 2.0, C) * jitter
+        obs_psf = GaussianPSF(sig, boxsize=P).get_model()
+    else:
+        fw = np.linspace(2.8, 4.2, C) * jitter
+        obs_psf = np.stack([_moffat(P, f) for f in fw])
+    diff = sfft.match_psf(obs_psf.astype(np.float32), model_psf.get_model().astype(np.float32), padding=10).image
+
+    margin = min(12, N // 4)
+    sources, truth = [], np.zeros((C, N, N))
+    for k in range(cfg["n_ext"] + cfg["n_pt"]):
+        cy, cx = rng.uniform(margin, N - margin, size=2)
+        amp = np.exp(rng.uniform(np.log(20), np.log(2000)))
+        sed = amp * rng.dirichlet(np.ones(C)) * C
+        if k < cfg["n_ext"]:
+            py, px = int(np.round(cy)), int(np.round(cx))
+            rs, q, th = rng.uniform(1.5, 4.0), rng.uniform(0.5, 1.0), rng.uniform(0, np.pi)
+            rs = min(rs, B / 10.0)
+            tm = _profile(B, cy - py, cx - px, rs, q, th)
+            init = _profile(B, 0.0, 0.0, rs * rng.uniform(0.7, 1.3), min(1.0, q * rng.uniform(0.8, 1.2)), th + rng.normal(0, 0.2))
+            origin = (py - B // 2, px - B // 2)
+            src = dict(kind="extended", center=(cy, cx), origin=origin, sed_true=sed, morph_true=tm,
+                       sed=(sed * rng.uniform(0.7, 1.3, C)).astype(np.float32), morph=init)
+        else:
+            b = model_psf.bbox.shape[1]
+            py, px = int(np.round(cy)), int(np.round(cx))
+            origin = (py - b // 2, px - b // 2)
+            box_center = np.array([origin[0] + b / 2, origin[1] + b / 2])  # the reference's convention (morphology.py:505)
+            tm = model_psf.get_model(offset=np.array([cy, cx]) - box_center)[0]
+            src = dict(kind="point", center_true=(cy, cx), origin=origin, sed_true=sed, morph_true=tm,
+                       sed=(sed * rng.uniform(0.7, 1.3, C)).astype(np.float32),
+                       center=(cy + rng.uniform(-0.3, 0.3), cx + rng.uniform(-0.3, 0.3)))
+        oy, ox = src["origin"]
+        bb = src["morph_true"].shape[0]
+        y0, y1, x0, x1 = max(0, oy), min(N, oy + bb), max(0, ox), min(N, ox + bb)
+        truth[:, y0:y1, x0:x1] += sed[:, None, None] * src["morph_true"][None, y0 - oy:y1 - oy, x0 - ox:x1 - ox]
+        sources.append(src)
+    clean = np.stack([signal.fftconvolve(truth[c], diff[c], mode="same") for c in range(C)])
+    images = (clean + rng.standard_normal(clean.shape)).astype(np.float32)
+    return dict(config=cfg, scene_id=scene_id, C=C, N=N, images=images, weights=np.ones_like(images),
+                obs_psf=obs_psf, model_sigma=MODEL_SIGMA, sources=sources, channels=[str(c) for c in range(C)])
+
+
+def make_blend(scene, precision=32, device=None):
+    """Build the scarlet_b200 objects (Frame, Observation, sources, Blend) for a scene dict."""
+    import scarlet_b200 as sb
+    C = scene["C"]
+    cfg = scene["config"]
+    model_psf = sb.GaussianPSF(sigma=(scene["model_sigma"],) * C)
+    frame = sb.Frame(scene["images"].shape, psf=model_psf, channels=scene["channels"])
+    obs = sb.Observation(scene["images"].copy(), psf=sb.ImagePSF(scene["obs_psf"].copy()), weights=scene["weights"].copy(),
+                         channels=scene["channels"])
+    obs.match(frame)
+    sources = []
+    for s in scene["sources"]:
+        if s["kind"] == "extended":
+            B = s["morph"].shape[0]
+            sources.append(sb.ExtendedSource(frame, s["center"], obs, spectrum=s["sed"].copy(), morphology=s["morph"].copy(),
+                                             bbox=sb.Box((B, B), origin=s["origin"]), monotonic="angle",
+                                             symmetric=cfg["symmetric"], resizing=False))
+        else:
+            sources.append(sb.PointSource(frame, s["center"], obs, spectrum=s["sed"].copy()))
+    return sb.Blend(sources, obs, precision=precision, device=device)
+
+
+def algorithmic_bytes(scene_or_cfg, fft_shape, elem=4):
+    """algorithmic bytes per iteration per scene."""
+    cfg = scene_or_cfg["config"] if "config" in scene_or_cfg else scene_or_cfg
+    C, N = cfg["C"], cfg["N"]
+    Fy, Fx = fft_shape
+    Fc = Fy * (Fx // 2 + 1)
+    src = cfg["n_ext"] * cfg["B"] ** 2 * (14 + C) + cfg["n_pt"] * 81 * (14 + C)
+    return elem * (6 * C * Fy * Fx + 3 * C * N * N + src) + 2 * elem * (6 * C * Fc)
