@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the proximal-gradient fitting path (BASELINE.json metric: PGM iterations/sec per scene).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+A "step" is one fit of a batch of independent synthetic scenes for a FIXED number of proximal-gradient iterations
+(no early stopping, so that every step does identical work).  One iteration = render + PSF convolution + residual
++ gradient back-propagation + AMSGrad/proximal update of every parameter.
+
+  value  : scene-iterations per second over all GPUs, inputs resident in HBM, CUDA-event timed (max over ranks)
+  e2e    : the same through the public API (BlendBatch.fit) with host buffers: pinned H2D copy of the observation
+           cubes, K^ and parameters, and D2H read-back of fitted parameters, optimiser state and losses, every step
+  roofline: dominant stage of an iteration, algorithmic bytes / CUDA-event time, against MEASURED_PEAKS.json
+  cpu_baseline: the oracle restatement of the reference loop on one host core (rank 0, N=1, bounded sample)
+Multi-GPU: independent scenes are sharded across ranks (weak scaling, no collective inside the loop); NCCL is used
+once per step for the final gather of the packed fitted parameters.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="cfg3", choices=["cfg2", "cfg3", "cfg5", "tiny"])
+    ap.add_argument("--scenes", type=int, default=0, help="scenes per GPU (default per config)")
+    ap.add_argument("--iters", type=int, default=0, help="iterations per step (default per config)")
+    ap.add_argument("--unique", type=int, default=16, help="distinct synthetic scenes generated per rank (then cycled)")
+    ap.add_argument("--precision", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single", action="store_true")
+    return ap.parse_args()
+
+
+DEFAULT_SCENES = {"cfg2": 256, "cfg3": 96, "cfg5": 512, "tiny": 64}
+DEFAULT_ITERS = {"cfg2": 50, "cfg3": 50, "cfg5": 50, "tiny": 20}
+
+
+def peaks():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = sorted(sm)[len(sm) // 2:] if sm else []  # upper half ~ samples under load
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the reference algorithm (oracle restatement; the reference itself cannot run here)
+# ---------------------------------------------------------------------------------------------------
+def _ref_worker(job):
+    config, scene_id, iters = job
+    from oracle import scenes
+    from scarlet_b200 import synthetic
+    o = scenes.build_oracle(synthetic.make_scene(config, scene_id))
+    t0 = time.perf_counter()
+    o.fit(max_iter=iters, e_rel=1e-3, min_iter=10 ** 9)
+    return time.perf_counter() - t0
+
+
+def cpu_iters_for(config):
+    return {"cfg2": 20, "cfg3": 6, "cfg5": 12, "tiny": 30}[config]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import monotonic_c
+    monotonic_c.build()
+    cores = os.cpu_count() or 1
+    iters = cpu_iters_for(args.config)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        def step(k):
+            t0 = time.perf_counter()
+            pool.map(_ref_worker, [(args.config, 1000 * k + i, iters) for i in range(cores)])
+            return time.perf_counter() - t0
+        for k in range(args.warmup):
+            step(k)
+        times = [step(args.warmup + k) for k in range(args.steps)]
+    total = float(np.sum(times))
+    value = cores * iters * args.steps / total
+    sample = "%d scenes (one per host thread) x %d iterations per step, %s" % (cores, iters, args.config)
+    from scarlet_b200 import synthetic
+    line = {"impl": "reference", "metric": "pgm_scene_iterations_per_sec", "value": value, "unit": "scene-iterations/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, synthetic.CONFIGS[args.config], cores, iters),
+            "cpu_baseline": {"value": value, "unit": "scene-iterations/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "scene-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cfg, scenes_per_unit, iters):
+    return {"workload": "%s: %d-band %dx%d scene, %d ExtendedSource + %d PointSource, %s PSF %dx%d, box %d, %s"
+                        % (args.config, cfg["C"], cfg["N"], cfg["N"], cfg["n_ext"], cfg["n_pt"], cfg["psf"], cfg["P"], cfg["P"], cfg["B"],
+                           "monotonic+symmetry" if cfg["symmetric"] else "monotonic"),
+            "scenes_per_gpu": scenes_per_unit, "iterations_per_step": iters, "stop_rule": "disabled (fixed iterations)",
+            "l2_policy": "inputs larger than L2 (per-GPU working set reported as device_bytes)"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------------
+class _DevArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from scarlet_b200 import BlendBatch, _native, synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if _native.lib().sb_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device -- scarlet_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    cfg = synthetic.CONFIGS[args.config]
+    S = args.scenes or DEFAULT_SCENES[args.config]
+    iters = args.iters or DEFAULT_ITERS[args.config]
+    uniq = min(S, args.unique)
+    base = [synthetic.make_scene(args.config, rank * 100000 + i) for i in range(uniq)]
+    blends = [synthetic.make_blend(base[i % uniq], precision=args.precision, device=local) for i in range(S)]
+    batch = BlendBatch(blends, precision=args.precision, device=local)
+    plan = batch.plan
+    fshape = plan.obs_meta[0]["metas"][0]["fshape"]
+    opts = _native.fit_opts(max_iter=iters, e_rel=1e-3, min_iter=1, prox_max_iter=10, check_every=10 ** 6, fixed_iterations=True)
+    init = [plan._pack(w) for w in range(4)]  # initial parameters + zero state, re-uploaded before every step
+
+    def reset():
+        for w, (sed, morph, cen) in enumerate(init):
+            _native.check(_native.lib().sb_plan_upload_params(plan._handle, w, _native.ptr(sed), _native.ptr(morph), _native.ptr(cen)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        plan.sync()
+
+    def gather_results():
+        """NCCL gather of the packed fitted parameters (the only collective of the job)."""
+        if world == 1:
+            return 0
+        dp = plan.device_params()
+        ts = "<f4" if dp["elem_bytes"] == 4 else "<f8"
+        sed = torch.as_tensor(_DevArray(dp["sed"], dp["n_sed"], "<f8"), device="cuda:%d" % local)
+        morph = torch.as_tensor(_DevArray(dp["morph"], dp["n_morph"], ts), device="cuda:%d" % local)
+        out_s = torch.empty(world * sed.numel(), dtype=sed.dtype, device=sed.device)
+        out_m = torch.empty(world * morph.numel(), dtype=morph.dtype, device=morph.device)
+        dist.all_gather_into_tensor(out_s, sed)
+        dist.all_gather_into_tensor(out_m, morph)
+        torch.cuda.synchronize()
+        return out_s.numel() * out_s.element_size() + out_m.numel() * out_m.element_size()
+
+    # ---- device-resident timing (value) ----------------------------------------------------------
+    def device_step():
+        reset()
+        barrier()
+        plan.timer_start()
+        plan.fit_enqueue(opts, iters)
+        ms = plan.timer_stop()
+        gather_results()
+        barrier()
+        return ms
+
+    for _ in range(args.warmup):
+        device_step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = plan.kernel_launches
+    ms_steps = [device_step() for _ in range(args.steps)]
+    launches = plan.kernel_launches - launches0
+    ms_local = float(np.sum(ms_steps))
+    if world > 1:
+        t = torch.tensor([ms_local], device="cuda:%d" % local, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    else:
+        ms_total = ms_local
+    value = world * S * iters * args.steps / (ms_total / 1e3)
+
+    # ---- end-to-end through the public API with host buffers (e2e) -------------------------------
+    h2d = d2h = 0
+
+    def e2e_step():
+        nonlocal h2d, d2h
+        # restore the host Parameters to their initial values (host-side bookkeeping, outside the timed region)
+        for w, (sed, morph, cen) in enumerate(init):
+            _native.check(_native.lib().sb_plan_upload_params(plan._handle, w, _native.ptr(sed), _native.ptr(morph), _native.ptr(cen)))
+        plan.download_parameters(state=True)
+        for b in blends:
+            b.loss.clear()
+        barrier()
+        t0 = time.perf_counter()
+        nb = plan.upload_observations()                      # H2D: data, weights, K^ (pinned staging)
+        batch.fit(max_iter=iters, e_rel=1e-3, fixed_iterations=True, check_every=10 ** 6)  # H2D params+state, loop, D2H
+        gather_results()
+        barrier()
+        dt = time.perf_counter() - t0
+        per = sum(a.nbytes for a in init[0]) * 4
+        h2d, d2h = nb + per, per + S * iters * 8 + S * 8
+        return dt
+
+    e2e_times = [e2e_step() for _ in range(max(1, min(args.warmup, 1)))]
+    e2e_times = [e2e_step() for _ in range(args.steps)]
+    e2e_local = float(np.sum(e2e_times))
+    if world > 1:
+        t = torch.tensor([e2e_local], device="cuda:%d" % local, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_total = float(t.item())
+    else:
+        e2e_total = e2e_local
+    e2e_value = world * S * iters * args.steps / e2e_total
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-stage CUDA-event profile + roofline (rank 0) -----------------------------------------
+    line = None
+    if rank == 0:
+        reset()
+        plan.profile(opts, 3)
+        reset()
+        n_prof = 10
+        stages = plan.profile(opts, n_prof)
+        peak, peak_src = peaks()
+        C, N, B = cfg["C"], cfg["N"], cfg["B"]
+        Fy, Fx = fshape
+        Fc = Fy * (Fx // 2 + 1)
+        eb = 4 if args.precision == 32 else 8
+        src_px = cfg["n_ext"] * B * B + cfg["n_pt"] * 81
+        stage_bytes = {  # algorithmic bytes per scene per launch
+            "render": eb * (C * N * N + src_px),
+            "fft_fwd_model": eb * C * Fy * Fx + 2 * eb * C * Fc,
+            "kmul": 3 * 2 * eb * C * Fc,
+            "fft_inv_model": eb * C * Fy * Fx + 2 * eb * C * Fc,
+            "residual_loss": 4 * eb * C * N * N,
+            "fft_fwd_resid": eb * C * Fy * Fx + 2 * eb * C * Fc,
+            "kmul_conj": 3 * 2 * eb * C * Fc,
+            "fft_inv_grad": eb * C * Fy * Fx + 2 * eb * C * Fc,
+            "source_update": eb * src_px * (C + 8),
+            "advance": 16,
+        }
+        own = {k: v for k, v in stages.items() if not k.startswith("fft_")}
+        dom = max(own, key=own.get)
+        dom_ms = stages[dom]
+        achieved = stage_bytes[dom] * S / (dom_ms / 1e3) / 1e9
+        iter_ms = sum(stages.values())
+        alg_iter = synthetic.algorithmic_bytes(cfg, fshape, eb)
+        whole = alg_iter * S / (ms_total / args.steps / iters / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": stage_bytes[dom] * S,
+                    "kernel_ms": dom_ms, "kernel_share_of_iteration": dom_ms / iter_ms,
+                    "iteration": {"algorithmic_bytes_per_scene": alg_iter, "achieved": whole, "frac": whole / peak,
+                                  "note": "SURVEY.md 8(d) whole-iteration accounting incl. cuFFT stages"},
+                    "stages_ms": stages,
+                    "stages_gbs": {k: (stage_bytes[k] * S / (v / 1e3) / 1e9 if v > 0 else None) for k, v in stages.items()}}
+
+        # single-scene latency (the 200 it/s target of the north star is a per-scene figure)
+        single = None
+        if not args.no_single:
+            one = BlendBatch([synthetic.make_blend(base[0], precision=args.precision, device=local)], precision=args.precision, device=local)
+            o1 = _native.fit_opts(max_iter=200, e_rel=1e-3, fixed_iterations=True, check_every=10 ** 6)
+            for _ in range(3):
+                one.plan.upload_parameters(state=True)
+                one.plan.timer_start()
+                one.plan.fit_enqueue(o1, 200)
+                ms1 = one.plan.timer_stop()
+            single = 200 / (ms1 / 1e3)
+            one.plan.close()
+
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import monotonic_c
+            monotonic_c.build()
+            n_cpu = cpu_iters_for(args.config)
+            _ref_worker((args.config, 0, 2))
+            dt = _ref_worker((args.config, 0, n_cpu))
+            cpu = {"value": n_cpu / dt, "unit": "scene-iterations/s", "cores": 1, "kind": "port",
+                   "sample": "1 %s scene x %d iterations on one host core (oracle restatement, NumPy f64 + C sweep); host has %d cores"
+                             % (args.config, n_cpu, os.cpu_count() or 1)}
+
+        conf = workload_config(args, cfg, S, iters)
+        conf.update({"fft_grid": list(fshape), "unique_scenes_per_gpu": uniq, "device_bytes_per_gpu": plan.device_bytes,
+                     "single_scene_iterations_per_sec": single, "cufft_execs_per_iteration": 4 * len(plan.obs_meta),
+                     "kernels_per_iteration": launches // max(args.steps * iters, 1), "precision": args.precision,
+                     "per_scene_psf": True})
+        line = {"metric": "pgm_scene_iterations_per_sec", "value": value, "unit": "scene-iterations/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic",
+                "config": conf, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "scene-iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": 1e3 * e2e_total / args.steps},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+    barrier()
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -71,6 +71,8 @@ class DevicePlan:
         self.device = nat.default_device() if device is None else int(device)
         self._handle = None
         self._keep = []  # host arrays referenced by the descriptor until sb_plan_create returns
+        self._host_obs = None
+        self._pinned_ptrs = []
         b0 = self.blends[0]
         self.frame_shape = tuple(b0.frame.shape)
         C, Ny, Nx = self.frame_shape
@@ -220,16 +222,33 @@ class DevicePlan:
         return dict(kind=kind, shape=tuple(obs.data.shape), chan_off=r.channel_offset, origin=tuple(r.origin),
                     fshape=tuple(int(f) for f in fshape), khat=khat, obs=obs, renderer=r)
 
-    def upload_observations(self):
+    def _pinned(self, shape, dtype):
+        """numpy view of pinned host memory (sb_host_alloc) -- staging for asynchronous H2D copies."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = nat.lib().sb_host_alloc(max(n, 8))
+        if not p:
+            raise MemoryError("sb_host_alloc(%d) failed" % n)
+        self._pinned_ptrs.append(p)
+        buf = (ctypes.c_byte * max(n, 8)).from_address(p)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def _stage_observations(self):
+        """Stack the per-scene cubes once into pinned staging buffers (host work, not repeated per upload)."""
         C, Ny, Nx = self.frame_shape
+        self._host_obs = []
         for o, om in enumerate(self.obs_meta):
             metas = om["metas"]
-            data = np.ascontiguousarray(np.stack([np.asarray(m["obs"].data, dtype=np.float32) for m in metas]))
-            weights = np.ascontiguousarray(np.stack([np.asarray(m["obs"].weights, dtype=np.float32) for m in metas]))
+            shp = (self.S,) + metas[0]["shape"]
+            data, weights = self._pinned(shp, np.float32), self._pinned(shp, np.float32)
+            for i, m in enumerate(metas):
+                data[i] = m["obs"].data
+                weights[i] = m["obs"].weights
             khat = None
             if metas[0]["kind"] == 0:
                 ks = [metas[0]["khat"]] if om["shared"] else [m["khat"] for m in metas]
-                khat = np.ascontiguousarray(np.stack(ks), dtype=np.complex128)
+                khat = self._pinned((len(ks),) + ks[0].shape, np.complex128)
+                for i, k in enumerate(ks):
+                    khat[i] = k
             consts = []
             for m in metas:
                 obs, (oy, ox) = m["obs"], m["origin"]
@@ -244,10 +263,20 @@ class DevicePlan:
                     dd = np.asarray(obs.data, dtype=np.float64)[:, outside]
                     extra = 0.5 * float((w * dd * dd).sum())
                 consts.append(float(obs.log_norm) + extra)
-            consts = np.asarray(consts, dtype=np.float64)
-            nat.check(nat.lib().sb_plan_upload_observation(self._handle, o, nat.ptr(data), nat.ptr(weights),
+            self._host_obs.append(dict(data=data, weights=weights, khat=khat, consts=np.asarray(consts, dtype=np.float64)))
+
+    def upload_observations(self):
+        """Host (pinned) -> device copy of data, weights, K^ and the per-scene loss constants."""
+        if self._host_obs is None:
+            self._stage_observations()
+        nbytes = 0
+        for o, h in enumerate(self._host_obs):
+            khat = h["khat"]
+            nat.check(nat.lib().sb_plan_upload_observation(self._handle, o, nat.ptr(h["data"]), nat.ptr(h["weights"]),
                                                            nat.ptr(khat.view(np.float64)) if khat is not None else None,
-                                                           nat.ptr(consts)))
+                                                           nat.ptr(h["consts"])))
+            nbytes += h["data"].nbytes + h["weights"].nbytes + (khat.nbytes if khat is not None else 0) + h["consts"].nbytes
+        return nbytes
 
     # -------------------------------------------------------------------------------------------------
     def _pack(self, which):
@@ -375,6 +404,10 @@ class DevicePlan:
         if self._handle is not None:
             nat.lib().sb_plan_destroy(self._handle)
             self._handle = None
+        self._host_obs = None
+        for p in self._pinned_ptrs:
+            nat.lib().sb_host_free(p)
+        self._pinned_ptrs = []
 
     def __del__(self):
         try:

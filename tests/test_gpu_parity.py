@@ -1,0 +1,381 @@
+"""GPU: the CUDA path (through the C ABI) against the CPU oracle and the reference-derived golden fixtures.
+
+Tolerances.  Integer/index work and the monotonic sweep: bit-exact.  Floating point: the north-star bar is
+<= 1e-5 relative in float32 on model pixels and SEDs; "relative" is measured against the peak of the reference
+array (max |a-b| <= tol * max |b|).  The float64 twin of every kernel must agree with the float64 oracle to
+~1e-10, which separates algorithmic differences from float32 rounding.
+"""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+from conftest import ARANGE25, MONO_KATS, SYM_HALF, golden
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_peak(a, b):
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(np.asarray(a, dtype=np.float64) - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+# --------------------------------------------------------------------------------------------------
+# monotonic wavefront kernel: bit-exact against the sequential sweep
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,min_grad,expect", MONO_KATS)
+def test_monotonic_reference_kat(kind, min_grad, expect):
+    import scarlet_b200 as sb
+    out = sb.MonotonicityConstraint(neighbor_weight=kind, min_gradient=min_grad)(ARANGE25.copy(), 0)
+    assert_allclose(out, expect, atol=5e-8)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(5, 5), (21, 21), (41, 41), (81, 81), (20, 31), (1, 1), (2, 3)])
+@pytest.mark.parametrize("kind", ["angle", "flat", "nearest"])
+def test_monotonic_bit_exact(dtype, shape, kind):
+    from oracle import monotonic_c
+    from scarlet_b200 import operator
+    from scarlet_b200.operators_pybind11 import prox_weighted_monotonic
+    rng = np.random.default_rng(hash((shape, kind)) % 2 ** 31)
+    center = (shape[0] // 2, shape[1] // 2)
+    w, off, idx = operator.monotonic_tables(shape, kind, center)
+    w = w.astype(dtype)
+    for mg in (0.0, 0.1):
+        X = (np.exp(-np.hypot(*np.mgrid[:shape[0], :shape[1]]) / 5.0) + 0.2 * rng.standard_normal(shape)).astype(dtype)
+        a, b = X.copy().reshape(-1), X.copy().reshape(-1)
+        monotonic_c.sweep(a, w, off, idx, mg)
+        prox_weighted_monotonic(b, w, off, idx, mg)
+        assert_array_equal(a, b)
+
+
+def test_monotonic_batch_and_arbitrary_order():
+    """a batch of images with one operator; and a scrambled dist_idx (hazard-exact scheduling)"""
+    from oracle import monotonic_c
+    from scarlet_b200 import operator
+    from scarlet_b200.operators_pybind11 import prox_weighted_monotonic
+    rng = np.random.default_rng(5)
+    shape = (15, 15)
+    w, off, idx = operator.monotonic_tables(shape, "angle", (7, 7))
+    X = rng.random((6, 225))
+    ref = X.copy()
+    for r in ref:
+        monotonic_c.sweep(r, w, off, idx, 0.05)
+    out = X.copy()
+    prox_weighted_monotonic(out, w, off, idx, 0.05)
+    assert_array_equal(out, ref)
+    scr = rng.permutation(idx).astype(np.int32)
+    a, b = X[0].copy(), X[0].copy()
+    monotonic_c.sweep(a, w, off, scr, 0.0)
+    prox_weighted_monotonic(b, w, off, scr, 0.0)
+    assert_array_equal(a, b)
+
+
+def test_native_errors_are_reported():
+    from scarlet_b200 import _native
+    from scarlet_b200.operators_pybind11 import prox_weighted_monotonic
+    w = np.ones((8, 9))
+    off = np.array([-4, -3, -2, -1, 1, 2, 3, 4], dtype=np.int32)
+    with pytest.raises(_native.NativeError):  # neighbour outside the image
+        prox_weighted_monotonic(np.zeros(9), w, off, np.arange(9, dtype=np.int32), 0.0)
+    with pytest.raises(TypeError):
+        prox_weighted_monotonic(np.zeros(9, dtype=np.int32), w, off, np.arange(9, dtype=np.int32), 0.0)
+
+
+# --------------------------------------------------------------------------------------------------
+# constraint chain
+# --------------------------------------------------------------------------------------------------
+def test_symmetry_and_elementwise_kats():
+    import scarlet_b200 as sb
+    assert_allclose(sb.SymmetryConstraint()(ARANGE25.copy(), 0), np.full((5, 5), 12.0))
+    assert_allclose(sb.SymmetryConstraint(0.5)(ARANGE25.copy(), 0), SYM_HALF)
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((6, 7))
+    assert (sb.PositivityConstraint(0.1)(X.copy(), 0) >= 0.1).all()
+    Y = np.abs(X) + 0.1
+    assert_allclose(sb.NormalizationConstraint("sum")(Y.copy(), 0).sum(), 1)
+    assert_allclose(sb.NormalizationConstraint("max")(Y.copy(), 0).max(), 1)
+    assert sb.CenterOnConstraint()(np.zeros((5, 5)), 0)[2, 2] > 0
+    # even-sized symmetry (zero line appended before the flip, operator.py:281-288)
+    from oracle import scarlet_oracle as so
+    E = rng.random((6, 5))
+    assert_allclose(sb.SymmetryConstraint(0.7)(E.copy(), 0), so.prox_symmetry(E.copy(), 0.7), atol=1e-15)
+
+
+def test_chain_vs_reference_fixture():
+    import scarlet_b200 as sb
+    g = golden("prox_chain.npz")
+    for i in range(int(g["n"])):
+        kind, sym, mg = g["cfg%d" % i]
+        cons = [sb.MonotonicityConstraint(neighbor_weight=str(kind), min_gradient=float(mg))]
+        if int(sym):
+            cons.append(sb.SymmetryConstraint())
+        cons += [sb.PositivityConstraint(), sb.CenterOnConstraint(), sb.NormalizationConstraint("max")]
+        chain = sb.ConstraintChain(*cons)
+        out64 = chain(g["in%d" % i].copy(), 0)
+        assert_allclose(out64, g["out%d" % i], rtol=0, atol=1e-14, err_msg="case %d" % i)
+        out32 = chain(g["in%d" % i].astype(np.float32), 0)
+        assert rel_peak(out32, g["out%d" % i]) < 1e-6
+
+
+def test_chain_idempotent_at_scale():
+    """projection property on large boxes: applying the ExtendedSource chain twice changes nothing beyond rounding"""
+    import scarlet_b200 as sb
+    rng = np.random.default_rng(11)
+    chain = sb.ConstraintChain(sb.MonotonicityConstraint("angle", 0), sb.SymmetryConstraint(), sb.PositivityConstraint(),
+                               sb.CenterOnConstraint(), sb.NormalizationConstraint("max"))
+    X = np.exp(-np.hypot(*(np.mgrid[:81, :81] - 40)) / 9.0) + 0.05 * rng.standard_normal((81, 81))
+    once = chain(X.copy(), 0)
+    twice = chain(once.copy(), 0)
+    assert_allclose(twice, once, atol=1e-12)
+    assert once.max() == 1.0 and (once >= 0).all()
+    assert_allclose(once, once[::-1, ::-1], atol=1e-15)
+
+
+def test_unknown_constraint_raises():
+    import scarlet_b200 as sb
+    from scarlet_b200.constraint import MonoTables, constraint_ops
+
+    class Mine(sb.Constraint):
+        pass
+
+    with pytest.raises(TypeError, match="Mine"):
+        constraint_ops(sb.ConstraintChain(sb.PositivityConstraint(), Mine()), (5, 5), MonoTables())
+
+
+# --------------------------------------------------------------------------------------------------
+# FFT convolution
+# --------------------------------------------------------------------------------------------------
+def test_observation_render_reference_scenario():
+    """reference tests/test_observation.py:12-47 through the product API"""
+    import scarlet_b200 as sb
+    g = golden("obs_render_loss.npz")
+    mpsf = sb.GaussianPSF(float(g["model_sigma"]), boxsize=int(g["model_boxsize"]))
+    channels = [0, 1, 2]
+    frame = sb.Frame((3, 43, 43), psf=mpsf, channels=channels)
+    obs = sb.Observation(g["images"].copy(), psf=sb.GaussianPSF(g["obs_sigmas"], boxsize=int(g["obs_boxsize"])), channels=channels)
+    obs.match(frame)
+    rendered = obs.render(g["model"].astype(np.float32))
+    assert rendered.dtype == np.float32
+    assert_allclose(rendered, g["obs_psf_image"], atol=1e-6)   # the reference's own assertion (assert_almost_equal)
+    assert rel_peak(rendered, g["rendered"]) < 1e-5
+    logL = obs.get_log_likelihood(g["model"].astype(np.float32))
+    assert_allclose(logL, float(g["logL"]), rtol=1e-6)
+    r64 = obs.render(g["model"].astype(np.float64))
+    assert rel_peak(r64, g["rendered"]) < 1e-6  # fixture itself carries complex64 noise
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 2e-6), (np.float64, 1e-13)])
+def test_convolve_and_adjoint_vs_oracle(dtype, tol):
+    from oracle import scarlet_oracle as so
+    from scarlet_b200 import fft as sfft
+    rng = np.random.default_rng(3)
+    img = rng.random((4, 37, 52)).astype(dtype)
+    ker = rng.random((4, 9, 11))
+    fshape, khat = sfft.kernel_transform(ker, img.shape)
+    assert list(fshape) == so.get_fft_shape(img.shape, ker.shape, 3, (1, 2))
+    out = sfft.device_convolve(img, khat, fshape)
+    ref = so.convolve(img.astype(np.float64), ker, axes=(1, 2))
+    assert rel_peak(out, ref) < tol
+    # adjoint: <K x, y> == <x, K^T y>
+    y = rng.random(img.shape).astype(dtype)
+    adj = sfft.device_convolve(y, khat, fshape, adjoint=True)
+    lhs, rhs = float((out.astype(np.float64) * y).sum()), float((img.astype(np.float64) * adj).sum())
+    assert abs(lhs - rhs) <= (1e-5 if dtype == np.float32 else 1e-12) * abs(lhs)
+
+
+def test_convolution_linearity_full_size():
+    """size-independent property at the cfg3 grid (5x256x256, 41x41 kernel, F=300): K(a+2b) = K a + 2 K b"""
+    from scarlet_b200 import fft as sfft
+    rng = np.random.default_rng(4)
+    a = rng.random((5, 256, 256)).astype(np.float32)
+    b = rng.random((5, 256, 256)).astype(np.float32)
+    ker = rng.random((5, 41, 41))
+    ker /= ker.sum(axis=(1, 2))[:, None, None]
+    fshape, khat = sfft.kernel_transform(ker, a.shape)
+    assert tuple(fshape) == (300, 300)
+    lhs = sfft.device_convolve(a + 2 * b, khat, fshape)
+    rhs = sfft.device_convolve(a, khat, fshape) + 2 * sfft.device_convolve(b, khat, fshape)
+    assert rel_peak(lhs, rhs) < 5e-6
+    assert_allclose(lhs.sum(axis=(1, 2)) / (a + 2 * b).sum(axis=(1, 2)), 1.0, atol=0.05)  # flux (up to edge losses)
+
+
+# --------------------------------------------------------------------------------------------------
+# scene forward / gradients
+# --------------------------------------------------------------------------------------------------
+def _blend_from_golden(g, precision):
+    import scarlet_b200 as sb
+    C = g["images"].shape[0]
+    channels = list(range(C))
+    mpsf = sb.GaussianPSF(sigma=(float(g["model_sigma"]),) * C)
+    frame = sb.Frame(g["images"].shape, psf=mpsf, channels=channels)
+    obs = sb.Observation(g["images"].copy(), psf=sb.ImagePSF(g["psfs"].copy()), weights=g["weights"].copy(), channels=channels)
+    obs.match(frame)
+    srcs = []
+    for k in range(int(g["n_sources"])):
+        if str(g["src%d_kind" % k]) == "PointSource":
+            srcs.append(sb.PointSource(frame, g["src%d_center" % k], obs, spectrum=g["src%d_spectrum" % k].copy()))
+        else:
+            img = g["src%d_image" % k]
+            srcs.append(sb.ExtendedSource(frame, (0, 0), obs, spectrum=g["src%d_spectrum" % k].copy(), morphology=img.copy(),
+                                          bbox=sb.Box(img.shape, origin=g["src%d_origin" % k][1:]), resizing=False))
+    return sb.Blend(srcs, obs, precision=precision), obs
+
+
+@pytest.mark.parametrize("name", ["hsc_cosmos_35.npz", "point_extended.npz"])
+@pytest.mark.parametrize("precision,tol", [(32, 1e-5), (64, 1e-6)])
+def test_scene_forward_vs_reference_fixture(name, precision, tol):
+    """model, render and logL of the reference's own forward code (boxes overhang the frame; masked weights)"""
+    g = golden(name)
+    blend, obs = _blend_from_golden(g, precision)
+    model = blend.get_model()
+    assert rel_peak(model, g["model"]) < tol
+    ev = blend._get_plan().evaluate(want=("rendered", "loss"))
+    assert rel_peak(ev["rendered"][0], g["rendered"]) < tol
+    assert_allclose(-ev["loss"][0], float(g["logL"]), rtol=1e-5)
+    assert rel_peak(obs.render(model), g["rendered"]) < 2 * tol
+
+
+@pytest.mark.parametrize("name", ["hsc_cosmos_35.npz", "point_extended.npz"])
+def test_scene_gradients_vs_oracle(name):
+    from test_oracle_golden import _scene_from_golden
+    g = golden(name)
+    for precision, tol in ((64, 1e-9), (32, 2e-5)):
+        blend, _ = _blend_from_golden(g, precision)
+        plan = blend._get_plan()
+        plan.upload_parameters(state=False)
+        ev = plan.evaluate(want=("loss", "grads"))
+        scene, _ = _scene_from_golden(g, frame_dtype=np.float64 if precision == 64 else np.float32)
+        loss, grads = scene.loss_and_grads()
+        assert_allclose(ev["loss"][0], loss, rtol=1e-9 if precision == 64 else 1e-5)
+        i = ie = ip = 0
+        for k, src in enumerate(scene.sources):
+            assert rel_peak(ev["g_sed"][k], grads[i]) < tol, (k, "sed")
+            if src.kind == "extended":
+                assert rel_peak(ev["g_morph"][ie], grads[i + 1]) < tol, (k, "morph")
+                # out-of-frame morphology pixels have exactly zero gradient (blend.py:41-44)
+                oy, ox = src.bbox.origin[1:]
+                yy, xx = np.mgrid[:src.bbox.shape[1], :src.bbox.shape[2]]
+                out = (yy + oy < 0) | (yy + oy >= scene.frame_shape[1]) | (xx + ox < 0) | (xx + ox >= scene.frame_shape[2])
+                assert (ev["g_morph"][ie][out] == 0).all()
+                ie += 1
+            else:
+                assert rel_peak(ev["g_center"][ip], grads[i + 1]) < 10 * tol, (k, "center")
+                ip += 1
+            i += len(src.parameters)
+
+
+# --------------------------------------------------------------------------------------------------
+# the fitting loop
+# --------------------------------------------------------------------------------------------------
+def _compare_fit(scene, n_iter, precision, tol_morph, tol_sed, e_rel=1e-3, fixed=True):
+    from oracle import scenes
+    from scarlet_b200 import synthetic
+    o = scenes.build_oracle(scene, frame_dtype=np.float32 if precision == 32 else np.float64)
+    if fixed:
+        o_n, o_logL = o.fit(max_iter=n_iter, e_rel=e_rel, min_iter=10 ** 9)
+    else:
+        o_n, o_logL = o.fit(max_iter=n_iter, e_rel=e_rel)
+    blend = synthetic.make_blend(scene, precision=precision)
+    n, logL = blend.fit(max_iter=n_iter, e_rel=e_rel, min_iter=10 ** 9 if fixed else 1, check_every=1)
+    assert n == o_n
+    assert_allclose(np.array(blend.loss), np.array(o.loss), rtol=1e-9 if precision == 64 else 2e-5)
+    worst = {}
+    for src, osrc in zip(blend.sources, o.sources):
+        ps = src.parameters
+        assert rel_peak(ps[0], osrc.spectrum.x) < tol_sed
+        assert rel_peak(ps[0].m, osrc.spectrum.m) < max(tol_sed, 1e-6) * 50
+        if osrc.kind == "extended":
+            worst["morph"] = max(worst.get("morph", 0), rel_peak(ps[1], osrc.image.x))
+            assert rel_peak(ps[1], osrc.image.x) < tol_morph
+            assert ps[1].std is not None and ps[1].m.shape == ps[1].shape
+        else:
+            assert np.abs(np.asarray(ps[1]) - osrc.center.x).max() < max(tol_morph, 1e-9) * 10
+    model = blend.get_model()
+    assert rel_peak(model, o.get_model()) < max(tol_morph, tol_sed)
+    return blend, o
+
+
+@pytest.mark.parametrize("n_iter", [1, 10, 30])
+def test_fit_float64_twin_matches_oracle(n_iter):
+    """algorithmic identity: the float64 twin follows the float64 oracle to rounding"""
+    from scarlet_b200 import synthetic
+    _compare_fit(synthetic.make_scene("tiny", 0), n_iter, 64, 1e-9, 1e-9)
+
+
+@pytest.mark.parametrize("n_iter", [1, 10, 30])
+def test_fit_float32_matches_oracle(n_iter):
+    from scarlet_b200 import synthetic
+    _compare_fit(synthetic.make_scene("tiny", 0), n_iter, 32, 1e-5, 1e-5)
+
+
+def test_fit_stop_rule_matches_oracle():
+    """same iteration count under the reference's convergence rule (blend.py:294-299)"""
+    from scarlet_b200 import synthetic
+    blend, o = _compare_fit(synthetic.make_scene("tiny", 2), 200, 64, 1e-8, 1e-8, e_rel=1e-3, fixed=False)
+    assert len(blend.loss) < 200
+
+
+def test_fit_cfg2_float32_matches_oracle():
+    """BASELINE config 2 shape (5x128x128, 10 ExtendedSource, Gaussian PSF), 50 iterations"""
+    from scarlet_b200 import synthetic
+    _compare_fit(synthetic.make_scene("cfg2", 0), 50, 32, 1e-5, 1e-5)
+
+
+def test_fit_cfg3_float32_matches_oracle():
+    """BASELINE config 3 shape (5x256x256, 20 ExtendedSource + 5 PointSource, ImagePSF, monotonic + symmetry)"""
+    from scarlet_b200 import synthetic
+    _compare_fit(synthetic.make_scene("cfg3", 0), 20, 32, 1e-5, 1e-5)
+
+
+def test_warm_start_second_fit():
+    """optimiser state lives on the Parameters: fit(5)+fit(5) == oracle fit(5)+fit(5) (blend.py:154-163)"""
+    from oracle import scenes
+    from scarlet_b200 import synthetic
+    sc = synthetic.make_scene("tiny", 4)
+    o = scenes.build_oracle(sc, frame_dtype=np.float64)
+    o.fit(max_iter=5, min_iter=10 ** 9)
+    o.fit(max_iter=5, min_iter=10 ** 9)
+    b = synthetic.make_blend(sc, precision=64)
+    b.fit(max_iter=5, min_iter=10 ** 9)
+    n, _ = b.fit(max_iter=5, min_iter=10 ** 9)
+    assert n == 10
+    assert_allclose(b.loss, o.loss, rtol=1e-9)
+    for src, osrc in zip(b.sources, o.sources):
+        assert rel_peak(src.parameters[0], osrc.spectrum.x) < 1e-9
+
+
+def test_batch_equals_individual_fits():
+    import scarlet_b200 as sb
+    from scarlet_b200 import synthetic
+    scs = [synthetic.make_scene("tiny", i) for i in range(5)]
+    singles = [synthetic.make_blend(s) for s in scs]
+    for b in singles:
+        b.fit(max_iter=15, e_rel=1e-4)
+    batch = [synthetic.make_blend(s) for s in scs]
+    res = sb.BlendBatch(batch).fit(max_iter=15, e_rel=1e-4)
+    for b1, b2, r in zip(singles, batch, res):
+        assert r[0] == len(b1.loss)
+        assert_array_equal(np.array(b1.loss), np.array(b2.loss))
+        for p1, p2 in zip(b1.parameters, b2.parameters):
+            assert_array_equal(np.asarray(p1), np.asarray(p2))
+
+
+def test_nonfinite_raises_arithmetic_error():
+    from scarlet_b200 import synthetic
+    sc = synthetic.make_scene("tiny", 0)
+    sc["images"][0, 5, 5] = np.inf
+    b = synthetic.make_blend(sc)
+    with pytest.raises(ArithmeticError):
+        b.fit(max_iter=5)
+
+
+def test_unsupported_features_raise():
+    import scarlet_b200 as sb
+    from scarlet_b200 import synthetic
+    sc = synthetic.make_scene("tiny", 0)
+    b = synthetic.make_blend(sc)
+    with pytest.raises(NotImplementedError):
+        b.fit(max_iter=2, scheme="adam")
+    b.sources[0].parameters[0].step = lambda X, it: 1.0
+    with pytest.raises(TypeError):
+        b.fit(max_iter=2)

@@ -1,0 +1,161 @@
+"""CPU: host-side mirror of the reference API, table builders, the C-ABI export list, and the no-fallback rule."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+from conftest import ROOT, golden
+
+
+def test_box_geometry():
+    """reference tests/test_bbox.py:6-54"""
+    from scarlet_b200 import Box, overlapped_slices
+    x = np.zeros((5, 6))
+    x[1:3, 2:5] = 1
+    b = Box.from_data(x)
+    assert b.shape == (2, 3) and b.origin == (1, 2)
+    assert b.contains((1, 2)) and not b.contains((3, 2))
+    img = np.arange(30).reshape(5, 6)
+    assert_array_equal(b.extract_from(img), img[1:3, 2:5])
+    # boxes hanging over the edge
+    over = Box((3, 3), origin=(-1, 4))
+    sub = over.extract_from(img)
+    assert_array_equal(sub[1:, :2], img[0:2, 4:6])
+    assert (sub[0] == 0).all() and (sub[:, 2] == 0).all()
+    canvas = np.zeros((5, 6), dtype=int)
+    over.insert_into(canvas, np.ones((3, 3), dtype=int))
+    assert canvas.sum() == 4
+    s1, s2 = overlapped_slices(Box((5, 6)), over)
+    assert s1 == (slice(0, 2), slice(4, 6)) and s2 == (slice(1, 3), slice(0, 2))
+    assert (Box((2,)) @ Box((3, 4), origin=(1, 1))).shape == (2, 3, 4)
+    assert (Box((3, 3)) | Box((2, 2), origin=(4, 4))).shape == (6, 6)
+    assert (Box((3, 3)) & Box((2, 2), origin=(4, 4))).shape == (0, 0)
+    assert Box((3, 3), origin=(1, 1)) + (1, 2) == Box((3, 3), origin=(2, 3))
+
+
+def test_pad_center_conventions():
+    """reference tests/test_fft.py:12-77"""
+    from scarlet_b200 import fft
+    a_pad = fft._pad(np.ones((1, 1)), (5, 4))
+    truth = np.zeros((5, 4))
+    truth[2, 2] = 1
+    assert_array_equal(a_pad, truth)
+    a0 = np.arange(10).reshape(5, 2)
+    a_pad = fft._pad(a0, (9, 11))
+    truth = np.zeros((9, 11), dtype=int)
+    truth[2:7, 5:7] = a0
+    assert_array_equal(a_pad, truth)
+    assert_array_equal(fft._centered(a_pad, (5, 2)), a0)
+    from oracle import scarlet_oracle as so
+    for s1, s2 in (((5, 58, 48), (5, 43, 43)), ((5, 128, 128), (5, 21, 21)), ((5, 256, 256), (5, 41, 41)), ((3, 17, 20), (3, 8, 6))):
+        assert fft._get_fft_shape(s1, s2, 3, (1, 2)) == so.get_fft_shape(s1, s2, 3, (1, 2))
+    assert fft._get_fft_shape((5, 256, 256), (5, 41, 41), 3, (1, 2)) == [300, 300]
+
+
+def test_weight_tables_vs_reference_fixture():
+    from scarlet_b200 import operator
+    g = golden("monotonic_weights.npz")
+    for i in range(int(g["n"])):
+        H, W, cy, cx = g["cfg%d" % i]
+        center = None if cy < 0 else (int(cy), int(cx))
+        w = operator.getRadialMonotonicWeights((int(H), int(W)), str(g["kind%d" % i]), center)
+        assert_allclose(w, g["w%d" % i], atol=1e-15, err_msg="case %d" % i)
+    w, off, idx = operator.monotonic_tables((5, 7), "angle", (2, 3))
+    assert w.shape == (8, 35) and idx.size == 34 and 2 * 7 + 3 not in idx
+    assert_array_equal(off, [-8, -7, -6, -1, 1, 6, 7, 8])
+
+
+def test_diff_kernel_vs_reference_fixture():
+    import scarlet_b200 as sb
+    g = golden("hsc_cosmos_35.npz")
+    C = g["images"].shape[0]
+    frame = sb.Frame(g["images"].shape, psf=sb.GaussianPSF(sigma=(0.8,) * C), channels=list(range(C)))
+    obs = sb.Observation(g["images"].copy(), psf=sb.ImagePSF(g["psfs"].copy()), weights=g["weights"].copy(), channels=list(range(C)))
+    obs.match(frame)
+    assert type(obs.renderer).__name__ == "ConvolutionRenderer"
+    assert_allclose(obs.renderer.diff_kernel.image, g["diff_kernel"], atol=2e-7)
+    assert_allclose(obs.log_norm, float(g["log_norm"]), rtol=1e-9)
+    assert_allclose(np.array(np.mean(obs.noise_rms, axis=(1, 2))), g["noise_rms_band"], rtol=1e-6)
+    fshape, khat = obs.renderer.kernel_transform()
+    assert tuple(fshape) == (108, 96) and khat.shape == (5, 108, 49)
+    pg = golden("obs_render_loss.npz")
+    assert_allclose(sb.GaussianPSF(pg["obs_sigmas"], boxsize=43).get_model(), pg["obs_psf_image"], atol=1e-15)
+
+
+def test_parameter_roundtrip_and_model_tree():
+    import pickle
+    import scarlet_b200 as sb
+    from scarlet_b200 import synthetic
+    p = sb.Parameter(np.arange(3.0), name="x", step=0.1, m=np.ones(3))
+    q = pickle.loads(pickle.dumps(p))
+    assert q.name == "x" and q.step == 0.1 and (q.m == 1).all() and (q[1:]).name == "x"
+    sc = synthetic.make_scene("tiny", 0)
+    b = synthetic.make_blend.__wrapped__(sc) if hasattr(synthetic.make_blend, "__wrapped__") else None
+    frame = sb.Frame(sc["images"].shape, psf=sb.GaussianPSF(sigma=(0.8,) * 3), channels=sc["channels"])
+    obs = sb.Observation(sc["images"], psf=sb.ImagePSF(sc["obs_psf"].copy()), weights=sc["weights"], channels=sc["channels"])
+    obs.match(frame)
+    s = sc["sources"][0]
+    src = sb.ExtendedSource(frame, s["center"], obs, spectrum=s["sed"], morphology=s["morph"], resizing=False)
+    names = [p.name for p in src.parameters]
+    assert names == ["spectrum", "image", "shift"]  # order of model.py:51-54 / morphology.py:112-113
+    assert src.bbox.shape == (3, 15, 15)
+    assert src.get_model().shape == (3, 15, 15)
+    assert_allclose(src.parameters[0].step(src.parameters[0], it=0), max(1.0, 0.01 * s["sed"].mean()))
+    pt = sb.PointSource(frame, (20.3, 11.8), obs, spectrum=s["sed"])
+    assert [p.name for p in pt.parameters] == ["spectrum", "center"] and pt.bbox.shape == (3, 9, 9)
+    from oracle import scarlet_oracle as so
+    po = so.PointSourceOracle(s["sed"], (20.3, 11.8), so.GaussianPSFOracle([0.8] * 3))
+    assert_allclose(pt.get_model(), po.get_model(), rtol=1e-6)
+    assert pt.bbox.origin == po.bbox.origin
+    bad = np.array([1.0, np.nan, 2.0])
+    with pytest.raises(ArithmeticError):
+        sb.TabulatedSpectrum(frame, bad)
+
+
+def test_abi_exports_every_declared_symbol():
+    """the shared library must export exactly what include/scarlet_b200.h declares (no compute calls here)"""
+    from scarlet_b200 import _build, _native
+    header = open(os.path.join(ROOT, "include", "scarlet_b200.h")).read()
+    declared = set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(_native.SYMBOLS), declared ^ set(_native.SYMBOLS)
+    path = _build.build()
+    handle = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(handle, name), name
+    lib = _native.lib()
+    assert lib.sb_version().startswith(b"scarlet_b200")
+    assert lib.sb_stage_name(0) == b"render"
+
+
+def test_no_cpu_fallback(has_gpu):
+    """without a CUDA device every compute entry point fails loudly"""
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    import scarlet_b200 as sb
+    from scarlet_b200 import _native, synthetic
+    with pytest.raises(_native.NativeError, match="no CUDA device"):
+        sb.PositivityConstraint()(np.zeros((3, 3)), 0)
+    b = synthetic.make_blend(synthetic.make_scene("tiny", 0))
+    with pytest.raises(_native.NativeError, match="no CUDA device"):
+        b.fit(max_iter=2)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "scarlet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "/root/reference" not in src, f
+
+
+def test_algorithmic_bytes_formula():
+    """SURVEY.md 8(d) figures"""
+    from scarlet_b200 import synthetic
+    assert abs(synthetic.algorithmic_bytes(synthetic.CONFIGS["cfg2"], (160, 160)) / 1e6 - 8.44) < 0.05
+    assert abs(synthetic.algorithmic_bytes(synthetic.CONFIGS["cfg5"], (180, 180)) / 1e6 - 10.3) < 0.1
