@@ -190,10 +190,6 @@ template <typename T> struct RenderArgs {
     int C, Ny, Nx, n_obs;
     DevObs<T> obs[SB_MAX_OBS];
     const int *done;
-    const int *it_ptr;
-    double *loss;            // [S][cap]
-    const double *loss_const; // [S]
-    int cap;
     T *model_out; // optional [S][C][Ny][Nx]
 };
 
@@ -201,8 +197,6 @@ template <typename T> __global__ void __launch_bounds__(256) k_render(const Rend
     const int s = blockIdx.z;
     if (a.done[s]) return;
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0)
-        a.loss[(size_t)s * a.cap + *a.it_ptr] = a.loss_const[s];
     if (x >= a.Nx || y >= a.Ny) return;
     T acc[SB_MAXC];
 #pragma unroll
@@ -269,11 +263,10 @@ k_kmul(typename Cx<T>::type *__restrict__ X, const typename Cx<T>::type *__restr
 // ======================================================================================================
 template <typename T> struct ResidualArgs {
     DevObs<T> ob;
-    int Ny, Nx, cap;
+    int Ny, Nx;
     const int *done;
-    const int *it_ptr;
-    double *loss;
-    T *rendered_out; // optional [S][C][H][W]
+    double *partials; // [S*C][gridDim.y*gridDim.x] chi^2 partial sums of this observation (deterministic reduction)
+    T *rendered_out;  // optional [S][C][H][W]
 };
 
 template <typename T> __global__ void __launch_bounds__(256) k_residual(const ResidualArgs<T> a) {
@@ -306,7 +299,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_residual(const Re
     if (lin < 32) {
         part = lin < 8 ? red[lin] : 0.0;
         part = warp_sum(part);
-        if (lin == 0 && part != 0.0) atomicAdd(a.loss + (size_t)s * a.cap + *a.it_ptr, 0.5 * part);
+        if (lin == 0) a.partials[(size_t)sc * (gridDim.x * gridDim.y) + blockIdx.y * gridDim.x + blockIdx.x] = part;
     }
 }
 
@@ -658,32 +651,53 @@ template <typename T> __global__ void __launch_bounds__(128) k_update(const Upda
 }
 
 // ======================================================================================================
-// K7  per-scene stop rule + iteration counter      reference: blend.py:276-302 (Blend._callback)
+// K7  per-scene loss reduction + stop rule + iteration counter      reference: blend.py:264-274, 276-302
 // ======================================================================================================
-__global__ void __launch_bounds__(256)
-k_advance(int S, int cap, const double *loss, int *done, int *n_iter, int *it_ptr, int *n_active, const int *status,
-          FitScalars fs) {
+struct LossArgs {
+    int n_obs;
+    const double *partials[SB_MAX_OBS]; // per observation: [S][n_part[o]]
+    int n_part[SB_MAX_OBS];
+    const double *loss_const; // [S]
+    double *loss;             // [S][cap]
+    int cap;
+    int *done, *n_iter, *n_active_next;
+    const int *it_ptr;
+    const int *status;
+    FitScalars fs;
+};
+
+// one block per scene: fixed-order reduction of the chi^2 partials -> loss[s][it], then the stop rule
+__global__ void __launch_bounds__(128) k_loss_stop(const LossArgs a) {
     __shared__ double red[40];
-    const int it = *it_ptr;
-    int active = 0;
-    for (int s = threadIdx.x; s < S; s += blockDim.x) {
-        if (done[s]) continue;
-        n_iter[s] = it + 1;
-        bool stop = status[s] != 0;
-        if (!fs.fixed_iterations && it > 0 && it > fs.min_iter) {
-            const double l1 = loss[(size_t)s * cap + it], l0 = loss[(size_t)s * cap + it - 1];
-            if (fabs(l1 - l0) < fs.e_rel * fabs(l1)) stop = true;
+    const int s = blockIdx.x;
+    if (a.done[s]) return;
+    const int it = *a.it_ptr;
+    double acc = 0.0;
+    for (int o = 0; o < a.n_obs; ++o) {
+        const double *p = a.partials[o] + (size_t)s * a.n_part[o];
+        for (int i = threadIdx.x; i < a.n_part[o]; i += blockDim.x) acc += p[i];
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+        const double l1 = a.loss_const[s] + 0.5 * acc;
+        a.loss[(size_t)s * a.cap + it] = l1;
+        a.n_iter[s] = it + 1;
+        bool stop = a.status[s] != 0;
+        if (!a.fs.fixed_iterations && it > 0 && it > a.fs.min_iter) {
+            const double l0 = a.loss[(size_t)s * a.cap + it - 1];
+            if (fabs(l1 - l0) < a.fs.e_rel * fabs(l1)) stop = true;
         }
         if (stop)
-            done[s] = 1;
+            a.done[s] = 1;
         else
-            active++;
+            atomicAdd(a.n_active_next, 1);
     }
-    const double tot = block_sum((double)active, red);
-    if (threadIdx.x == 0) {
-        *n_active = (int)tot;
-        *it_ptr = it + 1;
-    }
+}
+
+__global__ void k_tick(int *it_ptr, int *n_active, int *n_active_next) {
+    *it_ptr += 1;
+    *n_active = *n_active_next;
+    *n_active_next = 0;
 }
 
 // ======================================================================================================

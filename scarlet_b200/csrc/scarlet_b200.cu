@@ -215,7 +215,7 @@ template <typename T> struct PlanT : sb_plan {
     std::vector<DevSource> h_src;
     std::vector<int> h_start;
     DevBuf<DevSource> d_src;
-    DevBuf<int> d_start, d_done, d_niter, d_status, d_it, d_nactive;
+    DevBuf<int> d_start, d_done, d_niter, d_status, d_it, d_nactive, d_nactive_next;
     DevBuf<double> d_sed, d_sed_m, d_sed_v, d_sed_vhat, d_center, d_cen_m, d_cen_v, d_cen_vhat, d_loss, d_loss_const;
     DevBuf<double> d_gsed, d_gcenter, d_gmorph, d_stage;
     DevBuf<T> d_morph, d_morph_m, d_morph_v, d_morph_vhat, d_pmorph, d_model, d_rendered;
@@ -226,6 +226,8 @@ template <typename T> struct PlanT : sb_plan {
     struct Obs {
         DevObs<T> dev;
         DevBuf<T> A, B, data, weights;
+        DevBuf<double> partials;
+        int n_part = 0;
         DevBuf<cplx> Ahat, khat;
         cufftHandle fwd = 0, inv = 0;
         bool have_plans = false;
@@ -364,6 +366,7 @@ template <typename T> struct PlanT : sb_plan {
         SB_TRY(d_status.alloc(S));
         SB_TRY(d_it.alloc(1));
         SB_TRY(d_nactive.alloc(1));
+        SB_TRY(d_nactive_next.alloc(1));
         SB_TRY(d_loss_const.alloc(S));
         SB_TRY(d_loss_const.zero(stream));
         SB_TRY(ensure_loss_cap(256));
@@ -389,6 +392,9 @@ template <typename T> struct PlanT : sb_plan {
             SB_TRY(ob.data.zero(stream));
             SB_TRY(ob.weights.zero(stream));
             ob.loss_const.assign(S, 0.0);
+            ob.n_part = od.C * ((desc.Nx + 31) / 32) * ((desc.Ny + 7) / 8);
+            SB_TRY(ob.partials.alloc((size_t)S * ob.n_part));
+            SB_TRY(ob.partials.zero(stream));
             if (od.kind == 0) {
                 SB_TRY(ob.B.alloc(ngrid));
                 SB_TRY(ob.Ahat.alloc(ncplx));
@@ -437,6 +443,7 @@ template <typename T> struct PlanT : sb_plan {
         SB_TRY(d_niter.zero(stream));
         SB_TRY(d_status.zero(stream));
         SB_TRY(d_it.zero(stream));
+        SB_TRY(d_nactive_next.zero(stream));
         SB_CUDA(cudaMemcpyAsync(d_nactive.p, &S, sizeof(int), cudaMemcpyHostToDevice, stream));
         return SB_OK;
     }
@@ -599,7 +606,7 @@ template <typename T> struct PlanT : sb_plan {
             ra.src = d_src.p, ra.scene_src_start = d_start.p, ra.sed = d_sed.p, ra.morph = d_morph.p, ra.pmorph = d_pmorph.p;
             ra.C = C, ra.Ny = desc.Ny, ra.Nx = desc.Nx, ra.n_obs = (int)obs.size();
             for (size_t o = 0; o < obs.size(); ++o) ra.obs[o] = obs[o]->dev;
-            ra.done = d_done.p, ra.it_ptr = d_it.p, ra.loss = d_loss.p, ra.loss_const = d_loss_const.p, ra.cap = loss_cap;
+            ra.done = d_done.p;
             ra.model_out = model_out;
             dim3 grid((desc.Nx + 31) / 32, (desc.Ny + 7) / 8, S), block(32, 8);
             k_render<T><<<grid, block, 0, stream>>>(ra);
@@ -629,7 +636,7 @@ template <typename T> struct PlanT : sb_plan {
             {
                 ResidualArgs<T> ra;
                 memset(&ra, 0, sizeof ra);
-                ra.ob = d, ra.Ny = desc.Ny, ra.Nx = desc.Nx, ra.cap = loss_cap, ra.done = d_done.p, ra.it_ptr = d_it.p, ra.loss = d_loss.p;
+                ra.ob = d, ra.Ny = desc.Ny, ra.Nx = desc.Nx, ra.done = d_done.p, ra.partials = ob.partials.p;
                 ra.rendered_out = ((int)o == rendered_obs) ? rendered_out : nullptr;
                 dim3 grid((desc.Nx + 31) / 32, (desc.Ny + 7) / 8, S * d.C), block(32, 8);
                 k_residual<T><<<grid, block, 0, stream>>>(ra);
@@ -659,10 +666,22 @@ template <typename T> struct PlanT : sb_plan {
             ++nk;
         }
         mark();
-        if (mode == 0) {
-            k_advance<<<1, 256, 0, stream>>>(S, loss_cap, d_loss.p, d_done.p, d_niter.p, d_it.p, d_nactive.p, d_status.p, cur_fs);
+        {
+            LossArgs la;
+            memset(&la, 0, sizeof la);
+            la.n_obs = (int)obs.size();
+            for (size_t o = 0; o < obs.size(); ++o) la.partials[o] = obs[o]->partials.p, la.n_part[o] = obs[o]->n_part;
+            la.loss_const = d_loss_const.p, la.loss = d_loss.p, la.cap = loss_cap, la.done = d_done.p, la.n_iter = d_niter.p;
+            la.n_active_next = d_nactive_next.p, la.it_ptr = d_it.p, la.status = d_status.p, la.fs = cur_fs;
+            if (mode == 1) la.fs.fixed_iterations = 1;
+            k_loss_stop<<<S, 128, 0, stream>>>(la);
             SB_CUDA(cudaGetLastError());
             ++nk;
+            if (mode == 0) {
+                k_tick<<<1, 1, 0, stream>>>(d_it.p, d_nactive.p, d_nactive_next.p);
+                SB_CUDA(cudaGetLastError());
+                ++nk;
+            }
         }
         mark();
         kernels_per_iter = nk, ffts_per_iter = nf;

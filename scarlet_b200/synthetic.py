@@ -96,7 +96,9 @@ def make_blend(scene, precision=32, device=None):
     C = scene["C"]
     cfg = scene["config"]
     model_psf = sb.GaussianPSF(sigma=(scene["model_sigma"],) * C)
-    frame = sb.Frame(scene["images"].shape, psf=model_psf, channels=scene["channels"])
+    # the float64 twin also keeps the frame (PSF images, difference kernel) in float64, like the float64 oracle
+    frame = sb.Frame(scene["images"].shape, psf=model_psf, channels=scene["channels"],
+                     dtype=np.float32 if precision == 32 else np.float64)
     obs = sb.Observation(scene["images"].copy(), psf=sb.ImagePSF(scene["obs_psf"].copy()), weights=scene["weights"].copy(),
                          channels=scene["channels"])
     obs.match(frame)
