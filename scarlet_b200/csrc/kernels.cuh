@@ -357,6 +357,12 @@ template <typename T> struct UpdateArgs {
     int npix_max; // shared-memory array length
     int mode;     // 0 = update, 1 = gradients only
     double *g_sed, *g_morph, *g_center;
+    const int *work;        // generic kernel: source index per block (NULL: block index)
+    // grouped fast path (k_update_fast): one 64-thread group per source, groups of a CTA share one operator table
+    const int *fast_groups; // [n_cta][fast_G] source index or -1
+    int fast_G, fast_npix;  // groups per CTA, shared-memory image length per group
+    int fast_table_cap;     // task capacity of the shared-memory table
+    T *scratch_x, *scratch_ps; // packed like the morphologies: gradient-step result x and metric psi
 };
 
 // gradient of the loss wrt the model at frame pixel (y,x), channel c: sum over the observations that see c
@@ -639,7 +645,7 @@ template <typename T> __device__ void update_extended(const UpdateArgs<T> &a, co
 
 template <typename T> __global__ void __launch_bounds__(128) k_update(const UpdateArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int k = blockIdx.x;
+    const int k = a.work ? a.work[blockIdx.x] : blockIdx.x;
     const DevSource &d = a.src[k];
     if (a.done[d.scene]) return;
     if (d.kind == 0) {
@@ -648,6 +654,286 @@ template <typename T> __global__ void __launch_bounds__(128) k_update(const Upda
         double *red = reinterpret_cast<double *>(smem);
         update_point<T>(a, d, k, red);
     }
+}
+
+
+// ======================================================================================================
+// K4-fast  grouped source update: the throughput path for image morphologies.
+//
+// A CTA holds G groups of 64 threads (2 warps); each group owns one source.  All groups of a CTA use the same
+// constraint chain, hence the same radial-monotonicity operator, whose wavefront table is staged ONCE per CTA in
+// shared memory (struct-of-arrays: neighbour indices, weights, pixel).  Only the image being projected lives in
+// shared memory (the sweep and the symmetry partner need random access); the gradient-step result x, the metric
+// psi and the running iterate z are streamed through L2 (coalesced, touched once per proximal sub-iteration).
+// Groups synchronise with named barriers (bar.sync id, 64), so the 59-level sweep of one source never stalls the
+// other seven.  Arithmetic is identical to update_extended (same formulas, same evaluation order).
+// ======================================================================================================
+#define SB_GROUP 64
+
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(SB_GROUP) : "memory"); }
+
+struct GroupRed {
+    double *slot; // [2 parities][2 values][2 warps]
+    int g, par;
+};
+__device__ __forceinline__ void group_sum2(GroupRed &r, double &a, double &b) {
+    a = warp_sum(a);
+    b = warp_sum(b);
+    const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 1;
+    double *s = r.slot + r.par * 4;
+    if (lane == 0) s[w] = a, s[2 + w] = b;
+    group_bar(r.g);
+    a = s[0] + s[1];
+    b = s[2] + s[3];
+    r.par ^= 1; // the next reduction uses the other slot set; this one is rewritten only after another barrier
+}
+__device__ __forceinline__ double group_max(GroupRed &r, double a) {
+    a = warp_max(a);
+    const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 1;
+    double *s = r.slot + r.par * 4;
+    if (lane == 0) s[w] = a;
+    group_bar(r.g);
+    a = fmax(s[0], s[1]);
+    r.par ^= 1;
+    return a;
+}
+
+template <typename T> struct FastTable { // shared-memory image of a DevMono with nb == 4
+    const uint2 *nbr;
+    const W4<T> *w;
+    const unsigned short *pix;
+    const int *ls;
+    int n_levels;
+};
+
+template <typename T> __device__ __forceinline__ void group_sweep(T *img, const FastTable<T> &t, T min_gradient, int g) {
+    const T keep = T(1) - min_gradient;
+    const int lt = threadIdx.x & (SB_GROUP - 1);
+    int beg = t.ls[0];
+    for (int L = 0; L < t.n_levels; ++L) {
+        const int end = t.ls[L + 1];
+        for (int j = beg + lt; j < end; j += SB_GROUP) {
+            const uint2 nb = t.nbr[j];
+            const W4<T> w = t.w[j];
+            const int p = t.pix[j];
+            const unsigned n0 = nb.x & 0xffffu, n1 = nb.x >> 16, n2 = nb.y & 0xffffu, n3 = nb.y >> 16;
+            T ref = T(0);
+            if (n0 != 0xffffu) ref = add_rn(ref, mul_rn(img[n0], w.a));
+            if (n1 != 0xffffu) ref = add_rn(ref, mul_rn(img[n1], w.b));
+            if (n2 != 0xffffu) ref = add_rn(ref, mul_rn(img[n2], w.c));
+            if (n3 != 0xffffu) ref = add_rn(ref, mul_rn(img[n3], w.d));
+            const T cap = mul_rn(ref, keep);
+            if (cap < img[p]) img[p] = cap;
+        }
+        beg = end;
+        group_bar(g);
+    }
+}
+
+template <typename T>
+__device__ void group_chain(T *a, int By, int Bx, const DevChain &ch, const FastTable<T> &tab, GroupRed &red) {
+    const int n = By * Bx, lt = threadIdx.x & (SB_GROUP - 1), g = red.g;
+    for (int r = 0; r < ch.repeat; ++r) {
+        for (int o = 0; o < ch.n_ops; ++o) {
+            const sb_op op = ch.ops[o];
+            switch (op.code) {
+            case SB_OP_MONOTONIC:
+                group_sweep<T>(a, tab, (T)op.farg, g);
+                break;
+            case SB_OP_SYMMETRY: {
+                const T hs = (T)(0.5 * op.farg), om = (T)(1.0 - op.farg);
+                const int Hy = By + ((By & 1) == 0), Wx = Bx + ((Bx & 1) == 0);
+                for (int p = lt; p < n; p += SB_GROUP) {
+                    const int y = p / Bx, x = p - y * Bx;
+                    const int yr = Hy - 1 - y, xr = Wx - 1 - x;
+                    if (yr >= By || xr >= Bx) {
+                        const T u = a[p];
+                        a[p] = hs * (u + T(0)) + om * u;
+                    } else {
+                        const int q = yr * Bx + xr;
+                        if (q > p) {
+                            const T u = a[p], v = a[q];
+                            a[p] = hs * (u + v) + om * u;
+                            a[q] = hs * (v + u) + om * v;
+                        } else if (q == p) {
+                            const T u = a[p];
+                            a[p] = hs * (u + u) + om * u;
+                        }
+                    }
+                }
+                group_bar(g);
+                break;
+            }
+            case SB_OP_POSITIVITY: {
+                const T zero = (T)op.farg;
+                for (int p = lt; p < n; p += SB_GROUP) a[p] = a[p] > zero ? a[p] : zero;
+                group_bar(g);
+                break;
+            }
+            case SB_OP_CENTER_ON: {
+                if (lt == 0) {
+                    const int c = (By / 2) * Bx + Bx / 2;
+                    const T tiny = (T)op.farg;
+                    a[c] = a[c] > tiny ? a[c] : tiny;
+                }
+                group_bar(g);
+                break;
+            }
+            case SB_OP_NORMALIZE: {
+                double acc, dummy = 0.0;
+                if (op.iarg == 1) {
+                    acc = -INFINITY;
+                    for (int p = lt; p < n; p += SB_GROUP) acc = fmax(acc, (double)a[p]);
+                    acc = group_max(red, acc);
+                } else {
+                    acc = 0.0;
+                    for (int p = lt; p < n; p += SB_GROUP) acc += (double)a[p];
+                    group_sum2(red, acc, dummy);
+                }
+                const T den = (T)acc;
+                for (int p = lt; p < n; p += SB_GROUP) a[p] = a[p] / den;
+                group_bar(g);
+                break;
+            }
+            default:
+                break;
+            }
+        }
+    }
+}
+
+#define SB_FAST_MAXC 8
+template <typename T> __global__ void __launch_bounds__(512, 2) k_update_fast(const UpdateArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int G = a.fast_G, g = threadIdx.x / SB_GROUP, lt = threadIdx.x & (SB_GROUP - 1);
+    const int *mine = a.fast_groups + (size_t)blockIdx.x * G;
+    // ---- shared memory carve-up: table (W4 | uint2 | int ls | u16 pix), reduction slots, G images
+    const int cap = a.fast_table_cap;
+    W4<T> *s_w = reinterpret_cast<W4<T> *>(smem);
+    uint2 *s_nbr = reinterpret_cast<uint2 *>(s_w + cap);
+    double *s_red = reinterpret_cast<double *>(s_nbr + cap);
+    double *s_gsum = s_red + 8 * G;            // [G][SB_MAXC]
+    int *s_ls = reinterpret_cast<int *>(s_gsum + SB_MAXC * G); // [512]
+    unsigned short *s_pix = reinterpret_cast<unsigned short *>(s_ls + 512);
+    T *s_img = reinterpret_cast<T *>(s_pix + ((cap + 7) & ~7));
+
+    // ---- the CTA's common operator table -> shared memory (first live group defines the chain)
+    int k0 = -1;
+    for (int i = 0; i < G; ++i)
+        if (mine[i] >= 0) {
+            k0 = mine[i];
+            break;
+        }
+    FastTable<T> tab;
+    tab.nbr = s_nbr, tab.w = s_w, tab.pix = s_pix, tab.ls = s_ls, tab.n_levels = 0;
+    const DevChain &ch = a.chains[a.src[k0].chain];
+    for (int o = 0; o < ch.n_ops; ++o)
+        if (ch.ops[o].code == SB_OP_MONOTONIC) {
+            const DevMono &mo = a.monos[ch.ops[o].iarg];
+            const uint2 *gn = reinterpret_cast<const uint2 *>(mo.code);
+            const W4<T> *gw = reinterpret_cast<const W4<T> *>(mo.w);
+            for (int j = threadIdx.x; j < mo.n_tasks; j += blockDim.x) {
+                s_nbr[j] = gn[j];
+                s_w[j] = gw[j];
+                s_pix[j] = (unsigned short)mo.pix[j];
+            }
+            for (int j = threadIdx.x; j <= mo.n_levels; j += blockDim.x) s_ls[j] = mo.level_start[j];
+            tab.n_levels = mo.n_levels;
+        }
+    __syncthreads();
+    if (g >= G) return;
+    const int k = mine[g];
+    if (k < 0) return;
+    const DevSource &d = a.src[k];
+    const int s = d.scene;
+    if (a.done[s]) return;
+
+    const int it = *a.it_ptr, C = a.C, n = d.By * d.Bx, Bx = d.Bx;
+    T *zn = s_img + (size_t)g * a.fast_npix;
+    GroupRed red;
+    red.slot = s_red + 8 * g, red.g = g, red.par = 0;
+    double *gsum = s_gsum + SB_MAXC * g; // first holds the spectrum (read-only), then the spectrum gradient
+
+    T gs[SB_FAST_MAXC]; // per-thread partial sums in T (<= 27 terms each), reduced in double
+#pragma unroll
+    for (int c = 0; c < SB_FAST_MAXC; ++c) gs[c] = T(0);
+    if (lt < C) gsum[lt] = a.sed[(size_t)k * C + lt];
+    group_bar(g);
+    T *mp = a.morph + d.morph_off, *mm = a.morph_m + d.morph_off, *mv = a.morph_v + d.morph_off,
+      *mvh = a.morph_vhat + d.morph_off, *xs = a.scratch_x + d.morph_off, *ps = a.scratch_ps + d.morph_off;
+    const double alpha = d.morph_step;
+    const bool upd = !d.morph_fixed;
+    double pmax = 0.0;
+    for (int p = lt; p < n; p += SB_GROUP) {
+        const int by = p / Bx, bx = p - by * Bx, y = d.oy + by, x = d.ox + bx;
+        const T mval = mp[p];
+        double gm = 0.0;
+        if ((unsigned)y < (unsigned)a.Ny && (unsigned)x < (unsigned)a.Nx) {
+#pragma unroll
+            for (int c = 0; c < SB_FAST_MAXC; ++c) {
+                if (c < C) {
+                    const double gg = grad_at<T>(a, s, c, y, x);
+                    gm += gsum[c] * gg;
+                    gs[c] += (T)gg * mval;
+                }
+            }
+        }
+        if (upd) {
+            double m_ = (double)mm[p], v_ = (double)mv[p], vh_ = (double)mvh[p];
+            const double psi = amsgrad(gm, m_, v_, vh_, it, a.fs);
+            mm[p] = (T)m_, mv[p] = (T)v_, mvh[p] = (T)vh_;
+            const T xn = (T)((double)mval - alpha * m_ / psi);
+            xs[p] = xn;
+            mp[p] = xn; // z0 = x
+            ps[p] = (T)psi;
+            pmax = fmax(pmax, psi);
+        }
+    }
+    // spectrum gradient (pairs of bands per reduction); every thread is past its reads of the spectrum in gsum
+    group_bar(g);
+#pragma unroll
+    for (int c = 0; c < SB_FAST_MAXC; c += 2) {
+        if (c < C) {
+            double u = (double)gs[c], v = (double)gs[c + 1];
+            group_sum2(red, u, v);
+            if (lt == 0) {
+                gsum[c] = u;
+                if (c + 1 < C) gsum[c + 1] = v;
+            }
+        }
+    }
+    if (upd) {
+        const double psimax = group_max(red, pmax);
+        bool bad = false;
+        if (d.chain >= 0) {
+            const double gamma = alpha / psimax;
+            const double fac = gamma / alpha;
+            for (int sub = 0; sub < a.fs.prox_max_iter; ++sub) {
+                for (int p = lt; p < n; p += SB_GROUP) {
+                    const double zz = (double)mp[p];
+                    zn[p] = (T)(zz - fac * (double)ps[p] * (zz - (double)xs[p]));
+                }
+                group_bar(g);
+                group_chain<T>(zn, d.By, d.Bx, ch, tab, red);
+                double dd = 0.0, nn = 0.0;
+                bad = false;
+                for (int p = lt; p < n; p += SB_GROUP) {
+                    const double zo = (double)mp[p], zv = (double)zn[p];
+                    dd += (zv - zo) * (zv - zo);
+                    nn += zo * zo;
+                    mp[p] = zn[p];
+                    bad |= !isfinite(zv);
+                }
+                group_sum2(red, dd, nn);
+                if (dd <= a.fs.e_rel * a.fs.e_rel * nn) break;
+            }
+        } else {
+            for (int p = lt; p < n; p += SB_GROUP) bad |= !isfinite((double)mp[p]);
+        }
+        if (bad) atomicExch(a.status + s, SB_ERR_NONFINITE);
+    }
+    group_bar(g); // gsum visible to the updating thread
+    if (lt == 0 && !d.sed_fixed) sed_update<T>(a, d, k, gsum, it);
 }
 
 // ======================================================================================================

@@ -4,6 +4,7 @@
 // The plan replaces the closures that scarlet's Blend.fit hands to proxmin.adaprox
 // (reference scarlet/blend.py:103-180): gradient of the loss, step sizes, proximal operators, callback.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <map>
@@ -218,7 +219,11 @@ template <typename T> struct PlanT : sb_plan {
     DevBuf<int> d_start, d_done, d_niter, d_status, d_it, d_nactive, d_nactive_next;
     DevBuf<double> d_sed, d_sed_m, d_sed_v, d_sed_vhat, d_center, d_cen_m, d_cen_v, d_cen_vhat, d_loss, d_loss_const;
     DevBuf<double> d_gsed, d_gcenter, d_gmorph, d_stage;
-    DevBuf<T> d_morph, d_morph_m, d_morph_v, d_morph_vhat, d_pmorph, d_model, d_rendered;
+    DevBuf<T> d_morph, d_morph_m, d_morph_v, d_morph_vhat, d_pmorph, d_model, d_rendered, d_scratch_x, d_scratch_ps;
+    DevBuf<int> d_work, d_fast_groups;
+    int n_generic = 0, n_fast_cta = 0, fast_G = 0, fast_npix = 0, fast_table_cap = 0;
+    size_t fast_smem = 0;
+    std::vector<HostMono> hmonos;
     DevBuf<float> d_stage_f;
     DevBuf<DevChain> d_chains;
     DevBuf<DevMono> d_monos;
@@ -240,6 +245,7 @@ template <typename T> struct PlanT : sb_plan {
     FitScalars graph_fs;
     bool have_graph = false;
     int kernels_per_iter = 0, ffts_per_iter = 0;
+    bool use_fast = getenv("SB_NO_FAST_UPDATE") == nullptr;
 
     ~PlanT() override {
         if (graph) cudaGraphExecDestroy(graph);
@@ -283,6 +289,8 @@ template <typename T> struct PlanT : sb_plan {
             monos.emplace_back(new MonoDevice<T>());
             SB_TRY(monos.back()->upload(h, stream));
             hm[i] = monos.back()->dev;
+            h.nbr.clear(), h.w.clear(), h.pix.clear();
+            hmonos.push_back(h);
         }
         SB_TRY(d_monos.alloc(hm.size()));
         SB_CUDA(cudaMemcpy(d_monos.p, hm.data(), hm.size() * sizeof(DevMono), cudaMemcpyHostToDevice));
@@ -339,6 +347,7 @@ template <typename T> struct PlanT : sb_plan {
             }
         }
         npix_max = (npix_max + 3) & ~3;
+        SB_TRY(plan_fast_path());
         SB_TRY(d_src.alloc(std::max(n_src, 1)));
         SB_TRY(d_start.alloc(S + 1));
         if (n_src) SB_CUDA(cudaMemcpy(d_src.p, h_src.data(), n_src * sizeof(DevSource), cudaMemcpyHostToDevice));
@@ -424,6 +433,83 @@ template <typename T> struct PlanT : sb_plan {
         SB_CUDA(cudaStreamSynchronize(stream));
         dev_bytes += total_bytes();
         return SB_OK;
+    }
+
+    // Split the sources between the grouped fast kernel (k_update_fast) and the generic one (k_update).
+    int plan_fast_path() {
+        std::map<int, std::vector<int>> by_chain;
+        std::vector<int> generic;
+        int npix = 0, cap = 0;
+        for (int k = 0; k < n_src; ++k) {
+            const DevSource &d = h_src[k];
+            bool fast = d.kind == 0 && d.chain >= 0 && C <= SB_FAST_MAXC;
+            int tasks = 0;
+            if (fast) {
+                int n_mono_ops = 0;
+                const sb_chain_desc &ch = desc.chains[d.chain];
+                for (int i = 0; i < ch.n_ops; ++i)
+                    if (ch.ops[i].code == SB_OP_MONOTONIC) {
+                        const HostMono &h = hmonos[ch.ops[i].iarg];
+                        ++n_mono_ops;
+                        tasks = h.n_tasks;
+                        if (h.nb != 4 || h.n_levels + 1 > 512) fast = false;
+                    }
+                if (n_mono_ops > 1) fast = false;
+            }
+            if (fast) {
+                // must fit next to one image even with a single group per CTA
+                const size_t need = fast_smem_bytes(1, (d.By * d.Bx + 3) & ~3, (tasks + 7) & ~7);
+                if (need > 200 * 1024) fast = false;
+            }
+            if (fast) {
+                by_chain[d.chain].push_back(k);
+                npix = std::max(npix, (d.By * d.Bx + 3) & ~3);
+                cap = std::max(cap, (tasks + 7) & ~7);
+            } else
+                generic.push_back(k);
+        }
+        fast_npix = npix, fast_table_cap = std::max(cap, 8);
+        fast_G = 0;
+        for (int G : {8, 4, 2, 1}) { // prefer two resident CTAs per SM
+            if (fast_smem_bytes(G, fast_npix, fast_table_cap) <= 112 * 1024) {
+                fast_G = G;
+                break;
+            }
+        }
+        if (!fast_G)
+            for (int G : {4, 2, 1})
+                if (fast_smem_bytes(G, fast_npix, fast_table_cap) <= 220 * 1024) {
+                    fast_G = G;
+                    break;
+                }
+        std::vector<int> groups;
+        if (fast_G) {
+            for (auto &kv : by_chain) {
+                const std::vector<int> &v = kv.second;
+                for (size_t i = 0; i < v.size(); i += fast_G)
+                    for (int j = 0; j < fast_G; ++j) groups.push_back(i + j < v.size() ? v[i + j] : -1);
+            }
+        } else {
+            for (auto &kv : by_chain) generic.insert(generic.end(), kv.second.begin(), kv.second.end());
+            std::sort(generic.begin(), generic.end());
+        }
+        n_fast_cta = fast_G ? (int)(groups.size() / fast_G) : 0;
+        n_generic = (int)generic.size();
+        fast_smem = fast_G ? fast_smem_bytes(fast_G, fast_npix, fast_table_cap) : 0;
+        SB_TRY(d_work.alloc(std::max<size_t>(generic.size(), 1)));
+        SB_TRY(d_fast_groups.alloc(std::max<size_t>(groups.size(), 1)));
+        if (!generic.empty()) SB_CUDA(cudaMemcpy(d_work.p, generic.data(), generic.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if (!groups.empty()) SB_CUDA(cudaMemcpy(d_fast_groups.p, groups.data(), groups.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if (n_fast_cta) {
+            SB_TRY(d_scratch_x.alloc(std::max<long long>(n_morph, 1)));
+            SB_TRY(d_scratch_ps.alloc(std::max<long long>(n_morph, 1)));
+            SB_CUDA(cudaFuncSetAttribute(k_update_fast<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+        }
+        return SB_OK;
+    }
+    static size_t fast_smem_bytes(int G, int npix, int cap) {
+        return (size_t)cap * (sizeof(W4<T>) + sizeof(uint2)) + (size_t)G * (8 + SB_MAXC) * sizeof(double) + 512 * sizeof(int) +
+               (size_t)((cap + 7) & ~7) * sizeof(unsigned short) + (size_t)G * npix * sizeof(T);
     }
 
     size_t update_smem() const { return (size_t)4 * npix_max * sizeof(T) + (40 + SB_MAXC) * sizeof(double); }
@@ -580,6 +666,8 @@ template <typename T> struct PlanT : sb_plan {
         memcpy(a.psf_sigma, desc.psf_sigma, sizeof a.psf_sigma);
         a.npix_max = npix_max, a.mode = mode;
         a.g_sed = d_gsed.p, a.g_morph = d_gmorph.p, a.g_center = d_gcenter.p;
+        a.work = nullptr, a.fast_groups = d_fast_groups.p, a.fast_G = fast_G, a.fast_npix = fast_npix, a.fast_table_cap = fast_table_cap;
+        a.scratch_x = d_scratch_x.p, a.scratch_ps = d_scratch_ps.p;
         return a;
     }
 
@@ -661,9 +749,23 @@ template <typename T> struct PlanT : sb_plan {
         }
         if (n_src) {
             UpdateArgs<T> ua = update_args(mode);
-            k_update<T><<<n_src, 128, update_smem(), stream>>>(ua);
-            SB_CUDA(cudaGetLastError());
-            ++nk;
+            if (mode == 1 || !use_fast) { // gradients only / forced generic: every source through the generic kernel
+                k_update<T><<<n_src, 128, update_smem(), stream>>>(ua);
+                SB_CUDA(cudaGetLastError());
+                ++nk;
+            } else {
+                if (n_fast_cta) {
+                    k_update_fast<T><<<n_fast_cta, SB_GROUP * fast_G, fast_smem, stream>>>(ua);
+                    SB_CUDA(cudaGetLastError());
+                    ++nk;
+                }
+                if (n_generic) {
+                    ua.work = d_work.p;
+                    k_update<T><<<n_generic, 128, update_smem(), stream>>>(ua);
+                    SB_CUDA(cudaGetLastError());
+                    ++nk;
+                }
+            }
         }
         mark();
         {
