@@ -191,11 +191,13 @@ def run_b200(args):
     plan = batch.plan
     fshape = plan.obs_meta[0]["metas"][0]["fshape"]
     opts = _native.fit_opts(max_iter=iters, e_rel=1e-3, min_iter=1, prox_max_iter=10, check_every=10 ** 6, fixed_iterations=True)
-    init = [plan._pack(w) for w in range(4)]  # initial parameters + zero state, re-uploaded before every step
+    init = plan.pack_current()[0]  # initial parameter values (sed, morph, center); the optimiser state starts at zero
 
     def reset():
-        for w, (sed, morph, cen) in enumerate(init):
-            _native.check(_native.lib().sb_plan_upload_params(plan._handle, w, _native.ptr(sed), _native.ptr(morph), _native.ptr(cen)))
+        """device-side reset to the initial parameters and a cold optimiser state (outside every timed region)"""
+        sed, morph, cen = init
+        _native.check(_native.lib().sb_plan_upload_params(plan._handle, 0, _native.ptr(sed), _native.ptr(morph), _native.ptr(cen)))
+        _native.check(_native.lib().sb_plan_zero_state(plan._handle))
 
     def barrier():
         if world > 1:
@@ -251,21 +253,19 @@ def run_b200(args):
 
     def e2e_step():
         nonlocal h2d, d2h
-        # restore the host Parameters to their initial values (host-side bookkeeping, outside the timed region)
-        for w, (sed, morph, cen) in enumerate(init):
-            _native.check(_native.lib().sb_plan_upload_params(plan._handle, w, _native.ptr(sed), _native.ptr(morph), _native.ptr(cen)))
-        plan.download_parameters(state=True)
+        # restore the host Parameters to their initial values and forget the optimiser state (host-side bookkeeping,
+        # outside the timed region)
+        plan.forget_state(values=init)
         for b in blends:
             b.loss.clear()
         barrier()
         t0 = time.perf_counter()
-        nb = plan.upload_observations()                      # H2D: data, weights, K^ (pinned staging)
-        batch.fit(max_iter=iters, e_rel=1e-3, fixed_iterations=True, check_every=10 ** 6)  # H2D params+state, loop, D2H
+        nb = plan.upload_observations()                      # H2D: data, weights, difference kernels (pinned staging)
+        batch.fit(max_iter=iters, e_rel=1e-3, fixed_iterations=True, check_every=10 ** 6)  # H2D params, loop, D2H params+state+loss
         gather_results()
         barrier()
         dt = time.perf_counter() - t0
-        per = sum(a.nbytes for a in init[0]) * 4
-        h2d, d2h = nb + per, per + S * iters * 8 + S * 8
+        h2d, d2h = nb + batch.last_transfer_bytes[0], batch.last_transfer_bytes[1]
         return dt
 
     e2e_times = [e2e_step() for _ in range(max(1, min(args.warmup, 1)))]
@@ -327,6 +327,7 @@ def run_b200(args):
             one = BlendBatch([synthetic.make_blend(base[0], precision=args.precision, device=local)], precision=args.precision, device=local)
             o1 = _native.fit_opts(max_iter=200, e_rel=1e-3, fixed_iterations=True, check_every=10 ** 6)
             for _ in range(3):
+                one.plan.forget_state()
                 one.plan.upload_parameters(state=True)
                 one.plan.timer_start()
                 one.plan.fit_enqueue(o1, 200)

@@ -134,9 +134,20 @@ int64_t sb_plan_device_bytes(const sb_plan *plan);
  * chi^2 of data pixels outside the model frame. */
 int sb_plan_upload_observation(sb_plan *plan, int obs, const float *data, const float *weights,
                                const double *khat, const double *loss_const);
-/* same, but the buffers are pinned host memory obtained from sb_host_alloc and the copy is asynchronous */
+/* Difference-kernel images instead of a host-computed K^ (what fft.convolve does on every call, fft.py:385-388):
+ * kernels float64 [n][C][Py][Px] with n = 1 for an observation declared khat_shared, else n_scenes; (y0, x0) = grid
+ * index of kernel pixel (0,0) before wrapping, i.e. the reference's centre-pad + ifftshift placement
+ * (fft.py:82-113, 255-273; -(P//2) for odd P).  The device pads, wraps, transforms in double precision and stores
+ * K^/(Fy Fx) in the plan's precision.  The grid must satisfy F >= N + max(-y0, P-1+y0) per axis (no wrap-around
+ * inside the frame), else SB_ERR_ARG. */
+int sb_plan_upload_kernels(sb_plan *plan, int obs, const double *kernels, int Py, int Px, int y0, int x0);
+/* Pinned host memory for staging buffers: copies from/to it are asynchronous DMA. */
 void *sb_host_alloc(int64_t bytes);
 void sb_host_free(void *p);
+/* Pack / unpack the values of many small host arrays (the Parameter objects of a batch) into / from one
+ * contiguous float64 buffer: src[i] points at count[i] contiguous elements, float32 if is_f32[i] else float64. */
+int sb_host_gather_f64(double *dst, const void *const *src, const int64_t *count, const int32_t *is_f32, int64_t n);
+int sb_host_scatter_f64(const double *src, void *const *dst, const int64_t *count, const int32_t *is_f32, int64_t n);
 
 /* Parameters and optimiser state, concatenated over sources in plan order (Parameter.m/v/vhat,
  * parameter.py:42-71; warm start blend.py:154-163).  sed arrays: [n_sources][C]; morph arrays: concatenated
@@ -144,6 +155,8 @@ void sb_host_free(void *p);
  * Any pointer may be NULL (skipped). */
 int sb_plan_upload_params(sb_plan *plan, int which, const double *sed, const double *morph, const double *center);
 int sb_plan_download_params(sb_plan *plan, int which, double *sed, double *morph, double *center);
+/* m = v = vhat = 0 for every parameter: the cold start of blend.py:154-163 without shipping zeros. */
+int sb_plan_zero_state(sb_plan *plan);
 
 /* One gradient evaluation at the current parameters without an update: model (blend.py:200-244),
  * rendered models (observation.py:131-145), loss (blend.py:259-274) and the gradient of the loss wrt every

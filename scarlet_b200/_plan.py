@@ -15,7 +15,7 @@ from . import _native as nat
 from .component import CombinedComponent, FactorizedComponent
 from .constraint import MonoTables, chain_desc, constraint_ops
 from .morphology import ImageMorphology, PointSourceMorphology
-from .parameter import relative_step
+from .parameter import _StateLink, relative_step
 from .psf import GaussianPSF
 from .renderer import ConvolutionRenderer, NullRenderer
 from .spectrum import TabulatedSpectrum
@@ -62,6 +62,16 @@ def _const_step(p):
     return float(p.step)
 
 
+class _HostStore:
+    """Packed float64 host images (pinned) of every parameter of a plan: value and optimiser state."""
+    KEYS = ("value", "m", "v", "vhat")
+
+    def __init__(self):
+        self.arrays = {}
+        self.valid = False          # m/v/vhat hold the device state of the last fit
+        self.device_synced = False  # ... and the device still holds exactly that state
+
+
 class DevicePlan:
     """One CUDA plan for a batch of structurally identical scenes (same frame / observation shapes)."""
 
@@ -93,10 +103,10 @@ class DevicePlan:
             metas = [self._obs_meta(b, o) for b in self.blends]
             m0 = metas[0]
             for m in metas[1:]:
-                if (m["kind"], m["shape"], m["chan_off"], m["origin"], m["fshape"]) != \
-                        (m0["kind"], m0["shape"], m0["chan_off"], m0["origin"], m0["fshape"]):
+                if (m["kind"], m["shape"], m["chan_off"], m["origin"], m["fshape"], m["korigin"], m["kshape"]) != \
+                        (m0["kind"], m0["shape"], m0["chan_off"], m0["origin"], m0["fshape"], m0["korigin"], m0["kshape"]):
                     raise ValueError("all scenes of a batch need identically shaped observations")
-            shared = all(m["khat"] is m0["khat"] for m in metas)
+            shared = all(m["renderer"] is m0["renderer"] for m in metas)
             desc.obs[o] = nat.sb_obs_desc(m0["kind"], m0["shape"][0], m0["shape"][1], m0["shape"][2], m0["chan_off"],
                                           m0["origin"][0], m0["origin"][1], m0["fshape"][0], m0["fshape"][1], int(shared))
             self.obs_meta.append(dict(metas=metas, shared=shared))
@@ -201,6 +211,7 @@ class DevicePlan:
         handle = ctypes.c_void_p()
         nat.check(nat.lib().sb_plan_create(ctypes.byref(desc), self.device, ctypes.byref(handle)))
         self._handle = handle
+        self._build_store()
         self.upload_observations()
 
     # -------------------------------------------------------------------------------------------------
@@ -210,17 +221,19 @@ class DevicePlan:
         r = getattr(obs, "renderer", None)
         if r is None:
             raise RuntimeError("observation %d is not matched to the model frame (call obs.match(frame))" % o)
+        korigin, kernel = (0, 0), None
         if type(r) is ConvolutionRenderer:
-            fshape, khat = r.kernel_transform()
+            fshape, korigin, kernel = r.device_kernel()
             kind = 0
         elif type(r) is NullRenderer:
-            fshape, khat, kind = (blend.frame.shape[1], blend.frame.shape[2]), None, 1
+            fshape, kind = (blend.frame.shape[1], blend.frame.shape[2]), 1
         else:
             raise TypeError("renderer %s is not on the device path (ConvolutionRenderer / NullRenderer)" % type(r).__name__)
         if r.parameters:
             raise NotImplementedError("parameterised renderers (psf_shift) are not on the device path")
         return dict(kind=kind, shape=tuple(obs.data.shape), chan_off=r.channel_offset, origin=tuple(r.origin),
-                    fshape=tuple(int(f) for f in fshape), khat=khat, obs=obs, renderer=r)
+                    fshape=tuple(int(f) for f in fshape), kernel=kernel, korigin=tuple(korigin),
+                    kshape=None if kernel is None else kernel.shape, obs=obs, renderer=r)
 
     def _pinned(self, shape, dtype):
         """numpy view of pinned host memory (sb_host_alloc) -- staging for asynchronous H2D copies."""
@@ -243,12 +256,12 @@ class DevicePlan:
             for i, m in enumerate(metas):
                 data[i] = m["obs"].data
                 weights[i] = m["obs"].weights
-            khat = None
+            kernels = None
             if metas[0]["kind"] == 0:
-                ks = [metas[0]["khat"]] if om["shared"] else [m["khat"] for m in metas]
-                khat = self._pinned((len(ks),) + ks[0].shape, np.complex128)
+                ks = [metas[0]["kernel"]] if om["shared"] else [m["kernel"] for m in metas]
+                kernels = self._pinned((len(ks),) + ks[0].shape, np.float64)
                 for i, k in enumerate(ks):
-                    khat[i] = k
+                    kernels[i] = k
             consts = []
             for m in metas:
                 obs, (oy, ox) = m["obs"], m["origin"]
@@ -263,76 +276,170 @@ class DevicePlan:
                     dd = np.asarray(obs.data, dtype=np.float64)[:, outside]
                     extra = 0.5 * float((w * dd * dd).sum())
                 consts.append(float(obs.log_norm) + extra)
-            self._host_obs.append(dict(data=data, weights=weights, khat=khat, consts=np.asarray(consts, dtype=np.float64)))
+            self._host_obs.append(dict(data=data, weights=weights, kernels=kernels, korigin=metas[0]["korigin"],
+                                       consts=np.asarray(consts, dtype=np.float64)))
 
     def upload_observations(self):
-        """Host (pinned) -> device copy of data, weights, K^ and the per-scene loss constants."""
+        """Host (pinned) -> device copy of data, weights, difference-kernel images and the per-scene loss constants;
+        the device transforms the kernels to K^ itself (as fft.convolve does on every call, fft.py:385-388)."""
         if self._host_obs is None:
             self._stage_observations()
         nbytes = 0
         for o, h in enumerate(self._host_obs):
-            khat = h["khat"]
-            nat.check(nat.lib().sb_plan_upload_observation(self._handle, o, nat.ptr(h["data"]), nat.ptr(h["weights"]),
-                                                           nat.ptr(khat.view(np.float64)) if khat is not None else None,
+            ker = h["kernels"]
+            nat.check(nat.lib().sb_plan_upload_observation(self._handle, o, nat.ptr(h["data"]), nat.ptr(h["weights"]), None,
                                                            nat.ptr(h["consts"])))
-            nbytes += h["data"].nbytes + h["weights"].nbytes + (khat.nbytes if khat is not None else 0) + h["consts"].nbytes
+            if ker is not None:
+                nat.check(nat.lib().sb_plan_upload_kernels(self._handle, o, nat.ptr(ker), ker.shape[-2], ker.shape[-1],
+                                                           h["korigin"][0], h["korigin"][1]))
+            nbytes += h["data"].nbytes + h["weights"].nbytes + (ker.nbytes if ker is not None else 0) + h["consts"].nbytes
         return nbytes
 
     # -------------------------------------------------------------------------------------------------
-    def _pack(self, which):
-        """Host Parameters -> packed float64 arrays (which: 0 value, 1 m, 2 v, 3 vhat)."""
-        attr = (None, "m", "v", "vhat")[which]
-
-        def get(p):
-            a = p._data if attr is None else getattr(p, attr)
-            return np.zeros(p.shape) if a is None else np.asarray(a, dtype=np.float64)
-
-        sed = np.zeros((max(self.n_src, 1), self.C))
+    def _build_store(self):
+        """Pinned packed host images of the parameters (value, m, v, vhat) + pointer tables into the Parameters."""
+        nsed, nmorph, ncen = max(self.n_src, 1), max(self.n_morph, 1), max(len(self.pts), 1)
+        self.store = _HostStore()
+        for key in _HostStore.KEYS:
+            self.store.arrays[key] = dict(sed=self._pinned((nsed, self.C), np.float64), morph=self._pinned((nmorph,), np.float64),
+                                          center=self._pinned((ncen, 2), np.float64))
+            for a in self.store.arrays[key].values():
+                a[...] = 0
+        # (parameter, link) in device order, per group
+        self._linked = []
         for k, s in enumerate(self.slots):
-            sed[k] = get(s["spectrum"])
-        morph = np.zeros(max(self.n_morph, 1))
+            self._linked.append((s["spectrum"], _StateLink(self.store, "sed", k * self.C, (k + 1) * self.C, s["spectrum"].shape)))
         for s, a, b in zip(self.ext, self.morph_offsets[:-1], self.morph_offsets[1:]):
-            morph[a:b] = get(s["image"]).reshape(-1)
-        cen = np.zeros((max(len(self.pts), 1), 2))
+            self._linked.append((s["image"], _StateLink(self.store, "morph", int(a), int(b), s["image"].shape)))
         for i, s in enumerate(self.pts):
-            cen[i] = get(s["center"])
-        return sed, morph, cen
+            self._linked.append((s["center"], _StateLink(self.store, "center", 2 * i, 2 * i + 2, s["center"].shape)))
+        self._unused = [s["shift"] for s in self.ext if s.get("shift") is not None]
+        # pointer tables for the C gather/scatter of the values (float32/float64 contiguous parameters)
+        self._tables = {}
+        for group in ("sed", "morph", "center"):
+            params = [(p, l) for p, l in self._linked if l.group == group]
+            ok = all(p.flags.c_contiguous and p.dtype in (np.float32, np.float64) and p.size == l.stop - l.start for p, l in params)
+            if ok and params:
+                ptrs = np.array([p.ctypes.data for p, _ in params], dtype=np.uint64)
+                counts = np.array([p.size for p, _ in params], dtype=np.int64)
+                f32 = np.array([p.dtype == np.float32 for p, _ in params], dtype=np.int32)
+                self._tables[group] = (ptrs, counts, f32, len(params))
+            else:
+                self._tables[group] = None
+        self._param_refs = [p for p, _ in self._linked]  # keep the arrays (and their addresses) alive
+
+    def _gather_values(self):
+        vals = self.store.arrays["value"]
+        for group in ("sed", "morph", "center"):
+            t = self._tables[group]
+            dst = vals[group].reshape(-1)
+            if t is not None:
+                nat.check(nat.lib().sb_host_gather_f64(nat.ptr(dst), nat.ptr(t[0]), nat.ptr(t[1]), nat.ptr(t[2]), t[3]))
+            else:
+                for p, l in self._linked:
+                    if l.group == group:
+                        dst[l.start:l.stop] = np.asarray(p._data, dtype=np.float64).reshape(-1)
+
+    def _scatter_values(self):
+        vals = self.store.arrays["value"]
+        for group in ("sed", "morph", "center"):
+            t = self._tables[group]
+            src = vals[group].reshape(-1)
+            if t is not None:
+                nat.check(nat.lib().sb_host_scatter_f64(nat.ptr(src), nat.ptr(t[0]), nat.ptr(t[1]), nat.ptr(t[2]), t[3]))
+            else:
+                for p, l in self._linked:
+                    if l.group == group:
+                        p._data[...] = src[l.start:l.stop].reshape(p.shape)
+
+    def _upload(self, key):
+        a = self.store.arrays[key]
+        nat.check(nat.lib().sb_plan_upload_params(self._handle, _HostStore.KEYS.index(key), nat.ptr(a["sed"]), nat.ptr(a["morph"]),
+                                                  nat.ptr(a["center"])))
 
     def upload_parameters(self, state=True):
-        for which in ((0, 1, 2, 3) if state else (0,)):
-            sed, morph, cen = self._pack(which)
-            nat.check(nat.lib().sb_plan_upload_params(self._handle, which, nat.ptr(sed), nat.ptr(morph), nat.ptr(cen)))
+        """Host Parameters -> device.  Values are packed by one C call; optimiser state that still lives in this
+        plan's packed arrays (the result of the previous fit) is uploaded as is; a cold start (no m/v/vhat anywhere)
+        zeroes the state on the device instead of shipping zeros (blend.py:154-163)."""
+        self._gather_values()
+        self._upload("value")
+        nbytes = sum(a.nbytes for a in self.store.arrays["value"].values())
+        if not state:
+            return nbytes
+        store = self.store
+        cold = not store.valid
+        touched = False
+        for p, link in self._linked:
+            d = p.__dict__
+            own = d.get("_link")
+            if own is not None and own.store is not store and own.store.valid:  # state lives in another plan: adopt it
+                for key in ("m", "v", "vhat"):
+                    if d.get("_" + key) is None:
+                        d["_" + key] = own.view(key)
+            for key in ("m", "v", "vhat"):
+                val = d.get("_" + key)
+                if val is not None:
+                    if cold:  # first explicit state: the packed arrays become the truth (zeros elsewhere)
+                        for k2 in ("m", "v", "vhat"):
+                            for a in store.arrays[k2].values():
+                                a[...] = 0
+                        cold = False
+                        store.valid = True
+                    store.arrays[key][link.group].reshape(-1)[link.start:link.stop] = np.asarray(val, dtype=np.float64).reshape(-1)
+                    d["_" + key] = None
+                    touched = True
+            d["_link"] = link
+        if cold:
+            nat.check(nat.lib().sb_plan_zero_state(self._handle))
+            store.device_synced = False
+            return nbytes
+        if store.device_synced and not touched:
+            return nbytes  # the device still holds exactly this state (left there by the previous fit)
+        for key in ("m", "v", "vhat"):
+            self._upload(key)
+        store.device_synced = True
+        return 4 * nbytes
+
+    def forget_state(self, values=None):
+        """Benchmark helper: drop the optimiser state everywhere (next fit is a cold start) and optionally restore the
+        parameter values from a ``pack_current()`` snapshot."""
+        self.store.valid = False
+        self.store.device_synced = False
+        for p, link in self._linked:
+            d = p.__dict__
+            d["_m"] = d["_v"] = d["_vhat"] = d["_std"] = None
+        if values is not None:
+            for g, a in zip(("sed", "morph", "center"), values):
+                self.store.arrays["value"][g][...] = a
+            self._scatter_values()
 
     def download_parameters(self, state=True):
-        """Device -> the same host Parameter objects, in place (values keep their dtype; m/v/vhat float64)."""
-        for which in ((0, 1, 2, 3) if state else (0,)):
-            sed = np.zeros((max(self.n_src, 1), self.C))
-            morph = np.zeros(max(self.n_morph, 1))
-            cen = np.zeros((max(len(self.pts), 1), 2))
-            nat.check(nat.lib().sb_plan_download_params(self._handle, which, nat.ptr(sed), nat.ptr(morph), nat.ptr(cen)))
-            attr = (None, "m", "v", "vhat")[which]
-
-            def put(p, val):
-                if attr is None:
-                    p._data[...] = val.reshape(p.shape)
-                else:
-                    setattr(p, attr, np.array(val, dtype=np.float64).reshape(p.shape))
-
-            for k, s in enumerate(self.slots):
-                put(s["spectrum"], sed[k])
-            for s, a, b in zip(self.ext, self.morph_offsets[:-1], self.morph_offsets[1:]):
-                put(s["image"], morph[a:b])
-                sh = s.get("shift")
-                if sh is not None and attr is not None and getattr(sh, attr) is None:
-                    setattr(sh, attr, np.zeros(sh.shape))  # free but unused parameter: zero gradient forever
-            for i, s in enumerate(self.pts):
-                put(s["center"], cen[i])
+        """Device -> the same host Parameter objects: values in place (dtype preserved); m/v/vhat as views into the
+        plan's packed float64 arrays and std = 1/sqrt(masked v) (blend.py:189-192), both materialised when read."""
+        keys = _HostStore.KEYS if state else ("value",)
+        for which, key in enumerate(keys):
+            a = self.store.arrays[key]
+            nat.check(nat.lib().sb_plan_download_params(self._handle, which, nat.ptr(a["sed"]), nat.ptr(a["morph"]), nat.ptr(a["center"])))
+        self._scatter_values()
+        nbytes = sum(a.nbytes for a in self.store.arrays["value"].values()) * len(keys)
         if state:
-            for s in self.slots:
-                for key in ("spectrum", "image", "center", "shift"):
-                    p = s.get(key)
-                    if p is not None and p.v is not None:
-                        p.std = 1 / np.sqrt(ma.masked_equal(p.v, 0))
+            self.store.valid = True
+            self.store.device_synced = True
+            for p, link in self._linked:
+                d = p.__dict__
+                d["_m"] = d["_v"] = d["_vhat"] = d["_std"] = None
+                d["_link"] = link
+            for sh in self._unused:  # free but unused parameter (morphology.py:112-113): zero gradient forever
+                d = sh.__dict__
+                if d.get("_v") is None:
+                    d["_m"], d["_v"], d["_vhat"] = np.zeros(sh.shape), np.zeros(sh.shape), np.zeros(sh.shape)
+                d["_std"], d["_std_from_v"] = None, True  # std = 1/sqrt(masked v), evaluated when read
+        return nbytes
+
+    def pack_current(self):
+        """Snapshot (copies) of the packed host arrays: value, m, v, vhat -> tuples (sed, morph, center)."""
+        self._gather_values()
+        return [tuple(self.store.arrays[key][g].copy() for g in ("sed", "morph", "center")) for key in _HostStore.KEYS]
 
     # -------------------------------------------------------------------------------------------------
     def evaluate(self, obs=0, want=("model", "rendered", "loss", "grads")):
@@ -405,9 +512,28 @@ class DevicePlan:
             nat.lib().sb_plan_destroy(self._handle)
             self._handle = None
         self._host_obs = None
+        self._detach_store()
         for p in self._pinned_ptrs:
             nat.lib().sb_host_free(p)
         self._pinned_ptrs = []
+
+    def _detach_store(self):
+        """The pinned arrays are about to be freed: give every linked Parameter private copies of its state."""
+        store = getattr(self, "store", None)
+        if store is None:
+            return
+        for p, link in getattr(self, "_linked", []):
+            d = p.__dict__
+            if d.get("_link") is link:
+                if store.valid:
+                    for key in ("m", "v", "vhat"):
+                        if d.get("_" + key) is None:
+                            d["_" + key] = link.view(key).copy()
+                    if d.get("_std") is None:
+                        d["_std_from_v"] = True
+                d["_link"] = None
+        store.valid = False
+        self.store = None
 
     def __del__(self):
         try:

@@ -76,7 +76,7 @@ class Blend(CombinedComponent):
         n_iter, loss, status = plan.fit(opts)
         plan.download_parameters(state=True)
         n = int(n_iter[0])
-        self.loss.extend(float(x) for x in loss[0, :n])
+        self.loss.extend(loss[0, :n].tolist())
         if status[0] == nat.SB_ERR_NONFINITE:
             for src in self.sources:
                 src.check_parameters()  # raises ArithmeticError naming the parameter (model.py:153-165)
@@ -119,13 +119,14 @@ class BlendBatch:
     def fit(self, max_iter=200, e_rel=1e-3, min_iter=1, noise_factor=0, **alg_kwargs):
         check_every = int(alg_kwargs.pop("check_every", 10))
         opts = _fit_options(max_iter, e_rel, min_iter, noise_factor, alg_kwargs, check_every)
-        self.plan.upload_parameters(state=True)
+        h2d = self.plan.upload_parameters(state=True)
         n_iter, loss, status = self.plan.fit(opts)
-        self.plan.download_parameters(state=True)
+        d2h = self.plan.download_parameters(state=True)
+        self.last_transfer_bytes = (int(h2d), int(d2h + n_iter.nbytes + status.nbytes + loss.nbytes))
         results = []
         for s, b in enumerate(self.blends):
             n = int(n_iter[s])
-            b.loss.extend(float(x) for x in loss[s, :n])
+            b.loss.extend(loss[s, :n].tolist())
             if status[s] == nat.SB_ERR_NONFINITE:
                 raise ArithmeticError("scene %d: a parameter became non-finite during the fit" % s)
             results.append((len(b.loss), -b.loss[-1]))

@@ -1010,6 +1010,21 @@ template <typename T> __global__ void k_cast_scale_cplx(const double2 *in, typen
         out[i] = r;
     }
 }
+// kernel image [n_img][Py][Px] -> zeroed grid [n_img][Fy][Fx] with pixel (i,j) at ((i+y0) mod Fy, (j+x0) mod Fx):
+// the reference's centre-pad + ifftshift placement (fft.py:82-113, 255-273)
+__global__ void k_embed_kernel(const double *ker, double *grid, int n_img, int Py, int Px, int Fy, int Fx, int y0, int x0) {
+    const long long total = (long long)n_img * Py * Px;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = i % Px;
+        const long long t = i / Px;
+        const int y = t % Py;
+        const long long im = t / Py;
+        int gy = (y + y0) % Fy, gx = (x + x0) % Fx;
+        if (gy < 0) gy += Fy;
+        if (gx < 0) gx += Fx;
+        grid[(im * Fy + gy) * Fx + gx] = ker[i];
+    }
+}
 template <typename TI, typename TO> __global__ void k_cast(const TI *in, TO *out, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = (TO)in[i];

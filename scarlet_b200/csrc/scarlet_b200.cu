@@ -194,6 +194,8 @@ using namespace sb;
 struct sb_plan {
     virtual ~sb_plan() {}
     virtual int upload_observation(int obs, const float *data, const float *weights, const double *khat, const double *loss_const) = 0;
+    virtual int upload_kernels(int obs, const double *ker, int Py, int Px, int y0, int x0) = 0;
+    virtual int zero_state() = 0;
     virtual int upload_params(int which, const double *sed, const double *morph, const double *center) = 0;
     virtual int download_params(int which, double *sed, double *morph, double *center) = 0;
     virtual int evaluate(int obs, double *model, double *rendered, double *loss, double *g_sed, double *g_morph, double *g_center) = 0;
@@ -237,6 +239,12 @@ template <typename T> struct PlanT : sb_plan {
         cufftHandle fwd = 0, inv = 0;
         bool have_plans = false;
         std::vector<double> loss_const;
+        // kernel-image -> K^ (double precision, chunked over scenes)
+        cufftHandle kplan = 0;
+        bool have_kplan = false;
+        int kchunk = 0;
+        DevBuf<double> kimg, kgrid;
+        DevBuf<double2> kspec;
     };
     std::vector<std::unique_ptr<Obs>> obs;
     int loss_cap = 0;
@@ -249,11 +257,13 @@ template <typename T> struct PlanT : sb_plan {
 
     ~PlanT() override {
         if (graph) cudaGraphExecDestroy(graph);
-        for (auto &o : obs)
+        for (auto &o : obs) {
             if (o->have_plans) {
                 cufftDestroy(o->fwd);
                 cufftDestroy(o->inv);
             }
+            if (o->have_kplan) cufftDestroy(o->kplan);
+        }
         if (h_nactive) cudaFreeHost(h_nactive);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -571,6 +581,56 @@ template <typename T> struct PlanT : sb_plan {
             SB_CUDA(cudaMemcpyAsync(d_loss_const.p, tot.data(), S * sizeof(double), cudaMemcpyHostToDevice, stream));
         }
         SB_CUDA(cudaStreamSynchronize(stream));
+        return SB_OK;
+    }
+
+    int upload_kernels(int o, const double *ker, int Py, int Px, int y0, int x0) override {
+        if (o < 0 || o >= (int)obs.size()) return set_err(SB_ERR_ARG, "observation index %d out of range", o);
+        Obs &ob = *obs[o];
+        const DevObs<T> &d = ob.dev;
+        if (d.kind != 0) return set_err(SB_ERR_ARG, "observation %d has no convolution kernel", o);
+        if (!ker || Py <= 0 || Px <= 0 || Py > d.Fy || Px > d.Fx) return set_err(SB_ERR_ARG, "bad kernel image %dx%d", Py, Px);
+        if (d.Fy < desc.Ny + std::max(-y0, Py - 1 + y0) || d.Fx < desc.Nx + std::max(-x0, Px - 1 + x0) || y0 > 0 || x0 > 0 ||
+            Py - 1 + y0 < 0 || Px - 1 + x0 < 0)
+            return set_err(SB_ERR_ARG, "FFT grid %dx%d too small for frame %dx%d with a %dx%d kernel at (%d,%d)", d.Fy, d.Fx,
+                           desc.Ny, desc.Nx, Py, Px, y0, x0);
+        SB_CUDA(cudaSetDevice(device));
+        const int nk = d.khat_shared ? 1 : S;
+        const size_t per_img = (size_t)Py * Px, per_grid = (size_t)d.Fy * d.Fx, per_spec = (size_t)d.Fy * d.Fxc;
+        if (!ob.have_kplan) {
+            ob.kchunk = std::min(nk, 8);
+            int n[2] = {d.Fy, d.Fx};
+            SB_CUFFT(cufftPlanMany(&ob.kplan, 2, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_D2Z, ob.kchunk * d.C));
+            ob.have_kplan = true;
+            SB_CUFFT(cufftSetStream(ob.kplan, stream));
+            SB_TRY(ob.kgrid.alloc((size_t)ob.kchunk * d.C * per_grid));
+            SB_TRY(ob.kspec.alloc((size_t)ob.kchunk * d.C * per_spec));
+        }
+        if (ob.kimg.n < (size_t)nk * d.C * per_img) SB_TRY(ob.kimg.alloc((size_t)nk * d.C * per_img));
+        SB_CUDA(cudaMemcpyAsync(ob.kimg.p, ker, (size_t)nk * d.C * per_img * sizeof(double), cudaMemcpyHostToDevice, stream));
+        for (int s0 = 0; s0 < nk; s0 += ob.kchunk) {
+            const int nb = std::min(ob.kchunk, nk - s0);
+            SB_TRY(ob.kgrid.zero(stream));
+            const long long nimg = (long long)nb * d.C * per_img;
+            k_embed_kernel<<<grid_for(nimg), 256, 0, stream>>>(ob.kimg.p + (size_t)s0 * d.C * per_img, ob.kgrid.p, nb * d.C, Py, Px,
+                                                             d.Fy, d.Fx, y0, x0);
+            SB_CUDA(cudaGetLastError());
+            SB_CUFFT(cufftExecD2Z(ob.kplan, ob.kgrid.p, ob.kspec.p));
+            const long long nspec = (long long)nb * d.C * per_spec;
+            k_cast_scale_cplx<T><<<grid_for(nspec), 256, 0, stream>>>(ob.kspec.p, ob.khat.p + (size_t)s0 * d.C * per_spec, nspec,
+                                                                    1.0 / ((double)d.Fy * d.Fx));
+            SB_CUDA(cudaGetLastError());
+        }
+        SB_CUDA(cudaStreamSynchronize(stream));
+        return SB_OK;
+    }
+
+    int zero_state() override {
+        SB_CUDA(cudaSetDevice(device));
+        DevBuf<double> *dz[] = {&d_sed_m, &d_sed_v, &d_sed_vhat, &d_cen_m, &d_cen_v, &d_cen_vhat};
+        for (auto *bf : dz) SB_TRY(bf->zero(stream));
+        DevBuf<T> *dm[] = {&d_morph_m, &d_morph_v, &d_morph_vhat};
+        for (auto *bf : dm) SB_TRY(bf->zero(stream));
         return SB_OK;
     }
 
@@ -997,6 +1057,36 @@ void sb_host_free(void *p) {
 
 int sb_plan_upload_observation(sb_plan *plan, int obs, const float *data, const float *weights, const double *khat, const double *loss_const) {
     PLAN_CALL(upload_observation(obs, data, weights, khat, loss_const))
+}
+int sb_plan_upload_kernels(sb_plan *plan, int obs, const double *kernels, int Py, int Px, int y0, int x0) {
+    PLAN_CALL(upload_kernels(obs, kernels, Py, Px, y0, x0))
+}
+int sb_plan_zero_state(sb_plan *plan) { PLAN_CALL(zero_state()) }
+int sb_host_gather_f64(double *dst, const void *const *src, const int64_t *count, const int32_t *is_f32, int64_t n) {
+    if (!dst || !src || !count || !is_f32 || n < 0) return set_err(SB_ERR_ARG, "null argument");
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t c = count[i];
+        if (is_f32[i]) {
+            const float *p = static_cast<const float *>(src[i]);
+            for (int64_t j = 0; j < c; ++j) dst[j] = (double)p[j];
+        } else
+            memcpy(dst, src[i], (size_t)c * sizeof(double));
+        dst += c;
+    }
+    return SB_OK;
+}
+int sb_host_scatter_f64(const double *src, void *const *dst, const int64_t *count, const int32_t *is_f32, int64_t n) {
+    if (!dst || !src || !count || !is_f32 || n < 0) return set_err(SB_ERR_ARG, "null argument");
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t c = count[i];
+        if (is_f32[i]) {
+            float *p = static_cast<float *>(dst[i]);
+            for (int64_t j = 0; j < c; ++j) p[j] = (float)src[j];
+        } else
+            memcpy(dst[i], src, (size_t)c * sizeof(double));
+        src += c;
+    }
+    return SB_OK;
 }
 int sb_plan_upload_params(sb_plan *plan, int which, const double *sed, const double *morph, const double *center) {
     PLAN_CALL(upload_params(which, sed, morph, center))

@@ -6,6 +6,8 @@ Mirrors the slice of scarlet/fft.py the fitting path relies on: ``_centered`` 9-
 renderer.py:198-202); ``convolve`` -- the per-iteration operation -- runs on the GPU (cuFFT) through
 ``sb_fft_convolve_*`` with the kernel transform K^ computed once here.
 """
+import os
+
 import numpy as np
 from scipy import fftpack
 
@@ -116,6 +118,29 @@ def kernel_transform(kernel, image_shape, padding=3):
     kernel = np.asarray(kernel, dtype=np.float64)
     fshape = _get_fft_shape(image_shape, kernel.shape, padding, (1, 2))
     return fshape, np.ascontiguousarray(_as_fourier(kernel).fft(fshape, (1, 2)))
+
+
+def device_grid(image_shape, kernel_shape, padding=3):
+    """FFT grid of the device fitting loop for a (C, Ny, Nx) frame and a (C, Py, Px) kernel.
+
+    -> ``(Fy, Fx), (y0, x0)``.  ``(y0, x0)`` is the grid index of kernel pixel (0, 0) before wrapping under the
+    reference's rule (centre-pad to ITS fast shape, then ``ifftshift``; fft.py:82-113, 255-273) -- ``-(P//2)`` for
+    odd P.  The device keeps the frame at the grid origin and only ever reads back ``[0,N)``, so the grid only has
+    to be long enough that nothing wraps INTO the frame: ``F >= N + max(-k0, P-1+k0)``, which is shorter than the
+    reference's ``N + P + 3`` (e.g. 288 instead of 300 for N=256, P=41).  The convolution result inside the frame is
+    the same linear convolution; only the rounding differs."""
+    ref = _get_fft_shape(image_shape, kernel_shape, padding, (1, 2))
+    shape, origin = [], []
+    for F, N, P in zip(ref, image_shape[1:], kernel_shape[1:]):
+        k0 = (F - P + 1) // 2 - F // 2
+        f = int(fftpack.next_fast_len(int(N + max(-k0, P - 1 + k0))))
+        while f % 2:
+            f = int(fftpack.next_fast_len(f + 1))
+        if os.environ.get("SB_REFERENCE_GRID"):  # diagnostic: the reference's own (longer) fast shape
+            f = int(F)
+        shape.append(f)
+        origin.append(int(k0))
+    return tuple(shape), tuple(origin)
 
 
 def device_convolve(image, khat, fshape, adjoint=False):

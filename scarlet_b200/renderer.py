@@ -93,6 +93,13 @@ class ConvolutionRenderer(Renderer):
             self._khat = fft.kernel_transform(self.diff_kernel.image, sub_shape, padding=3)
         return self._khat
 
+    def device_kernel(self):
+        """(fft_shape, (y0, x0), float64 kernel image) for the device fitting loop, which transforms the kernel itself."""
+        sub_shape = (self.data_frame.C,) + tuple(self.model_frame.shape[1:])
+        ker = np.ascontiguousarray(self.diff_kernel.image, dtype=np.float64)
+        fshape, origin = fft.device_grid(sub_shape, ker.shape, padding=3)
+        return fshape, origin, ker
+
     def convolve(self, model, convolution_type=None, psf_shift=None):
         fshape, khat = self.kernel_transform()
         return fft.device_convolve(np.asarray(model), khat, fshape)

@@ -159,3 +159,48 @@ def test_algorithmic_bytes_formula():
     from scarlet_b200 import synthetic
     assert abs(synthetic.algorithmic_bytes(synthetic.CONFIGS["cfg2"], (160, 160)) / 1e6 - 8.44) < 0.05
     assert abs(synthetic.algorithmic_bytes(synthetic.CONFIGS["cfg5"], (180, 180)) / 1e6 - 10.3) < 0.1
+
+
+def test_host_gather_scatter_roundtrip():
+    """the C pack/unpack helpers behind Parameter transfer (no GPU involved)"""
+    from scarlet_b200 import _native as nat
+    rng = np.random.default_rng(0)
+    arrs = [rng.random(5).astype(np.float32), rng.random((7, 3)), rng.random(1), rng.random((4, 4)).astype(np.float32)]
+    ptrs = np.array([a.ctypes.data for a in arrs], dtype=np.uint64)
+    counts = np.array([a.size for a in arrs], dtype=np.int64)
+    f32 = np.array([a.dtype == np.float32 for a in arrs], dtype=np.int32)
+    packed = np.zeros(int(counts.sum()))
+    nat.check(nat.lib().sb_host_gather_f64(nat.ptr(packed), nat.ptr(ptrs), nat.ptr(counts), nat.ptr(f32), len(arrs)))
+    assert_array_equal(packed, np.concatenate([a.reshape(-1).astype(np.float64) for a in arrs]))
+    keep = [a.copy() for a in arrs]
+    packed2 = packed * 2
+    nat.check(nat.lib().sb_host_scatter_f64(nat.ptr(packed2), nat.ptr(ptrs), nat.ptr(counts), nat.ptr(f32), len(arrs)))
+    for a, k in zip(arrs, keep):
+        assert_allclose(a, 2 * k, rtol=1e-7)
+
+
+def test_parameter_lazy_state_links():
+    """m/v/vhat/std of a Parameter linked to a plan's packed host arrays (what download_parameters leaves behind)"""
+    import pickle
+    import scarlet_b200 as sb
+    from scarlet_b200._plan import _HostStore
+    from scarlet_b200.parameter import _StateLink
+    store = _HostStore()
+    for key in _HostStore.KEYS:
+        store.arrays[key] = dict(morph=np.arange(12.0) + 100 * _HostStore.KEYS.index(key))
+    p = sb.Parameter(np.zeros((2, 3)), name="image", step=0.01)
+    p.__dict__["_link"] = _StateLink(store, "morph", 6, 12, (2, 3))
+    assert p.m is None and p.std is None          # store not valid yet: nothing to show
+    store.valid = True
+    assert_array_equal(p.v, (np.arange(6.0) + 206).reshape(2, 3))
+    assert p.v.base is not None                    # a view, not a copy
+    assert_allclose(p.std, 1 / np.sqrt(p.v))
+    store.arrays["v"]["morph"][6] = 0
+    assert p.std.mask[0, 0] and not p.std.mask[1, 2]   # masked where v == 0 (blend.py:189-192)
+    p.m = np.ones((2, 3))                          # explicit assignment wins
+    assert (p.m == 1).all()
+    q = pickle.loads(pickle.dumps(p))
+    assert_array_equal(q.v, p.v)
+    assert q.name == "image"
+    assert (q.m == 1).all() and q.std is not None
+    assert (p[0]).name == "image" and p[0].v.shape == (2, 3)   # attributes travel by reference to views
