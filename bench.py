@@ -288,12 +288,25 @@ def run_b200(args):
         reset()
         n_prof = 10
         stages = plan.profile(opts, n_prof)
+        fused = plan.spectral_mode == 1
+        if fused:  # the same marks carry the fused kernels (csrc/scarlet_b200.cu: enqueue_iteration)
+            relabel = {"fft_fwd_model": "spec_render", "kmul": "spec_column", "residual_loss": "spec_residual",
+                       "kmul_conj": "spec_column_adj", "fft_inv_grad": "spec_grad"}
+            stages = {relabel.get(k, k): v for k, v in stages.items() if k in relabel or k in ("source_update", "advance")}
         peak, peak_src = peaks()
         C, N, B = cfg["C"], cfg["N"], cfg["B"]
         Fy, Fx = fshape
         Fc = Fy * (Fx // 2 + 1)
         eb = 4 if args.precision == 32 else 8
         src_px = cfg["n_ext"] * B * B + cfg["n_pt"] * 81
+        Xc = N * (Fx // 2 + 1)  # complex elements of one band's row spectra (Ny rows x Fx/2+1)
+        fused_bytes = {  # algorithmic bytes per scene per launch of the fused spectral kernels
+            "spec_render": eb * src_px + 2 * eb * C * Xc,
+            "spec_column": 2 * 2 * eb * C * Xc + 2 * eb * C * Fc,
+            "spec_residual": 2 * 2 * eb * C * Xc + 2 * eb * C * N * N,
+            "spec_column_adj": 2 * 2 * eb * C * Xc + 2 * eb * C * Fc,
+            "spec_grad": 2 * eb * C * Xc + eb * C * N * N,
+        }
         stage_bytes = {  # algorithmic bytes per scene per launch
             "render": eb * (C * N * N + src_px),
             "fft_fwd_model": eb * C * Fy * Fx + 2 * eb * C * Fc,
@@ -306,6 +319,7 @@ def run_b200(args):
             "source_update": eb * src_px * (C + 8),
             "advance": 16,
         }
+        stage_bytes.update(fused_bytes)
         own = {k: v for k, v in stages.items() if not k.startswith("fft_")}
         dom = max(own, key=own.get)
         dom_ms = stages[dom]
@@ -348,7 +362,9 @@ def run_b200(args):
 
         conf = workload_config(args, cfg, S, iters)
         conf.update({"fft_grid": list(fshape), "unique_scenes_per_gpu": uniq, "device_bytes_per_gpu": plan.device_bytes,
-                     "single_scene_iterations_per_sec": single, "cufft_execs_per_iteration": 4 * len(plan.obs_meta),
+                     "single_scene_iterations_per_sec": single,
+                     "spectral": "fused row/column kernels" if fused else "cuFFT",
+                     "cufft_execs_per_iteration": 0 if fused else 4 * len(plan.obs_meta),
                      "kernels_per_iteration": launches // max(args.steps * iters, 1), "precision": args.precision,
                      "per_scene_psf": True})
         line = {"metric": "pgm_scene_iterations_per_sec", "value": value, "unit": "scene-iterations/s", "n_gpus": world,

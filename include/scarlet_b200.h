@@ -123,10 +123,17 @@ const char *sb_last_error(void);
 int sb_device_count(void);
 const char *sb_version(void);
 
+/* Transform lengths of the fused spectral kernels (csrc/spectral.cuh): smallest supported length >= need, 0 if the
+ * request exceeds the largest one (the plan then runs the convolutions through cuFFT on any 2/3/5/7-smooth grid). */
+int sb_fft_supported_length(int need);
+
 /* ---- plan life cycle: replaces the closures Blend.fit hands to proxmin.adaprox (blend.py:103-180) */
 int sb_plan_create(const sb_batch_desc *desc, int device, sb_plan **out);
 void sb_plan_destroy(sb_plan *plan);
 int64_t sb_plan_device_bytes(const sb_plan *plan);
+/* 1: the convolutions of this plan run in the fused row/column spectral kernels; 0: cuFFT + separate kernels
+ * (grids with unsupported lengths, NullRenderer observations, or SB_SPECTRAL=cufft in the environment). */
+int sb_plan_spectral_mode(const sb_plan *plan);
 
 /* Observation data: data/weights float32 [n_scenes][C][H][W] (frame dtype, frame.py:29); K^ = rfftn of the
  * padded, ifftshifted difference kernel (renderer.py:198-202, fft.py:255-273) as interleaved complex128

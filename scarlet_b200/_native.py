@@ -63,6 +63,8 @@ SYMBOLS = {
     "sb_last_error": (C.c_char_p, []),
     "sb_device_count": (C.c_int, []),
     "sb_version": (C.c_char_p, []),
+    "sb_fft_supported_length": (C.c_int, [C.c_int]),
+    "sb_plan_spectral_mode": (C.c_int, [_P]),
     "sb_plan_create": (C.c_int, [C.POINTER(sb_batch_desc), C.c_int, C.POINTER(_P)]),
     "sb_plan_destroy": (None, [_P]),
     "sb_plan_device_bytes": (C.c_int64, [_P]),

@@ -493,6 +493,11 @@ class DevicePlan:
         return dict(zip(names, (ms / max(n_iterations, 1)).tolist()))
 
     @property
+    def spectral_mode(self):
+        """1: fused row/column spectral kernels, 0: cuFFT pipeline."""
+        return int(nat.lib().sb_plan_spectral_mode(self._handle))
+
+    @property
     def kernel_launches(self):
         return int(nat.lib().sb_plan_kernel_launches(self._handle))
 

@@ -83,8 +83,10 @@ struct DevChain {
 
 template <typename T> struct DevObs {
     int kind, C, H, W, chan_off, oy, ox, Fy, Fx, Fxc, khat_shared;
+    int Kp;                        // row pitch of khat (complex elements)
+    int Bh, Bw;                    // rows per image and row pitch of B: (Fy, Fx) on the cuFFT path, (Ny, Nx) on the fused path
     T *A;                          // [S][C][Fy][Fx] real grid: model in, residual in (pad region stays zero)
-    T *B;                          // [S][C][Fy][Fx] real grid: convolution out
+    T *B;                          // [S][C][Bh][Bw] convolution out: rendered model, later the gradient wrt the model
     typename Cx<T>::type *Ahat;    // [S][C][Fy][Fxc]
     typename Cx<T>::type *khat;    // [S or 1][C][Fy][Fxc], 1/(Fy*Fx) folded in
     const T *data, *weights;       // [S][C][H][W]

@@ -372,7 +372,7 @@ __device__ __forceinline__ double grad_at(const UpdateArgs<T> &a, int s, int c, 
     for (int o = 0; o < a.n_obs; ++o) {
         const DevObs<T> &ob = a.obs[o];
         const int co = c - ob.chan_off;
-        if (co >= 0 && co < ob.C) g += (double)ob.B[(((size_t)s * ob.C + co) * ob.Fy + y) * ob.Fx + x];
+        if (co >= 0 && co < ob.C) g += (double)ob.B[(((size_t)s * ob.C + co) * ob.Bh + y) * ob.Bw + x];
     }
     return g;
 }
@@ -1002,6 +1002,19 @@ __global__ void __launch_bounds__(128) k_chain_only(T *img, int By, int Bx, cons
     for (int p = threadIdx.x; p < n; p += blockDim.x) g[p] = a[p];
 }
 
+// [rows][w] complex128 -> [rows][pitch] complex T, scaled
+template <typename T>
+__global__ void k_cast_scale_cplx_pitched(const double2 *in, typename Cx<T>::type *out, long long rows, int w, int pitch, double scale) {
+    const long long n = rows * w;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / w;
+        const int k = (int)(i - r * w);
+        typename Cx<T>::type v;
+        v.x = (T)(in[i].x * scale);
+        v.y = (T)(in[i].y * scale);
+        out[r * pitch + k] = v;
+    }
+}
 template <typename T> __global__ void k_cast_scale_cplx(const double2 *in, typename Cx<T>::type *out, long long n, double scale) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         typename Cx<T>::type r;

@@ -11,6 +11,7 @@
 #include <memory>
 
 #include "kernels.cuh"
+#include "spectral.cuh"
 
 namespace sb {
 
@@ -203,6 +204,7 @@ struct sb_plan {
     virtual int fit_enqueue(const sb_fit_opts *o, int n) = 0;
     virtual int profile(const sb_fit_opts *o, int n, float *stage_ms) = 0;
     virtual int device_params(void **sed, int64_t *n_sed, void **morph, int64_t *n_morph, int *elem_bytes) = 0;
+    virtual int spectral_mode() const = 0;
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -239,6 +241,14 @@ template <typename T> struct PlanT : sb_plan {
         cufftHandle fwd = 0, inv = 0;
         bool have_plans = false;
         std::vector<double> loss_const;
+        // fused spectral path (spectral.cuh)
+        bool fused = false;
+        SpecObs<T> sdev;
+        SpecKernels<T> kx, ky;
+        DevBuf<cplx> X, tw_x, tw_y;
+        DevBuf<T> G;
+        int npair = 1, cb = 1, row_threads = 0;
+        size_t smem_render = 0, smem_row = 0, smem_col = 0;
         // kernel-image -> K^ (double precision, chunked over scenes)
         cufftHandle kplan = 0;
         bool have_kplan = false;
@@ -254,6 +264,8 @@ template <typename T> struct PlanT : sb_plan {
     bool have_graph = false;
     int kernels_per_iter = 0, ffts_per_iter = 0;
     bool use_fast = getenv("SB_NO_FAST_UPDATE") == nullptr;
+    bool fused = false; // every observation runs the fused spectral kernels (else: cuFFT path for all)
+    int max_src_scene = 0;
 
     ~PlanT() override {
         if (graph) cudaGraphExecDestroy(graph);
@@ -273,7 +285,9 @@ template <typename T> struct PlanT : sb_plan {
     int64_t total_bytes() {
         int64_t b = d_src.bytes() + d_sed.bytes() * 4 + d_center.bytes() * 4 + d_loss.bytes() + d_morph.bytes() * 4 + d_pmorph.bytes() +
                     d_model.bytes() + d_rendered.bytes() + d_gmorph.bytes();
-        for (auto &o : obs) b += o->A.bytes() + o->B.bytes() + o->data.bytes() + o->weights.bytes() + o->Ahat.bytes() + o->khat.bytes();
+        for (auto &o : obs)
+            b += o->A.bytes() + o->B.bytes() + o->data.bytes() + o->weights.bytes() + o->Ahat.bytes() + o->khat.bytes() + o->X.bytes() +
+                 o->G.bytes();
         return b;
     }
 
@@ -391,6 +405,16 @@ template <typename T> struct PlanT : sb_plan {
         SB_TRY(ensure_loss_cap(256));
 
         // ---- observations
+        for (int s_ = 0; s_ < S; ++s_) max_src_scene = std::max(max_src_scene, h_start[s_ + 1] - h_start[s_]);
+        {
+            const char *mode = getenv("SB_SPECTRAL");
+            fused = !(mode && strcmp(mode, "cufft") == 0);
+            for (int o = 0; o < desc.n_obs && fused; ++o) {
+                const sb_obs_desc &od = desc.obs[o];
+                SpecKernels<T> k;
+                if (od.kind != 0 || !spec_kernels<T>(od.Fx, &k) || !spec_kernels<T>(od.Fy, &k)) fused = false;
+            }
+        }
         for (int o = 0; o < desc.n_obs; ++o) {
             const sb_obs_desc &od = desc.obs[o];
             obs.emplace_back(new Obs());
@@ -401,16 +425,62 @@ template <typename T> struct PlanT : sb_plan {
             if (od.kind == 1) Fy = desc.Ny, Fx = desc.Nx;
             if (Fy < desc.Ny || Fx < desc.Nx) return set_err(SB_ERR_ARG, "observation %d: FFT grid %dx%d smaller than the frame", o, Fy, Fx);
             DevObs<T> &d = ob.dev;
+            memset(&d, 0, sizeof d);
             d.kind = od.kind, d.C = od.C, d.H = od.H, d.W = od.W, d.chan_off = od.chan_off, d.oy = od.oy, d.ox = od.ox;
             d.Fy = Fy, d.Fx = Fx, d.Fxc = Fx / 2 + 1, d.khat_shared = od.khat_shared;
-            const size_t ngrid = (size_t)S * od.C * Fy * Fx, ncplx = (size_t)S * od.C * Fy * d.Fxc, ndata = (size_t)S * od.C * od.H * od.W;
-            SB_TRY(ob.A.alloc(ngrid));
-            SB_TRY(ob.A.zero(stream));
+            const size_t ndata = (size_t)S * od.C * od.H * od.W;
             SB_TRY(ob.data.alloc(ndata));
             SB_TRY(ob.weights.alloc(ndata));
             SB_TRY(ob.data.zero(stream));
             SB_TRY(ob.weights.zero(stream));
             ob.loss_const.assign(S, 0.0);
+            ob.fused = fused;
+            if (fused) {
+                spec_kernels<T>(Fx, &ob.kx);
+                spec_kernels<T>(Fy, &ob.ky);
+                const int Xp = (d.Fxc + (sizeof(T) == 4 ? 3 : 1)) & ~(sizeof(T) == 4 ? 3 : 1);
+                d.Kp = Xp, d.Bh = desc.Ny, d.Bw = desc.Nx;
+                SB_TRY(ob.X.alloc((size_t)S * od.C * desc.Ny * Xp));
+                SB_TRY(ob.X.zero(stream));
+                SB_TRY(ob.G.alloc((size_t)S * od.C * desc.Ny * desc.Nx));
+                SB_TRY(ob.G.zero(stream));
+                SB_TRY(ob.khat.alloc((size_t)(od.khat_shared ? 1 : S) * od.C * Fy * Xp));
+                SB_TRY(ob.khat.zero(stream));
+                SB_TRY(upload_twiddles(ob.tw_x, ob.kx.R1, ob.kx.R2));
+                SB_TRY(upload_twiddles(ob.tw_y, ob.ky.R1, ob.ky.R2));
+                // launch geometry of the row kernels: cb bands x npair row pairs per CTA
+                const int rmax = std::max(ob.kx.R1, ob.kx.R2), limit = sizeof(T) == 4 ? 512 : 256;
+                ob.cb = std::min(od.C, 8);
+                while (ob.cb > 1 && ob.cb * rmax > limit) --ob.cb;
+                ob.npair = std::max(1, std::min(4, 224 / (ob.cb * rmax)));
+                ob.row_threads = ((ob.npair * ob.cb * rmax + 31) / 32) * 32;
+                if (ob.row_threads > limit) ob.row_threads = ob.npair * ob.cb * rmax;
+                const size_t nb = (size_t)ob.npair * ob.cb;
+                ob.smem_row = (nb * ob.kx.sf + (size_t)Fx) * sizeof(cplx) + 16;
+                ob.smem_render = ob.smem_row + (size_t)ob.cb * 2 * ob.npair * desc.Nx * sizeof(T) + (size_t)(max_src_scene + 1) * sizeof(int);
+                ob.smem_col = ((size_t)ob.ky.NBcol * ob.ky.sf + (size_t)Fy) * sizeof(cplx) + 16;
+                if (ob.smem_render > 227 * 1024 || ob.smem_col > 227 * 1024)
+                    return set_err(SB_ERR_ARG, "observation %d: frame too wide for the fused spectral kernels", o);
+                SB_CUDA(cudaFuncSetAttribute((const void *)ob.kx.render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ob.smem_render));
+                SB_CUDA(cudaFuncSetAttribute((const void *)ob.kx.residual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ob.smem_row));
+                SB_CUDA(cudaFuncSetAttribute((const void *)ob.kx.grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ob.smem_row));
+                SB_CUDA(cudaFuncSetAttribute((const void *)ob.ky.column, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ob.smem_col));
+                ob.n_part = ((desc.Ny + 2 * ob.npair - 1) / (2 * ob.npair)) * ((od.C + ob.cb - 1) / ob.cb);
+                SB_TRY(ob.partials.alloc((size_t)S * ob.n_part));
+                SB_TRY(ob.partials.zero(stream));
+                d.A = nullptr, d.B = ob.G.p, d.Ahat = nullptr, d.khat = ob.khat.p, d.data = ob.data.p, d.weights = ob.weights.p;
+                SpecObs<T> &sd = ob.sdev;
+                memset(&sd, 0, sizeof sd);
+                sd.C = od.C, sd.H = od.H, sd.W = od.W, sd.chan_off = od.chan_off, sd.oy = od.oy, sd.ox = od.ox;
+                sd.Fy = Fy, sd.Fx = Fx, sd.Fxc = d.Fxc, sd.Xp = Xp, sd.khat_shared = od.khat_shared;
+                sd.X = ob.X.p, sd.khat = ob.khat.p, sd.G = ob.G.p, sd.data = ob.data.p, sd.weights = ob.weights.p;
+                sd.tw_x = ob.tw_x.p, sd.tw_y = ob.tw_y.p;
+                continue;
+            }
+            d.Kp = d.Fxc, d.Bh = Fy, d.Bw = Fx;
+            const size_t ngrid = (size_t)S * od.C * Fy * Fx, ncplx = (size_t)S * od.C * Fy * d.Fxc;
+            SB_TRY(ob.A.alloc(ngrid));
+            SB_TRY(ob.A.zero(stream));
             ob.n_part = od.C * ((desc.Nx + 31) / 32) * ((desc.Ny + 7) / 8);
             SB_TRY(ob.partials.alloc((size_t)S * ob.n_part));
             SB_TRY(ob.partials.zero(stream));
@@ -442,6 +512,20 @@ template <typename T> struct PlanT : sb_plan {
         SB_TRY(reset_counters());
         SB_CUDA(cudaStreamSynchronize(stream));
         dev_bytes += total_bytes();
+        return SB_OK;
+    }
+
+    // [R1][R2] table exp(-2 pi i n2 k1 / (R1 R2)) of the two-stage transforms (fft_core.cuh), computed in double
+    int upload_twiddles(DevBuf<cplx> &buf, int R1, int R2) {
+        const int L = R1 * R2;
+        std::vector<cplx> h(L);
+        for (int k1 = 0; k1 < R1; ++k1)
+            for (int n2 = 0; n2 < R2; ++n2) {
+                const sbfft::TwPair t = sbfft::ct_twiddle(n2 * k1, L);
+                h[k1 * R2 + n2].x = (T)t.c, h[k1 * R2 + n2].y = (T)(-t.s);
+            }
+        SB_TRY(buf.alloc(L));
+        SB_CUDA(cudaMemcpy(buf.p, h.data(), L * sizeof(cplx), cudaMemcpyHostToDevice));
         return SB_OK;
     }
 
@@ -566,10 +650,12 @@ template <typename T> struct PlanT : sb_plan {
         }
         if (khat && ob.dev.kind == 0) {
             DevBuf<double2> ks;
-            SB_TRY(ks.alloc(ob.khat.n));
-            SB_CUDA(cudaMemcpyAsync(ks.p, khat, ob.khat.n * sizeof(double2), cudaMemcpyHostToDevice, stream));
-            k_cast_scale_cplx<T><<<grid_for(ob.khat.n), 256, 0, stream>>>(ks.p, ob.khat.p, (long long)ob.khat.n,
-                                                                          1.0 / ((double)ob.dev.Fy * ob.dev.Fx));
+            const size_t nk = (size_t)(ob.dev.khat_shared ? 1 : S) * ob.dev.C * ob.dev.Fy * ob.dev.Fxc;
+            SB_TRY(ks.alloc(nk));
+            SB_CUDA(cudaMemcpyAsync(ks.p, khat, nk * sizeof(double2), cudaMemcpyHostToDevice, stream));
+            const long long nrows = (long long)(ob.dev.khat_shared ? 1 : S) * ob.dev.C * ob.dev.Fy;
+            k_cast_scale_cplx_pitched<T><<<grid_for(nrows * ob.dev.Fxc), 256, 0, stream>>>(ks.p, ob.khat.p, nrows, ob.dev.Fxc, ob.dev.Kp,
+                                                                                         1.0 / ((double)ob.dev.Fy * ob.dev.Fx));
             SB_CUDA(cudaGetLastError());
             SB_CUDA(cudaStreamSynchronize(stream));
         }
@@ -616,9 +702,9 @@ template <typename T> struct PlanT : sb_plan {
                                                              d.Fy, d.Fx, y0, x0);
             SB_CUDA(cudaGetLastError());
             SB_CUFFT(cufftExecD2Z(ob.kplan, ob.kgrid.p, ob.kspec.p));
-            const long long nspec = (long long)nb * d.C * per_spec;
-            k_cast_scale_cplx<T><<<grid_for(nspec), 256, 0, stream>>>(ob.kspec.p, ob.khat.p + (size_t)s0 * d.C * per_spec, nspec,
-                                                                    1.0 / ((double)d.Fy * d.Fx));
+            const long long nspec = (long long)nb * d.C * per_spec, nrows = (long long)nb * d.C * d.Fy;
+            k_cast_scale_cplx_pitched<T><<<grid_for(nspec), 256, 0, stream>>>(ob.kspec.p, ob.khat.p + (size_t)s0 * d.C * d.Fy * d.Kp, nrows,
+                                                                            d.Fxc, d.Kp, 1.0 / ((double)d.Fy * d.Fx));
             SB_CUDA(cudaGetLastError());
         }
         SB_CUDA(cudaStreamSynchronize(stream));
@@ -691,6 +777,7 @@ template <typename T> struct PlanT : sb_plan {
         SB_CUDA(cudaStreamSynchronize(stream));
         return SB_OK;
     }
+    int spectral_mode() const override { return fused ? 1 : 0; }
     int device_params(void **sed, int64_t *n_sed, void **morph, int64_t *nm, int *elem_bytes) override {
         if (sed) *sed = d_sed.p;
         if (n_sed) *n_sed = (int64_t)n_src * C;
@@ -748,7 +835,7 @@ template <typename T> struct PlanT : sb_plan {
         };
         int nk = 0, nf = 0;
         mark();
-        {
+        if (!fused) {
             RenderArgs<T> ra;
             memset(&ra, 0, sizeof ra);
             ra.src = d_src.p, ra.scene_src_start = d_start.p, ra.sed = d_sed.p, ra.morph = d_morph.p, ra.pmorph = d_pmorph.p;
@@ -762,8 +849,39 @@ template <typename T> struct PlanT : sb_plan {
             ++nk;
         }
         mark();
+        // fused spectral path: marks after {render+rowFFT, column, -, rowIFFT+residual+rowFFT, -, column*, rowIFFT}
+        for (size_t o = 0; fused && o < obs.size(); ++o) {
+            Obs &ob = *obs[o];
+            SpecArgs<T> sa;
+            memset(&sa, 0, sizeof sa);
+            sa.ob = ob.sdev, sa.Ny = desc.Ny, sa.Nx = desc.Nx, sa.Cm = C, sa.npair = ob.npair, sa.cb = ob.cb, sa.done = d_done.p;
+            sa.src = d_src.p, sa.scene_src_start = d_start.p, sa.sed = d_sed.p, sa.morph = d_morph.p, sa.pmorph = d_pmorph.p;
+            sa.model_out = model_out, sa.partials = ob.partials.p;
+            sa.rendered_out = ((int)o == rendered_obs) ? rendered_out : nullptr;
+            const dim3 rgrid((desc.Ny + 2 * ob.npair - 1) / (2 * ob.npair), S, (ob.sdev.C + ob.cb - 1) / ob.cb);
+            const dim3 cgrid((ob.sdev.Fxc + ob.ky.NBcol - 1) / ob.ky.NBcol, S * ob.sdev.C);
+            const int cthreads = ob.ky.NBcol * std::max(ob.ky.R1, ob.ky.R2);
+            ob.kx.render<<<rgrid, ob.row_threads, ob.smem_render, stream>>>(sa);
+            SB_CUDA(cudaGetLastError());
+            mark();
+            sa.conj = 0;
+            ob.ky.column<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
+            SB_CUDA(cudaGetLastError());
+            mark(), mark();
+            ob.kx.residual<<<rgrid, ob.row_threads, ob.smem_row, stream>>>(sa);
+            SB_CUDA(cudaGetLastError());
+            mark(), mark();
+            sa.conj = 1;
+            ob.ky.column<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
+            SB_CUDA(cudaGetLastError());
+            mark();
+            ob.kx.grad<<<rgrid, ob.row_threads, ob.smem_row, stream>>>(sa);
+            SB_CUDA(cudaGetLastError());
+            mark();
+            nk += 5;
+        }
         // stage order inside the marks: fwd, kmul, inv, residual, fwd, kmul*, inv (summed over observations)
-        for (size_t o = 0; o < obs.size(); ++o) {
+        for (size_t o = 0; !fused && o < obs.size(); ++o) {
             Obs &ob = *obs[o];
             const DevObs<T> &d = ob.dev;
             const long long per_scene = (long long)d.C * d.Fy * d.Fxc, total = per_scene * S;
@@ -957,7 +1075,10 @@ template <typename T> struct PlanT : sb_plan {
         SB_TRY(ensure_loss_cap(1));
         SB_TRY(reset_counters());
         const size_t nmodel = (size_t)S * C * desc.Ny * desc.Nx, nrend = obs[o]->data.n;
-        if (model && d_model.n < nmodel) SB_TRY(d_model.alloc(nmodel));
+        if (model) {
+            if (d_model.n < nmodel) SB_TRY(d_model.alloc(nmodel));
+            SB_CUDA(cudaMemsetAsync(d_model.p, 0, nmodel * sizeof(T), stream));
+        }
         if (rendered) {
             if (d_rendered.n < nrend) SB_TRY(d_rendered.alloc(nrend));
             SB_CUDA(cudaMemsetAsync(d_rendered.p, 0, nrend * sizeof(T), stream));
@@ -1108,6 +1229,8 @@ int sb_plan_profile_iterations(sb_plan *plan, const sb_fit_opts *opts, int n_ite
 int sb_plan_device_params(sb_plan *plan, void **sed, int64_t *n_sed, void **morph, int64_t *n_morph, int *elem_bytes) {
     PLAN_CALL(device_params(sed, n_sed, morph, n_morph, elem_bytes))
 }
+int sb_plan_spectral_mode(const sb_plan *plan) { return plan ? plan->spectral_mode() : -1; }
+int sb_fft_supported_length(int need) { return spec_supported_length(need); }
 int sb_plan_sync(sb_plan *plan) {
     if (!plan) return set_err(SB_ERR_ARG, "null plan");
     SB_CUDA(cudaSetDevice(plan->device));

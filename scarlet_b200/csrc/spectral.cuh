@@ -1,0 +1,402 @@
+// Fused spectral-convolution kernels of the fitting loop (sm_100a).
+//
+// The reference convolves the model cube with the per-band PSF difference kernel by padding, transforming with
+// numpy.fft.rfftn, multiplying, transforming back and cropping (scarlet/renderer.py:215-259, scarlet/fft.py:200-273,
+// 316-396), and autograd runs the same pipeline backwards for the gradient.  Here the 2-D transform is split into a
+// row pass and a column pass, and every pass is fused with the work next to it, so that neither the zero-padded real
+// grids nor the cropped-away part of the result ever touch HBM:
+//
+//   k_spec_render    render sed x morph (component.py:144-171, blend.py:200-244) for 2*npair frame rows in shared
+//                    memory, real-to-complex row FFTs (two real rows packed as one complex transform), store the
+//                    Ny x (Fx/2+1) half spectra X                                   [writes X]
+//   k_spec_column    column FFT of the Ny non-zero rows (length Fy), multiply by K^ (or conj K^ for the adjoint,
+//                    fft.py:316-331), inverse column FFT, keep rows [0,Ny)              [X in place, reads K^]
+//   k_spec_residual  inverse row FFTs -> rendered model rows; r = w (m - d), chi^2 partial sums
+//                    (observation.py:147-170, renderer.py:130-161); forward row FFTs of r   [X in place, reads d, w]
+//   k_spec_column    (adjoint)
+//   k_spec_grad      inverse row FFTs -> gradient of the loss wrt the model, rows [0,Ny) x [0,Nx)   [writes G]
+//
+// X: [S][C][Ny][Xp] complex, G: [S][C][Ny][Nx] real.  All transforms are unnormalised; 1/(Fy Fx) is folded into K^.
+#pragma once
+#include "common.cuh"
+#include "fft_core.cuh"
+
+namespace sb {
+
+template <typename T> struct SpecObs {
+    int C, H, W, chan_off, oy, ox; // data cube and its placement in the model frame
+    int Fy, Fx, Fxc, Xp;           // grid, half-spectrum width Fx/2+1, row pitch of X and K^ (complex elements)
+    int khat_shared;
+    typename Cx<T>::type *X;          // [S][C][Ny][Xp]
+    const typename Cx<T>::type *khat; // [S or 1][C][Fy][Xp]
+    T *G;                             // [S][C][Ny][Nx]
+    const T *data, *weights;          // [S][C][H][W]
+    const typename Cx<T>::type *tw_x, *tw_y; // [R1][R2] tables exp(-2 pi i n2 k1 / L) for L = Fx and L = Fy
+};
+
+template <typename T> struct SpecArgs {
+    SpecObs<T> ob;
+    int Ny, Nx, Cm; // model frame (Cm = number of model channels)
+    int npair;      // row pairs per CTA (row kernels)
+    int cb;         // bands per CTA (row kernels): blockIdx.z selects bands [z*cb, z*cb+cb)
+    const int *done;
+    // render
+    const DevSource *src;
+    const int *scene_src_start;
+    const double *sed;
+    const T *morph, *pmorph;
+    T *model_out; // optional [S][Cm][Ny][Nx]
+    // residual
+    double *partials; // [S][gridDim.x]
+    T *rendered_out;  // optional [S][C][H][W]
+    int conj;         // column kernel: multiply by conj(K^)
+};
+
+// ---- shared helpers of the row kernels -------------------------------------------------------------------------
+// natural-order spectrum Z of a packed row pair (row y real part, row y+1 imaginary part) -> half spectra A, B
+template <typename T, int R1, int R2>
+__device__ __forceinline__ void split_and_store(const SpecArgs<T> &a, const typename Cx<T>::type *fbuf, int NB, int s, int y0,
+                                                int c0, int Cb) {
+    typedef typename Cx<T>::type C2;
+    typedef sbfft::Plan2<R1, R2> P;
+    const SpecObs<T> &ob = a.ob;
+    const int Fxc = ob.Fxc, Fx = ob.Fx, Co = ob.C;
+    for (int idx = threadIdx.x; idx < NB * Fxc; idx += blockDim.x) {
+        const int f = idx / Fxc, k = idx - f * Fxc, p = f / Cb, c = c0 + f - p * Cb, y = y0 + 2 * p;
+        if (y >= a.Ny) continue;
+        const C2 z = fbuf[f * P::SF + k], zc = fbuf[f * P::SF + (k ? Fx - k : 0)];
+        C2 A, B;
+        A.x = T(0.5) * (z.x + zc.x), A.y = T(0.5) * (z.y - zc.y);
+        B.x = T(0.5) * (z.y + zc.y), B.y = T(0.5) * (zc.x - z.x);
+        C2 *row = ob.X + ((size_t)(s * Co + c) * a.Ny + y) * ob.Xp + k;
+        row[0] = A;
+        if (y + 1 < a.Ny) row[ob.Xp] = B;
+    }
+}
+
+// half spectra of rows y, y+1 -> natural-order full spectrum of the packed pair in fbuf
+template <typename T, int R1, int R2>
+__device__ __forceinline__ void load_and_merge(const SpecArgs<T> &a, typename Cx<T>::type *fbuf, int NB, int s, int y0, int c0,
+                                               int Cb) {
+    typedef typename Cx<T>::type C2;
+    typedef sbfft::Plan2<R1, R2> P;
+    const SpecObs<T> &ob = a.ob;
+    const int Fxc = ob.Fxc, Fx = ob.Fx, Co = ob.C;
+    for (int idx = threadIdx.x; idx < NB * Fxc; idx += blockDim.x) {
+        const int f = idx / Fxc, k = idx - f * Fxc, p = f / Cb, c = c0 + f - p * Cb, y = y0 + 2 * p;
+        C2 A = {T(0), T(0)}, B = {T(0), T(0)};
+        if (y < a.Ny) {
+            const C2 *row = ob.X + ((size_t)(s * Co + c) * a.Ny + y) * ob.Xp + k;
+            A = row[0];
+            if (y + 1 < a.Ny) B = row[ob.Xp];
+        }
+        fbuf[f * P::SF + k] = C2{A.x - B.y, A.y + B.x};
+        if (k > 0 && 2 * k < Fx) fbuf[f * P::SF + Fx - k] = C2{A.x + B.y, B.x - A.y};
+    }
+}
+
+template <typename T, int R1, int R2>
+__device__ __forceinline__ void stage_twiddles(typename Cx<T>::type *dst, const typename Cx<T>::type *src) {
+    for (int i = threadIdx.x; i < R1 * R2; i += blockDim.x) dst[i] = src[i];
+}
+
+// inverse row transform of the merged spectra in fbuf: lane (f, n2) ends with a_[n1] = (row y, row y+1) at x = n1 R2 + n2
+template <typename T, int R1, int R2>
+__device__ __forceinline__ void rows_inverse(typename Cx<T>::type (&a_)[R1], typename Cx<T>::type *fbuf,
+                                             const typename Cx<T>::type *tw, int NB) {
+    typedef typename Cx<T>::type C2;
+    typedef sbfft::Plan2<R1, R2> P;
+    const int tid = threadIdx.x;
+    C2 b_[R2];
+    const int fb = tid / R1, k1 = tid - fb * R1;
+    if (tid < NB * R1) sbfft::static_for<0, R2>([&](auto i) { b_[decltype(i)::value] = fbuf[fb * P::SF + k1 + R1 * decltype(i)::value]; });
+    __syncthreads();
+    if (tid < NB * R1) sbfft::inv_stage_b<R1, R2>(b_, k1, tw, fbuf + fb * P::SF);
+    __syncthreads();
+    const int fa = tid / R2, n2 = tid - fa * R2;
+    if (tid < NB * R2) sbfft::inv_stage_a<R1, R2>(a_, n2, fbuf + fa * P::SF);
+}
+
+// forward row transform of a_ (lane (f, n2)); leaves the natural-order spectrum in fbuf
+template <typename T, int R1, int R2>
+__device__ __forceinline__ void rows_forward(typename Cx<T>::type (&a_)[R1], typename Cx<T>::type *fbuf,
+                                             const typename Cx<T>::type *tw, int NB) {
+    typedef typename Cx<T>::type C2;
+    typedef sbfft::Plan2<R1, R2> P;
+    const int tid = threadIdx.x;
+    const int fa = tid / R2, n2 = tid - fa * R2;
+    if (tid < NB * R2) sbfft::fwd_stage_a<R1, R2>(a_, n2, tw, fbuf + fa * P::SF);
+    __syncthreads();
+    C2 b_[R2];
+    const int fb = tid / R1, k1 = tid - fb * R1;
+    if (tid < NB * R1) sbfft::fwd_stage_b<R1, R2>(b_, k1, fbuf + fb * P::SF);
+    __syncthreads();
+    if (tid < NB * R1) sbfft::static_for<0, R2>([&](auto i) { fbuf[fb * P::SF + k1 + R1 * decltype(i)::value] = b_[decltype(i)::value]; });
+    __syncthreads();
+}
+
+// ======================================================================================================
+// render + forward row FFT
+// ======================================================================================================
+template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) k_spec_render(const SpecArgs<T> a) {
+    typedef typename Cx<T>::type C2;
+    typedef sbfft::Plan2<R1, R2> P;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_ncand;
+    const int s = blockIdx.y;
+    if (a.done[s]) return;
+    const SpecObs<T> &ob = a.ob;
+    const int Co = ob.C, Nx = a.Nx, Ny = a.Ny, rows = 2 * a.npair, y0 = blockIdx.x * rows;
+    const int c0 = blockIdx.z * a.cb, Cb = min(a.cb, Co - c0), NB = a.npair * Cb;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    C2 *fbuf = reinterpret_cast<C2 *>(smem);
+    C2 *tw = fbuf + NB * P::SF;
+    T *tile = reinterpret_cast<T *>(tw + R1 * R2);
+    int *cand = reinterpret_cast<int *>(tile + (size_t)a.cb * rows * Nx);
+    stage_twiddles<T, R1, R2>(tw, ob.tw_x);
+    // sources whose boxes intersect these rows, in scene order (deterministic accumulation order)
+    const int k0 = a.scene_src_start[s], k1 = a.scene_src_start[s + 1];
+    if (tid < 32) {
+        int cnt = 0;
+        for (int base = k0; base < k1; base += 32) {
+            const int k = base + tid;
+            bool ok = false;
+            if (k < k1) {
+                const DevSource &d = a.src[k];
+                ok = d.oy < y0 + rows && d.oy + d.By > y0;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) cand[cnt + __popc(m & ((1u << tid) - 1u))] = k;
+            cnt += __popc(m);
+        }
+        if (tid == 0) s_ncand = cnt;
+    }
+    __syncthreads();
+    const int ncand = s_ncand;
+    for (int idx = tid; idx < rows * Nx; idx += nt) {
+        const int r = idx / Nx, x = idx - r * Nx, y = y0 + r;
+        T acc[SB_MAXC];
+#pragma unroll
+        for (int c = 0; c < SB_MAXC; ++c) acc[c] = T(0);
+        if (y < Ny) {
+            for (int i = 0; i < ncand; ++i) {
+                const int k = cand[i];
+                const DevSource &d = a.src[k];
+                const int by = y - d.oy, bx = x - d.ox;
+                if ((unsigned)by < (unsigned)d.By && (unsigned)bx < (unsigned)d.Bx) {
+                    const double *sed = a.sed + (size_t)k * a.Cm + ob.chan_off + c0;
+                    if (d.kind == 0) {
+                        const T mv = a.morph[d.morph_off + (size_t)by * d.Bx + bx];
+#pragma unroll
+                        for (int c = 0; c < SB_MAXC; ++c)
+                            if (c < Cb) acc[c] += (T)sed[c] * mv;
+                    } else {
+                        const int plane = d.By * d.Bx;
+                        const T *pm = a.pmorph + d.morph_off + (size_t)(ob.chan_off + c0) * plane + (size_t)by * d.Bx + bx;
+#pragma unroll
+                        for (int c = 0; c < SB_MAXC; ++c)
+                            if (c < Cb) acc[c] += (T)sed[c] * pm[(size_t)c * plane];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < SB_MAXC; ++c)
+            if (c < Cb) {
+                tile[((size_t)c * rows + r) * Nx + x] = acc[c];
+                if (a.model_out && y < Ny) a.model_out[(((size_t)s * a.Cm + ob.chan_off + c0 + c) * Ny + y) * Nx + x] = acc[c];
+            }
+    }
+    __syncthreads();
+    C2 a_[R1];
+    {
+        const int f = tid / R2, n2 = tid - f * R2;
+        if (tid < NB * R2) {
+            const int p = f / Cb, c = f - p * Cb;
+            const T *t0 = tile + ((size_t)c * rows + 2 * p) * Nx, *t1 = t0 + Nx;
+            sbfft::static_for<0, R1>([&](auto i) {
+                const int n = decltype(i)::value * R2 + n2;
+                a_[decltype(i)::value] = n < Nx ? C2{t0[n], t1[n]} : C2{T(0), T(0)};
+            });
+        }
+    }
+    rows_forward<T, R1, R2>(a_, fbuf, tw, NB);
+    split_and_store<T, R1, R2>(a, fbuf, NB, s, y0, c0, Cb);
+}
+
+// ======================================================================================================
+// inverse row FFT -> residual + loss -> forward row FFT
+// ======================================================================================================
+template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) k_spec_residual(const SpecArgs<T> a) {
+    typedef typename Cx<T>::type C2;
+    typedef sbfft::Plan2<R1, R2> P;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ double red[40];
+    const int s = blockIdx.y;
+    if (a.done[s]) return;
+    const SpecObs<T> &ob = a.ob;
+    const int Co = ob.C, Nx = a.Nx, Ny = a.Ny, rows = 2 * a.npair, y0 = blockIdx.x * rows;
+    const int c0 = blockIdx.z * a.cb, Cb = min(a.cb, Co - c0), NB = a.npair * Cb;
+    const int tid = threadIdx.x;
+    C2 *fbuf = reinterpret_cast<C2 *>(smem);
+    C2 *tw = fbuf + NB * P::SF;
+    stage_twiddles<T, R1, R2>(tw, ob.tw_x);
+    load_and_merge<T, R1, R2>(a, fbuf, NB, s, y0, c0, Cb);
+    __syncthreads();
+    C2 a_[R1];
+    rows_inverse<T, R1, R2>(a_, fbuf, tw, NB);
+    double part = 0.0;
+    {
+        const int f = tid / R2, n2 = tid - f * R2;
+        if (tid < NB * R2) {
+            const int p = f / Cb, c = c0 + f - p * Cb, y = y0 + 2 * p;
+            const int dy0 = y - ob.oy, dy1 = dy0 + 1;
+            const bool row0 = y < Ny && (unsigned)dy0 < (unsigned)ob.H, row1 = y + 1 < Ny && (unsigned)dy1 < (unsigned)ob.H;
+            const size_t base0 = ((size_t)(s * Co + c) * ob.H + dy0) * ob.W, base1 = base0 + ob.W;
+            sbfft::static_for<0, R1>([&](auto i) {
+                constexpr int n1 = decltype(i)::value;
+                const int x = n1 * R2 + n2, dx = x - ob.ox;
+                const bool col = x < Nx && (unsigned)dx < (unsigned)ob.W;
+                T r0 = T(0), r1 = T(0);
+                if (col && row0) {
+                    const T m = a_[n1].x, w = ob.weights[base0 + dx], diff = m - ob.data[base0 + dx];
+                    r0 = w * diff;
+                    part += (double)w * (double)diff * (double)diff;
+                    if (a.rendered_out) a.rendered_out[base0 + dx] = m;
+                }
+                if (col && row1) {
+                    const T m = a_[n1].y, w = ob.weights[base1 + dx], diff = m - ob.data[base1 + dx];
+                    r1 = w * diff;
+                    part += (double)w * (double)diff * (double)diff;
+                    if (a.rendered_out) a.rendered_out[base1 + dx] = m;
+                }
+                a_[n1] = C2{r0, r1};
+            });
+        }
+    }
+    __syncthreads(); // every lane has read its inverse-transform output before fbuf is reused
+    rows_forward<T, R1, R2>(a_, fbuf, tw, NB);
+    split_and_store<T, R1, R2>(a, fbuf, NB, s, y0, c0, Cb);
+    part = block_sum(part, red);
+    if (tid == 0) a.partials[((size_t)s * gridDim.z + blockIdx.z) * gridDim.x + blockIdx.x] = part;
+}
+
+// ======================================================================================================
+// inverse row FFT -> gradient wrt the model
+// ======================================================================================================
+template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) k_spec_grad(const SpecArgs<T> a) {
+    typedef typename Cx<T>::type C2;
+    typedef sbfft::Plan2<R1, R2> P;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int s = blockIdx.y;
+    if (a.done[s]) return;
+    const SpecObs<T> &ob = a.ob;
+    const int Co = ob.C, Nx = a.Nx, Ny = a.Ny, rows = 2 * a.npair, y0 = blockIdx.x * rows;
+    const int c0 = blockIdx.z * a.cb, Cb = min(a.cb, Co - c0), NB = a.npair * Cb;
+    const int tid = threadIdx.x;
+    C2 *fbuf = reinterpret_cast<C2 *>(smem);
+    C2 *tw = fbuf + NB * P::SF;
+    stage_twiddles<T, R1, R2>(tw, ob.tw_x);
+    load_and_merge<T, R1, R2>(a, fbuf, NB, s, y0, c0, Cb);
+    __syncthreads();
+    C2 a_[R1];
+    rows_inverse<T, R1, R2>(a_, fbuf, tw, NB);
+    const int f = tid / R2, n2 = tid - f * R2;
+    if (tid < NB * R2) {
+        const int p = f / Cb, c = c0 + f - p * Cb, y = y0 + 2 * p;
+        if (y < Ny) {
+            T *g0 = ob.G + ((size_t)(s * Co + c) * Ny + y) * Nx;
+            const bool row1 = y + 1 < Ny;
+            sbfft::static_for<0, R1>([&](auto i) {
+                constexpr int n1 = decltype(i)::value;
+                const int x = n1 * R2 + n2;
+                if (x < Nx) {
+                    g0[x] = a_[n1].x;
+                    if (row1) g0[Nx + x] = a_[n1].y;
+                }
+            });
+        }
+    }
+}
+
+// ======================================================================================================
+// column pass: forward column FFT, x K^ (or conj K^), inverse column FFT; NB adjacent columns per CTA
+// ======================================================================================================
+template <typename T, int R1, int R2, int NB> __global__ void __launch_bounds__(NB *sbfft::Plan2<R1, R2>::RMAX) k_spec_column(const SpecArgs<T> a) {
+    typedef typename Cx<T>::type C2;
+    typedef sbfft::Plan2<R1, R2> P;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SpecObs<T> &ob = a.ob;
+    const int img = blockIdx.y, s = img / ob.C;
+    if (a.done[s]) return;
+    const int Ny = a.Ny, tid = threadIdx.x;
+    C2 *fbuf = reinterpret_cast<C2 *>(smem);
+    C2 *tw = fbuf + NB * P::SF;
+    stage_twiddles<T, R1, R2>(tw, ob.tw_y);
+    const int f = tid % NB, j = tid / NB, kx = blockIdx.x * NB + f;
+    const bool col = kx < ob.Fxc;
+    C2 *sm = fbuf + f * P::SF;
+    C2 *X = ob.X + (size_t)img * Ny * ob.Xp + kx;
+    __syncthreads();
+    C2 a_[R1];
+    if (j < R2) {
+        sbfft::static_for<0, R1>([&](auto i) {
+            const int n = decltype(i)::value * R2 + j;
+            a_[decltype(i)::value] = (col && n < Ny) ? X[(size_t)n * ob.Xp] : C2{T(0), T(0)};
+        });
+        sbfft::fwd_stage_a<R1, R2>(a_, j, tw, sm);
+    }
+    __syncthreads();
+    C2 b_[R2];
+    if (j < R1) {
+        sbfft::fwd_stage_b<R1, R2>(b_, j, sm);
+        const C2 *K = ob.khat + (size_t)(ob.khat_shared ? img - s * ob.C : img) * ob.Fy * ob.Xp + kx;
+        if (col) {
+            if (a.conj)
+                sbfft::static_for<0, R2>([&](auto i) {
+                    constexpr int k2 = decltype(i)::value;
+                    b_[k2] = sbfft::cmul_conj(b_[k2], K[(size_t)(j + R1 * k2) * ob.Xp]);
+                });
+            else
+                sbfft::static_for<0, R2>([&](auto i) {
+                    constexpr int k2 = decltype(i)::value;
+                    b_[k2] = sbfft::cmul(b_[k2], K[(size_t)(j + R1 * k2) * ob.Xp]);
+                });
+        }
+    }
+    __syncthreads();
+    if (j < R1) sbfft::inv_stage_b<R1, R2>(b_, j, tw, sm);
+    __syncthreads();
+    if (j < R2) {
+        sbfft::inv_stage_a<R1, R2>(a_, j, sm);
+        if (col)
+            sbfft::static_for<0, R1>([&](auto i) {
+                const int n = decltype(i)::value * R2 + j;
+                if (n < Ny) X[(size_t)n * ob.Xp] = a_[decltype(i)::value];
+            });
+    }
+}
+
+// ---- dispatch table ----------------------------------------------------------------------------------
+// supported transform lengths L = R1 * R2 (both the row length Fx and the column length Fy must be in this list)
+#define SB_SPEC_LENGTHS(X) \
+    X(6, 8) X(8, 8) X(8, 9) X(8, 10) X(8, 12) X(8, 16) X(12, 12) X(10, 16) X(12, 16) X(15, 16) X(16, 16) X(16, 18) X(16, 20) X(16, 24)
+
+template <typename T> struct SpecKernels {
+    typedef void (*fn)(const SpecArgs<T>);
+    int R1 = 0, R2 = 0, NBcol = 0;
+    fn render = nullptr, residual = nullptr, grad = nullptr, column = nullptr;
+    size_t sf = 0; // Plan2::SF
+};
+template <typename T> struct SpecColNB { static const int value = sizeof(T) == 4 ? 16 : 8; };
+
+// defined in spectral_f32.cu / spectral_f64.cu
+bool spec_kernels_f32(int L, SpecKernels<float> *out);
+bool spec_kernels_f64(int L, SpecKernels<double> *out);
+int spec_supported_length(int need); // smallest supported L >= need, 0 if none
+
+template <typename T> inline bool spec_kernels(int L, SpecKernels<T> *out);
+template <> inline bool spec_kernels<float>(int L, SpecKernels<float> *out) { return spec_kernels_f32(L, out); }
+template <> inline bool spec_kernels<double>(int L, SpecKernels<double> *out) { return spec_kernels_f64(L, out); }
+
+} // namespace sb

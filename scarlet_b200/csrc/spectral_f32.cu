@@ -1,0 +1,31 @@
+// float32 instantiations of the fused spectral kernels (separate translation unit: compiled in parallel).
+#include "spectral.cuh"
+
+namespace sb {
+
+bool spec_kernels_f32(int L, SpecKernels<float> *out) {
+#define X(A, B)                                                                   \
+    if (L == (A) * (B)) {                                                         \
+        out->R1 = A, out->R2 = B, out->NBcol = SpecColNB<float>::value;           \
+        out->render = k_spec_render<float, A, B>;                                 \
+        out->residual = k_spec_residual<float, A, B>;                             \
+        out->grad = k_spec_grad<float, A, B>;                                     \
+        out->column = k_spec_column<float, A, B, SpecColNB<float>::value>;        \
+        out->sf = sbfft::Plan2<A, B>::SF;                                         \
+        return true;                                                              \
+    }
+    SB_SPEC_LENGTHS(X)
+#undef X
+    return false;
+}
+
+int spec_supported_length(int need) {
+    int best = 0;
+#define X(A, B) \
+    if ((A) * (B) >= need && (best == 0 || (A) * (B) < best)) best = (A) * (B);
+    SB_SPEC_LENGTHS(X)
+#undef X
+    return best;
+}
+
+} // namespace sb

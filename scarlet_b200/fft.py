@@ -128,14 +128,18 @@ def device_grid(image_shape, kernel_shape, padding=3):
     odd P.  The device keeps the frame at the grid origin and only ever reads back ``[0,N)``, so the grid only has
     to be long enough that nothing wraps INTO the frame: ``F >= N + max(-k0, P-1+k0)``, which is shorter than the
     reference's ``N + P + 3`` (e.g. 288 instead of 300 for N=256, P=41).  The convolution result inside the frame is
-    the same linear convolution; only the rounding differs."""
+    the same linear convolution; only the rounding differs.  Lengths are taken from the set the fused spectral kernels
+    are instantiated for."""
     ref = _get_fft_shape(image_shape, kernel_shape, padding, (1, 2))
     shape, origin = [], []
     for F, N, P in zip(ref, image_shape[1:], kernel_shape[1:]):
         k0 = (F - P + 1) // 2 - F // 2
-        f = int(fftpack.next_fast_len(int(N + max(-k0, P - 1 + k0))))
-        while f % 2:
-            f = int(fftpack.next_fast_len(f + 1))
+        need = int(N + max(-k0, P - 1 + k0))
+        f = int(nat.lib().sb_fft_supported_length(need))  # lengths of the fused spectral kernels (csrc/spectral.cuh)
+        if f == 0:  # larger than any of them: any even 5-smooth length will do for cuFFT
+            f = int(fftpack.next_fast_len(need))
+            while f % 2:
+                f = int(fftpack.next_fast_len(f + 1))
         if os.environ.get("SB_REFERENCE_GRID"):  # diagnostic: the reference's own (longer) fast shape
             f = int(F)
         shape.append(f)
