@@ -803,7 +803,47 @@ __device__ void group_chain(T *a, int By, int Bx, const DevChain &ch, const Fast
 }
 
 #define SB_FAST_MAXC 8
-template <typename T> __global__ void __launch_bounds__(512, 2) k_update_fast(const UpdateArgs<T> a) {
+
+// group-wide maximum in the image type (exact: a maximum needs no extra precision)
+template <typename T> __device__ __forceinline__ T group_max_t(GroupRed &r, T a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const T b = __shfl_down_sync(0xffffffffu, a, o);
+        a = b > a ? b : a;
+    }
+    const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 1;
+    T *s = reinterpret_cast<T *>(r.slot + r.par * 4);
+    if (lane == 0) s[w] = a;
+    group_bar(r.g);
+    a = s[0] > s[1] ? s[0] : s[1];
+    r.par ^= 1;
+    return a;
+}
+
+// The ExtendedSource chain Monotonicity -> [Symmetry] -> Positivity -> CenterOn -> Normalization("max")
+// (morphology.py:644-669) on an odd x odd box, recognised so that everything after the sweep runs in two passes.
+struct FusedChain {
+    int ok, has_sym;
+    double mono_grad, sym, zero, tiny;
+};
+__device__ inline FusedChain fused_chain_of(const DevChain &ch, int By, int Bx) {
+    FusedChain f;
+    f.ok = 0, f.has_sym = 0, f.mono_grad = 0, f.sym = 0, f.zero = 0, f.tiny = 0;
+    if (ch.repeat != 1 || !(By & 1) || !(Bx & 1)) return f;
+    int i = 0;
+    if (i >= ch.n_ops || ch.ops[i].code != SB_OP_MONOTONIC) return f;
+    f.mono_grad = ch.ops[i++].farg;
+    if (i < ch.n_ops && ch.ops[i].code == SB_OP_SYMMETRY) f.has_sym = 1, f.sym = ch.ops[i++].farg;
+    if (i >= ch.n_ops || ch.ops[i].code != SB_OP_POSITIVITY) return f;
+    f.zero = ch.ops[i++].farg;
+    if (i >= ch.n_ops || ch.ops[i].code != SB_OP_CENTER_ON) return f;
+    f.tiny = ch.ops[i++].farg;
+    if (i >= ch.n_ops || ch.ops[i].code != SB_OP_NORMALIZE || ch.ops[i].iarg != 1) return f;
+    f.ok = (i + 1 == ch.n_ops);
+    return f;
+}
+
+template <typename T> __global__ void __launch_bounds__(1024, 1) k_update_fast(const UpdateArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int G = a.fast_G, g = threadIdx.x / SB_GROUP, lt = threadIdx.x & (SB_GROUP - 1);
     const int *mine = a.fast_groups + (size_t)blockIdx.x * G;
@@ -849,6 +889,7 @@ template <typename T> __global__ void __launch_bounds__(512, 2) k_update_fast(co
     if (a.done[s]) return;
 
     const int it = *a.it_ptr, C = a.C, n = d.By * d.Bx, Bx = d.Bx;
+    const unsigned magic = 0xffffffffu / (unsigned)Bx + 1u; // p / Bx == umulhi(p, magic) for p, Bx < 65536
     T *zn = s_img + (size_t)g * a.fast_npix;
     GroupRed red;
     red.slot = s_red + 8 * g, red.g = g, red.par = 0;
@@ -864,29 +905,46 @@ template <typename T> __global__ void __launch_bounds__(512, 2) k_update_fast(co
     const double alpha = d.morph_step;
     const bool upd = !d.morph_fixed;
     double pmax = 0.0;
-    for (int p = lt; p < n; p += SB_GROUP) {
-        const int by = p / Bx, bx = p - by * Bx, y = d.oy + by, x = d.ox + bx;
-        const T mval = mp[p];
-        double gm = 0.0;
-        if ((unsigned)y < (unsigned)a.Ny && (unsigned)x < (unsigned)a.Nx) {
+    for (int p0 = lt; p0 < n; p0 += 2 * SB_GROUP) { // two pixels per trip: all loads first (see pass B below)
+        T mval[2], m0[2], v0[2], vh0[2];
+        double gm[2];
 #pragma unroll
-            for (int c = 0; c < SB_FAST_MAXC; ++c) {
-                if (c < C) {
-                    const double gg = grad_at<T>(a, s, c, y, x);
-                    gm += gsum[c] * gg;
-                    gs[c] += (T)gg * mval;
+        for (int i = 0; i < 2; ++i) {
+            const int p = p0 + i * SB_GROUP;
+            mval[i] = m0[i] = v0[i] = vh0[i] = T(0);
+            gm[i] = 0.0;
+            if (p < n) {
+                const int by = (int)__umulhi((unsigned)p, magic), bx = p - by * Bx, y = d.oy + by, x = d.ox + bx;
+                mval[i] = mp[p];
+                if (upd) m0[i] = mm[p], v0[i] = mv[p], vh0[i] = mvh[p];
+                if ((unsigned)y < (unsigned)a.Ny && (unsigned)x < (unsigned)a.Nx) {
+#pragma unroll
+                    for (int c = 0; c < SB_FAST_MAXC; ++c) {
+                        if (c < C) {
+                            const double gg = grad_at<T>(a, s, c, y, x);
+                            gm[i] += gsum[c] * gg;
+                            gs[c] += (T)gg * mval[i];
+                        }
+                    }
                 }
             }
         }
         if (upd) {
-            double m_ = (double)mm[p], v_ = (double)mv[p], vh_ = (double)mvh[p];
-            const double psi = amsgrad(gm, m_, v_, vh_, it, a.fs);
-            mm[p] = (T)m_, mv[p] = (T)v_, mvh[p] = (T)vh_;
-            const T xn = (T)((double)mval - alpha * m_ / psi);
-            xs[p] = xn;
-            mp[p] = xn; // z0 = x
-            ps[p] = (T)psi;
-            pmax = fmax(pmax, psi);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int p = p0 + i * SB_GROUP;
+                if (p < n) {
+                    double m_ = (double)m0[i], v_ = (double)v0[i], vh_ = (double)vh0[i];
+                    const double psi = amsgrad(gm[i], m_, v_, vh_, it, a.fs);
+                    mm[p] = (T)m_, mv[p] = (T)v_, mvh[p] = (T)vh_;
+                    const T xn = (T)((double)mval[i] - alpha * m_ / psi);
+                    xs[p] = xn;
+                    mp[p] = xn; // z0 = x
+                    zn[p] = xn; // first proximal argument: z0 - psi/max(psi) (z0 - x) = x exactly
+                    ps[p] = (T)psi;
+                    pmax = fmax(pmax, psi);
+                }
+            }
         }
     }
     // spectrum gradient (pairs of bands per reduction); every thread is past its reads of the spectrum in gsum
@@ -908,24 +966,90 @@ template <typename T> __global__ void __launch_bounds__(512, 2) k_update_fast(co
         if (d.chain >= 0) {
             const double gamma = alpha / psimax;
             const double fac = gamma / alpha;
-            for (int sub = 0; sub < a.fs.prox_max_iter; ++sub) {
-                for (int p = lt; p < n; p += SB_GROUP) {
-                    const double zz = (double)mp[p];
-                    zn[p] = (T)(zz - fac * (double)ps[p] * (zz - (double)xs[p]));
+            const FusedChain fc = fused_chain_of(ch, d.By, d.Bx);
+            const double e2 = a.fs.e_rel * a.fs.e_rel;
+            if (fc.ok) {
+                const T hs = (T)(0.5 * fc.sym), om = (T)(1.0 - fc.sym), zero = (T)fc.zero, tiny = (T)fc.tiny;
+                const int half = (n - 1) >> 1; // centre pixel index (odd x odd box): its 180-degree partner is itself
+                for (int sub = 0; sub < a.fs.prox_max_iter; ++sub) {
+                    group_sweep<T>(zn, tab, (T)fc.mono_grad, g);
+                    // pass A: symmetry (pairs p, n-1-p), positivity, centre floor, running maximum
+                    T mx = -INFINITY;
+                    for (int p = lt; p <= half; p += SB_GROUP) {
+                        const int q = n - 1 - p;
+                        T u = zn[p], v = zn[q];
+                        if (fc.has_sym) {
+                            const T un = hs * (u + v) + om * u, vn = hs * (v + u) + om * v;
+                            u = un, v = vn;
+                        }
+                        u = u > zero ? u : zero;
+                        v = v > zero ? v : zero;
+                        if (p == half) {
+                            u = u > tiny ? u : tiny;
+                            v = u;
+                        }
+                        zn[p] = u, zn[q] = v;
+                        mx = u > mx ? u : mx;
+                        mx = v > mx ? v : mx;
+                    }
+                    const T den = group_max_t<T>(red, mx); // barrier inside: pass A is complete for the whole group
+                    // pass B: normalise, convergence sums, store z, next proximal argument
+                    double dd = 0.0, nn = 0.0;
+                    bad = false;
+                    const bool last = sub + 1 == a.fs.prox_max_iter;
+                    // (loads of a batch are issued before its stores: the compiler cannot reorder them itself because
+                    // mp, ps and xs may alias as far as it knows, and one L2 round trip per pixel would dominate)
+                    for (int p0 = lt; p0 < n; p0 += 4 * SB_GROUP) {
+                        T zr[4], zo_[4], ps_[4], xs_[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int p = p0 + i * SB_GROUP;
+                            zr[i] = zo_[i] = ps_[i] = xs_[i] = T(0);
+                            if (p < n) {
+                                zr[i] = zn[p];
+                                zo_[i] = mp[p];
+                                if (!last) ps_[i] = ps[p], xs_[i] = xs[p];
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int p = p0 + i * SB_GROUP;
+                            if (p < n) {
+                                const T r = zr[i] / den;
+                                const double zo = (double)zo_[i], zv = (double)r;
+                                dd += (zv - zo) * (zv - zo);
+                                nn += zo * zo;
+                                mp[p] = r;
+                                bad |= !isfinite(zv);
+                                if (!last) zn[p] = (T)(zv - fac * (double)ps_[i] * (zv - (double)xs_[i]));
+                            }
+                        }
+                    }
+                    group_sum2(red, dd, nn); // barrier inside: zn is complete before the next sweep
+                    if (dd <= e2 * nn) break;
                 }
-                group_bar(g);
-                group_chain<T>(zn, d.By, d.Bx, ch, tab, red);
-                double dd = 0.0, nn = 0.0;
-                bad = false;
-                for (int p = lt; p < n; p += SB_GROUP) {
-                    const double zo = (double)mp[p], zv = (double)zn[p];
-                    dd += (zv - zo) * (zv - zo);
-                    nn += zo * zo;
-                    mp[p] = zn[p];
-                    bad |= !isfinite(zv);
+            } else {
+                for (int sub = 0; sub < a.fs.prox_max_iter; ++sub) {
+                    if (sub > 0) {
+                        for (int p = lt; p < n; p += SB_GROUP) {
+                            const double zz = (double)mp[p];
+                            zn[p] = (T)(zz - fac * (double)ps[p] * (zz - (double)xs[p]));
+                        }
+                    }
+                    group_bar(g);
+                    group_chain<T>(zn, d.By, d.Bx, ch, tab, red);
+                    double dd = 0.0, nn = 0.0;
+                    bad = false;
+                    for (int p = lt; p < n; p += SB_GROUP) {
+                        const double zo = (double)mp[p], zv = (double)zn[p];
+                        dd += (zv - zo) * (zv - zo);
+                        nn += zo * zo;
+                        mp[p] = zn[p];
+                        bad |= !isfinite(zv);
+                    }
+                    group_sum2(red, dd, nn);
+                    if (dd <= e2 * nn) break;
                 }
-                group_sum2(red, dd, nn);
-                if (dd <= a.fs.e_rel * a.fs.e_rel * nn) break;
             }
         } else {
             for (int p = lt; p < n; p += SB_GROUP) bad |= !isfinite((double)mp[p]);

@@ -563,19 +563,22 @@ template <typename T> struct PlanT : sb_plan {
                 generic.push_back(k);
         }
         fast_npix = npix, fast_table_cap = std::max(cap, 8);
+        // One CTA per SM, every SM the same number of 64-thread groups (= sources): the kernel is bound by the
+        // latency of the per-source proximal loop, so balance matters more than occupancy.
         fast_G = 0;
-        for (int G : {8, 4, 2, 1}) { // prefer two resident CTAs per SM
-            if (fast_smem_bytes(G, fast_npix, fast_table_cap) <= 112 * 1024) {
-                fast_G = G;
-                break;
+        {
+            size_t n_fast = 0;
+            for (auto &kv : by_chain) n_fast += kv.second.size();
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+            if (n_fast) {
+                const int waves = (int)((n_fast + (size_t)sms * 16 - 1) / ((size_t)sms * 16));
+                int G = (int)((n_fast + (size_t)sms * waves - 1) / ((size_t)sms * waves));
+                G = std::max(1, std::min(16, G));
+                while (G > 1 && fast_smem_bytes(G, fast_npix, fast_table_cap) > 220 * 1024) --G;
+                if (fast_smem_bytes(G, fast_npix, fast_table_cap) <= 220 * 1024) fast_G = G;
             }
         }
-        if (!fast_G)
-            for (int G : {4, 2, 1})
-                if (fast_smem_bytes(G, fast_npix, fast_table_cap) <= 220 * 1024) {
-                    fast_G = G;
-                    break;
-                }
         std::vector<int> groups;
         if (fast_G) {
             for (auto &kv : by_chain) {

@@ -34,6 +34,8 @@ template <typename T> struct SpecObs {
     const typename Cx<T>::type *tw_x, *tw_y; // [R1][R2] tables exp(-2 pi i n2 k1 / L) for L = Fx and L = Fy
 };
 
+#define SB_SPEC_MAXCB 8 // bands per CTA of the row kernels (SpecArgs::cb <= this)
+
 template <typename T> struct SpecArgs {
     SpecObs<T> ob;
     int Ny, Nx, Cm; // model frame (Cm = number of model channels)
@@ -173,12 +175,14 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
     }
     __syncthreads();
     const int ncand = s_ncand;
+#pragma unroll 1
     for (int idx = tid; idx < rows * Nx; idx += nt) {
         const int r = idx / Nx, x = idx - r * Nx, y = y0 + r;
-        T acc[SB_MAXC];
+        T acc[SB_SPEC_MAXCB];
 #pragma unroll
-        for (int c = 0; c < SB_MAXC; ++c) acc[c] = T(0);
+        for (int c = 0; c < SB_SPEC_MAXCB; ++c) acc[c] = T(0);
         if (y < Ny) {
+#pragma unroll 1
             for (int i = 0; i < ncand; ++i) {
                 const int k = cand[i];
                 const DevSource &d = a.src[k];
@@ -188,20 +192,20 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
                     if (d.kind == 0) {
                         const T mv = a.morph[d.morph_off + (size_t)by * d.Bx + bx];
 #pragma unroll
-                        for (int c = 0; c < SB_MAXC; ++c)
+                        for (int c = 0; c < SB_SPEC_MAXCB; ++c)
                             if (c < Cb) acc[c] += (T)sed[c] * mv;
                     } else {
                         const int plane = d.By * d.Bx;
                         const T *pm = a.pmorph + d.morph_off + (size_t)(ob.chan_off + c0) * plane + (size_t)by * d.Bx + bx;
 #pragma unroll
-                        for (int c = 0; c < SB_MAXC; ++c)
+                        for (int c = 0; c < SB_SPEC_MAXCB; ++c)
                             if (c < Cb) acc[c] += (T)sed[c] * pm[(size_t)c * plane];
                     }
                 }
             }
         }
 #pragma unroll
-        for (int c = 0; c < SB_MAXC; ++c)
+        for (int c = 0; c < SB_SPEC_MAXCB; ++c)
             if (c < Cb) {
                 tile[((size_t)c * rows + r) * Nx + x] = acc[c];
                 if (a.model_out && y < Ny) a.model_out[(((size_t)s * a.Cm + ob.chan_off + c0 + c) * Ny + y) * Nx + x] = acc[c];
