@@ -905,11 +905,12 @@ template <typename T> __global__ void __launch_bounds__(1024, 1) k_update_fast(c
     const double alpha = d.morph_step;
     const bool upd = !d.morph_fixed;
     double pmax = 0.0;
-    for (int p0 = lt; p0 < n; p0 += 2 * SB_GROUP) { // two pixels per trip: all loads first (see pass B below)
-        T mval[2], m0[2], v0[2], vh0[2];
-        double gm[2];
+    constexpr int PB = 2; // pixels per trip: all loads first (see pass B below)
+    for (int p0 = lt; p0 < n; p0 += PB * SB_GROUP) {
+        T mval[PB], m0[PB], v0[PB], vh0[PB];
+        double gm[PB];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < PB; ++i) {
             const int p = p0 + i * SB_GROUP;
             mval[i] = m0[i] = v0[i] = vh0[i] = T(0);
             gm[i] = 0.0;
@@ -931,7 +932,7 @@ template <typename T> __global__ void __launch_bounds__(1024, 1) k_update_fast(c
         }
         if (upd) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < PB; ++i) {
                 const int p = p0 + i * SB_GROUP;
                 if (p < n) {
                     double m_ = (double)m0[i], v_ = (double)v0[i], vh_ = (double)vh0[i];

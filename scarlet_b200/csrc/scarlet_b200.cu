@@ -457,7 +457,8 @@ template <typename T> struct PlanT : sb_plan {
                 if (ob.row_threads > limit) ob.row_threads = ob.npair * ob.cb * rmax;
                 const size_t nb = (size_t)ob.npair * ob.cb;
                 ob.smem_row = (nb * ob.kx.sf + (size_t)Fx) * sizeof(cplx) + 16;
-                ob.smem_render = ob.smem_row + (size_t)ob.cb * 2 * ob.npair * desc.Nx * sizeof(T) + (size_t)(max_src_scene + 1) * sizeof(int);
+                ob.smem_render = ob.smem_row + (size_t)ob.cb * 2 * ob.npair * desc.Nx * sizeof(T) + 16 +
+                                 (size_t)(max_src_scene + 1) * (sizeof(int) + sizeof(SpecCand<T>));
                 ob.smem_col = ((size_t)ob.ky.NBcol * ob.ky.sf + (size_t)Fy) * sizeof(cplx) + 16;
                 if (ob.smem_render > 227 * 1024 || ob.smem_col > 227 * 1024)
                     return set_err(SB_ERR_ARG, "observation %d: frame too wide for the fused spectral kernels", o);
@@ -860,6 +861,7 @@ template <typename T> struct PlanT : sb_plan {
             sa.ob = ob.sdev, sa.Ny = desc.Ny, sa.Nx = desc.Nx, sa.Cm = C, sa.npair = ob.npair, sa.cb = ob.cb, sa.done = d_done.p;
             sa.src = d_src.p, sa.scene_src_start = d_start.p, sa.sed = d_sed.p, sa.morph = d_morph.p, sa.pmorph = d_pmorph.p;
             sa.model_out = model_out, sa.partials = ob.partials.p;
+            sa.magic_nx = 0xffffffffu / (unsigned)desc.Nx + 1u, sa.max_cand = max_src_scene + 1;
             sa.rendered_out = ((int)o == rendered_obs) ? rendered_out : nullptr;
             const dim3 rgrid((desc.Ny + 2 * ob.npair - 1) / (2 * ob.npair), S, (ob.sdev.C + ob.cb - 1) / ob.cb);
             const dim3 cgrid((ob.sdev.Fxc + ob.ky.NBcol - 1) / ob.ky.NBcol, S * ob.sdev.C);

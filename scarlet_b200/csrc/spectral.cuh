@@ -52,6 +52,16 @@ template <typename T> struct SpecArgs {
     double *partials; // [S][gridDim.x]
     T *rendered_out;  // optional [S][C][H][W]
     int conj;         // column kernel: multiply by conj(K^)
+    unsigned magic_nx; // 2^32 / Nx + 1: idx / Nx == umulhi(idx, magic_nx)
+    int max_cand;      // capacity of the render kernel's candidate list (largest number of sources in a scene)
+};
+
+// what the render kernel needs to know about one source whose box intersects the CTA's rows
+template <typename T> struct __align__(16) SpecCand {
+    int oy, ox, By, Bx;
+    const T *mp; // morphology image (or first per-band plane of a point source)
+    int plane, pad;
+    T sed[SB_SPEC_MAXCB];
 };
 
 // ---- shared helpers of the row kernels -------------------------------------------------------------------------
@@ -62,17 +72,21 @@ __device__ __forceinline__ void split_and_store(const SpecArgs<T> &a, const type
     typedef typename Cx<T>::type C2;
     typedef sbfft::Plan2<R1, R2> P;
     const SpecObs<T> &ob = a.ob;
-    const int Fxc = ob.Fxc, Fx = ob.Fx, Co = ob.C;
-    for (int idx = threadIdx.x; idx < NB * Fxc; idx += blockDim.x) {
-        const int f = idx / Fxc, k = idx - f * Fxc, p = f / Cb, c = c0 + f - p * Cb, y = y0 + 2 * p;
+    const int Fxc = ob.Fxc, Fx = ob.Fx, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int f = threadIdx.x >> 5; f < NB; f += nw) { // one warp per transform: no per-element index arithmetic
+        const int p = f / Cb, c = c0 + f - p * Cb, y = y0 + 2 * p;
         if (y >= a.Ny) continue;
-        const C2 z = fbuf[f * P::SF + k], zc = fbuf[f * P::SF + (k ? Fx - k : 0)];
-        C2 A, B;
-        A.x = T(0.5) * (z.x + zc.x), A.y = T(0.5) * (z.y - zc.y);
-        B.x = T(0.5) * (z.y + zc.y), B.y = T(0.5) * (zc.x - z.x);
-        C2 *row = ob.X + ((size_t)(s * Co + c) * a.Ny + y) * ob.Xp + k;
-        row[0] = A;
-        if (y + 1 < a.Ny) row[ob.Xp] = B;
+        const C2 *z0 = fbuf + f * P::SF;
+        C2 *row = ob.X + ((size_t)(s * ob.C + c) * a.Ny + y) * ob.Xp;
+        const bool two = y + 1 < a.Ny;
+        for (int k = lane; k < Fxc; k += 32) {
+            const C2 z = z0[k], zc = z0[k ? Fx - k : 0];
+            C2 A, B;
+            A.x = T(0.5) * (z.x + zc.x), A.y = T(0.5) * (z.y - zc.y);
+            B.x = T(0.5) * (z.y + zc.y), B.y = T(0.5) * (zc.x - z.x);
+            row[k] = A;
+            if (two) row[ob.Xp + k] = B;
+        }
     }
 }
 
@@ -83,17 +97,19 @@ __device__ __forceinline__ void load_and_merge(const SpecArgs<T> &a, typename Cx
     typedef typename Cx<T>::type C2;
     typedef sbfft::Plan2<R1, R2> P;
     const SpecObs<T> &ob = a.ob;
-    const int Fxc = ob.Fxc, Fx = ob.Fx, Co = ob.C;
-    for (int idx = threadIdx.x; idx < NB * Fxc; idx += blockDim.x) {
-        const int f = idx / Fxc, k = idx - f * Fxc, p = f / Cb, c = c0 + f - p * Cb, y = y0 + 2 * p;
-        C2 A = {T(0), T(0)}, B = {T(0), T(0)};
-        if (y < a.Ny) {
-            const C2 *row = ob.X + ((size_t)(s * Co + c) * a.Ny + y) * ob.Xp + k;
-            A = row[0];
-            if (y + 1 < a.Ny) B = row[ob.Xp];
+    const int Fxc = ob.Fxc, Fx = ob.Fx, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int f = threadIdx.x >> 5; f < NB; f += nw) {
+        const int p = f / Cb, c = c0 + f - p * Cb, y = y0 + 2 * p;
+        C2 *z0 = fbuf + f * P::SF;
+        const bool one = y < a.Ny, two = y + 1 < a.Ny;
+        const C2 *row = ob.X + ((size_t)(s * ob.C + c) * a.Ny + (one ? y : 0)) * ob.Xp;
+        for (int k = lane; k < Fxc; k += 32) {
+            C2 A = {T(0), T(0)}, B = {T(0), T(0)};
+            if (one) A = row[k];
+            if (two) B = row[ob.Xp + k];
+            z0[k] = C2{A.x - B.y, A.y + B.x};
+            if (k > 0 && 2 * k < Fx) z0[Fx - k] = C2{A.x + B.y, B.x - A.y};
         }
-        fbuf[f * P::SF + k] = C2{A.x - B.y, A.y + B.x};
-        if (k > 0 && 2 * k < Fx) fbuf[f * P::SF + Fx - k] = C2{A.x + B.y, B.x - A.y};
     }
 }
 
@@ -152,9 +168,11 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
     const int c0 = blockIdx.z * a.cb, Cb = min(a.cb, Co - c0), NB = a.npair * Cb;
     const int tid = threadIdx.x, nt = blockDim.x;
     C2 *fbuf = reinterpret_cast<C2 *>(smem);
-    C2 *tw = fbuf + NB * P::SF;
+    C2 *tw = fbuf + (size_t)a.npair * a.cb * P::SF;
     T *tile = reinterpret_cast<T *>(tw + R1 * R2);
-    int *cand = reinterpret_cast<int *>(tile + (size_t)a.cb * rows * Nx);
+    SpecCand<T> *recs = reinterpret_cast<SpecCand<T> *>(
+        (reinterpret_cast<uintptr_t>(tile + (size_t)a.cb * rows * Nx) + 15) & ~(uintptr_t)15);
+    int *cand = reinterpret_cast<int *>(recs + a.max_cand);
     stage_twiddles<T, R1, R2>(tw, ob.tw_x);
     // sources whose boxes intersect these rows, in scene order (deterministic accumulation order)
     const int k0 = a.scene_src_start[s], k1 = a.scene_src_start[s + 1];
@@ -175,32 +193,37 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
     }
     __syncthreads();
     const int ncand = s_ncand;
+    for (int i = tid; i < ncand; i += nt) { // compact records: everything the pixel loop needs, in shared memory
+        const int k = cand[i];
+        const DevSource &d = a.src[k];
+        SpecCand<T> rc;
+        rc.oy = d.oy, rc.ox = d.ox, rc.By = d.By, rc.Bx = d.Bx;
+        const int plane = d.kind == 0 ? 0 : d.By * d.Bx;
+        rc.plane = plane;
+        rc.mp = (d.kind == 0 ? a.morph : a.pmorph + (size_t)(ob.chan_off + c0) * plane) + d.morph_off;
+        const double *sed = a.sed + (size_t)k * a.Cm + ob.chan_off + c0;
+#pragma unroll
+        for (int c = 0; c < SB_SPEC_MAXCB; ++c) rc.sed[c] = c < Cb ? (T)sed[c] : T(0);
+        recs[i] = rc;
+    }
+    __syncthreads();
 #pragma unroll 1
     for (int idx = tid; idx < rows * Nx; idx += nt) {
-        const int r = idx / Nx, x = idx - r * Nx, y = y0 + r;
+        const int r = (int)__umulhi((unsigned)idx, a.magic_nx), x = idx - r * Nx, y = y0 + r;
         T acc[SB_SPEC_MAXCB];
 #pragma unroll
         for (int c = 0; c < SB_SPEC_MAXCB; ++c) acc[c] = T(0);
         if (y < Ny) {
 #pragma unroll 1
             for (int i = 0; i < ncand; ++i) {
-                const int k = cand[i];
-                const DevSource &d = a.src[k];
-                const int by = y - d.oy, bx = x - d.ox;
-                if ((unsigned)by < (unsigned)d.By && (unsigned)bx < (unsigned)d.Bx) {
-                    const double *sed = a.sed + (size_t)k * a.Cm + ob.chan_off + c0;
-                    if (d.kind == 0) {
-                        const T mv = a.morph[d.morph_off + (size_t)by * d.Bx + bx];
+                const SpecCand<T> &rc = recs[i];
+                const int by = y - rc.oy, bx = x - rc.ox;
+                if ((unsigned)by < (unsigned)rc.By && (unsigned)bx < (unsigned)rc.Bx) {
+                    const T *pm = rc.mp + by * rc.Bx + bx;
+                    const int plane = rc.plane; // 0: one morphology image for all bands; else per-band planes (point sources)
 #pragma unroll
-                        for (int c = 0; c < SB_SPEC_MAXCB; ++c)
-                            if (c < Cb) acc[c] += (T)sed[c] * mv;
-                    } else {
-                        const int plane = d.By * d.Bx;
-                        const T *pm = a.pmorph + d.morph_off + (size_t)(ob.chan_off + c0) * plane + (size_t)by * d.Bx + bx;
-#pragma unroll
-                        for (int c = 0; c < SB_SPEC_MAXCB; ++c)
-                            if (c < Cb) acc[c] += (T)sed[c] * pm[(size_t)c * plane];
-                    }
+                    for (int c = 0; c < SB_SPEC_MAXCB; ++c)
+                        if (c < Cb) acc[c] += rc.sed[c] * pm[c * plane];
                 }
             }
         }
@@ -249,7 +272,7 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
     __syncthreads();
     C2 a_[R1];
     rows_inverse<T, R1, R2>(a_, fbuf, tw, NB);
-    double part = 0.0;
+    T part_t = T(0); // <= 2 R1 terms per lane in the working precision; lanes are then summed in double
     {
         const int f = tid / R2, n2 = tid - f * R2;
         if (tid < NB * R2) {
@@ -265,13 +288,13 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
                 if (col && row0) {
                     const T m = a_[n1].x, w = ob.weights[base0 + dx], diff = m - ob.data[base0 + dx];
                     r0 = w * diff;
-                    part += (double)w * (double)diff * (double)diff;
+                    part_t += r0 * diff;
                     if (a.rendered_out) a.rendered_out[base0 + dx] = m;
                 }
                 if (col && row1) {
                     const T m = a_[n1].y, w = ob.weights[base1 + dx], diff = m - ob.data[base1 + dx];
                     r1 = w * diff;
-                    part += (double)w * (double)diff * (double)diff;
+                    part_t += r1 * diff;
                     if (a.rendered_out) a.rendered_out[base1 + dx] = m;
                 }
                 a_[n1] = C2{r0, r1};
@@ -281,7 +304,7 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
     __syncthreads(); // every lane has read its inverse-transform output before fbuf is reused
     rows_forward<T, R1, R2>(a_, fbuf, tw, NB);
     split_and_store<T, R1, R2>(a, fbuf, NB, s, y0, c0, Cb);
-    part = block_sum(part, red);
+    const double part = block_sum((double)part_t, red);
     if (tid == 0) a.partials[((size_t)s * gridDim.z + blockIdx.z) * gridDim.x + blockIdx.x] = part;
 }
 
