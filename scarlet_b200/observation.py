@@ -30,7 +30,15 @@ class Observation(Frame):
                 if self.wcs is model_frame.wcs:
                     self.renderer = ConvolutionRenderer(self, model_frame, convolution_type="fft")
                 else:
-                    self.renderer = ResolutionRenderer(self, model_frame)
+                    from . import interpolation
+                    assert self.wcs is not None and model_frame.wcs is not None
+                    angle, h = interpolation.get_angles(self.wcs, model_frame.wcs)
+                    same_res = abs(h - 1) < np.finfo(float).eps
+                    same_rot = (np.abs(angle[1]) ** 2) < np.finfo(float).eps
+                    if same_res and same_rot:
+                        self.renderer = ConvolutionRenderer(self, model_frame, convolution_type="fft")
+                    else:
+                        self.renderer = ResolutionRenderer(self, model_frame)
         else:
             assert isinstance(renderer, Renderer)
             self.renderer = renderer

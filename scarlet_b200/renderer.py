@@ -111,6 +111,92 @@ class ConvolutionRenderer(Renderer):
 
 
 class ResolutionRenderer(Renderer):
-    def __init__(self, *a, **k):
-        raise NotImplementedError("ResolutionRenderer (multi-resolution k-space resampling) is scheduled after the "
-                                  "same-resolution path meets its bar (SURVEY 8a-17)")
+    """Observation on a different pixel grid than the model: resample + convolve (scarlet/renderer.py:262-547).
+
+    Set-up follows the reference: difference kernel between the observed PSF, sinc-resampled to the model pixel scale,
+    and the model PSF (``build_diffkernel`` 365-412); fast grid ``_fft_shape``; positions of the low-resolution pixel rows
+    and columns in model-frame coordinates (``shifts`` 308-316).  Rotated grids are not on the device path.
+
+    The reference then tabulates, for every low-resolution row, the kernel Fourier-shifted to that row
+    (``_resconv_op``, (C, n_y, Fy*Fx)) and evaluates a render as Fourier shifts of the model to every low-resolution
+    column followed by a skinny matrix product (478-547).  Both steps are shifts on the same periodic grid, so with
+    Parseval's theorem the render is
+
+        LR[c,i,j] = h^2/(Fy Fx) * sum_{ky,kx} Ey[i,ky] Ex[j,kx] K^[c,ky,kx] conj(M^[c,ky,kx])
+
+    with ``Ey/Ex = exp(-2 pi i f s)`` (Nyquist bins real, the ``irfftn`` semantics of the reference).  This identity is
+    what the device evaluates (csrc/spectral.cuh: resampling kernels) and what ``get_model`` evaluates in NumPy for
+    stand-alone ``Observation.render`` calls; it agrees with the reference's own render to 1e-13 in float64
+    (tests/golden/multires.npz).
+    """
+
+    def __init__(self, data_frame, model_frame, padding=10):
+        from . import interpolation
+        super().__init__(data_frame, model_frame)
+        self.angle, self.h = interpolation.get_angles(data_frame.wcs, model_frame.wcs)
+        self.isrot = (np.abs(self.angle[1]) ** 2) > np.finfo(float).eps
+        if self.isrot:
+            raise NotImplementedError("rotated observations are outside the device path (SURVEY 8a-17: aligned grids)")
+        lr_shape = data_frame.shape[1:]
+        if lr_shape[0] != lr_shape[1]:
+            raise ValueError("ResolutionRenderer needs square observations (as the reference does, renderer.py:274)")
+        pixels = np.stack((np.arange(lr_shape[0]), np.arange(lr_shape[1])), axis=1)
+        coord_hr = np.array(data_frame.convert_pixel_to(model_frame, pixel=pixels), dtype=np.float64)
+        diff_psf, psf_hr = self.build_diffkernel(data_frame, model_frame)
+        self.small_axis = data_frame.Nx <= data_frame.Ny
+        self._fft_shape = fft._get_fft_shape(psf_hr, np.zeros(model_frame.shape), padding=3, axes=[-2, -1], max=False)
+        if self._fft_shape[-2] < diff_psf.shape[-2] or self._fft_shape[-1] < diff_psf.shape[-1]:
+            diff_psf = fft.Fourier(fft._centered(diff_psf.image, np.array([diff_psf.shape[0] + 1, *self._fft_shape]) - 1))
+        self.diff_kernel = fft.Fourier(fft._pad(diff_psf.image, self._fft_shape, axes=(-2, -1)))
+        Fy, Fx = self._fft_shape
+        center_y = int(Fy / 2.0 - (Fy - model_frame.Ny) / 2.0) + ((Fy % 2) != 0) * ((model_frame.Ny % 2) == 0)
+        center_x = int(Fx / 2.0 - (Fx - model_frame.Nx) / 2.0) - ((Fx % 2) != 0) * ((model_frame.Nx % 2) == 0)
+        self.shifts = coord_hr.T.copy()
+        self.shifts[0] -= center_y
+        self.shifts[1] -= center_x
+        self.other_shifts = np.copy(self.shifts)
+        self.origin = (0, 0)
+        self._operator = None
+
+    def build_diffkernel(self, data_frame, model_frame):
+        from . import interpolation
+        psf_hr = np.array(model_frame.psf.get_model(), dtype=np.float64)
+        psf_lr = np.array(data_frame.psf.get_model()).astype(model_frame.dtype)
+        pad_shape = np.array((np.array(data_frame.shape[-2:]) + np.array(psf_lr.shape[-2:])) / 2).astype(int) * 2 + 1
+        h_lr = interpolation.get_pixel_size(np.asarray(interpolation.get_affine(data_frame.wcs)))
+        h_hr = interpolation.get_pixel_size(np.asarray(interpolation.get_affine(model_frame.wcs)))
+        angle, _ = interpolation.get_angles(model_frame.wcs, data_frame.wcs)
+        psf_lr_hr = interpolation.sinc_interp_inplace(psf_lr, h_lr, h_hr, angle, pad_shape=pad_shape)
+        psf_hr = psf_hr / np.sum(psf_hr)
+        psf_lr_hr = psf_lr_hr / np.sum(psf_lr_hr)
+        return fft.match_psf(fft.Fourier(psf_lr_hr), fft.Fourier(psf_hr)), psf_hr
+
+    def device_operator(self):
+        """What the device needs: K^ of the centred-padded kernel (half spectrum along x, complex128 (C, Fy, Fx/2+1)), the
+        shift matrices for the model frame stored at the grid origin, and the overall scale h^2 / (Fy Fx)."""
+        if self._operator is None:
+            from . import interpolation
+            Fy, Fx = (int(f) for f in self._fft_shape)
+            Ny, Nx = self.model_frame.shape[1:]
+            oy, ox = (Fy - Ny + 1) // 2, (Fx - Nx + 1) // 2  # where fft._pad puts the model inside the grid
+            khat = np.ascontiguousarray(np.fft.rfft2(np.asarray(self.diff_kernel.image, dtype=np.float64), axes=(1, 2)))
+            Ey = np.ascontiguousarray(interpolation.shift_weights(Fy, self.shifts[0] - oy))
+            Ex = np.ascontiguousarray(interpolation.shift_weights(Fx, self.shifts[1] - ox)[:, :Fx // 2 + 1])
+            self._operator = dict(fshape=(Fy, Fx), khat=khat, Ey=Ey, Ex=Ex, scale=float(self.h ** 2 / (Fy * Fx)))
+        return self._operator
+
+    def get_model(self, *parameters):
+        def transform(model):
+            """Stand-alone render (host NumPy, float64): the forward identity of the class docstring."""
+            op = self.device_operator()
+            Fy, Fx = op["fshape"]
+            m = np.asarray(self.map_channels(model), dtype=np.float64)
+            mhat = np.fft.rfft2(m, s=(Fy, Fx), axes=(1, 2))
+            t1 = np.einsum("iy,cyx->cix", op["Ey"], op["khat"] * np.conj(mhat))
+            wgt = np.full(Fx // 2 + 1, 2.0)
+            wgt[0] = 1.0
+            if Fx % 2 == 0:
+                wgt[-1] = 1.0
+            out = op["scale"] * np.einsum("cix,jx,x->cij", t1, op["Ex"], wgt).real
+            return out.astype(np.asarray(model).dtype)
+        return transform

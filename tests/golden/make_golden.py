@@ -242,10 +242,57 @@ def monotonic_weights(sc):
     save("monotonic_weights.npz", **out)
 
 
+def multires_inputs(seed=7):
+    """Plain arrays of the two-observation multi-resolution scenario (also used by the tests to rebuild the scene)."""
+    def gauss(P, sig):
+        y, x = np.mgrid[:P, :P] - P // 2
+        out = np.stack([np.exp(-(x * x + y * y) / (2 * s * s)) for s in sig])
+        return out / out.sum(axis=(1, 2))[:, None, None]
+
+    rng = np.random.default_rng(seed)
+    return dict(hr_images=rng.standard_normal((3, 40, 40)).astype(np.float32), lr_images=rng.standard_normal((5, 8, 8)).astype(np.float32),
+                hr_psfs=gauss(15, [1.8, 2.0, 2.2]), lr_psfs=gauss(11, [1.0, 1.1, 1.2, 1.3, 1.4]),
+                hr_cd=np.diag([0.03, 0.03]), lr_cd=np.diag([0.2, 0.2]), hr_crpix=np.array([19.5, 19.5]), lr_crpix=np.array([3.5, 3.5]),
+                lr_weights=rng.uniform(0.5, 2.0, (5, 8, 8)).astype(np.float32), hr_weights=rng.uniform(0.5, 2.0, (3, 40, 40)).astype(np.float32))
+
+
+def multires(sc):
+    """Two observations on different pixel grids (5 bands at 0.2"/px, 3 bands at 0.03"/px): Frame.from_observations,
+    ResolutionRenderer set-up and render through the reference's own code (affine WCS stand-in: astropy is absent)."""
+    from scarlet_b200.wcs import AffineWCS
+    RefWCS = type("RefWCS", (AffineWCS, sys.modules["astropy.wcs"].WCS), {})
+    inp = multires_inputs()
+    out = dict(inp)
+    for dtype, tag in ((np.float32, ""), (np.float64, "64")):
+        obs_hr = sc.observation.Observation(inp["hr_images"].copy(), psf=sc.psf.ImagePSF(inp["hr_psfs"].copy()), weights=inp["hr_weights"].copy(),
+                                            wcs=RefWCS(inp["hr_cd"], crpix=inp["hr_crpix"]), channels=["h0", "h1", "h2"])
+        obs_lr = sc.observation.Observation(inp["lr_images"].copy(), psf=sc.psf.ImagePSF(inp["lr_psfs"].copy()), weights=inp["lr_weights"].copy(),
+                                            wcs=RefWCS(inp["lr_cd"], crpix=inp["lr_crpix"]), channels=["l0", "l1", "l2", "l3", "l4"])
+        frame = sc.frame.Frame.from_observations([obs_lr, obs_hr], coverage="union")
+        if dtype is np.float64:  # same frame in float64: the reference then keeps its resampling operator in float64
+            frame = sc.frame.Frame(frame.shape, channels=frame.channels, psf=frame.psf, wcs=frame.wcs, dtype=np.float64)
+            obs_lr.match(frame)
+            obs_hr.match(frame)
+        r, r2 = obs_lr.renderer, obs_hr.renderer
+        assert type(r).__name__ == "ResolutionRenderer" and type(r2).__name__ == "ConvolutionRenderer"
+        rng = np.random.default_rng(11)
+        yy, xx = np.mgrid[:frame.shape[1], :frame.shape[2]]
+        model = np.stack([rng.uniform(1, 5) * np.exp(-((yy - rng.uniform(25, 50)) ** 2 + (xx - rng.uniform(25, 50)) ** 2) / (2 * rng.uniform(2, 5) ** 2))
+                          for _ in range(frame.shape[0])]) + 0.01 * rng.random(frame.shape)
+        model = model.astype(dtype)
+        out.update({"frame_shape" + tag: np.array(frame.shape), "model_psf" + tag: frame.psf.get_model(), "model" + tag: model,
+                    "lr_h" + tag: np.array(r.h), "lr_fft_shape" + tag: np.array(r._fft_shape), "lr_shifts" + tag: np.array(r.shifts),
+                    "lr_diff_kernel" + tag: np.asarray(r.diff_kernel.image), "lr_small_axis" + tag: np.array(r.small_axis),
+                    "lr_rendered" + tag: obs_lr.render(model), "lr_logL" + tag: np.array(obs_lr.get_log_likelihood(model)),
+                    "hr_diff_kernel" + tag: np.asarray(r2.diff_kernel.image), "hr_rendered" + tag: obs_hr.render(model),
+                    "hr_logL" + tag: np.array(obs_hr.get_log_likelihood(model)),
+                    "hr_model_slice_start" + tag: np.array([r2.slices[1][1].start, r2.slices[1][2].start]),
+                    "model_crpix" + tag: np.array(frame.wcs.wcs.crpix)})
+    save("multires.npz", **out)
+
+
 if __name__ == "__main__":
     sc = ref_shim.install()
-    obs_render_loss(sc)
-    hsc_cosmos_35(sc)
-    point_extended(sc)
-    prox_chain(sc)
-    monotonic_weights(sc)
+    which = sys.argv[1:] or ["obs_render_loss", "hsc_cosmos_35", "point_extended", "prox_chain", "monotonic_weights", "multires"]
+    for name in which:
+        globals()[name](sc)

@@ -204,3 +204,41 @@ def test_parameter_lazy_state_links():
     assert q.name == "image"
     assert (q.m == 1).all() and q.std is not None
     assert (p[0]).name == "image" and p[0].v.shape == (2, 3)   # attributes travel by reference to views
+
+
+def _multires_scene(dtype=np.float32):
+    import scarlet_b200 as sb
+    from scarlet_b200.wcs import AffineWCS
+    g = golden("multires.npz")
+    obs_hr = sb.Observation(g["hr_images"].copy(), psf=sb.ImagePSF(g["hr_psfs"].copy()), weights=g["hr_weights"].copy(),
+                            wcs=AffineWCS(g["hr_cd"], crpix=g["hr_crpix"]), channels=["h0", "h1", "h2"])
+    obs_lr = sb.Observation(g["lr_images"].copy(), psf=sb.ImagePSF(g["lr_psfs"].copy()), weights=g["lr_weights"].copy(),
+                            wcs=AffineWCS(g["lr_cd"], crpix=g["lr_crpix"]), channels=["l0", "l1", "l2", "l3", "l4"])
+    frame = sb.Frame.from_observations([obs_lr, obs_hr], coverage="union")
+    if dtype is np.float64:
+        frame = sb.Frame(frame.shape, channels=frame.channels, psf=frame.psf, wcs=frame.wcs, dtype=np.float64)
+        obs_lr.match(frame)
+        obs_hr.match(frame)
+    return g, frame, obs_lr, obs_hr
+
+
+def test_multiresolution_setup_vs_reference_fixture():
+    """Frame.from_observations + ResolutionRenderer set-up against the reference's own (tests/golden/make_golden.py:multires),
+    and the Fourier identity the device evaluates against the reference's render"""
+    g, frame, obs_lr, obs_hr = _multires_scene(np.float64)
+    assert tuple(frame.shape) == tuple(g["frame_shape64"])
+    assert_allclose(frame.psf.get_model(), g["model_psf64"], atol=1e-15)
+    assert_allclose(frame.wcs.wcs.crpix, g["model_crpix64"])
+    r, r2 = obs_lr.renderer, obs_hr.renderer
+    assert type(r).__name__ == "ResolutionRenderer" and type(r2).__name__ == "ConvolutionRenderer"
+    assert_allclose(r.h, float(g["lr_h64"]))
+    assert list(r._fft_shape) == list(g["lr_fft_shape64"]) and bool(r.small_axis) == bool(g["lr_small_axis64"])
+    assert_allclose(r.shifts, g["lr_shifts64"], atol=1e-12)
+    assert_allclose(r.diff_kernel.image, g["lr_diff_kernel64"], atol=1e-12)
+    assert_allclose(r2.diff_kernel.image, g["hr_diff_kernel64"], atol=1e-12)
+    assert r2.origin == tuple(g["hr_model_slice_start64"]) and r.channel_offset == 0 and r2.channel_offset == 5
+    lr = obs_lr.render(g["model64"])
+    assert_allclose(lr, g["lr_rendered64"], atol=1e-11 * np.abs(g["lr_rendered64"]).max())
+    # the reference's default float32 frame (float32 model, float32 resampling operator) only agrees to float32 rounding
+    assert np.abs(lr - g["lr_rendered"]).max() < 5e-5 * np.abs(g["lr_rendered"]).max()
+    assert_allclose(obs_lr.get_log_likelihood(g["model64"]), float(g["lr_logL64"]), rtol=1e-10)
