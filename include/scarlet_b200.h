@@ -66,7 +66,8 @@ typedef struct sb_mono_desc {
 
 /* One Observation matched to the model frame (observation.py:59-114, renderer.py:164-202). */
 typedef struct sb_obs_desc {
-    int32_t kind;     /* 0 = ConvolutionRenderer (fft), 1 = NullRenderer */
+    int32_t kind;     /* 0 = ConvolutionRenderer (fft), 1 = NullRenderer, 2 = ResolutionRenderer (aligned grids; H x W is the
+                         low-resolution cube, Fy x Fx the reference's _fft_shape, renderer.py:288-290) */
     int32_t C, H, W;  /* data cube */
     int32_t chan_off; /* first model-frame channel (channel map = slice, renderer.py:26-51) */
     int32_t oy, ox;   /* position of data pixel (0,0) in the model frame (translation only) */
@@ -148,6 +149,11 @@ int sb_plan_upload_observation(sb_plan *plan, int obs, const float *data, const 
  * K^/(Fy Fx) in the plan's precision.  The grid must satisfy F >= N + max(-y0, P-1+y0) per axis (no wrap-around
  * inside the frame), else SB_ERR_ARG. */
 int sb_plan_upload_kernels(sb_plan *plan, int obs, const double *kernels, int Py, int Px, int y0, int x0);
+/* Resampling observation (kind 2; ResolutionRenderer, renderer.py:262-547): K^ = rfft2 of the centre-padded difference
+ * kernel WITHOUT origin shift goes through sb_plan_upload_observation(khat); this call adds the Fourier-shift matrices
+ * Ey complex128 [H][Fy], Ex complex128 [W][Fx/2+1] (exp(-2 pi i f s), Nyquist bins real, for the low-resolution pixel
+ * rows / columns in model-frame grid coordinates) and h2 = (pixel-scale ratio)^2. */
+int sb_plan_upload_resampling(sb_plan *plan, int obs, const double *ey, const double *ex, double h2);
 /* Pinned host memory for staging buffers: copies from/to it are asynchronous DMA. */
 void *sb_host_alloc(int64_t bytes);
 void sb_host_free(void *p);

@@ -626,6 +626,63 @@ class ObservationOracle:
         return nll, self.render_adjoint(w * diff)
 
 
+class ResolutionObservationOracle(ObservationOracle):
+    """Observation on a coarser, aligned pixel grid rendered with the reference's ``ResolutionRenderer`` algorithm
+    (renderer.py:262-547), restated literally: the padded difference kernel Fourier-shifted to every low-resolution
+    row is tabulated once (``_resconv_op``, 352-363, ``sinc_shift`` 414-476); a render Fourier-shifts the padded model
+    to every low-resolution column and contracts with that table (478-547).  The set-up products (padded difference
+    kernel, ``shifts``, ``h``, ``_fft_shape``) are inputs: they are pinned against the reference's own set-up in
+    tests/test_host_api.py::test_multiresolution_setup_vs_reference_fixture.  The adjoint is the transpose of the
+    same two linear maps (a real Fourier shift by ``s`` transposes to the shift by ``-s``)."""
+
+    def __init__(self, data, weights, diff_kernel_padded, shifts, h, frame_dtype=np.float32, channel_offset=0):
+        super().__init__(data, weights, None, frame_dtype=frame_dtype, channel_offset=channel_offset)
+        self.kernel = np.asarray(diff_kernel_padded, dtype=np.float64)  # (C, Fy, Fx), centred in the grid
+        self.fshape = self.kernel.shape[1:]
+        self.shifts = np.asarray(shifts, dtype=np.float64)
+        self.h = float(h)
+        # rows of the operator: kernel shifted along y to every low-resolution row, times h^2
+        self.op = self.h ** 2 * np.stack([self._shift(self.kernel, s, axis=1) for s in self.shifts[0]], axis=1)  # (C, ny, Fy, Fx)
+
+    @staticmethod
+    def _shift(arr, s, axis):
+        """Fourier shift by ``s`` pixels along ``axis`` with a real transform (mk_shifter(real=True) + irfft)."""
+        n = arr.shape[axis]
+        spec = np.fft.rfft(arr, axis=axis)
+        shape = [1] * arr.ndim
+        shape[axis] = spec.shape[axis]
+        ramp = np.exp(-2j * np.pi * np.fft.rfftfreq(n) * s).reshape(shape)
+        return np.fft.irfft(spec * ramp, n=n, axis=axis)
+
+    def match(self, frame_shape, model_psf, padding=10):
+        self.frame_shape = tuple(frame_shape)
+        Fy, Fx = self.fshape
+        Ny, Nx = self.frame_shape[1:]
+        self.pad0 = ((Fy - Ny + 1) // 2, (Fx - Nx + 1) // 2)  # fft._pad: centre-right rule
+        return self
+
+    def render(self, model):
+        C = self.data.shape[0]
+        sub = np.asarray(model[self.channel_offset:self.channel_offset + C], dtype=np.float64)
+        Fy, Fx = self.fshape
+        Ny, Nx = self.frame_shape[1:]
+        padded = np.zeros((C, Fy, Fx))
+        padded[:, self.pad0[0]:self.pad0[0] + Ny, self.pad0[1]:self.pad0[1] + Nx] = sub
+        # model shifted along x by -xs_j for every low-resolution column j: (C, nx, Fy, Fx)
+        conv = np.stack([self._shift(padded, -s, axis=2) for s in self.shifts[1]], axis=1)
+        return np.einsum("ciyx,cjyx->cij", self.op, conv).astype(self.frame_dtype)
+
+    def render_adjoint(self, grad_render):
+        C = self.data.shape[0]
+        Ny, Nx = self.frame_shape[1:]
+        g = np.asarray(grad_render, dtype=np.float64)
+        t = np.einsum("cij,ciyx->cjyx", g, self.op)  # d/d conv
+        padded = sum(self._shift(t[:, j], s, axis=2) for j, s in enumerate(self.shifts[1]))
+        out = np.zeros(self.frame_shape, dtype=np.float64)
+        out[self.channel_offset:self.channel_offset + C] = padded[:, self.pad0[0]:self.pad0[0] + Ny, self.pad0[1]:self.pad0[1] + Nx]
+        return out
+
+
 # ----------------------------------------------------------------------------------------------
 # the blend
 # ----------------------------------------------------------------------------------------------

@@ -17,7 +17,7 @@ from .constraint import MonoTables, chain_desc, constraint_ops
 from .morphology import ImageMorphology, PointSourceMorphology
 from .parameter import _StateLink, relative_step
 from .psf import GaussianPSF
-from .renderer import ConvolutionRenderer, NullRenderer
+from .renderer import ConvolutionRenderer, NullRenderer, ResolutionRenderer
 from .spectrum import TabulatedSpectrum
 
 
@@ -221,19 +221,26 @@ class DevicePlan:
         r = getattr(obs, "renderer", None)
         if r is None:
             raise RuntimeError("observation %d is not matched to the model frame (call obs.match(frame))" % o)
-        korigin, kernel = (0, 0), None
+        korigin, kernel, operator = (0, 0), None, None
         if type(r) is ConvolutionRenderer:
             fshape, korigin, kernel = r.device_kernel()
             kind = 0
         elif type(r) is NullRenderer:
             fshape, kind = (blend.frame.shape[1], blend.frame.shape[2]), 1
+        elif type(r) is ResolutionRenderer:
+            operator = r.device_operator()
+            fshape, kind = operator["fshape"], 2
+            if nat.lib().sb_fft_supported_length(int(fshape[0])) != fshape[0] or nat.lib().sb_fft_supported_length(int(fshape[1])) != fshape[1]:
+                raise NotImplementedError("ResolutionRenderer grid %s: the Fourier interpolation is tied to the reference's grid, and the "
+                                          "fused spectral kernels are not instantiated for these lengths" % (tuple(fshape),))
         else:
-            raise TypeError("renderer %s is not on the device path (ConvolutionRenderer / NullRenderer)" % type(r).__name__)
+            raise TypeError("renderer %s is not on the device path (ConvolutionRenderer / NullRenderer / ResolutionRenderer)"
+                            % type(r).__name__)
         if r.parameters:
             raise NotImplementedError("parameterised renderers (psf_shift) are not on the device path")
         return dict(kind=kind, shape=tuple(obs.data.shape), chan_off=r.channel_offset, origin=tuple(r.origin),
                     fshape=tuple(int(f) for f in fshape), kernel=kernel, korigin=tuple(korigin),
-                    kshape=None if kernel is None else kernel.shape, obs=obs, renderer=r)
+                    kshape=None if kernel is None else kernel.shape, obs=obs, renderer=r, operator=operator)
 
     def _pinned(self, shape, dtype):
         """numpy view of pinned host memory (sb_host_alloc) -- staging for asynchronous H2D copies."""
@@ -262,9 +269,23 @@ class DevicePlan:
                 kernels = self._pinned((len(ks),) + ks[0].shape, np.float64)
                 for i, k in enumerate(ks):
                     kernels[i] = k
+            resamp = None
+            if metas[0]["kind"] == 2:
+                ops = [metas[0]["operator"]] if om["shared"] else [m["operator"] for m in metas]
+                for op in ops[1:]:
+                    if not (np.array_equal(op["Ey"], ops[0]["Ey"]) and np.array_equal(op["Ex"], ops[0]["Ex"]) and op["scale"] == ops[0]["scale"]):
+                        raise ValueError("all scenes of a batch need the same resampling geometry")
+                khat = self._pinned((len(ops),) + ops[0]["khat"].shape, np.complex128)
+                for i, op in enumerate(ops):
+                    khat[i] = op["khat"]
+                Fy, Fx = ops[0]["fshape"]
+                resamp = dict(khat=khat, Ey=ops[0]["Ey"], Ex=ops[0]["Ex"], h2=ops[0]["scale"] * Fy * Fx)
             consts = []
             for m in metas:
                 obs, (oy, ox) = m["obs"], m["origin"]
+                if m["kind"] == 2:  # resampled observation: every pixel is rendered
+                    consts.append(float(obs.log_norm))
+                    continue
                 H, W = obs.data.shape[1:]
                 outside = np.ones((H, W), dtype=bool)
                 y0, y1, x0, x1 = max(0, -oy), min(H, Ny - oy), max(0, -ox), min(W, Nx - ox)
@@ -276,7 +297,7 @@ class DevicePlan:
                     dd = np.asarray(obs.data, dtype=np.float64)[:, outside]
                     extra = 0.5 * float((w * dd * dd).sum())
                 consts.append(float(obs.log_norm) + extra)
-            self._host_obs.append(dict(data=data, weights=weights, kernels=kernels, korigin=metas[0]["korigin"],
+            self._host_obs.append(dict(data=data, weights=weights, kernels=kernels, korigin=metas[0]["korigin"], resamp=resamp,
                                        consts=np.asarray(consts, dtype=np.float64)))
 
     def upload_observations(self):
@@ -286,9 +307,14 @@ class DevicePlan:
             self._stage_observations()
         nbytes = 0
         for o, h in enumerate(self._host_obs):
-            ker = h["kernels"]
-            nat.check(nat.lib().sb_plan_upload_observation(self._handle, o, nat.ptr(h["data"]), nat.ptr(h["weights"]), None,
+            ker, rs = h["kernels"], h["resamp"]
+            nat.check(nat.lib().sb_plan_upload_observation(self._handle, o, nat.ptr(h["data"]), nat.ptr(h["weights"]),
+                                                           nat.ptr(rs["khat"].view(np.float64)) if rs is not None else None,
                                                            nat.ptr(h["consts"])))
+            if rs is not None:
+                nat.check(nat.lib().sb_plan_upload_resampling(self._handle, o, nat.ptr(rs["Ey"].view(np.float64)),
+                                                              nat.ptr(rs["Ex"].view(np.float64)), rs["h2"]))
+                nbytes += rs["khat"].nbytes + rs["Ey"].nbytes + rs["Ex"].nbytes
             if ker is not None:
                 nat.check(nat.lib().sb_plan_upload_kernels(self._handle, o, nat.ptr(ker), ker.shape[-2], ker.shape[-1],
                                                            h["korigin"][0], h["korigin"][1]))

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <map>
 #include <memory>
+#include <mutex>
 
 #include "kernels.cuh"
 #include "spectral.cuh"
@@ -180,6 +181,20 @@ static int check_chain(const sb_chain_desc &c, int n_mono) {
     return SB_OK;
 }
 
+// The dynamic shared-memory limit of a kernel is a per-device function attribute shared by every plan of the process:
+// only ever raise it (a second, smaller plan must not lower the limit under a plan that is still alive).
+static std::mutex g_smem_mutex;
+static std::map<std::pair<int, const void *>, size_t> g_smem_limit;
+static int raise_smem_limit(int device, const void *fn, size_t bytes) {
+    std::lock_guard<std::mutex> lock(g_smem_mutex);
+    size_t &cur = g_smem_limit[std::make_pair(device, fn)];
+    if (bytes > cur) {
+        SB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
+    return SB_OK;
+}
+
 static inline int grid_for(long long n, int block = 256, int cap = 148 * 16) {
     long long g = (n + block - 1) / block;
     return (int)std::max<long long>(1, std::min<long long>(g, cap));
@@ -197,6 +212,7 @@ struct sb_plan {
     virtual int upload_observation(int obs, const float *data, const float *weights, const double *khat, const double *loss_const) = 0;
     virtual int upload_kernels(int obs, const double *ker, int Py, int Px, int y0, int x0) = 0;
     virtual int zero_state() = 0;
+    virtual int upload_resampling(int obs, const double *ey, const double *ex, double h2) = 0;
     virtual int upload_params(int which, const double *sed, const double *morph, const double *center) = 0;
     virtual int download_params(int which, double *sed, double *morph, double *center) = 0;
     virtual int evaluate(int obs, double *model, double *rendered, double *loss, double *g_sed, double *g_morph, double *g_center) = 0;
@@ -245,7 +261,7 @@ template <typename T> struct PlanT : sb_plan {
         bool fused = false;
         SpecObs<T> sdev;
         SpecKernels<T> kx, ky;
-        DevBuf<cplx> X, tw_x, tw_y;
+        DevBuf<cplx> X, tw_x, tw_y, Pbuf, T1buf, Ey, Ex; // Pbuf..Ex: resampling observations (kind 2) only
         DevBuf<T> G;
         int npair = 1, cb = 1, row_threads = 0;
         size_t smem_render = 0, smem_row = 0, smem_col = 0;
@@ -412,7 +428,7 @@ template <typename T> struct PlanT : sb_plan {
             for (int o = 0; o < desc.n_obs && fused; ++o) {
                 const sb_obs_desc &od = desc.obs[o];
                 SpecKernels<T> k;
-                if (od.kind != 0 || !spec_kernels<T>(od.Fx, &k) || !spec_kernels<T>(od.Fy, &k)) fused = false;
+                if ((od.kind != 0 && od.kind != 2) || !spec_kernels<T>(od.Fx, &k) || !spec_kernels<T>(od.Fy, &k)) fused = false;
             }
         }
         for (int o = 0; o < desc.n_obs; ++o) {
@@ -420,7 +436,10 @@ template <typename T> struct PlanT : sb_plan {
             obs.emplace_back(new Obs());
             Obs &ob = *obs.back();
             if (od.C <= 0 || od.chan_off < 0 || od.chan_off + od.C > C) return set_err(SB_ERR_ARG, "observation %d: channels outside the model frame", o);
-            if (od.kind != 0 && od.kind != 1) return set_err(SB_ERR_ARG, "observation %d: unsupported renderer kind %d", o, od.kind);
+            if (od.kind != 0 && od.kind != 1 && od.kind != 2) return set_err(SB_ERR_ARG, "observation %d: unsupported renderer kind %d", o, od.kind);
+            if (od.kind == 2 && !fused)
+                return set_err(SB_ERR_ARG, "observation %d: a resampling observation needs FFT lengths of the fused spectral kernels "
+                                           "(got %dx%d) and no NullRenderer observation in the same plan", o, od.Fy, od.Fx);
             int Fy = od.Fy, Fx = od.Fx;
             if (od.kind == 1) Fy = desc.Ny, Fx = desc.Nx;
             if (Fy < desc.Ny || Fx < desc.Nx) return set_err(SB_ERR_ARG, "observation %d: FFT grid %dx%d smaller than the frame", o, Fy, Fx);
@@ -462,11 +481,26 @@ template <typename T> struct PlanT : sb_plan {
                 ob.smem_col = ((size_t)ob.ky.NBcol * ob.ky.sf + (size_t)Fy) * sizeof(cplx) + 16;
                 if (ob.smem_render > 227 * 1024 || ob.smem_col > 227 * 1024)
                     return set_err(SB_ERR_ARG, "observation %d: frame too wide for the fused spectral kernels", o);
-                SB_CUDA(cudaFuncSetAttribute((const void *)ob.kx.render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ob.smem_render));
-                SB_CUDA(cudaFuncSetAttribute((const void *)ob.kx.residual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ob.smem_row));
-                SB_CUDA(cudaFuncSetAttribute((const void *)ob.kx.grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ob.smem_row));
-                SB_CUDA(cudaFuncSetAttribute((const void *)ob.ky.column, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ob.smem_col));
+                SB_TRY(raise_smem((const void *)ob.kx.render, ob.smem_render));
+                SB_TRY(raise_smem((const void *)ob.kx.residual, ob.smem_row));
+                SB_TRY(raise_smem((const void *)ob.kx.grad, ob.smem_row));
+                SB_TRY(raise_smem((const void *)ob.ky.column, ob.smem_col));
                 ob.n_part = ((desc.Ny + 2 * ob.npair - 1) / (2 * ob.npair)) * ((od.C + ob.cb - 1) / ob.cb);
+                if (od.kind == 2) {
+                    ob.n_part = od.C;
+                    SB_TRY(ob.Pbuf.alloc((size_t)S * od.C * Fy * Xp));
+                    SB_TRY(ob.T1buf.alloc((size_t)S * od.C * od.H * Xp));
+                    SB_TRY(ob.Ey.alloc((size_t)od.H * Fy));
+                    SB_TRY(ob.Ex.alloc((size_t)od.W * d.Fxc));
+                    SB_TRY(ob.Pbuf.zero(stream));
+                    SB_TRY(ob.T1buf.zero(stream));
+                    SB_TRY(ob.Ey.zero(stream));
+                    SB_TRY(ob.Ex.zero(stream));
+                    if ((size_t)od.H * od.W * sizeof(T) > 200 * 1024) return set_err(SB_ERR_ARG, "observation %d: resampled image too large", o);
+                    SB_TRY(raise_smem((const void *)ob.ky.column_fwd, ob.smem_col));
+                    SB_TRY(raise_smem((const void *)ob.ky.column_inv, ob.smem_col));
+                    SB_TRY(raise_smem((const void *)k_resample_lr<T>, (size_t)od.H * od.W * sizeof(T)));
+                }
                 SB_TRY(ob.partials.alloc((size_t)S * ob.n_part));
                 SB_TRY(ob.partials.zero(stream));
                 d.A = nullptr, d.B = ob.G.p, d.Ahat = nullptr, d.khat = ob.khat.p, d.data = ob.data.p, d.weights = ob.weights.p;
@@ -476,6 +510,7 @@ template <typename T> struct PlanT : sb_plan {
                 sd.Fy = Fy, sd.Fx = Fx, sd.Fxc = d.Fxc, sd.Xp = Xp, sd.khat_shared = od.khat_shared;
                 sd.X = ob.X.p, sd.khat = ob.khat.p, sd.G = ob.G.p, sd.data = ob.data.p, sd.weights = ob.weights.p;
                 sd.tw_x = ob.tw_x.p, sd.tw_y = ob.tw_y.p;
+                sd.P = ob.Pbuf.p, sd.T1 = ob.T1buf.p, sd.Ey = ob.Ey.p, sd.Ex = ob.Ex.p, sd.h2 = T(1);
                 continue;
             }
             d.Kp = d.Fxc, d.Bh = Fy, d.Bw = Fx;
@@ -509,12 +544,14 @@ template <typename T> struct PlanT : sb_plan {
         // dynamic shared memory of the update kernel
         const size_t smem = update_smem();
         if (smem > 227 * 1024) return set_err(SB_ERR_ARG, "largest morphology box (%d px) does not fit in shared memory", npix_max);
-        SB_CUDA(cudaFuncSetAttribute(k_update<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_TRY(raise_smem((const void *)k_update<T>, smem));
         SB_TRY(reset_counters());
         SB_CUDA(cudaStreamSynchronize(stream));
         dev_bytes += total_bytes();
         return SB_OK;
     }
+
+    int raise_smem(const void *fn, size_t bytes) { return sb::raise_smem_limit(device, fn, bytes); }
 
     // [R1][R2] table exp(-2 pi i n2 k1 / (R1 R2)) of the two-stage transforms (fft_core.cuh), computed in double
     int upload_twiddles(DevBuf<cplx> &buf, int R1, int R2) {
@@ -601,7 +638,7 @@ template <typename T> struct PlanT : sb_plan {
         if (n_fast_cta) {
             SB_TRY(d_scratch_x.alloc(std::max<long long>(n_morph, 1)));
             SB_TRY(d_scratch_ps.alloc(std::max<long long>(n_morph, 1)));
-            SB_CUDA(cudaFuncSetAttribute(k_update_fast<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+            SB_TRY(raise_smem((const void *)k_update_fast<T>, fast_smem));
         }
         return SB_OK;
     }
@@ -652,7 +689,7 @@ template <typename T> struct PlanT : sb_plan {
                 SB_CUDA(cudaGetLastError());
             }
         }
-        if (khat && ob.dev.kind == 0) {
+        if (khat && (ob.dev.kind == 0 || ob.dev.kind == 2)) {
             DevBuf<double2> ks;
             const size_t nk = (size_t)(ob.dev.khat_shared ? 1 : S) * ob.dev.C * ob.dev.Fy * ob.dev.Fxc;
             SB_TRY(ks.alloc(nk));
@@ -678,7 +715,7 @@ template <typename T> struct PlanT : sb_plan {
         if (o < 0 || o >= (int)obs.size()) return set_err(SB_ERR_ARG, "observation index %d out of range", o);
         Obs &ob = *obs[o];
         const DevObs<T> &d = ob.dev;
-        if (d.kind != 0) return set_err(SB_ERR_ARG, "observation %d has no convolution kernel", o);
+        if (d.kind != 0) return set_err(SB_ERR_ARG, "observation %d takes no kernel image (NullRenderer, or a resampling observation whose K^ is uploaded as is)", o);
         if (!ker || Py <= 0 || Px <= 0 || Py > d.Fy || Px > d.Fx) return set_err(SB_ERR_ARG, "bad kernel image %dx%d", Py, Px);
         if (d.Fy < desc.Ny + std::max(-y0, Py - 1 + y0) || d.Fx < desc.Nx + std::max(-x0, Px - 1 + x0) || y0 > 0 || x0 > 0 ||
             Py - 1 + y0 < 0 || Px - 1 + x0 < 0)
@@ -712,6 +749,26 @@ template <typename T> struct PlanT : sb_plan {
             SB_CUDA(cudaGetLastError());
         }
         SB_CUDA(cudaStreamSynchronize(stream));
+        return SB_OK;
+    }
+
+    int upload_resampling(int o, const double *ey, const double *ex, double h2) override {
+        if (o < 0 || o >= (int)obs.size()) return set_err(SB_ERR_ARG, "observation index %d out of range", o);
+        Obs &ob = *obs[o];
+        if (ob.dev.kind != 2 || !ey || !ex) return set_err(SB_ERR_ARG, "observation %d is not a resampling observation", o);
+        SB_CUDA(cudaSetDevice(device));
+        DevBuf<double2> st;
+        SB_TRY(st.alloc(std::max(ob.Ey.n, ob.Ex.n)));
+        SB_CUDA(cudaMemcpyAsync(st.p, ey, ob.Ey.n * sizeof(double2), cudaMemcpyHostToDevice, stream));
+        k_cast_scale_cplx<T><<<grid_for(ob.Ey.n), 256, 0, stream>>>(st.p, ob.Ey.p, (long long)ob.Ey.n, 1.0);
+        SB_CUDA(cudaGetLastError());
+        SB_CUDA(cudaStreamSynchronize(stream));
+        SB_CUDA(cudaMemcpyAsync(st.p, ex, ob.Ex.n * sizeof(double2), cudaMemcpyHostToDevice, stream));
+        k_cast_scale_cplx<T><<<grid_for(ob.Ex.n), 256, 0, stream>>>(st.p, ob.Ex.p, (long long)ob.Ex.n, 1.0);
+        SB_CUDA(cudaGetLastError());
+        SB_CUDA(cudaStreamSynchronize(stream));
+        ob.sdev.h2 = (T)h2;
+        have_graph = false; // h2 travels in the kernel arguments
         return SB_OK;
     }
 
@@ -869,6 +926,26 @@ template <typename T> struct PlanT : sb_plan {
             ob.kx.render<<<rgrid, ob.row_threads, ob.smem_render, stream>>>(sa);
             SB_CUDA(cudaGetLastError());
             mark();
+            if (ob.dev.kind == 2) { // resampling observation: M^ -> K^ conj(M^) -> Ey . -> LR, residual -> . Ex, Ey^T . -> K^ Q^ -> G
+                const SpecObs<T> &sd = ob.sdev;
+                const dim3 tgrid((sd.Fxc + 127) / 128, (sd.H + 7) / 8, S * sd.C), qgrid((sd.Fxc + 127) / 128, sd.Fy, S * sd.C);
+                ob.ky.column_fwd<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
+                k_resample_t1<T><<<tgrid, 128, 0, stream>>>(sa);
+                SB_CUDA(cudaGetLastError());
+                mark(), mark();
+                k_resample_lr<T><<<S * sd.C, 256, (size_t)sd.H * sd.W * sizeof(T), stream>>>(sa);
+                SB_CUDA(cudaGetLastError());
+                mark(), mark();
+                k_resample_q<T><<<qgrid, 128, 0, stream>>>(sa);
+                ob.ky.column_inv<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
+                SB_CUDA(cudaGetLastError());
+                mark();
+                ob.kx.grad<<<rgrid, ob.row_threads, ob.smem_row, stream>>>(sa);
+                SB_CUDA(cudaGetLastError());
+                mark();
+                nk += 7;
+                continue;
+            }
             sa.conj = 0;
             ob.ky.column<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
             SB_CUDA(cudaGetLastError());
@@ -1188,6 +1265,9 @@ int sb_plan_upload_kernels(sb_plan *plan, int obs, const double *kernels, int Py
     PLAN_CALL(upload_kernels(obs, kernels, Py, Px, y0, x0))
 }
 int sb_plan_zero_state(sb_plan *plan) { PLAN_CALL(zero_state()) }
+int sb_plan_upload_resampling(sb_plan *plan, int obs, const double *ey, const double *ex, double h2) {
+    PLAN_CALL(upload_resampling(obs, ey, ex, h2))
+}
 int sb_host_gather_f64(double *dst, const void *const *src, const int64_t *count, const int32_t *is_f32, int64_t n) {
     if (!dst || !src || !count || !is_f32 || n < 0) return set_err(SB_ERR_ARG, "null argument");
     for (int64_t i = 0; i < n; ++i) {
@@ -1289,7 +1369,7 @@ static int run_chain(T *img, int By, int Bx, int n_img, const sb_chain_desc *cha
     SB_CUDA(cudaMemcpy(dch.p, &hc, sizeof hc, cudaMemcpyHostToDevice));
     SB_CUDA(cudaMemcpy(dimg.p, img, (size_t)n * n_img * sizeof(T), cudaMemcpyHostToDevice));
     const size_t smem = (size_t)(((n + 1) & ~1) + 2) * sizeof(T) + 48 * sizeof(double);
-    SB_CUDA(cudaFuncSetAttribute(k_chain_only<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SB_TRY(raise_smem_limit(device, (const void *)k_chain_only<T>, smem));
     k_chain_only<T><<<n_img, 128, smem>>>(dimg.p, By, Bx, dch.p, dmo.p);
     SB_CUDA(cudaGetLastError());
     SB_CUDA(cudaMemcpy(img, dimg.p, (size_t)n * n_img * sizeof(T), cudaMemcpyDeviceToHost));

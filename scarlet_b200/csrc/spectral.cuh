@@ -32,6 +32,12 @@ template <typename T> struct SpecObs {
     T *G;                             // [S][C][Ny][Nx]
     const T *data, *weights;          // [S][C][H][W]
     const typename Cx<T>::type *tw_x, *tw_y; // [R1][R2] tables exp(-2 pi i n2 k1 / L) for L = Fx and L = Fy
+    // resampling observations (ResolutionRenderer, renderer.py:262-547): full-height spectra, shift matrices
+    typename Cx<T>::type *P;          // [S][C][Fy][Xp]  K^ conj(M^)  /  h^2 K^ Q^
+    typename Cx<T>::type *T1;         // [S][C][H][Xp]   Ey P  /  R Ex
+    const typename Cx<T>::type *Ey;   // [H][Fy]   exp(-2 pi i f_ky ys_i), Nyquist real
+    const typename Cx<T>::type *Ex;   // [W][Fxc]  exp(-2 pi i f_kx xs_j), Nyquist real
+    T h2;                             // (pixel-scale ratio)^2
 };
 
 #define SB_SPEC_MAXCB 8 // bands per CTA of the row kernels (SpecArgs::cb <= this)
@@ -404,6 +410,185 @@ template <typename T, int R1, int R2, int NB> __global__ void __launch_bounds__(
     }
 }
 
+// ======================================================================================================
+// Resampling observation (ResolutionRenderer, scarlet/renderer.py:262-547).  With Parseval's theorem the reference's
+// "Fourier-shift the kernel to every low-resolution row, Fourier-shift the model to every low-resolution column,
+// multiply and sum" (its _resconv_op matrix product, renderer.py:478-547) is
+//     LR[c,i,j] = h^2 sum_{ky,kx} Ey[i,ky] Ex[j,kx] K^[c,ky,kx] conj(M^[c,ky,kx])          (K^ carries 1/(Fy Fx))
+// and its adjoint  G = h^2 IDFT2( K^ (Ey^T R Ex) ).  M^ comes from k_spec_render + k_spec_column_fwd, G leaves through
+// k_spec_column_inv + k_spec_grad; in between sit three small dense contractions over ky, kx and (i, j).
+// ======================================================================================================
+// forward column FFT of the Ny non-zero rows; P = K^ conj(M^) for all Fy rows
+template <typename T, int R1, int R2, int NB> __global__ void __launch_bounds__(NB *sbfft::Plan2<R1, R2>::RMAX) k_spec_column_fwd(const SpecArgs<T> a) {
+    typedef typename Cx<T>::type C2;
+    typedef sbfft::Plan2<R1, R2> P;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SpecObs<T> &ob = a.ob;
+    const int img = blockIdx.y, s = img / ob.C;
+    if (a.done[s]) return;
+    const int Ny = a.Ny, tid = threadIdx.x;
+    C2 *fbuf = reinterpret_cast<C2 *>(smem);
+    C2 *tw = fbuf + NB * P::SF;
+    stage_twiddles<T, R1, R2>(tw, ob.tw_y);
+    const int f = tid % NB, j = tid / NB, kx = blockIdx.x * NB + f;
+    const bool col = kx < ob.Fxc;
+    C2 *sm = fbuf + f * P::SF;
+    const C2 *X = ob.X + (size_t)img * Ny * ob.Xp + kx;
+    __syncthreads();
+    C2 a_[R1];
+    if (j < R2) {
+        sbfft::static_for<0, R1>([&](auto i) {
+            const int n = decltype(i)::value * R2 + j;
+            a_[decltype(i)::value] = (col && n < Ny) ? X[(size_t)n * ob.Xp] : C2{T(0), T(0)};
+        });
+        sbfft::fwd_stage_a<R1, R2>(a_, j, tw, sm);
+    }
+    __syncthreads();
+    if (j < R1) {
+        C2 b_[R2];
+        sbfft::fwd_stage_b<R1, R2>(b_, j, sm);
+        if (col) {
+            const C2 *K = ob.khat + (size_t)(ob.khat_shared ? img - s * ob.C : img) * ob.Fy * ob.Xp + kx;
+            C2 *Pout = ob.P + (size_t)img * ob.Fy * ob.Xp + kx;
+            sbfft::static_for<0, R2>([&](auto i) {
+                constexpr int k2 = decltype(i)::value;
+                const size_t ky = j + R1 * k2;
+                Pout[ky * ob.Xp] = sbfft::cmul_conj(K[ky * ob.Xp], b_[k2]); // K^ conj(M^)
+            });
+        }
+    }
+}
+
+// inverse column FFT of full-height spectra P -> rows [0,Ny) of X
+template <typename T, int R1, int R2, int NB> __global__ void __launch_bounds__(NB *sbfft::Plan2<R1, R2>::RMAX) k_spec_column_inv(const SpecArgs<T> a) {
+    typedef typename Cx<T>::type C2;
+    typedef sbfft::Plan2<R1, R2> P;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SpecObs<T> &ob = a.ob;
+    const int img = blockIdx.y, s = img / ob.C;
+    if (a.done[s]) return;
+    const int Ny = a.Ny, tid = threadIdx.x;
+    C2 *fbuf = reinterpret_cast<C2 *>(smem);
+    C2 *tw = fbuf + NB * P::SF;
+    stage_twiddles<T, R1, R2>(tw, ob.tw_y);
+    const int f = tid % NB, j = tid / NB, kx = blockIdx.x * NB + f;
+    const bool col = kx < ob.Fxc;
+    C2 *sm = fbuf + f * P::SF;
+    __syncthreads();
+    if (j < R1) {
+        C2 b_[R2];
+        const C2 *Pin = ob.P + (size_t)img * ob.Fy * ob.Xp + kx;
+        sbfft::static_for<0, R2>([&](auto i) {
+            constexpr int k2 = decltype(i)::value;
+            b_[k2] = col ? Pin[(size_t)(j + R1 * k2) * ob.Xp] : C2{T(0), T(0)};
+        });
+        sbfft::inv_stage_b<R1, R2>(b_, j, tw, sm);
+    }
+    __syncthreads();
+    if (j < R2) {
+        C2 a_[R1];
+        sbfft::inv_stage_a<R1, R2>(a_, j, sm);
+        C2 *X = ob.X + (size_t)img * Ny * ob.Xp + kx;
+        if (col)
+            sbfft::static_for<0, R1>([&](auto i) {
+                const int n = decltype(i)::value * R2 + j;
+                if (n < Ny) X[(size_t)n * ob.Xp] = a_[decltype(i)::value];
+            });
+    }
+}
+
+// T1[img][i][kx] = sum_ky Ey[i][ky] P[img][ky][kx];  grid (ceil(Fxc/128), ceil(H/8), S*C), 128 threads
+template <typename T> __global__ void __launch_bounds__(128) k_resample_t1(const SpecArgs<T> a) {
+    typedef typename Cx<T>::type C2;
+    const SpecObs<T> &ob = a.ob;
+    const int img = blockIdx.z, s = img / ob.C;
+    if (a.done[s]) return;
+    const int kx = blockIdx.x * 128 + threadIdx.x, i0 = blockIdx.y * 8;
+    if (kx >= ob.Fxc) return;
+    C2 acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = C2{T(0), T(0)};
+    const C2 *Pc = ob.P + (size_t)img * ob.Fy * ob.Xp + kx;
+    for (int ky = 0; ky < ob.Fy; ++ky) {
+        const C2 p = Pc[(size_t)ky * ob.Xp];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (i0 + q < ob.H) {
+                const C2 e = ob.Ey[(size_t)(i0 + q) * ob.Fy + ky];
+                acc[q].x += e.x * p.x - e.y * p.y;
+                acc[q].y += e.x * p.y + e.y * p.x;
+            }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        if (i0 + q < ob.H) ob.T1[((size_t)img * ob.H + i0 + q) * ob.Xp + kx] = acc[q];
+}
+
+// one CTA per (scene, band): LR = h^2 sum_kx c_kx Re(Ex T1), residual r = w (LR - d), chi^2 partial, then U = r Ex -> T1
+template <typename T> __global__ void __launch_bounds__(256) k_resample_lr(const SpecArgs<T> a) {
+    typedef typename Cx<T>::type C2;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ double red[40];
+    const SpecObs<T> &ob = a.ob;
+    const int img = blockIdx.x, s = img / ob.C;
+    if (a.done[s]) return;
+    const int H = ob.H, W = ob.W, Fxc = ob.Fxc, tid = threadIdx.x, nt = blockDim.x;
+    T *r = reinterpret_cast<T *>(smem); // [H][W]
+    C2 *T1 = ob.T1 + (size_t)img * H * ob.Xp;
+    const bool even = (ob.Fx & 1) == 0;
+    double part = 0.0;
+    for (int idx = tid; idx < H * W; idx += nt) {
+        const int i = idx / W, j = idx - i * W;
+        const C2 *t = T1 + (size_t)i * ob.Xp, *e = ob.Ex + (size_t)j * Fxc;
+        T acc = T(0);
+        for (int kx = 0; kx < Fxc; ++kx) {
+            const T re = e[kx].x * t[kx].x - e[kx].y * t[kx].y;
+            acc += (kx == 0 || (even && kx == Fxc - 1)) ? re : T(2) * re;
+        }
+        const T m = ob.h2 * acc;
+        const size_t di = (size_t)img * H * W + idx;
+        const T w = ob.weights[di], diff = m - ob.data[di];
+        r[idx] = w * diff;
+        part += (double)w * (double)diff * (double)diff;
+        if (a.rendered_out) a.rendered_out[di] = m;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < H * Fxc; idx += nt) {
+        const int i = idx / Fxc, kx = idx - i * Fxc;
+        C2 acc = C2{T(0), T(0)};
+        for (int j = 0; j < W; ++j) {
+            const C2 e = ob.Ex[(size_t)j * Fxc + kx];
+            const T rv = r[i * W + j];
+            acc.x += rv * e.x, acc.y += rv * e.y;
+        }
+        T1[(size_t)i * ob.Xp + kx] = acc;
+    }
+    part = block_sum(part, red);
+    if (tid == 0) a.partials[img] = part;
+}
+
+// P[img][ky][kx] = h^2 K^[ky][kx] sum_i Ey[i][ky] U[img][i][kx];  grid (ceil(Fxc/128), Fy, S*C)
+template <typename T> __global__ void __launch_bounds__(128) k_resample_q(const SpecArgs<T> a) {
+    typedef typename Cx<T>::type C2;
+    const SpecObs<T> &ob = a.ob;
+    const int img = blockIdx.z, s = img / ob.C;
+    if (a.done[s]) return;
+    const int kx = blockIdx.x * 128 + threadIdx.x, ky = blockIdx.y;
+    if (kx >= ob.Fxc) return;
+    C2 acc = C2{T(0), T(0)};
+    const C2 *U = ob.T1 + (size_t)img * ob.H * ob.Xp + kx;
+    for (int i = 0; i < ob.H; ++i) {
+        const C2 e = ob.Ey[(size_t)i * ob.Fy + ky], u = U[(size_t)i * ob.Xp];
+        acc.x += e.x * u.x - e.y * u.y;
+        acc.y += e.x * u.y + e.y * u.x;
+    }
+    const C2 k = ob.khat[((size_t)(ob.khat_shared ? img - s * ob.C : img) * ob.Fy + ky) * ob.Xp + kx];
+    C2 out;
+    out.x = ob.h2 * (k.x * acc.x - k.y * acc.y);
+    out.y = ob.h2 * (k.x * acc.y + k.y * acc.x);
+    ob.P[((size_t)img * ob.Fy + ky) * ob.Xp + kx] = out;
+}
+
 // ---- dispatch table ----------------------------------------------------------------------------------
 // supported transform lengths L = R1 * R2 (both the row length Fx and the column length Fy must be in this list)
 #define SB_SPEC_LENGTHS(X) \
@@ -412,7 +597,7 @@ template <typename T, int R1, int R2, int NB> __global__ void __launch_bounds__(
 template <typename T> struct SpecKernels {
     typedef void (*fn)(const SpecArgs<T>);
     int R1 = 0, R2 = 0, NBcol = 0;
-    fn render = nullptr, residual = nullptr, grad = nullptr, column = nullptr;
+    fn render = nullptr, residual = nullptr, grad = nullptr, column = nullptr, column_fwd = nullptr, column_inv = nullptr;
     size_t sf = 0; // Plan2::SF
 };
 template <typename T> struct SpecColNB { static const int value = sizeof(T) == 4 ? 16 : 8; };

@@ -296,6 +296,54 @@ def test_fused_spectral_kernels_vs_cufft_path(config, monkeypatch):
 
 
 # --------------------------------------------------------------------------------------------------
+# multi-resolution: ResolutionRenderer + ConvolutionRenderer on one model frame (BASELINE config 4 structure)
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,tol", [(64, 1e-10), (32, 1e-5)])
+def test_multiresolution_forward_and_gradients_vs_oracle(precision, tol):
+    """rendered low- and high-resolution models, loss and all gradients of one evaluation; the oracle restates the
+    reference's ResolutionRenderer literally (tabulated shifted kernels + matrix product) and is pinned to the
+    reference's own render (tests/test_oracle_golden.py), the device evaluates the equivalent Fourier contraction"""
+    from multires_scene import oracle_scene, product_scene
+    g, blend, obs_lr, obs_hr = product_scene(precision)
+    _, o = oracle_scene(np.float64 if precision == 64 else np.float32)
+    plan = blend._get_plan()
+    assert plan.spectral_mode == 1
+    plan.upload_parameters(state=False)
+    model = o.get_model()
+    ev0 = plan.evaluate(obs=0, want=("model", "rendered", "loss", "grads"))
+    ev1 = plan.evaluate(obs=1, want=("rendered",))
+    assert rel_peak(ev0["model"][0], model) < tol
+    # A resampled render is a non-uniform inverse DFT: float32 noise of every frequency bin adds up, ~5e-5 of the peak
+    # here; the reference's own float32 render (float32 operator + np.dot) is 1.1e-5 from its float64 render on the
+    # fixture scene (tests/test_host_api.py).  The float64 twin pins the algorithm at 1e-10.
+    assert rel_peak(ev0["rendered"][0], o.observations[0].render(model)) < (tol if precision == 64 else 1e-4)
+    assert rel_peak(ev1["rendered"][0], o.observations[1].render(model)) < tol
+    loss, grads = o.loss_and_grads()
+    assert_allclose(ev0["loss"][0], loss, rtol=max(tol, 1e-9))
+    gscale = max(np.abs(gr).max() for gr in grads[1::3])
+    for k in range(len(o.sources)):
+        assert rel_peak(ev0["g_sed"][k], grads[3 * k]) < 20 * tol
+        assert np.abs(ev0["g_morph"][k] - grads[3 * k + 1]).max() < 20 * tol * gscale
+
+
+@pytest.mark.parametrize("precision,tol", [(64, 1e-8), (32, 2e-5)])
+def test_multiresolution_fit_matches_oracle(precision, tol):
+    from multires_scene import oracle_scene, product_scene
+    g, blend, obs_lr, obs_hr = product_scene(precision)
+    _, o = oracle_scene(np.float64 if precision == 64 else np.float32)
+    n_iter = 12
+    o.fit(max_iter=n_iter, e_rel=1e-3, min_iter=10 ** 9)
+    n, logL = blend.fit(max_iter=n_iter, e_rel=1e-3, min_iter=10 ** 9)
+    assert n == n_iter
+    assert_allclose(np.array(blend.loss), np.array(o.loss), rtol=max(tol, 1e-9))
+    sed_scale = max(float(np.abs(np.asarray(s.spectrum.x, dtype=np.float64)).max()) for s in o.sources)
+    for src, osrc in zip(blend.sources, o.sources):
+        assert np.abs(np.asarray(src.parameters[0], dtype=np.float64) - osrc.spectrum.x).max() < tol * sed_scale
+        assert rel_peak(src.parameters[1], osrc.image.x) < tol
+    assert rel_peak(blend.get_model(), o.get_model()) < tol
+
+
+# --------------------------------------------------------------------------------------------------
 # the fitting loop
 # --------------------------------------------------------------------------------------------------
 def _compare_fit(scene, n_iter, precision, tol_morph, tol_sed, e_rel=1e-3, fixed=True, tol_model=None):
