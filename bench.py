@@ -162,11 +162,6 @@ def workload_config(args, cfg, scenes_per_unit, iters):
 # ---------------------------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------------------------
-class _DevArray:
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
-
-
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -179,6 +174,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device -- scarlet_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     cfg = synthetic.CONFIGS[args.config]
@@ -209,16 +205,8 @@ def run_b200(args):
         """NCCL gather of the packed fitted parameters (the only collective of the job)."""
         if world == 1:
             return 0
-        dp = plan.device_params()
-        ts = "<f4" if dp["elem_bytes"] == 4 else "<f8"
-        sed = torch.as_tensor(_DevArray(dp["sed"], dp["n_sed"], "<f8"), device="cuda:%d" % local)
-        morph = torch.as_tensor(_DevArray(dp["morph"], dp["n_morph"], ts), device="cuda:%d" % local)
-        out_s = torch.empty(world * sed.numel(), dtype=sed.dtype, device=sed.device)
-        out_m = torch.empty(world * morph.numel(), dtype=morph.dtype, device=morph.device)
-        dist.all_gather_into_tensor(out_s, sed)
-        dist.all_gather_into_tensor(out_m, morph)
-        torch.cuda.synchronize()
-        return out_s.numel() * out_s.element_size() + out_m.numel() * out_m.element_size()
+        from scarlet_b200.distributed import gather_device_parameters
+        return gather_device_parameters(plan, local)[2]
 
     # ---- device-resident timing (value) ----------------------------------------------------------
     def device_step():
