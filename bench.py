@@ -315,8 +315,20 @@ def run_b200(args):
         iter_ms = sum(stages.values())
         alg_iter = synthetic.algorithmic_bytes(cfg, fshape, eb)
         whole = alg_iter * S / (ms_total / args.steps / iters / 1e3) / 1e9
+        # DRAM bytes of the same kernel from the committed `ncu --set full` capture of this workload (per launch)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_%s_s%d.json" % (args.config, S))
+        kname = {"source_update": "k_update_fast", "spec_render": "k_spec_render", "spec_column": "k_spec_column",
+                 "spec_column_adj": "k_spec_column", "spec_residual": "k_spec_residual", "spec_grad": "k_spec_grad"}.get(dom)
+        if args.precision == 32 and fused and kname and os.path.exists(tpath):
+            try:
+                traffic = float(json.load(open(tpath))["kernels"][kname]["dram_bytes_per_launch"])
+                traffic_src = "profiles/" + os.path.basename(tpath)
+            except Exception:
+                traffic = None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": stage_bytes[dom] * S,
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": stage_bytes[dom] * S,
                     "kernel_ms": dom_ms, "kernel_share_of_iteration": dom_ms / iter_ms,
                     "iteration": {"algorithmic_bytes_per_scene": alg_iter, "achieved": whole, "frac": whole / peak,
                                   "note": "SURVEY.md 8(d) whole-iteration accounting incl. cuFFT stages"},

@@ -668,32 +668,37 @@ template <typename T> __global__ void __launch_bounds__(128) k_update(const Upda
 // Groups synchronise with named barriers (bar.sync id, 64), so the 59-level sweep of one source never stalls the
 // other seven.  Arithmetic is identical to update_extended (same formulas, same evaluation order).
 // ======================================================================================================
-#define SB_GROUP 64
+// GT = threads per group (64 or 128), a template parameter of everything below
 
-__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(SB_GROUP) : "memory"); }
+template <int GT> __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(GT) : "memory"); }
 
 struct GroupRed {
-    double *slot; // [2 parities][2 values][2 warps]
+    double *slot; // [2 parities][2 values][GT/32 warps]
     int g, par;
 };
-__device__ __forceinline__ void group_sum2(GroupRed &r, double &a, double &b) {
+template <int GT> __device__ __forceinline__ void group_sum2(GroupRed &r, double &a, double &b) {
+    constexpr int NW = GT / 32;
     a = warp_sum(a);
     b = warp_sum(b);
-    const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 1;
-    double *s = r.slot + r.par * 4;
-    if (lane == 0) s[w] = a, s[2 + w] = b;
-    group_bar(r.g);
-    a = s[0] + s[1];
-    b = s[2] + s[3];
+    const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & (NW - 1);
+    double *s = r.slot + r.par * 2 * NW;
+    if (lane == 0) s[w] = a, s[NW + w] = b;
+    group_bar<GT>(r.g);
+    a = s[0], b = s[NW];
+#pragma unroll
+    for (int i = 1; i < NW; ++i) a += s[i], b += s[NW + i];
     r.par ^= 1; // the next reduction uses the other slot set; this one is rewritten only after another barrier
 }
-__device__ __forceinline__ double group_max(GroupRed &r, double a) {
+template <int GT> __device__ __forceinline__ double group_max(GroupRed &r, double a) {
+    constexpr int NW = GT / 32;
     a = warp_max(a);
-    const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 1;
-    double *s = r.slot + r.par * 4;
+    const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & (NW - 1);
+    double *s = r.slot + r.par * 2 * NW;
     if (lane == 0) s[w] = a;
-    group_bar(r.g);
-    a = fmax(s[0], s[1]);
+    group_bar<GT>(r.g);
+    a = s[0];
+#pragma unroll
+    for (int i = 1; i < NW; ++i) a = fmax(a, s[i]);
     r.par ^= 1;
     return a;
 }
@@ -706,44 +711,45 @@ template <typename T> struct FastTable { // shared-memory image of a DevMono wit
     int n_levels;
 };
 
-template <typename T> __device__ __forceinline__ void group_sweep(T *img, const FastTable<T> &t, T min_gradient, int g) {
+// Empty neighbour slots of the shared-memory table point at a spare cell behind the image that always holds 0 and carry
+// weight 0, so the four products need no predicates: (+0) is added at the END of the reference's summation order
+// (empty slots are trailing), which leaves the sum bit-identical.
+template <typename T, int GT> __device__ __forceinline__ void group_sweep(T *img, const FastTable<T> &t, T min_gradient, int g) {
     const T keep = T(1) - min_gradient;
-    const int lt = threadIdx.x & (SB_GROUP - 1);
+    const int lt = threadIdx.x & (GT - 1);
     int beg = t.ls[0];
     for (int L = 0; L < t.n_levels; ++L) {
         const int end = t.ls[L + 1];
-        for (int j = beg + lt; j < end; j += SB_GROUP) {
+        for (int j = beg + lt; j < end; j += GT) {
             const uint2 nb = t.nbr[j];
             const W4<T> w = t.w[j];
             const int p = t.pix[j];
-            const unsigned n0 = nb.x & 0xffffu, n1 = nb.x >> 16, n2 = nb.y & 0xffffu, n3 = nb.y >> 16;
-            T ref = T(0);
-            if (n0 != 0xffffu) ref = add_rn(ref, mul_rn(img[n0], w.a));
-            if (n1 != 0xffffu) ref = add_rn(ref, mul_rn(img[n1], w.b));
-            if (n2 != 0xffffu) ref = add_rn(ref, mul_rn(img[n2], w.c));
-            if (n3 != 0xffffu) ref = add_rn(ref, mul_rn(img[n3], w.d));
+            T ref = mul_rn(img[nb.x & 0xffffu], w.a);
+            ref = add_rn(ref, mul_rn(img[nb.x >> 16], w.b));
+            ref = add_rn(ref, mul_rn(img[nb.y & 0xffffu], w.c));
+            ref = add_rn(ref, mul_rn(img[nb.y >> 16], w.d));
             const T cap = mul_rn(ref, keep);
             if (cap < img[p]) img[p] = cap;
         }
         beg = end;
-        group_bar(g);
+        group_bar<GT>(g);
     }
 }
 
-template <typename T>
+template <typename T, int GT>
 __device__ void group_chain(T *a, int By, int Bx, const DevChain &ch, const FastTable<T> &tab, GroupRed &red) {
-    const int n = By * Bx, lt = threadIdx.x & (SB_GROUP - 1), g = red.g;
+    const int n = By * Bx, lt = threadIdx.x & (GT - 1), g = red.g;
     for (int r = 0; r < ch.repeat; ++r) {
         for (int o = 0; o < ch.n_ops; ++o) {
             const sb_op op = ch.ops[o];
             switch (op.code) {
             case SB_OP_MONOTONIC:
-                group_sweep<T>(a, tab, (T)op.farg, g);
+                group_sweep<T, GT>(a, tab, (T)op.farg, g);
                 break;
             case SB_OP_SYMMETRY: {
                 const T hs = (T)(0.5 * op.farg), om = (T)(1.0 - op.farg);
                 const int Hy = By + ((By & 1) == 0), Wx = Bx + ((Bx & 1) == 0);
-                for (int p = lt; p < n; p += SB_GROUP) {
+                for (int p = lt; p < n; p += GT) {
                     const int y = p / Bx, x = p - y * Bx;
                     const int yr = Hy - 1 - y, xr = Wx - 1 - x;
                     if (yr >= By || xr >= Bx) {
@@ -761,13 +767,13 @@ __device__ void group_chain(T *a, int By, int Bx, const DevChain &ch, const Fast
                         }
                     }
                 }
-                group_bar(g);
+                group_bar<GT>(g);
                 break;
             }
             case SB_OP_POSITIVITY: {
                 const T zero = (T)op.farg;
-                for (int p = lt; p < n; p += SB_GROUP) a[p] = a[p] > zero ? a[p] : zero;
-                group_bar(g);
+                for (int p = lt; p < n; p += GT) a[p] = a[p] > zero ? a[p] : zero;
+                group_bar<GT>(g);
                 break;
             }
             case SB_OP_CENTER_ON: {
@@ -776,23 +782,23 @@ __device__ void group_chain(T *a, int By, int Bx, const DevChain &ch, const Fast
                     const T tiny = (T)op.farg;
                     a[c] = a[c] > tiny ? a[c] : tiny;
                 }
-                group_bar(g);
+                group_bar<GT>(g);
                 break;
             }
             case SB_OP_NORMALIZE: {
                 double acc, dummy = 0.0;
                 if (op.iarg == 1) {
                     acc = -INFINITY;
-                    for (int p = lt; p < n; p += SB_GROUP) acc = fmax(acc, (double)a[p]);
-                    acc = group_max(red, acc);
+                    for (int p = lt; p < n; p += GT) acc = fmax(acc, (double)a[p]);
+                    acc = group_max<GT>(red, acc);
                 } else {
                     acc = 0.0;
-                    for (int p = lt; p < n; p += SB_GROUP) acc += (double)a[p];
-                    group_sum2(red, acc, dummy);
+                    for (int p = lt; p < n; p += GT) acc += (double)a[p];
+                    group_sum2<GT>(red, acc, dummy);
                 }
                 const T den = (T)acc;
-                for (int p = lt; p < n; p += SB_GROUP) a[p] = a[p] / den;
-                group_bar(g);
+                for (int p = lt; p < n; p += GT) a[p] = a[p] / den;
+                group_bar<GT>(g);
                 break;
             }
             default:
@@ -805,17 +811,20 @@ __device__ void group_chain(T *a, int By, int Bx, const DevChain &ch, const Fast
 #define SB_FAST_MAXC 8
 
 // group-wide maximum in the image type (exact: a maximum needs no extra precision)
-template <typename T> __device__ __forceinline__ T group_max_t(GroupRed &r, T a) {
+template <typename T, int GT> __device__ __forceinline__ T group_max_t(GroupRed &r, T a) {
+    constexpr int NW = GT / 32;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const T b = __shfl_down_sync(0xffffffffu, a, o);
         a = b > a ? b : a;
     }
-    const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 1;
-    T *s = reinterpret_cast<T *>(r.slot + r.par * 4);
+    const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & (NW - 1);
+    T *s = reinterpret_cast<T *>(r.slot + r.par * 2 * NW);
     if (lane == 0) s[w] = a;
-    group_bar(r.g);
-    a = s[0] > s[1] ? s[0] : s[1];
+    group_bar<GT>(r.g);
+    a = s[0];
+#pragma unroll
+    for (int i = 1; i < NW; ++i) a = s[i] > a ? s[i] : a;
     r.par ^= 1;
     return a;
 }
@@ -843,16 +852,16 @@ __device__ inline FusedChain fused_chain_of(const DevChain &ch, int By, int Bx) 
     return f;
 }
 
-template <typename T> __global__ void __launch_bounds__(1024, 1) k_update_fast(const UpdateArgs<T> a) {
+template <typename T, int GT> __global__ void __launch_bounds__(1024, 1) k_update_fast(const UpdateArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int G = a.fast_G, g = threadIdx.x / SB_GROUP, lt = threadIdx.x & (SB_GROUP - 1);
+    const int G = a.fast_G, g = threadIdx.x / GT, lt = threadIdx.x & (GT - 1);
     const int *mine = a.fast_groups + (size_t)blockIdx.x * G;
     // ---- shared memory carve-up: table (W4 | uint2 | int ls | u16 pix), reduction slots, G images
     const int cap = a.fast_table_cap;
     W4<T> *s_w = reinterpret_cast<W4<T> *>(smem);
     uint2 *s_nbr = reinterpret_cast<uint2 *>(s_w + cap);
     double *s_red = reinterpret_cast<double *>(s_nbr + cap);
-    double *s_gsum = s_red + 8 * G;            // [G][SB_MAXC]
+    double *s_gsum = s_red + 4 * (GT / 32) * G; // [G][SB_MAXC]
     int *s_ls = reinterpret_cast<int *>(s_gsum + SB_MAXC * G); // [512]
     unsigned short *s_pix = reinterpret_cast<unsigned short *>(s_ls + 512);
     T *s_img = reinterpret_cast<T *>(s_pix + ((cap + 7) & ~7));
@@ -872,8 +881,14 @@ template <typename T> __global__ void __launch_bounds__(1024, 1) k_update_fast(c
             const DevMono &mo = a.monos[ch.ops[o].iarg];
             const uint2 *gn = reinterpret_cast<const uint2 *>(mo.code);
             const W4<T> *gw = reinterpret_cast<const W4<T> *>(mo.w);
+            const unsigned spare = (unsigned)mo.n_pix; // index of the always-zero cell behind each image
             for (int j = threadIdx.x; j < mo.n_tasks; j += blockDim.x) {
-                s_nbr[j] = gn[j];
+                uint2 v = gn[j];
+                if ((v.x & 0xffffu) == 0xffffu) v.x = (v.x & 0xffff0000u) | spare;
+                if ((v.x >> 16) == 0xffffu) v.x = (v.x & 0xffffu) | (spare << 16);
+                if ((v.y & 0xffffu) == 0xffffu) v.y = (v.y & 0xffff0000u) | spare;
+                if ((v.y >> 16) == 0xffffu) v.y = (v.y & 0xffffu) | (spare << 16);
+                s_nbr[j] = v;
                 s_w[j] = gw[j];
                 s_pix[j] = (unsigned short)mo.pix[j];
             }
@@ -892,26 +907,27 @@ template <typename T> __global__ void __launch_bounds__(1024, 1) k_update_fast(c
     const unsigned magic = 0xffffffffu / (unsigned)Bx + 1u; // p / Bx == umulhi(p, magic) for p, Bx < 65536
     T *zn = s_img + (size_t)g * a.fast_npix;
     GroupRed red;
-    red.slot = s_red + 8 * g, red.g = g, red.par = 0;
+    red.slot = s_red + 4 * (GT / 32) * g, red.g = g, red.par = 0;
     double *gsum = s_gsum + SB_MAXC * g; // first holds the spectrum (read-only), then the spectrum gradient
 
     T gs[SB_FAST_MAXC]; // per-thread partial sums in T (<= 27 terms each), reduced in double
 #pragma unroll
     for (int c = 0; c < SB_FAST_MAXC; ++c) gs[c] = T(0);
     if (lt < C) gsum[lt] = a.sed[(size_t)k * C + lt];
-    group_bar(g);
+    if (lt == 0) zn[n] = T(0); // the spare cell of group_sweep
+    group_bar<GT>(g);
     T *mp = a.morph + d.morph_off, *mm = a.morph_m + d.morph_off, *mv = a.morph_v + d.morph_off,
       *mvh = a.morph_vhat + d.morph_off, *xs = a.scratch_x + d.morph_off, *ps = a.scratch_ps + d.morph_off;
     const double alpha = d.morph_step;
     const bool upd = !d.morph_fixed;
     double pmax = 0.0;
     constexpr int PB = 2; // pixels per trip: all loads first (see pass B below)
-    for (int p0 = lt; p0 < n; p0 += PB * SB_GROUP) {
+    for (int p0 = lt; p0 < n; p0 += PB * GT) {
         T mval[PB], m0[PB], v0[PB], vh0[PB];
         double gm[PB];
 #pragma unroll
         for (int i = 0; i < PB; ++i) {
-            const int p = p0 + i * SB_GROUP;
+            const int p = p0 + i * GT;
             mval[i] = m0[i] = v0[i] = vh0[i] = T(0);
             gm[i] = 0.0;
             if (p < n) {
@@ -933,7 +949,7 @@ template <typename T> __global__ void __launch_bounds__(1024, 1) k_update_fast(c
         if (upd) {
 #pragma unroll
             for (int i = 0; i < PB; ++i) {
-                const int p = p0 + i * SB_GROUP;
+                const int p = p0 + i * GT;
                 if (p < n) {
                     double m_ = (double)m0[i], v_ = (double)v0[i], vh_ = (double)vh0[i];
                     const double psi = amsgrad(gm[i], m_, v_, vh_, it, a.fs);
@@ -949,12 +965,12 @@ template <typename T> __global__ void __launch_bounds__(1024, 1) k_update_fast(c
         }
     }
     // spectrum gradient (pairs of bands per reduction); every thread is past its reads of the spectrum in gsum
-    group_bar(g);
+    group_bar<GT>(g);
 #pragma unroll
     for (int c = 0; c < SB_FAST_MAXC; c += 2) {
         if (c < C) {
             double u = (double)gs[c], v = (double)gs[c + 1];
-            group_sum2(red, u, v);
+            group_sum2<GT>(red, u, v);
             if (lt == 0) {
                 gsum[c] = u;
                 if (c + 1 < C) gsum[c + 1] = v;
@@ -962,7 +978,7 @@ template <typename T> __global__ void __launch_bounds__(1024, 1) k_update_fast(c
         }
     }
     if (upd) {
-        const double psimax = group_max(red, pmax);
+        const double psimax = group_max<GT>(red, pmax);
         bool bad = false;
         if (d.chain >= 0) {
             const double gamma = alpha / psimax;
@@ -973,10 +989,10 @@ template <typename T> __global__ void __launch_bounds__(1024, 1) k_update_fast(c
                 const T hs = (T)(0.5 * fc.sym), om = (T)(1.0 - fc.sym), zero = (T)fc.zero, tiny = (T)fc.tiny;
                 const int half = (n - 1) >> 1; // centre pixel index (odd x odd box): its 180-degree partner is itself
                 for (int sub = 0; sub < a.fs.prox_max_iter; ++sub) {
-                    group_sweep<T>(zn, tab, (T)fc.mono_grad, g);
+                    group_sweep<T, GT>(zn, tab, (T)fc.mono_grad, g);
                     // pass A: symmetry (pairs p, n-1-p), positivity, centre floor, running maximum
                     T mx = -INFINITY;
-                    for (int p = lt; p <= half; p += SB_GROUP) {
+                    for (int p = lt; p <= half; p += GT) {
                         const int q = n - 1 - p;
                         T u = zn[p], v = zn[q];
                         if (fc.has_sym) {
@@ -993,18 +1009,18 @@ template <typename T> __global__ void __launch_bounds__(1024, 1) k_update_fast(c
                         mx = u > mx ? u : mx;
                         mx = v > mx ? v : mx;
                     }
-                    const T den = group_max_t<T>(red, mx); // barrier inside: pass A is complete for the whole group
+                    const T den = group_max_t<T, GT>(red, mx); // barrier inside: pass A is complete for the whole group
                     // pass B: normalise, convergence sums, store z, next proximal argument
                     double dd = 0.0, nn = 0.0;
                     bad = false;
                     const bool last = sub + 1 == a.fs.prox_max_iter;
                     // (loads of a batch are issued before its stores: the compiler cannot reorder them itself because
                     // mp, ps and xs may alias as far as it knows, and one L2 round trip per pixel would dominate)
-                    for (int p0 = lt; p0 < n; p0 += 4 * SB_GROUP) {
+                    for (int p0 = lt; p0 < n; p0 += 4 * GT) {
                         T zr[4], zo_[4], ps_[4], xs_[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const int p = p0 + i * SB_GROUP;
+                            const int p = p0 + i * GT;
                             zr[i] = zo_[i] = ps_[i] = xs_[i] = T(0);
                             if (p < n) {
                                 zr[i] = zn[p];
@@ -1014,7 +1030,7 @@ template <typename T> __global__ void __launch_bounds__(1024, 1) k_update_fast(c
                         }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const int p = p0 + i * SB_GROUP;
+                            const int p = p0 + i * GT;
                             if (p < n) {
                                 const T r = zr[i] / den;
                                 const double zo = (double)zo_[i], zv = (double)r;
@@ -1026,38 +1042,38 @@ template <typename T> __global__ void __launch_bounds__(1024, 1) k_update_fast(c
                             }
                         }
                     }
-                    group_sum2(red, dd, nn); // barrier inside: zn is complete before the next sweep
+                    group_sum2<GT>(red, dd, nn); // barrier inside: zn is complete before the next sweep
                     if (dd <= e2 * nn) break;
                 }
             } else {
                 for (int sub = 0; sub < a.fs.prox_max_iter; ++sub) {
                     if (sub > 0) {
-                        for (int p = lt; p < n; p += SB_GROUP) {
+                        for (int p = lt; p < n; p += GT) {
                             const double zz = (double)mp[p];
                             zn[p] = (T)(zz - fac * (double)ps[p] * (zz - (double)xs[p]));
                         }
                     }
-                    group_bar(g);
-                    group_chain<T>(zn, d.By, d.Bx, ch, tab, red);
+                    group_bar<GT>(g);
+                    group_chain<T, GT>(zn, d.By, d.Bx, ch, tab, red);
                     double dd = 0.0, nn = 0.0;
                     bad = false;
-                    for (int p = lt; p < n; p += SB_GROUP) {
+                    for (int p = lt; p < n; p += GT) {
                         const double zo = (double)mp[p], zv = (double)zn[p];
                         dd += (zv - zo) * (zv - zo);
                         nn += zo * zo;
                         mp[p] = zn[p];
                         bad |= !isfinite(zv);
                     }
-                    group_sum2(red, dd, nn);
+                    group_sum2<GT>(red, dd, nn);
                     if (dd <= e2 * nn) break;
                 }
             }
         } else {
-            for (int p = lt; p < n; p += SB_GROUP) bad |= !isfinite((double)mp[p]);
+            for (int p = lt; p < n; p += GT) bad |= !isfinite((double)mp[p]);
         }
         if (bad) atomicExch(a.status + s, SB_ERR_NONFINITE);
     }
-    group_bar(g); // gsum visible to the updating thread
+    group_bar<GT>(g); // gsum visible to the updating thread
     if (lt == 0 && !d.sed_fixed) sed_update<T>(a, d, k, gsum, it);
 }
 

@@ -241,7 +241,7 @@ template <typename T> struct PlanT : sb_plan {
     DevBuf<double> d_gsed, d_gcenter, d_gmorph, d_stage;
     DevBuf<T> d_morph, d_morph_m, d_morph_v, d_morph_vhat, d_pmorph, d_model, d_rendered, d_scratch_x, d_scratch_ps;
     DevBuf<int> d_work, d_fast_groups;
-    int n_generic = 0, n_fast_cta = 0, fast_G = 0, fast_npix = 0, fast_table_cap = 0;
+    int n_generic = 0, n_fast_cta = 0, fast_G = 0, fast_GT = 64, fast_npix = 0, fast_table_cap = 0;
     size_t fast_smem = 0;
     std::vector<HostMono> hmonos;
     DevBuf<float> d_stage_f;
@@ -590,31 +590,37 @@ template <typename T> struct PlanT : sb_plan {
             }
             if (fast) {
                 // must fit next to one image even with a single group per CTA
-                const size_t need = fast_smem_bytes(1, (d.By * d.Bx + 3) & ~3, (tasks + 7) & ~7);
+                const size_t need = fast_smem_bytes(1, (d.By * d.Bx + 4) & ~3, (tasks + 7) & ~7);
                 if (need > 200 * 1024) fast = false;
             }
             if (fast) {
                 by_chain[d.chain].push_back(k);
-                npix = std::max(npix, (d.By * d.Bx + 3) & ~3);
+                npix = std::max(npix, (d.By * d.Bx + 4) & ~3); // + the spare zero cell of group_sweep
                 cap = std::max(cap, (tasks + 7) & ~7);
             } else
                 generic.push_back(k);
         }
         fast_npix = npix, fast_table_cap = std::max(cap, 8);
-        // One CTA per SM, every SM the same number of 64-thread groups (= sources): the kernel is bound by the
-        // latency of the per-source proximal loop, so balance matters more than occupancy.
+        // Every SM gets the same number of groups (= sources): the kernel is bound by the latency of the per-source
+        // proximal loop, so balance matters more than occupancy.  One CTA per SM (64 registers x 1024 threads fill the
+        // register file): up to 16 groups of GT = 64 threads (default), or 8 groups of 128 (SB_UPDATE_GROUP=128).
         fast_G = 0;
         {
+            const char *gt = getenv("SB_UPDATE_GROUP");
+            fast_GT = (gt && atoi(gt) == 128) ? 128 : 64;
             size_t n_fast = 0;
             for (auto &kv : by_chain) n_fast += kv.second.size();
             int sms = 148;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+            const int ctas_per_sm = 1, gmax = 1024 / fast_GT;
+            const size_t smem_cap = (size_t)220 * 1024;
             if (n_fast) {
-                const int waves = (int)((n_fast + (size_t)sms * 16 - 1) / ((size_t)sms * 16));
-                int G = (int)((n_fast + (size_t)sms * waves - 1) / ((size_t)sms * waves));
-                G = std::max(1, std::min(16, G));
-                while (G > 1 && fast_smem_bytes(G, fast_npix, fast_table_cap) > 220 * 1024) --G;
-                if (fast_smem_bytes(G, fast_npix, fast_table_cap) <= 220 * 1024) fast_G = G;
+                const size_t slots = (size_t)sms * ctas_per_sm;
+                const int waves = (int)((n_fast + slots * gmax - 1) / (slots * gmax));
+                int G = (int)((n_fast + slots * waves - 1) / (slots * waves));
+                G = std::max(1, std::min(gmax, G));
+                while (G > 1 && fast_smem_bytes(G, fast_npix, fast_table_cap) > smem_cap) --G;
+                if (fast_smem_bytes(G, fast_npix, fast_table_cap) <= (size_t)220 * 1024) fast_G = G;
             }
         }
         std::vector<int> groups;
@@ -638,12 +644,12 @@ template <typename T> struct PlanT : sb_plan {
         if (n_fast_cta) {
             SB_TRY(d_scratch_x.alloc(std::max<long long>(n_morph, 1)));
             SB_TRY(d_scratch_ps.alloc(std::max<long long>(n_morph, 1)));
-            SB_TRY(raise_smem((const void *)k_update_fast<T>, fast_smem));
+            SB_TRY(raise_smem(fast_GT == 128 ? (const void *)k_update_fast<T, 128> : (const void *)k_update_fast<T, 64>, fast_smem));
         }
         return SB_OK;
     }
     static size_t fast_smem_bytes(int G, int npix, int cap) {
-        return (size_t)cap * (sizeof(W4<T>) + sizeof(uint2)) + (size_t)G * (8 + SB_MAXC) * sizeof(double) + 512 * sizeof(int) +
+        return (size_t)cap * (sizeof(W4<T>) + sizeof(uint2)) + (size_t)G * (16 + SB_MAXC) * sizeof(double) + 512 * sizeof(int) +
                (size_t)((cap + 7) & ~7) * sizeof(unsigned short) + (size_t)G * npix * sizeof(T);
     }
 
@@ -1015,7 +1021,10 @@ template <typename T> struct PlanT : sb_plan {
                 ++nk;
             } else {
                 if (n_fast_cta) {
-                    k_update_fast<T><<<n_fast_cta, SB_GROUP * fast_G, fast_smem, stream>>>(ua);
+                    if (fast_GT == 128)
+                        k_update_fast<T, 128><<<n_fast_cta, 128 * fast_G, fast_smem, stream>>>(ua);
+                    else
+                        k_update_fast<T, 64><<<n_fast_cta, 64 * fast_G, fast_smem, stream>>>(ua);
                     SB_CUDA(cudaGetLastError());
                     ++nk;
                 }

@@ -54,5 +54,34 @@ def full(path):
             print("%-80s %-14s %s" % (w, rows[1][i], [r[i] for r in rows[2:]]))
 
 
+def traffic(path):
+    """JSON of DRAM bytes (read + write) and duration per launch, per kernel, for bench.py's roofline.traffic."""
+    import json
+    import re
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    h, units = rows[0], rows[1]
+
+    def col(name, r):
+        i = h.index(name)
+        v = float(r[i].replace(",", ""))
+        u = units[i].lower()
+        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1, "second": 1,
+                    "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9}.get(u, 1)
+
+    agg = {}
+    for r in rows[2:]:
+        name = re.sub(r"^void |\(.*$", "", r[h.index("Kernel Name")])
+        name = re.sub(r"<.*", "", name).replace("sb::", "")
+        a = agg.setdefault(name, {"launches": 0, "dram_bytes": 0.0, "seconds": 0.0})
+        a["launches"] += 1
+        a["dram_bytes"] += col("dram__bytes_read.sum", r) + col("dram__bytes_write.sum", r)
+        a["seconds"] += col("gpu__time_duration.sum", r)
+    for a in agg.values():
+        a["dram_bytes_per_launch"] = a.pop("dram_bytes") / a["launches"]
+        a["us_per_launch_under_ncu"] = 1e6 * a.pop("seconds") / a["launches"]
+    print(json.dumps({"source": path, "kernels": agg}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
