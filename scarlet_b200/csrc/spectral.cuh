@@ -274,6 +274,19 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
     C2 *fbuf = reinterpret_cast<C2 *>(smem);
     C2 *tw = fbuf + NB * P::SF;
     stage_twiddles<T, R1, R2>(tw, ob.tw_x);
+    // data and weights are needed only after the inverse transform: pull their lines into L2 now (no registers held)
+    {
+        const int lines = (Nx * (int)sizeof(T) + 127) / 128; // 128-byte lines per row
+        for (int idx = tid; idx < Cb * rows * lines; idx += blockDim.x) {
+            const int l = idx % lines, rc = idx / lines, r = rc % rows, c = c0 + rc / rows;
+            const int y = y0 + r, dy = y - ob.oy, dx = l * (128 / (int)sizeof(T)) - ob.ox;
+            if (y < Ny && (unsigned)dy < (unsigned)ob.H && (unsigned)dx < (unsigned)ob.W) {
+                const size_t off = ((size_t)(s * Co + c) * ob.H + dy) * ob.W + dx;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ob.data + off));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ob.weights + off));
+            }
+        }
+    }
     load_and_merge<T, R1, R2>(a, fbuf, NB, s, y0, c0, Cb);
     __syncthreads();
     C2 a_[R1];
@@ -355,7 +368,7 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
 // ======================================================================================================
 // column pass: forward column FFT, x K^ (or conj K^), inverse column FFT; NB adjacent columns per CTA
 // ======================================================================================================
-template <typename T, int R1, int R2, int NB> __global__ void __launch_bounds__(NB *sbfft::Plan2<R1, R2>::RMAX) k_spec_column(const SpecArgs<T> a) {
+template <typename T, int R1, int R2, int NB> __global__ void __launch_bounds__(NB *sbfft::Plan2<R1, R2>::RMAX, (sizeof(T) == 4 && sbfft::Plan2<R1, R2>::RMAX <= 20) ? 4 : 1) k_spec_column(const SpecArgs<T> a) {
     typedef typename Cx<T>::type C2;
     typedef sbfft::Plan2<R1, R2> P;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -370,6 +383,7 @@ template <typename T, int R1, int R2, int NB> __global__ void __launch_bounds__(
     const bool col = kx < ob.Fxc;
     C2 *sm = fbuf + f * P::SF;
     C2 *X = ob.X + (size_t)img * Ny * ob.Xp + kx;
+    const C2 *K = ob.khat + (size_t)(ob.khat_shared ? img - s * ob.C : img) * ob.Fy * ob.Xp + kx;
     __syncthreads();
     C2 a_[R1];
     if (j < R2) {
@@ -383,7 +397,6 @@ template <typename T, int R1, int R2, int NB> __global__ void __launch_bounds__(
     C2 b_[R2];
     if (j < R1) {
         sbfft::fwd_stage_b<R1, R2>(b_, j, sm);
-        const C2 *K = ob.khat + (size_t)(ob.khat_shared ? img - s * ob.C : img) * ob.Fy * ob.Xp + kx;
         if (col) {
             if (a.conj)
                 sbfft::static_for<0, R2>([&](auto i) {
