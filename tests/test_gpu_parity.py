@@ -401,7 +401,7 @@ def test_fit_cfg2_float32_matches_oracle():
     """BASELINE config 2 shape (5x128x128, 10 ExtendedSource, Gaussian PSF): 30 iterations at the 1e-5 bar; after 50
     iterations model pixels and SEDs still meet 1e-5, while the worst pixel of the worst individual morphology image
     sits at 0.9-1.9e-5 depending on the FFT grid / rounding order (float32 noise amplified by the non-smooth
-    projections; tools/parity_probe.py), hence 3e-5 for that one quantity."""
+    projections; tests/parity_probe.py), hence 3e-5 for that one quantity."""
     from scarlet_b200 import synthetic
     _compare_fit(synthetic.make_scene("cfg2", 0), 30, 32, 1e-5, 1e-5)
     _compare_fit(synthetic.make_scene("cfg2", 0), 50, 32, 3e-5, 1e-5, tol_model=1e-5)
