@@ -20,3 +20,31 @@ def build_oracle(scene, frame_dtype=np.float32, sed_dtype=np.float32):
         else:
             sources.append(so.PointSourceOracle(s["sed"], s["center"], model_psf, min_step=min_step, sed_dtype=sed_dtype))
     return so.SceneOracle((C, N, N), model_psf, sources, [obs], frame_dtype=frame_dtype)
+
+
+def build_multires_oracle(scene, setup, frame_dtype=np.float32, sed_dtype=np.float32):
+    """cfg4 (two observations on different pixel grids) from a ``synthetic.make_multires_scene`` dict.  ``setup`` carries
+    the host set-up products of the low-resolution renderer (``frame_shape``, ``model_psf`` image, ``lr_kernel`` = padded
+    difference kernel, ``lr_shifts``, ``lr_h``, ``hr_origin``), which are pinned to the reference's own set-up by
+    tests/test_host_api.py::test_multiresolution_setup_vs_reference_fixture."""
+    frame_shape = tuple(int(v) for v in setup["frame_shape"])
+    model_psf = so.ImagePSFOracle(setup["model_psf"])
+    lr = so.ResolutionObservationOracle(scene["lr_images"], scene["lr_weights"], setup["lr_kernel"], setup["lr_shifts"], setup["lr_h"],
+                                        frame_dtype=frame_dtype, channel_offset=0)
+    lr.match(frame_shape, None)
+    hr = so.ObservationOracle(scene["hr_images"], scene["hr_weights"], so.ImagePSFOracle(scene["hr_psfs"]), frame_dtype=frame_dtype,
+                              channel_offset=5, origin=tuple(int(v) for v in setup["hr_origin"]))
+    hr.match(frame_shape, model_psf)
+    min_step = np.concatenate([lr.channel_noise_rms(), hr.channel_noise_rms()])
+    sources = [so.ExtendedSourceOracle(s["sed"], s["morph"], s["origin"], min_step=min_step, monotonic="angle", symmetric=True,
+                                       sed_dtype=sed_dtype) for s in scene["sources"]]
+    return so.SceneOracle(frame_shape, model_psf, sources, [lr, hr], frame_dtype=frame_dtype)
+
+
+def multires_setup(blend):
+    """The set-up products ``build_multires_oracle`` needs, read off a product Blend (host objects only)."""
+    obs_lr, obs_hr = blend.observations
+    r = obs_lr.renderer
+    return dict(frame_shape=blend.frame.shape, model_psf=np.asarray(blend.frame.psf.get_model(), dtype=np.float64),
+                lr_kernel=np.asarray(r.diff_kernel.image, dtype=np.float64), lr_shifts=np.asarray(r.shifts), lr_h=float(r.h),
+                hr_origin=obs_hr.renderer.origin)

@@ -122,3 +122,100 @@ def algorithmic_bytes(scene_or_cfg, fft_shape, elem=4):
     Fc = Fy * (Fx // 2 + 1)
     src = cfg["n_ext"] * cfg["B"] ** 2 * (14 + C) + cfg["n_pt"] * 81 * (14 + C)
     return elem * (6 * C * Fy * Fx + 3 * C * N * N + src) + 2 * elem * (6 * C * Fc)
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE config 4: two observations on different pixel grids (5 bands at 0.2"/px + 3 bands at 0.03"/px)
+# ---------------------------------------------------------------------------------------------------
+# (narrow 9x9 high-resolution PSFs: the reference's PSF matching is a plain Fourier division, which is only stable when
+#  the model PSF is narrow; they also make the reference's grid 228 + 9 + 3 = 240, a length of the fused kernels)
+CFG4 = dict(hr_n=200, lr_n=30, hr_scale=0.03, lr_scale=0.2, n_ext=8, B=41, hr_P=9, lr_P=15, config_id=4)
+
+
+def _gauss_img(P, sig):
+    y, x = np.mgrid[:P, :P] - P // 2
+    out = np.stack([np.exp(-(x * x + y * y) / (2 * s * s)) for s in sig])
+    return out / out.sum(axis=(1, 2))[:, None, None]
+
+
+_MR_CACHE = {}
+
+
+def _multires_observations(scene, dtype=np.float32):
+    """Frame + matched observations of a cfg4 scene.  Every cfg4 scene shares PSFs and WCS, so the (expensive, host-side)
+    renderer set-up is done once per dtype and re-attached through ``Observation.match(frame, renderer=...)``."""
+    import scarlet_b200 as sb
+    from .wcs import AffineWCS
+    cfg = scene["config"]
+    hr_c, lr_c = (cfg["hr_n"] - 1) / 2.0, (cfg["lr_n"] - 1) / 2.0
+    key = (tuple(sorted(cfg.items())), np.dtype(dtype).name)
+    cached = _MR_CACHE.get(key)
+    wcs_hr = cached["wcs_hr"] if cached else AffineWCS(np.diag([cfg["hr_scale"]] * 2), crpix=(hr_c, hr_c))
+    wcs_lr = cached["wcs_lr"] if cached else AffineWCS(np.diag([cfg["lr_scale"]] * 2), crpix=(lr_c, lr_c))
+    obs_hr = sb.Observation(scene["hr_images"].copy(), psf=sb.ImagePSF(scene["hr_psfs"].copy()), weights=scene["hr_weights"].copy(),
+                            wcs=wcs_hr, channels=["h0", "h1", "h2"])
+    obs_lr = sb.Observation(scene["lr_images"].copy(), psf=sb.ImagePSF(scene["lr_psfs"].copy()), weights=scene["lr_weights"].copy(),
+                            wcs=wcs_lr, channels=["l0", "l1", "l2", "l3", "l4"])
+    if cached:
+        frame = cached["frame"]
+        obs_lr.match(frame, renderer=cached["r_lr"])
+        obs_hr.match(frame, renderer=cached["r_hr"])
+        return frame, obs_lr, obs_hr
+    frame = sb.Frame.from_observations([obs_lr, obs_hr], coverage="union")
+    if dtype is np.float64:
+        frame = sb.Frame(frame.shape, channels=frame.channels, psf=frame.psf, wcs=frame.wcs, dtype=np.float64)
+        obs_lr.match(frame)
+        obs_hr.match(frame)
+    _MR_CACHE[key] = dict(frame=frame, r_lr=obs_lr.renderer, r_hr=obs_hr.renderer, wcs_hr=wcs_hr, wcs_lr=wcs_lr)
+    return frame, obs_lr, obs_hr
+
+
+def make_multires_scene(scene_id=0, config=None):
+    """Plain arrays of one cfg4 scene: truth galaxies in the common model frame, observed once through the
+    low-resolution resampling renderer and once through the high-resolution convolution, unit-variance noise."""
+    cfg = dict(CFG4 if config is None else config)
+    rng = np.random.default_rng(1000 * cfg["config_id"] + scene_id)
+    hr_n, lr_n, B = cfg["hr_n"], cfg["lr_n"], cfg["B"]
+    scene = dict(config=cfg, scene_id=scene_id,
+                 hr_images=np.zeros((3, hr_n, hr_n), np.float32), lr_images=np.zeros((5, lr_n, lr_n), np.float32),
+                 hr_weights=np.ones((3, hr_n, hr_n), np.float32), lr_weights=np.ones((5, lr_n, lr_n), np.float32),
+                 hr_psfs=_gauss_img(cfg["hr_P"], np.linspace(0.8, 1.0, 3)), lr_psfs=_gauss_img(cfg["lr_P"], np.linspace(1.0, 1.4, 5)))
+    frame, obs_lr, obs_hr = _multires_observations(scene, np.float64)
+    C, Ny, Nx = frame.shape
+    margin = B // 2 + 4
+    sources, truth = [], np.zeros((C, Ny, Nx))
+    for k in range(cfg["n_ext"]):
+        cy, cx = rng.uniform(margin, Ny - margin), rng.uniform(margin, Nx - margin)
+        py, px = int(np.round(cy)), int(np.round(cx))
+        rs, q, th = rng.uniform(2.0, 4.0), rng.uniform(0.5, 1.0), rng.uniform(0, np.pi)
+        sed = np.exp(rng.uniform(np.log(20), np.log(500))) * rng.dirichlet(np.ones(C)) * C
+        tm = _profile(B, cy - py, cx - px, rs, q, th)
+        init = _profile(B, 0.0, 0.0, rs * rng.uniform(0.7, 1.3), min(1.0, q * rng.uniform(0.8, 1.2)), th + rng.normal(0, 0.2))
+        origin = (py - B // 2, px - B // 2)
+        truth[:, origin[0]:origin[0] + B, origin[1]:origin[1] + B] += sed[:, None, None] * tm[None]
+        sources.append(dict(kind="extended", center=(cy, cx), origin=origin, sed_true=sed, morph_true=tm,
+                            sed=(sed * rng.uniform(0.7, 1.3, C)).astype(np.float32), morph=init))
+    lr_clean = obs_lr.renderer.get_model()(truth)
+    r2 = obs_hr.renderer
+    hr_sub = truth[r2.channel_offset:r2.channel_offset + 3]
+    hr_conv = np.stack([signal.fftconvolve(hr_sub[c], np.asarray(r2.diff_kernel.image[c], dtype=np.float64), mode="same") for c in range(3)])
+    oy, ox = r2.origin
+    scene["hr_images"] = (hr_conv[:, oy:oy + hr_n, ox:ox + hr_n] + rng.standard_normal((3, hr_n, hr_n))).astype(np.float32)
+    scene["lr_images"] = (lr_clean + rng.standard_normal(lr_clean.shape)).astype(np.float32)
+    scene["sources"] = sources
+    scene["frame_shape"] = (int(C), int(Ny), int(Nx))
+    return scene
+
+
+def make_multires_blend(scene, precision=32, device=None):
+    """scarlet_b200 objects of a cfg4 scene: -> Blend over [low-resolution, high-resolution] observations."""
+    import scarlet_b200 as sb
+    frame, obs_lr, obs_hr = _multires_observations(scene, np.float32 if precision == 32 else np.float64)
+    observations = [obs_lr, obs_hr]
+    srcs = []
+    for s in scene["sources"]:
+        B = s["morph"].shape[0]
+        srcs.append(sb.ExtendedSource(frame, frame.get_sky_coord(np.array(s["center"])), observations, spectrum=s["sed"].copy(),
+                                      morphology=s["morph"].copy(), bbox=sb.Box((B, B), origin=s["origin"]), monotonic="angle",
+                                      symmetric=True, resizing=False))
+    return sb.Blend(srcs, observations, precision=precision, device=device)

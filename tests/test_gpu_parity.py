@@ -343,6 +343,28 @@ def test_multiresolution_fit_matches_oracle(precision, tol):
     assert rel_peak(blend.get_model(), o.get_model()) < tol
 
 
+def test_multiresolution_cfg4_full_size():
+    """BASELINE config 4 shape: 5 bands 30x30 at 0.2"/px + 3 bands 200x200 at 0.03"/px, model frame (8,228,228), grid 240^2,
+    8 ExtendedSource: 5 iterations against the oracle.  Model pixels and SEDs at 1e-5 of their peaks; morphologies at
+    5e-5 (the low-resolution bands' float32 render noise, see test_multiresolution_forward_and_gradients_vs_oracle)."""
+    from oracle import scenes
+    from scarlet_b200 import synthetic
+    scene = synthetic.make_multires_scene(0)
+    blend = synthetic.make_multires_blend(scene, precision=32)
+    assert tuple(blend.frame.shape) == (8, 228, 228) and list(blend.observations[0].renderer._fft_shape) == [240, 240]
+    o = scenes.build_multires_oracle(scene, scenes.multires_setup(blend))
+    n_iter = 5
+    o.fit(max_iter=n_iter, e_rel=1e-3, min_iter=10 ** 9)
+    n, _ = blend.fit(max_iter=n_iter, e_rel=1e-3, min_iter=10 ** 9)
+    assert n == n_iter and blend._get_plan().spectral_mode == 1
+    assert_allclose(np.array(blend.loss), np.array(o.loss), rtol=2e-5)
+    sed_scale = max(float(np.abs(np.asarray(s.spectrum.x, dtype=np.float64)).max()) for s in o.sources)
+    for src, osrc in zip(blend.sources, o.sources):
+        assert np.abs(np.asarray(src.parameters[0], dtype=np.float64) - osrc.spectrum.x).max() < 1e-5 * sed_scale
+        assert rel_peak(src.parameters[1], osrc.image.x) < 5e-5
+    assert rel_peak(blend.get_model(), o.get_model()) < 1e-5
+
+
 # --------------------------------------------------------------------------------------------------
 # the fitting loop
 # --------------------------------------------------------------------------------------------------
