@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="cfg3", choices=["cfg2", "cfg3", "cfg5", "tiny"])
+    ap.add_argument("--config", default="cfg3", choices=["cfg2", "cfg3", "cfg4", "cfg5", "tiny"])
     ap.add_argument("--scenes", type=int, default=0, help="scenes per GPU (default per config)")
     ap.add_argument("--iters", type=int, default=0, help="iterations per step (default per config)")
     ap.add_argument("--unique", type=int, default=16, help="distinct synthetic scenes generated per rank (then cycled)")
@@ -46,8 +46,8 @@ def parse():
     return ap.parse_args()
 
 
-DEFAULT_SCENES = {"cfg2": 256, "cfg3": 96, "cfg5": 512, "tiny": 64}
-DEFAULT_ITERS = {"cfg2": 50, "cfg3": 50, "cfg5": 50, "tiny": 20}
+DEFAULT_SCENES = {"cfg2": 256, "cfg3": 96, "cfg4": 64, "cfg5": 512, "tiny": 64}
+DEFAULT_ITERS = {"cfg2": 50, "cfg3": 50, "cfg4": 50, "cfg5": 50, "tiny": 20}
 
 
 def peaks():
@@ -105,18 +105,42 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # reference arm: the reference algorithm (oracle restatement; the reference itself cannot run here)
 # ---------------------------------------------------------------------------------------------------
+def _make_scene(config, scene_id):
+    from scarlet_b200 import synthetic
+    return synthetic.make_multires_scene(scene_id) if config == "cfg4" else synthetic.make_scene(config, scene_id)
+
+
+def _make_blend(config, scene, precision=32, device=None):
+    from scarlet_b200 import synthetic
+    if config == "cfg4":
+        return synthetic.make_multires_blend(scene, precision=precision, device=device)
+    return synthetic.make_blend(scene, precision=precision, device=device)
+
+
+def _config_dict(config):
+    from scarlet_b200 import synthetic
+    if config == "cfg4":
+        c = synthetic.CFG4
+        return dict(C=8, N=228, n_ext=c["n_ext"], n_pt=0, psf="gaussian-image", P=c["hr_P"], B=c["B"], symmetric=True,
+                    note="5 bands 30x30 at 0.2 arcsec/px (ResolutionRenderer) + 3 bands 200x200 at 0.03 arcsec/px (ConvolutionRenderer)")
+    return synthetic.CONFIGS[config]
+
+
 def _ref_worker(job):
     config, scene_id, iters = job
     from oracle import scenes
-    from scarlet_b200 import synthetic
-    o = scenes.build_oracle(synthetic.make_scene(config, scene_id))
+    scene = _make_scene(config, scene_id)
+    if config == "cfg4":  # the set-up products of the low-resolution renderer come from the host objects (no GPU involved)
+        o = scenes.build_multires_oracle(scene, scenes.multires_setup(_make_blend(config, scene)))
+    else:
+        o = scenes.build_oracle(scene)
     t0 = time.perf_counter()
     o.fit(max_iter=iters, e_rel=1e-3, min_iter=10 ** 9)
     return time.perf_counter() - t0
 
 
 def cpu_iters_for(config):
-    return {"cfg2": 20, "cfg3": 6, "cfg5": 12, "tiny": 30}[config]
+    return {"cfg2": 20, "cfg3": 6, "cfg4": 4, "cfg5": 12, "tiny": 30}[config]
 
 
 def run_reference(args):
@@ -144,7 +168,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "pgm_scene_iterations_per_sec", "value": value, "unit": "scene-iterations/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, synthetic.CONFIGS[args.config], cores, iters),
+            "config": workload_config(args, _config_dict(args.config), cores, iters),
             "cpu_baseline": {"value": value, "unit": "scene-iterations/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "scene-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -177,12 +201,12 @@ def run_b200(args):
         os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    cfg = synthetic.CONFIGS[args.config]
+    cfg = _config_dict(args.config)
     S = args.scenes or DEFAULT_SCENES[args.config]
     iters = args.iters or DEFAULT_ITERS[args.config]
     uniq = min(S, args.unique)
-    base = [synthetic.make_scene(args.config, rank * 100000 + i) for i in range(uniq)]
-    blends = [synthetic.make_blend(base[i % uniq], precision=args.precision, device=local) for i in range(S)]
+    base = [_make_scene(args.config, rank * 100000 + i) for i in range(uniq)]
+    blends = [_make_blend(args.config, base[i % uniq], precision=args.precision, device=local) for i in range(S)]
     batch = BlendBatch(blends, precision=args.precision, device=local)
     plan = batch.plan
     fshape = plan.obs_meta[0]["metas"][0]["fshape"]
@@ -308,12 +332,16 @@ def run_b200(args):
             "advance": 16,
         }
         stage_bytes.update(fused_bytes)
-        own = {k: v for k, v in stages.items() if not k.startswith("fft_")}
+        own = {k: v for k, v in stages.items() if not k.startswith("fft_") and stage_bytes.get(k, 0) > 0}
         dom = max(own, key=own.get)
         dom_ms = stages[dom]
         achieved = stage_bytes[dom] * S / (dom_ms / 1e3) / 1e9
         iter_ms = sum(stages.values())
         alg_iter = synthetic.algorithmic_bytes(cfg, fshape, eb)
+        if args.config == "cfg4":  # two observations on different grids: only the per-source kernel has a closed-form byte count here
+            for k in list(stage_bytes):
+                if k not in ("source_update", "advance"):
+                    stage_bytes[k] = 0
         whole = alg_iter * S / (ms_total / args.steps / iters / 1e3) / 1e9
         # DRAM bytes of the same kernel from the committed `ncu --set full` capture of this workload (per launch)
         traffic, traffic_src = None, None
@@ -333,12 +361,15 @@ def run_b200(args):
                     "iteration": {"algorithmic_bytes_per_scene": alg_iter, "achieved": whole, "frac": whole / peak,
                                   "note": "SURVEY.md 8(d) whole-iteration accounting incl. cuFFT stages"},
                     "stages_ms": stages,
-                    "stages_gbs": {k: (stage_bytes[k] * S / (v / 1e3) / 1e9 if v > 0 else None) for k, v in stages.items()}}
+                    "stages_gbs": {k: (stage_bytes[k] * S / (v / 1e3) / 1e9 if v > 0 and stage_bytes.get(k, 0) > 0 else None)
+                                   for k, v in stages.items()}}
+        if args.config == "cfg4":
+            roofline["iteration"] = None
 
         # single-scene latency (the 200 it/s target of the north star is a per-scene figure)
         single = None
         if not args.no_single:
-            one = BlendBatch([synthetic.make_blend(base[0], precision=args.precision, device=local)], precision=args.precision, device=local)
+            one = BlendBatch([_make_blend(args.config, base[0], precision=args.precision, device=local)], precision=args.precision, device=local)
             o1 = _native.fit_opts(max_iter=200, e_rel=1e-3, fixed_iterations=True, check_every=10 ** 6)
             for _ in range(3):
                 one.plan.forget_state()
@@ -366,7 +397,9 @@ def run_b200(args):
                      "spectral": "fused row/column kernels" if fused else "cuFFT",
                      "cufft_execs_per_iteration": 0 if fused else 4 * len(plan.obs_meta),
                      "kernels_per_iteration": launches // max(args.steps * iters, 1), "precision": args.precision,
-                     "per_scene_psf": True})
+                     "per_scene_psf": args.config != "cfg4"})
+        if cfg.get("note"):
+            conf["observations"] = cfg["note"]
         line = {"metric": "pgm_scene_iterations_per_sec", "value": value, "unit": "scene-iterations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic",
