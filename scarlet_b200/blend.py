@@ -110,24 +110,55 @@ class Blend(CombinedComponent):
 
 
 class BlendBatch:
-    """Many independent, structurally identical scenes fitted together on one GPU."""
+    """Many independent, structurally identical scenes fitted together on one GPU.
 
-    def __init__(self, blends, precision=32, device=None):
+    ``n_streams > 1`` splits the batch into that many plans (each with its own CUDA stream) driven by one host thread
+    each: the host<->device copies of one part then overlap the fitting loop of another (the loops themselves do not
+    run faster side by side -- tools/stream_overlap_probe.py)."""
+
+    def __init__(self, blends, precision=32, device=None, n_streams=1):
+        from .distributed import shard_bounds
         self.blends = list(blends)
-        self.plan = DevicePlan(self.blends, precision=precision, device=device)
+        n_streams = max(1, min(int(n_streams), len(self.blends)))
+        self.parts = [self.blends[a:b] for a, b in shard_bounds(len(self.blends), n_streams)]
+        self.plans = [DevicePlan(part, precision=precision, device=device) for part in self.parts]
+        self.plan = self.plans[0]
+        self.last_transfer_bytes = (0, 0)
 
-    def fit(self, max_iter=200, e_rel=1e-3, min_iter=1, noise_factor=0, **alg_kwargs):
+    def _each(self, fn):
+        if len(self.plans) == 1:
+            return [fn(0)]
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(len(self.plans)) as pool:
+            return list(pool.map(fn, range(len(self.plans))))
+
+    def upload_observations(self):
+        return sum(self._each(lambda i: self.plans[i].upload_observations()))
+
+    def fit(self, max_iter=200, e_rel=1e-3, min_iter=1, noise_factor=0, upload_observations=False, **alg_kwargs):
         check_every = int(alg_kwargs.pop("check_every", 10))
         opts = _fit_options(max_iter, e_rel, min_iter, noise_factor, alg_kwargs, check_every)
-        h2d = self.plan.upload_parameters(state=True)
-        n_iter, loss, status = self.plan.fit(opts)
-        d2h = self.plan.download_parameters(state=True)
-        self.last_transfer_bytes = (int(h2d), int(d2h + n_iter.nbytes + status.nbytes + loss.nbytes))
+
+        def one(i):
+            plan = self.plans[i]
+            h2d = plan.upload_observations() if upload_observations else 0
+            h2d += plan.upload_parameters(state=True)
+            n_iter, loss, status = plan.fit(opts)
+            d2h = plan.download_parameters(state=True) + n_iter.nbytes + status.nbytes + loss.nbytes
+            return n_iter, loss, status, h2d, d2h
+
+        outs = self._each(one)
+        self.last_transfer_bytes = (int(sum(o[3] for o in outs)), int(sum(o[4] for o in outs)))
         results = []
-        for s, b in enumerate(self.blends):
-            n = int(n_iter[s])
-            b.loss.extend(loss[s, :n].tolist())
-            if status[s] == nat.SB_ERR_NONFINITE:
-                raise ArithmeticError("scene %d: a parameter became non-finite during the fit" % s)
-            results.append((len(b.loss), -b.loss[-1]))
+        for part, (n_iter, loss, status, _, _) in zip(self.parts, outs):
+            for s, b in enumerate(part):
+                n = int(n_iter[s])
+                b.loss.extend(loss[s, :n].tolist())
+                if status[s] == nat.SB_ERR_NONFINITE:
+                    raise ArithmeticError("scene %d: a parameter became non-finite during the fit" % self.blends.index(b))
+                results.append((len(b.loss), -b.loss[-1]))
         return results
+
+    def close(self):
+        for p in self.plans:
+            p.close()

@@ -95,5 +95,5 @@ def fit_sharded(make_blend, scene_ids, max_iter=200, e_rel=1e-3, precision=32, d
             records.append(dict(scene_id=sid, n_iter=int(n), logL=float(logL),
                                 sed=[np.array(s.parameters[0]) for s in b.sources],
                                 morph=[np.array(s.parameters[1]) for s in b.sources]))
-        batch.plan.close()
+        batch.close()
     return gather_host_results(records)
