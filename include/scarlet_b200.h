@@ -114,6 +114,10 @@ typedef struct sb_fit_opts { /* Blend.fit / proxmin.adaprox arguments, blend.py:
     int32_t check_every; /* host polls the device stop flags every this many iterations */
     int32_t fixed_iterations; /* 1: ignore the stop rule (benchmark mode) */
     int32_t overwrite_vhat_at_it0; /* oracle switch (1), SURVEY 8c open point (1) */
+    int32_t resume;    /* 1: continue the previous sb_plan_fit call of this plan (iteration counter, stop flags and loss
+                          history are kept) -- one proxmin.adaprox call split at the points where Blend._callback
+                          inspects the sources (every 10 iterations, blend.py:284-292) */
+    int32_t run_until; /* stop this call when the iteration counter reaches run_until (0: max_iter) */
     double e_rel;
     double b1, b2, eps;
 } sb_fit_opts;

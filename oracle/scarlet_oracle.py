@@ -433,7 +433,8 @@ class ExtendedSourceOracle:
     kind = "extended"
 
     def __init__(self, sed, morph, origin, min_step=0.0, monotonic="angle", symmetric=False, min_grad=0.0,
-                 sed_dtype=np.float32):
+                 sed_dtype=np.float32, resizing=False):
+        self.resizing = resizing
         sed = np.asarray(sed, dtype=sed_dtype)
         morph = np.array(morph, dtype=np.float64)
         self.min_step = np.asarray(min_step, dtype=np.float64)
@@ -457,6 +458,51 @@ class ExtendedSourceOracle:
         g_sed = np.einsum("cyx,yx->c", gbox, morph)
         g_morph = np.einsum("c,cyx->yx", np.asarray(sed, dtype=np.float64), gbox)
         return (g_sed, g_morph, np.zeros(2))
+
+    def _new_image(self, data, m, v, vhat, origin_shift):
+        old = self.image
+        self.image = OParam(np.array(data, dtype=np.float64), "image", old.step / 2, old.prox, old.fixed)
+        self.image.m, self.image.v, self.image.vhat = np.array(m), np.array(v), np.array(vhat)
+        C = self.bbox.shape[0]
+        oy, ox = self.bbox.origin[1] + origin_shift, self.bbox.origin[2] + origin_shift
+        self.bbox = OBox((C,) + self.image.x.shape, (0, oy, ox))
+
+    def update(self):
+        """Dynamic box of ``ImageMorphology.update`` / ``shrink_box`` (morphology.py:52-68, 132-207).  Returns True
+        when the box changed (the reference raises ``UpdateException``)."""
+        image = self.image
+        if not self.resizing or image.fixed:
+            return False
+        x = image.x
+        size = max(x.shape)
+        dist = 0
+        while (np.all(x[dist, :] <= 0) and np.all(x[-dist - 1, :] <= 0) and np.all(x[:, dist] <= 0) and np.all(x[:, -dist - 1] <= 0)):
+            dist += 1
+        newsize = minimal_boxsize(size - 2 * dist)
+        if newsize < size:
+            d = (size - newsize) // 2
+            sl = (slice(d, d + newsize), slice(d, d + newsize))
+            self._new_image(x[sl], image.m[sl], image.v[sl], image.vhat[sl], d)
+            return True
+        if image.m is not None:
+            gu = -image.m / np.sqrt(np.sqrt(np.ma.masked_equal(image.v, 0))) * image.step
+            pull = gu * (x > 0)
+            edge = np.array((pull[:, 0].mean(), pull[:, -1].mean(), pull[0, :].mean(), pull[-1, :].mean()))
+            if np.any(edge > 0.1):
+                newsize = minimal_boxsize(size + 1)
+                pad = (newsize - size) // 2
+                self._new_image(np.pad(x, pad, mode="linear_ramp"), np.pad(image.m, pad, mode="constant"),
+                                np.pad(image.v, pad, mode="constant"), np.pad(image.vhat, pad, mode="constant"), -pad)
+                return True
+        return False
+
+
+def minimal_boxsize(size, min_size=21, increment=10):
+    """initialization.py:173-177."""
+    boxsize = min_size
+    while boxsize < size:
+        boxsize += increment
+    return boxsize
 
 
 class PointSourceOracle:
@@ -751,33 +797,47 @@ class SceneOracle:
 
     def fit(self, max_iter=200, e_rel=1e-3, min_iter=1, prox_max_iter=10, b1=0.9, b2=0.999, eps=1e-8,
             callback=None):
-        """``Blend.fit`` with ``scheme="amsgrad"`` and no box resizing.  Returns (n_iter, logL)."""
-        params = self.parameters
-        for p in params:
-            if p.m is None:
-                p.m = np.zeros(p.x.shape)
-            if p.v is None:
-                p.v = np.zeros(p.x.shape)
-            if p.vhat is None:
-                p.vhat = np.zeros(p.x.shape)
-        for it in range(max_iter):
-            loss, grads = self.loss_and_grads()
-            self.loss.append(loss)
-            steps = [p.step_size(it) for p in params]
-            for p, g, a in zip(params, grads, steps):
-                if p.fixed:
-                    continue
-                adaprox_step(p, g, a, it, e_rel=e_rel, prox_max_iter=prox_max_iter, b1=b1, b2=b2, eps=eps)
-            # ---- Blend._callback, blend.py:276-302 ----
+        """``Blend.fit`` with ``scheme="amsgrad"`` (blend.py:85-198): one ``adaprox`` call per pass of the outer loop;
+        after its iterations 10, 20, ... the sources may adapt their boxes (``_callback``, blend.py:276-302), which
+        aborts the call and restarts it with warm state and ``it = len(self.loss)``.  Returns (n_iter, logL)."""
+        it_outer = 0
+        while it_outer < max_iter:
+            params = self.parameters
             for p in params:
-                if not np.isfinite(p.x).all():
-                    raise ArithmeticErrorNonFinite("parameter '%s' is not finite" % p.name)
-            if it > min_iter and abs(self.loss[-1] - self.loss[-2]) < e_rel * abs(self.loss[-1]):
+                if p.m is None:
+                    p.m = np.zeros(p.x.shape)
+                if p.v is None:
+                    p.v = np.zeros(p.x.shape)
+                if p.vhat is None:
+                    p.vhat = np.zeros(p.x.shape)
+            restarted = False
+            for it in range(max_iter - it_outer):  # proxmin's own counter starts at 0 in every call
+                loss, grads = self.loss_and_grads()
+                self.loss.append(loss)
+                steps = [p.step_size(it) for p in params]
+                for p, g, a in zip(params, grads, steps):
+                    if p.fixed:
+                        continue
+                    adaprox_step(p, g, a, it, e_rel=e_rel, prox_max_iter=prox_max_iter, b1=b1, b2=b2, eps=eps)
+                # ---- Blend._callback, blend.py:276-302 ----
+                for p in params:
+                    if not np.isfinite(p.x).all():
+                        raise ArithmeticErrorNonFinite("parameter '%s' is not finite" % p.name)
+                if it > 0 and it % 10 == 0:
+                    changed = [src.update() for src in self.sources if hasattr(src, "update")]
+                    if any(changed):
+                        it_outer = len(self.loss)
+                        restarted = True
+                        break
+                if it > min_iter and abs(self.loss[-1] - self.loss[-2]) < e_rel * abs(self.loss[-1]):
+                    break
+                if callback is not None:
+                    callback(it)
+            if not restarted:
                 break
-            if callback is not None:
-                callback(it)
-        for p in params:
-            p.std = 1 / np.sqrt(np.ma.masked_equal(p.v, 0))
+        for p in self.parameters:
+            if p.v is not None:
+                p.std = 1 / np.sqrt(np.ma.masked_equal(p.v, 0))
         return len(self.loss), -self.loss[-1]
 
 

@@ -16,7 +16,8 @@ def build_oracle(scene, frame_dtype=np.float32, sed_dtype=np.float32):
     for s in scene["sources"]:
         if s["kind"] == "extended":
             sources.append(so.ExtendedSourceOracle(s["sed"], s["morph"], s["origin"], min_step=min_step, monotonic="angle",
-                                                   symmetric=cfg["symmetric"], sed_dtype=sed_dtype))
+                                                   symmetric=cfg["symmetric"], sed_dtype=sed_dtype,
+                                                   resizing=bool(cfg.get("resizing", False))))
         else:
             sources.append(so.PointSourceOracle(s["sed"], s["center"], model_psf, min_step=min_step, sed_dtype=sed_dtype))
     return so.SceneOracle((C, N, N), model_psf, sources, [obs], frame_dtype=frame_dtype)

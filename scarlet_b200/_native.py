@@ -53,7 +53,8 @@ class sb_batch_desc(C.Structure):
 
 class sb_fit_opts(C.Structure):
     _fields_ = [("max_iter", C.c_int32), ("min_iter", C.c_int32), ("prox_max_iter", C.c_int32), ("check_every", C.c_int32),
-                ("fixed_iterations", C.c_int32), ("overwrite_vhat_at_it0", C.c_int32), ("e_rel", C.c_double),
+                ("fixed_iterations", C.c_int32), ("overwrite_vhat_at_it0", C.c_int32), ("resume", C.c_int32),
+                ("run_until", C.c_int32), ("e_rel", C.c_double),
                 ("b1", C.c_double), ("b2", C.c_double), ("eps", C.c_double)]
 
 
@@ -140,9 +141,10 @@ def default_device():
 
 
 def fit_opts(max_iter=200, e_rel=1e-3, min_iter=1, prox_max_iter=10, check_every=10, fixed_iterations=False,
-             b1=0.9, b2=0.999, eps=1e-8, overwrite_vhat_at_it0=True):
+             b1=0.9, b2=0.999, eps=1e-8, overwrite_vhat_at_it0=True, resume=False, run_until=0):
     return sb_fit_opts(int(max_iter), int(min_iter), int(prox_max_iter), int(check_every), int(bool(fixed_iterations)),
-                       int(bool(overwrite_vhat_at_it0)), float(e_rel), float(b1), float(b2), float(eps))
+                       int(bool(overwrite_vhat_at_it0)), int(bool(resume)), int(run_until), float(e_rel), float(b1), float(b2),
+                       float(eps))
 
 
 def as_array(x, dtype):

@@ -11,8 +11,9 @@ import logging
 import numpy as np
 
 from . import _native as nat
-from ._plan import DevicePlan
+from ._plan import DevicePlan, leaf_components as _leaves
 from .component import CombinedComponent
+from .model import UpdateException
 
 logger = logging.getLogger("scarlet_b200.blend")
 
@@ -64,23 +65,57 @@ class Blend(CombinedComponent):
 
     # -- the fitting loop -----------------------------------------------------------------------------
     def fit(self, max_iter=200, e_rel=1e-3, min_iter=1, noise_factor=0, **alg_kwargs):
-        """Fit the model of every source to the data.  Returns ``(len(self.log_likelihood), logL)``."""
+        """Fit the model of every source to the data.  Returns ``(len(self.log_likelihood), logL)``.
+
+        Control flow of the reference (blend.py:85-198, 276-302): one ``adaprox`` call runs until ``max_iter`` or
+        convergence; after its iterations 10, 20, ... every source may adapt its box (``src.update()``), which aborts the
+        call (``UpdateException``) and restarts the optimiser with the new shapes, warm state and ``it = len(self.loss)``.
+        Here one ``adaprox`` call is one device plan driven in slices that end exactly at those inspection points."""
         check_every = int(alg_kwargs.pop("check_every", 10))
         opts = _fit_options(max_iter, e_rel, min_iter, noise_factor, alg_kwargs, check_every)
         for src in self.sources:
             src.check_parameters()
         if max_iter <= 0:
             return len(self.loss), (-self.loss[-1] if self.loss else None)
-        plan = self._get_plan()
-        plan.upload_parameters(state=True)
-        n_iter, loss, status = plan.fit(opts)
-        plan.download_parameters(state=True)
-        n = int(n_iter[0])
-        self.loss.extend(loss[0, :n].tolist())
-        if status[0] == nat.SB_ERR_NONFINITE:
-            for src in self.sources:
-                src.check_parameters()  # raises ArithmeticError naming the parameter (model.py:153-165)
-            raise ArithmeticError("a parameter became non-finite during the fit")
+        resizing = any(getattr(c.children[1], "resizing", False) and not c.children[1].parameters[0].fixed
+                       for c in _leaves(self.sources) if hasattr(c.children[1], "resizing"))
+        it = 0
+        while it < max_iter:
+            plan = self._get_plan()
+            plan.upload_parameters(state=True)
+            budget = max_iter - it  # iterations this adaprox call may run
+            opts.max_iter, opts.resume, k_done, restarted = budget, 0, 0, False
+            n0 = len(self.loss)
+            while k_done < budget:
+                # without resizable boxes nobody inspects the sources: run the whole call in one go
+                stop = budget if not resizing else min(budget, 11 if k_done == 0 else k_done + 10)
+                opts.run_until = stop
+                n_iter, loss, status = plan.fit(opts)
+                opts.resume = 1
+                n = int(n_iter[0])  # gradient evaluations of this call so far
+                plan.download_parameters(state=True)
+                self.loss[n0:] = loss[0, :n].tolist()
+                if status[0] == nat.SB_ERR_NONFINITE:
+                    for src in self.sources:
+                        src.check_parameters()  # raises ArithmeticError naming the parameter (model.py:153-165)
+                    raise ArithmeticError("a parameter became non-finite during the fit")
+                k_done = stop
+                last = n - 1  # index of the last iteration of this call (proxmin's ``it``)
+                if resizing and n == stop and last > 0 and last % 10 == 0:
+                    changed = False
+                    for src in self.sources:
+                        try:
+                            src.update()
+                        except UpdateException:
+                            changed = True
+                    if changed:  # blend.py:196-198
+                        it = len(self.loss)
+                        restarted = True
+                        break
+                if n < stop:  # converged inside the slice (StopIteration in the reference)
+                    break
+            if not restarted:
+                break
         logger.info("scarlet ran for {0} iterations to logL = {1}".format(len(self.loss), -self.loss[-1]))
         return len(self.loss), -self.loss[-1]
 
@@ -119,6 +154,12 @@ class BlendBatch:
     def __init__(self, blends, precision=32, device=None, n_streams=1):
         from .distributed import shard_bounds
         self.blends = list(blends)
+        for b in self.blends:
+            for c in _leaves(b.sources):
+                morph = c.children[1]
+                if getattr(morph, "resizing", False) and not morph.parameters[0].fixed:
+                    raise NotImplementedError("BlendBatch fits fixed boxes: build the sources with resizing=False (dynamic boxes "
+                                              "re-plan a scene every few iterations; use Blend.fit for those)")
         n_streams = max(1, min(int(n_streams), len(self.blends)))
         self.parts = [self.blends[a:b] for a, b in shard_bounds(len(self.blends), n_streams)]
         self.plans = [DevicePlan(part, precision=precision, device=device) for part in self.parts]

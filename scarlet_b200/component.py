@@ -4,7 +4,7 @@ import numpy as np
 
 from .bbox import Box, overlapped_slices
 from .frame import Frame
-from .model import Model
+from .model import Model, UpdateException
 from .morphology import Morphology
 from .spectrum import Spectrum
 
@@ -71,6 +71,16 @@ class FactorizedComponent(Component):
             model = self.model_to_box(frame.bbox, model)
         return model
 
+    def update(self):
+        """Let the children adapt (dynamic morphology box); re-derive the component box (component.py:173-181)."""
+        for child in self.children:
+            try:
+                child.update()
+            except UpdateException as e:
+                spectrum, morphology = self.children
+                self.bbox = spectrum.bbox @ morphology.bbox[-2:]
+                raise e
+
     @property
     def spectrum(self):
         return self.children[0]
@@ -91,6 +101,17 @@ class CombinedComponent(Component):
         if operation != "add":
             raise NotImplementedError("only the additive combination is on the device path")
         self.operation = operation
+
+    def update(self):
+        for child in self.children:
+            try:
+                child.update()
+            except UpdateException as e:
+                box = self.children[0].bbox.copy()
+                for c in self.children[1:]:
+                    box = box | c.bbox
+                self.bbox = box
+                raise e
 
     def get_model(self, *parameters, frame=None):
         models = self.get_models_of_children(*parameters, frame=None)

@@ -1101,17 +1101,23 @@ template <typename T> struct PlanT : sb_plan {
         return SB_OK;
     }
 
+    int cur_it = 0; // host mirror of the device iteration counter (every graph launch advances it by one)
+
     int fit(const sb_fit_opts *o, int32_t *n_iter, double *loss, int32_t *status) override {
         SB_TRY(check_opts(o));
         SB_CUDA(cudaSetDevice(device));
         SB_TRY(ensure_loss_cap(std::max(o->max_iter, 1)));
         SB_TRY(ensure_graph(o));
-        SB_TRY(reset_counters());
+        if (!o->resume) {
+            SB_TRY(reset_counters());
+            cur_it = 0;
+        }
+        const int end = o->run_until > 0 ? std::min(o->run_until, o->max_iter) : o->max_iter;
         int done_iters = 0;
-        for (int it = 0; it < o->max_iter; ++it) {
+        while (cur_it < end) {
             SB_CUDA(cudaGraphLaunch(graph, stream));
-            ++done_iters;
-            if (!o->fixed_iterations && ((it + 1) % o->check_every == 0)) {
+            ++done_iters, ++cur_it;
+            if (!o->fixed_iterations && (cur_it % o->check_every == 0)) {
                 SB_CUDA(cudaMemcpyAsync(h_nactive, d_nactive.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
                 SB_CUDA(cudaStreamSynchronize(stream));
                 if (*h_nactive == 0) break;

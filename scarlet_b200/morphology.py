@@ -6,7 +6,8 @@ from .bbox import Box
 from .constraint import (CenterOnConstraint, ConstraintChain, MonotonicityConstraint, NormalizationConstraint,
                          PositivityConstraint, SymmetryConstraint)
 from .frame import Frame
-from .model import Model
+from .bbox import overlapped_slices
+from .model import Model, UpdateException
 from .parameter import Parameter, prepare_param, relative_step
 from .psf import PSF
 
@@ -21,10 +22,33 @@ class Morphology(Model):
         self.bbox = bbox
         super().__init__(*parameters)
 
+    def shrink_box(self, image, thresh=0):
+        """Peel the onion: drop outer rings that are entirely <= thresh, down to the next allowed box size
+        (morphology.py:52-68)."""
+        size = max(image.shape)
+        dist = 0
+        while (np.all(image[dist, :] <= thresh) and np.all(image[-dist - 1, :] <= thresh)
+               and np.all(image[:, dist] <= thresh) and np.all(image[:, -dist - 1] <= thresh)):
+            dist += 1
+        newsize = get_minimal_boxsize(size - 2 * dist)
+        if newsize < size:
+            dist = (size - newsize) // 2
+            self.bbox = Box((newsize, newsize), origin=tuple(o + dist for o in self.bbox.origin))
+
+
+def get_minimal_boxsize(size, min_size=21, increment=10):
+    """Smallest allowed box size >= size (initialization.py:173-177)."""
+    boxsize = min_size
+    while boxsize < size:
+        boxsize += increment
+    return boxsize
+
 
 class ImageMorphology(Morphology):
-    """Free-form image.  ``shifting`` (Fourier sub-pixel shift) and ``resizing`` (dynamic box) are accepted for
-    API parity; the device path currently fits ``shifting=False`` and treats the box as fixed (see Blend.fit)."""
+    """Free-form image.  ``resizing=True``: every 10 iterations ``Blend.fit`` calls ``update`` (host), which shrinks the
+    box when its outer rings are empty or grows it when the optimiser keeps pulling flux towards an edge; the device
+    loop is then re-planned with the new shapes and warm optimiser state (morphology.py:132-207, blend.py:196-198).
+    ``shifting`` (Fourier sub-pixel shift) is a 'next' row (SURVEY f-3)."""
 
     def __init__(self, frame, image, bbox=None, shifting=False, shift=None, resizing=True):
         if isinstance(image, Parameter):
@@ -53,6 +77,42 @@ class ImageMorphology(Morphology):
         if self.shifting:
             raise NotImplementedError("Fourier-shifted morphologies are a 'next' row (SURVEY f-3)")
         return self.get_parameter(0, *parameters)
+
+    def _replace_image(self, old, data, m, v, vhat):
+        """New image Parameter (private, contiguous copies: the old arrays may live in a plan's staging memory), step halved."""
+        def own(a):
+            return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        image = Parameter(np.ascontiguousarray(data), name=old.name, prior=old.prior, constraint=old.constraint, step=old.step / 2,
+                          fixed=old.fixed, m=own(m), v=own(v), vhat=own(vhat))
+        self._parameters = (image,) + self._parameters[1:]
+
+    def update(self):
+        """Dynamic box: shrink / grow and raise ``UpdateException`` when the box changed (morphology.py:132-207)."""
+        import numpy.ma as ma
+        image = self._parameters[0]
+        if not self.resizing or image.fixed:
+            return
+        bbox = self.bbox.copy()
+        self.shrink_box(image._data)
+        if bbox != self.bbox:
+            sl, _ = overlapped_slices(bbox, self.bbox)
+            m, v, vhat = image.m, image.v, image.vhat
+            self._replace_image(image, image._data[sl], None if m is None else m[sl], None if v is None else v[sl],
+                                None if vhat is None else vhat[sl])
+            raise UpdateException
+        elif image.m is not None:
+            # next gradient update, in units of the peak (= 1 at the centre): does the optimiser pull flux to an edge?
+            gu = -image.m / np.sqrt(np.sqrt(ma.masked_equal(image.v, 0))) * image.step
+            gu_pull = gu * (image._data > 0)
+            edge_pull = np.array((gu_pull[:, 0].mean(), gu_pull[:, -1].mean(), gu_pull[0, :].mean(), gu_pull[-1, :].mean()))
+            if np.any(edge_pull > 0.1):
+                size = max(bbox.shape)
+                newsize = get_minimal_boxsize(size + 1)
+                pad = (newsize - size) // 2
+                self._replace_image(image, np.pad(image._data, pad, mode="linear_ramp"), np.pad(image.m, pad, mode="constant"),
+                                    np.pad(image.v, pad, mode="constant"), np.pad(image.vhat, pad, mode="constant"))
+                self.bbox = Box((newsize, newsize), origin=tuple(o - pad for o in self.bbox.origin))
+                raise UpdateException
 
 
 class PointSourceMorphology(Morphology):

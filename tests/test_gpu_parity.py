@@ -468,6 +468,56 @@ def test_batch_equals_individual_fits():
             assert_array_equal(np.asarray(p1), np.asarray(p2))
 
 
+def _resizing_scene():
+    """a wide and a compact galaxy in 31x31 boxes that are too small for what the data pull in: the boxes grow several
+    times within 45 iterations (dynamic boxes on, morphology.py:132-207)"""
+    from scarlet_b200 import synthetic
+    scene = synthetic.make_scene(dict(C=3, N=70, n_ext=2, n_pt=0, psf="gaussian", P=15, B=31, symmetric=True, iters=40, config_id=11,
+                                      resizing=True), 0)
+    y, x = np.mgrid[:31, :31] - 15
+    wide = np.exp(-np.hypot(y, x) / 9.0)
+    compact = np.exp(-np.hypot(y, x) / 1.5) * (np.hypot(y, x) < 6)
+    for s, morph, cen, amp in zip(scene["sources"], (wide, compact), ((24, 26), (50, 46)), (900.0, 300.0)):
+        s["morph"], s["origin"], s["center"] = morph / morph.max(), (cen[0] - 15, cen[1] - 15), cen
+        s["sed"] = (amp * np.array([1.0, 0.8, 0.6])).astype(np.float32)
+    truth = sum(s["sed"][:, None, None].astype(np.float64) * np.pad(np.exp(-np.hypot(*(np.mgrid[:70, :70] - np.array(s["center"])[:, None, None])) / r), 0)
+                for s, r in zip(scene["sources"], (9.0, 1.5)))
+    from scipy import signal
+    from scarlet_b200 import fft as sfft
+    from scarlet_b200.psf import GaussianPSF
+    diff = sfft.match_psf(scene["obs_psf"].astype(np.float32), GaussianPSF(sigma=(0.8,) * 3).get_model().astype(np.float32), padding=10).image
+    rng = np.random.default_rng(5)
+    scene["images"] = (np.stack([signal.fftconvolve(truth[c], diff[c], mode="same") for c in range(3)])
+                       + rng.standard_normal((3, 70, 70))).astype(np.float32)
+    return scene
+
+
+@pytest.mark.parametrize("precision,tol", [(64, 1e-8), (32, 2e-3)])
+def test_dynamic_box_resize_matches_oracle(precision, tol):
+    """boxes shrink / grow every 10 iterations, the optimiser restarts with warm state and halved step.
+    The float64 twin follows the oracle through every restart to 1e-8.  The scene starts far from its optimum on
+    purpose (the loss oscillates for the first 30 iterations), which amplifies float32 rounding to ~2e-4 in the loss
+    history: the float32 run checks the control flow (same box sizes, origins, restart points, iteration count)."""
+    from oracle import scenes
+    from scarlet_b200 import synthetic
+    scene = _resizing_scene()
+    o = scenes.build_oracle(scene, frame_dtype=np.float32 if precision == 32 else np.float64)
+    o.fit(max_iter=45, e_rel=1e-6)
+    blend = synthetic.make_blend(scene, precision=precision)
+    n, logL = blend.fit(max_iter=45, e_rel=1e-6)
+    shapes = [tuple(s.parameters[1].shape) for s in blend.sources]
+    assert shapes == [tuple(s.image.x.shape) for s in o.sources]
+    assert shapes[0][0] > 41 and shapes[1][0] > 31, shapes          # several resize + restart cycles happened
+    assert [s.bbox.origin[1:] for s in blend.sources] == [s.bbox.origin[1:] for s in o.sources]
+    assert n == len(o.loss)
+    assert_allclose(np.array(blend.loss), np.array(o.loss), rtol=max(tol, 1e-9))
+    for src, osrc in zip(blend.sources, o.sources):
+        assert rel_peak(src.parameters[0], osrc.spectrum.x) < tol
+        assert rel_peak(src.parameters[1], osrc.image.x) < tol
+        assert src.parameters[1].step == osrc.image.step
+    assert rel_peak(blend.get_model(), o.get_model()) < tol
+
+
 def test_nonfinite_raises_arithmetic_error():
     from scarlet_b200 import synthetic
     sc = synthetic.make_scene("tiny", 0)
