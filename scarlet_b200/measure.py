@@ -1,0 +1,51 @@
+"""Post-fit measurements on component models: the step right after the fitting path.
+
+Same call signatures as scarlet/measure.py (``max_pixel`` 6-21, ``flux`` 24-38, ``centroid`` 41-59, ``snr`` 62-104): each
+takes a component (anything with ``get_model()`` and ``bbox``) or a plain (C, Ny, Nx) cube.  Plain reductions over
+models that are already on the host after ``Blend.fit`` wrote the parameters back; ``snr`` renders through the
+observations (device convolution for ``ConvolutionRenderer``)."""
+import numpy as np
+
+
+def _cube(component, frame=None):
+    """-> (model cube, origin of its box)"""
+    if hasattr(component, "get_model"):
+        model = component.get_model(frame=frame) if frame is not None else component.get_model()
+        return np.asarray(model), np.asarray((0, 0, 0) if frame is not None else component.bbox.origin)
+    return np.asarray(component), np.zeros(np.ndim(component), dtype=int)
+
+
+def max_pixel(component):
+    """(channel, y, x) of the brightest model pixel, in frame coordinates."""
+    model, origin = _cube(component)
+    return tuple(np.array(np.unravel_index(int(np.argmax(model)), model.shape)) + origin)
+
+
+def flux(component):
+    """Model flux per channel."""
+    return _cube(component)[0].sum(axis=(1, 2))
+
+
+def centroid(component):
+    """Flux-weighted mean position (channel, y, x) in frame coordinates."""
+    model, origin = _cube(component)
+    total = model.sum()
+    grids = np.indices(model.shape)
+    return np.array([(g * model).sum() / total for g in grids]) + origin
+
+
+def snr(component, observations):
+    """Matched-filter signal-to-noise with the rendered model itself as weight function (Erben et al. 2001, eq. 16,
+    summed over all pixels and bands of all observations)."""
+    if not hasattr(observations, "__iter__"):
+        observations = (observations,)
+    model, _ = _cube(component, frame=observations[0].model_frame)
+    signal = weight2 = 0.0
+    for obs in observations:
+        rendered = np.asarray(obs.render(model), dtype=np.float64)
+        w = rendered / rendered.sum(axis=(-2, -1))[:, None, None]
+        var = np.asarray(np.ma.filled(obs.noise_rms, np.inf), dtype=np.float64) ** 2
+        finite = np.isfinite(var)
+        signal += float((rendered * w).sum())
+        weight2 += float((var[finite] * w[finite] ** 2).sum())
+    return signal / np.sqrt(weight2)

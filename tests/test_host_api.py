@@ -242,3 +242,23 @@ def test_multiresolution_setup_vs_reference_fixture():
     # the reference's default float32 frame (float32 model, float32 resampling operator) only agrees to float32 rounding
     assert np.abs(lr - g["lr_rendered"]).max() < 5e-5 * np.abs(g["lr_rendered"]).max()
     assert_allclose(obs_lr.get_log_likelihood(g["model64"]), float(g["lr_logL64"]), rtol=1e-10)
+
+
+def test_measure_helpers():
+    """scarlet/measure.py:6-59 on a component and on a plain cube (host reductions; no device involved)"""
+    import scarlet_b200 as sb
+    from scarlet_b200 import measure, synthetic
+    sc = synthetic.make_scene("tiny", 0)
+    frame = sb.Frame(sc["images"].shape, psf=sb.GaussianPSF(sigma=(0.8,) * 3), channels=sc["channels"])
+    s = sc["sources"][0]
+    B = s["morph"].shape[0]
+    src = sb.ExtendedSource(frame, s["center"], None, spectrum=s["sed"], morphology=s["morph"], bbox=sb.Box((B, B), origin=s["origin"]),
+                            resizing=False)
+    model = s["sed"][:, None, None].astype(np.float64) * s["morph"][None]
+    assert_allclose(measure.flux(src), model.sum(axis=(1, 2)), rtol=1e-6)
+    c, y, x = measure.max_pixel(src)
+    assert (y, x) == (s["origin"][0] + B // 2, s["origin"][1] + B // 2)
+    cen = measure.centroid(src)
+    yy, xx = np.mgrid[:B, :B]
+    assert_allclose(cen[1:], [(yy * s["morph"]).sum() / s["morph"].sum() + s["origin"][0], (xx * s["morph"]).sum() / s["morph"].sum() + s["origin"][1]], rtol=1e-6)
+    assert_allclose(measure.flux(model), model.sum(axis=(1, 2)))
