@@ -518,6 +518,34 @@ def test_dynamic_box_resize_matches_oracle(precision, tol):
     assert rel_peak(blend.get_model(), o.get_model()) < tol
 
 
+def test_ragged_batch_and_many_channels():
+    """scenes with different numbers of sources in one batch, and a 10-band scene (more bands than one CTA of the row
+    kernels takes at once, and more than the grouped update kernel handles: band chunking + the generic update kernel)"""
+    import scarlet_b200 as sb
+    from oracle import scenes
+    from scarlet_b200 import synthetic
+    base = dict(C=3, N=40, n_pt=1, psf="gaussian", P=15, B=15, symmetric=True, iters=10, config_id=21)
+    scs = [synthetic.make_scene(dict(base, n_ext=n), i) for i, n in enumerate((1, 4, 2, 3))]
+    batch = [synthetic.make_blend(s) for s in scs]
+    res = sb.BlendBatch(batch).fit(max_iter=10, e_rel=1e-3, min_iter=10 ** 9)
+    for sc, b in zip(scs, batch):
+        o = scenes.build_oracle(sc)
+        o.fit(max_iter=10, e_rel=1e-3, min_iter=10 ** 9)
+        assert_allclose(np.array(b.loss), np.array(o.loss), rtol=2e-5)
+        assert rel_peak(b.get_model(), o.get_model()) < 1e-5
+    wide = synthetic.make_scene(dict(base, C=10, n_ext=3, config_id=22), 0)
+    for precision, tol in ((64, 1e-9), (32, 1e-5)):
+        o = scenes.build_oracle(wide, frame_dtype=np.float32 if precision == 32 else np.float64)
+        o.fit(max_iter=10, e_rel=1e-3, min_iter=10 ** 9)
+        b = synthetic.make_blend(wide, precision=precision)
+        b.fit(max_iter=10, e_rel=1e-3, min_iter=10 ** 9)
+        assert b._get_plan().spectral_mode == 1
+        assert_allclose(np.array(b.loss), np.array(o.loss), rtol=max(2 * tol, 1e-9))
+        assert rel_peak(b.get_model(), o.get_model()) < tol
+        for src, osrc in zip(b.sources, o.sources):
+            assert rel_peak(src.parameters[0], osrc.spectrum.x) < tol
+
+
 def test_nonfinite_raises_arithmetic_error():
     from scarlet_b200 import synthetic
     sc = synthetic.make_scene("tiny", 0)
