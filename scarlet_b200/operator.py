@@ -114,3 +114,59 @@ def prox_soft_symmetry(X, step, strength=1):
     """``strength/2 (X + rot180 X) + (1-strength) X`` -- on the GPU through the constraint-chain kernel."""
     from .constraint import SymmetryConstraint
     return SymmetryConstraint(strength)(X, step)
+
+
+# --------------------------------------------------------------------------------------------------
+# operators used by the source initialisation (scarlet/operator.py:207-271)
+# --------------------------------------------------------------------------------------------------
+def prox_sdss_symmetry(X, step):
+    """Symmetrise by the MINIMUM of every pixel and its 180-degree partner (in place)."""
+    X[:] = np.minimum(X, X[::-1, ::-1])
+    return X
+
+
+def uncentered_operator(X, func, center=None, fill=None, **kwargs):
+    """Apply ``func`` on the largest sub-array of ``X`` that is centred on ``center`` (default: the peak); the rest
+    keeps its values, or is set to ``fill``."""
+    py, px = np.unravel_index(np.argmax(X), X.shape) if center is None else center
+    cy, cx = np.array(X.shape) // 2
+    if py == cy and px == cx:
+        return func(X, **kwargs)
+    dy, dx = int(2 * (py - cy)) + (X.shape[0] % 2 == 0), int(2 * (px - cx)) + (X.shape[1] % 2 == 0)
+    ysl = slice(None, dy) if dy < 0 else slice(dy, None)
+    xsl = slice(None, dx) if dx < 0 else slice(dx, None)
+    if fill is not None:
+        out = np.full(X.shape, fill, dtype=X.dtype)
+        out[ysl, xsl] = func(X[ysl, xsl], **kwargs)
+        X[:] = out
+    else:
+        X[ysl, xsl] = func(X[ysl, xsl], **kwargs)
+    return X
+
+
+def prox_uncentered_symmetry(X, step, center=None, algorithm="sdss", fill=None, strength=0.5):
+    """Symmetry about an off-centre pixel.  Only the variants used on the fitting path and its initialisation exist here:
+    ``"sdss"`` (minimum of partners) and ``"soft"``; the k-space variant needs ``fft.shift``."""
+    if algorithm == "sdss":
+        return uncentered_operator(X, prox_sdss_symmetry, center, step=step, fill=fill)
+    if algorithm == "soft":
+        return uncentered_operator(X, prox_soft_symmetry, center, step=step, strength=strength, fill=fill)
+    raise NotImplementedError("symmetry algorithm %r is outside the device path" % (algorithm,))
+
+
+def windowed_monotonic(image, center_index, neighbor_weight="flat", min_gradient=0, half_width=127):
+    """Radial monotonicity about ``center_index`` on a whole detection image (what ``SingleExtendedSource.init_morph`` does
+    with ``prox_weighted_monotonic(im.shape, center=...)``, source.py:488-498), executed by the CUDA wavefront kernel.
+
+    The sweep only ever reads pixels that are closer to the centre, so a square window centred on the source gives the
+    same values as the whole image inside the window; the window is capped at 255 x 255 pixels (the kernel's 16-bit pixel
+    indices), pixels outside it are cleared -- sources wider than that cannot be initialised here."""
+    H, W = image.shape
+    cy, cx = int(center_index[0]), int(center_index[1])
+    y0, y1, x0, x1 = max(0, cy - half_width), min(H, cy + half_width + 1), max(0, cx - half_width), min(W, cx + half_width + 1)
+    win = np.ascontiguousarray(image[y0:y1, x0:x1], dtype=np.float64)
+    prox = prox_weighted_monotonic(win.shape, neighbor_weight=neighbor_weight, min_gradient=min_gradient, center=(cy - y0, cx - x0))
+    win = prox(win, 0).reshape(win.shape)
+    out = np.zeros_like(image, dtype=np.float64)
+    out[y0:y1, x0:x1] = win
+    return out
