@@ -199,8 +199,19 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device -- scarlet_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the communicator is first used: route stdout to stderr until then,
+        # so that rank 0's stdout carries exactly one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     cfg = _config_dict(args.config)
     S = args.scenes or DEFAULT_SCENES[args.config]
