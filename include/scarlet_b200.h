@@ -84,7 +84,11 @@ typedef struct sb_source_desc {
     int32_t sed_chain; /* spectrum constraint chain index, -1 = none */
     int32_t sed_is_f32; /* spectrum Parameter is float32 on the host (rounded after each update) */
     int32_t morph_fixed, sed_fixed;
-    int32_t _pad0, _pad1;
+    int32_t shifting;       /* kind 0 only: the model uses fft.shift(image, shift) (morphology.py:124-130, fft.py:399-428); the
+                               free ``shift`` parameter then travels in the centre arrays like a point-source centre */
+    int32_t shift_Fy, shift_Fx; /* the reference's fast grid of that shift: _get_fft_shape(image, image, padding=10) */
+    int32_t _pad0;
+    double shift_step;      /* constant step of the shift parameter (1e-1, morphology.py:672-675) */
     double morph_step;      /* constant step of the image / center parameter */
     double sed_step_factor; /* relative_step factor (parameter.py:126-129); <0: constant step = sed_step_min[0] */
     double sed_step_min[SB_MAX_CHANNELS]; /* per-band minimum step (spectrum.py:56, source.py:412-416) */
@@ -168,7 +172,8 @@ int sb_host_scatter_f64(const double *src, void *const *dst, const int64_t *coun
 
 /* Parameters and optimiser state, concatenated over sources in plan order (Parameter.m/v/vhat,
  * parameter.py:42-71; warm start blend.py:154-163).  sed arrays: [n_sources][C]; morph arrays: concatenated
- * By*Bx images of the kind-0 sources; center arrays: [n_point][2].  which: 0 = value, 1 = m, 2 = v, 3 = vhat.
+ * By*Bx images of the kind-0 sources; center arrays: [n_point + n_shifting][2] in source order (point-source centres and
+ * the shifts of shifting image morphologies).  which: 0 = value, 1 = m, 2 = v, 3 = vhat.
  * Any pointer may be NULL (skipped). */
 int sb_plan_upload_params(sb_plan *plan, int which, const double *sed, const double *morph, const double *center);
 int sb_plan_download_params(sb_plan *plan, int which, double *sed, double *morph, double *center);

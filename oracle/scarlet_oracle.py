@@ -433,15 +433,17 @@ class ExtendedSourceOracle:
     kind = "extended"
 
     def __init__(self, sed, morph, origin, min_step=0.0, monotonic="angle", symmetric=False, min_grad=0.0,
-                 sed_dtype=np.float32, resizing=False):
+                 sed_dtype=np.float32, resizing=False, shift=None):
         self.resizing = resizing
+        self.shifting = shift is not None
         sed = np.asarray(sed, dtype=sed_dtype)
         morph = np.array(morph, dtype=np.float64)
         self.min_step = np.asarray(min_step, dtype=np.float64)
         self.spectrum = OParam(sed, "spectrum", lambda x, it: relative_step(x, it, 1e-2, self.min_step),
                                ChainSpec([("positivity", 1e-20)]))
         self.image = OParam(morph, "image", 1e-2, extended_source_chain(monotonic, symmetric, min_grad))
-        self.shift = OParam(np.zeros(2), "shift", 1e-2, None)
+        # morphology.py:112-113 (free, unused, step 1e-2) or, with shifting=True, morphology.py:672-675 (step 1e-1)
+        self.shift = OParam(np.zeros(2), "shift", 1e-2, None) if shift is None else OParam(np.array(shift, dtype=np.float64), "shift", 1e-1, None)
         C = sed.shape[0]
         self.bbox = OBox((C,) + morph.shape, (0, int(origin[0]), int(origin[1])))
 
@@ -450,14 +452,18 @@ class ExtendedSourceOracle:
         return (self.spectrum, self.image, self.shift)
 
     def get_model(self, values=None):
-        sed, morph = (self.spectrum.x, self.image.x) if values is None else values[:2]
+        sed, morph, shift = (self.spectrum.x, self.image.x, self.shift.x) if values is None else values[:3]
+        if self.shifting:
+            morph = fourier_shift(morph, shift)
         return sed[:, None, None] * morph[None, :, :]
 
     def param_grads(self, gbox, values=None):
-        sed, morph = (self.spectrum.x, self.image.x) if values is None else values[:2]
-        g_sed = np.einsum("cyx,yx->c", gbox, morph)
-        g_morph = np.einsum("c,cyx->yx", np.asarray(sed, dtype=np.float64), gbox)
-        return (g_sed, g_morph, np.zeros(2))
+        sed, morph, shift = (self.spectrum.x, self.image.x, self.shift.x) if values is None else values[:3]
+        g_shifted = np.einsum("c,cyx->yx", np.asarray(sed, dtype=np.float64), gbox)
+        if not self.shifting:
+            return (np.einsum("cyx,yx->c", gbox, morph), g_shifted, np.zeros(2))
+        shifted, g_morph, g_shift = fourier_shift_vjp(morph, shift, g_shifted)
+        return (np.einsum("cyx,yx->c", gbox, shifted), g_morph, g_shift)
 
     def _new_image(self, data, m, v, vhat, origin_shift):
         old = self.image
@@ -495,6 +501,38 @@ class ExtendedSourceOracle:
                                 np.pad(image.v, pad, mode="constant"), np.pad(image.vhat, pad, mode="constant"), -pad)
                 return True
         return False
+
+
+def fourier_shift(image, shift, padding=10):
+    """``fft.shift(image, shift, return_Fourier=False)`` (fft.py:399-428), literally: centre-pad to the fast shape of
+    (image, image, padding 10), ifftshift, rfftn, multiply by exp(-2 pi i (fftfreq_y s0 + rfftfreq_x s1)), irfftn,
+    fftshift, centre-crop."""
+    image = np.asarray(image, dtype=np.float64)
+    fshape = get_fft_shape(image.shape, image.shape, padding, (0, 1))
+    spec = forward_fft(image, fshape, (0, 1))
+    ramp = np.exp(-2j * np.pi * np.fft.fftfreq(fshape[0]) * shift[0])[:, None] * np.exp(-2j * np.pi * np.fft.rfftfreq(fshape[1]) * shift[1])[None, :]
+    return np.real(inverse_fft(spec * ramp, fshape, image.shape, (0, 1)))
+
+
+def fourier_shift_vjp(image, shift, g_out):
+    """(shifted image, d<g_out, shifted>/d image, d<g_out, shifted>/d shift) by torch double-precision autograd through
+    the same pipeline as ``fourier_shift`` (torch.fft follows numpy's rfftn / irfftn semantics, including what the
+    real inverse transform does with the non-Hermitian Nyquist row that a fractional shift along y creates)."""
+    import torch
+    img = torch.tensor(np.asarray(image, dtype=np.float64), requires_grad=True)
+    sh = torch.tensor(np.asarray(shift, dtype=np.float64), requires_grad=True)
+    By, Bx = img.shape
+    Fy, Fx = get_fft_shape((By, Bx), (By, Bx), 10, (0, 1))
+    oy, ox = (Fy - By + 1) // 2, (Fx - Bx + 1) // 2
+    pad = torch.zeros((Fy, Fx), dtype=torch.float64)
+    pad = torch.nn.functional.pad(img, (ox, Fx - Bx - ox, oy, Fy - By - oy))
+    spec = torch.fft.rfftn(torch.fft.ifftshift(pad))
+    fy = torch.tensor(np.fft.fftfreq(Fy))
+    fx = torch.tensor(np.fft.rfftfreq(Fx))
+    ramp = torch.exp(-2j * np.pi * fy * sh[0])[:, None] * torch.exp(-2j * np.pi * fx * sh[1])[None, :]
+    out = torch.fft.fftshift(torch.fft.irfftn(spec * ramp, s=(Fy, Fx)))[oy:oy + By, ox:ox + Bx]
+    (out * torch.tensor(np.asarray(g_out, dtype=np.float64))).sum().backward()
+    return out.detach().numpy(), img.grad.numpy(), sh.grad.numpy()
 
 
 def minimal_boxsize(size, min_size=21, increment=10):

@@ -17,7 +17,8 @@ def build_oracle(scene, frame_dtype=np.float32, sed_dtype=np.float32):
         if s["kind"] == "extended":
             sources.append(so.ExtendedSourceOracle(s["sed"], s["morph"], s["origin"], min_step=min_step, monotonic="angle",
                                                    symmetric=cfg["symmetric"], sed_dtype=sed_dtype,
-                                                   resizing=bool(cfg.get("resizing", False))))
+                                                   resizing=bool(cfg.get("resizing", False)),
+                                                   shift=(np.array(s["center"]) - np.round(s["center"])) if cfg.get("shifting") else None))
         else:
             sources.append(so.PointSourceOracle(s["sed"], s["center"], model_psf, min_step=min_step, sed_dtype=sed_dtype))
     return so.SceneOracle((C, N, N), model_psf, sources, [obs], frame_dtype=frame_dtype)

@@ -40,7 +40,8 @@ class sb_obs_desc(C.Structure):
 class sb_source_desc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("By", C.c_int32), ("Bx", C.c_int32), ("oy", C.c_int32), ("ox", C.c_int32),
                 ("chain", C.c_int32), ("sed_chain", C.c_int32), ("sed_is_f32", C.c_int32), ("morph_fixed", C.c_int32),
-                ("sed_fixed", C.c_int32), ("_pad0", C.c_int32), ("_pad1", C.c_int32), ("morph_step", C.c_double),
+                ("sed_fixed", C.c_int32), ("shifting", C.c_int32), ("shift_Fy", C.c_int32), ("shift_Fx", C.c_int32),
+                ("_pad0", C.c_int32), ("shift_step", C.c_double), ("morph_step", C.c_double),
                 ("sed_step_factor", C.c_double), ("sed_step_min", C.c_double * SB_MAX_CHANNELS)]
 
 

@@ -173,15 +173,23 @@ class DevicePlan:
                     d.morph_fixed = int(bool(cen.fixed))
                     slot.update(kind=1, center=cen)
                 elif isinstance(morph, ImageMorphology):
-                    if morph.shifting:
-                        raise NotImplementedError("shifting=True is a 'next' row (SURVEY f-3)")
                     img = morph.parameters[0]
                     d.kind, d.By, d.Bx = 0, img.shape[0], img.shape[1]
                     d.oy, d.ox = morph.bbox.origin[-2], morph.bbox.origin[-1]
                     d.chain = chain_index(img.constraint, img.shape)
                     d.morph_step = _const_step(img)
                     d.morph_fixed = int(bool(img.fixed))
-                    slot.update(kind=0, image=img, shift=morph.parameters[1] if len(morph.parameters) > 1 else None)
+                    shift = morph.parameters[1] if len(morph.parameters) > 1 else None
+                    if morph.shifting:  # the shift is a fitted parameter: it travels in the centre arrays
+                        from . import fft
+                        if shift is None or shift.constraint is not None:
+                            raise TypeError("a shifting morphology needs an unconstrained 'shift' parameter")
+                        fshape = fft._get_fft_shape(img._data, img._data, padding=10, axes=(0, 1))
+                        d.shifting, d.shift_Fy, d.shift_Fx = 1, int(fshape[0]), int(fshape[1])
+                        d.shift_step = 0.0 if shift.fixed else _const_step(shift)
+                        slot.update(kind=0, image=img, shift=None, center=shift)
+                    else:
+                        slot.update(kind=0, image=img, shift=shift)
                 else:
                     raise TypeError("morphology model %s is not on the device path" % type(morph).__name__)
                 src_descs.append(d)
@@ -190,7 +198,7 @@ class DevicePlan:
         self.n_src = len(src_descs)
         self.C = C
         self.ext = [s for s in self.slots if s["kind"] == 0]
-        self.pts = [s for s in self.slots if s["kind"] == 1]
+        self.pts = [s for s in self.slots if s.get("center") is not None]  # point-source centres and image shifts
         self.morph_sizes = [s["image"].size for s in self.ext]
         self.morph_offsets = np.concatenate([[0], np.cumsum(self.morph_sizes)]).astype(np.int64)
         self.n_morph = int(self.morph_offsets[-1])

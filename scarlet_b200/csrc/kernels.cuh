@@ -187,6 +187,7 @@ template <typename T> struct RenderArgs {
     const double *sed; // [n_src][C]
     const T *morph;
     const T *pmorph;
+    const T *smorph; // Fourier-shifted images of the shifting sources
     int C, Ny, Nx, n_obs;
     DevObs<T> obs[SB_MAX_OBS];
     const int *done;
@@ -209,7 +210,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_render(const Rend
         if ((unsigned)by < (unsigned)d.By && (unsigned)bx < (unsigned)d.Bx) {
             const double *sed = a.sed + (size_t)k * C;
             if (d.kind == 0) {
-                const T mv = a.morph[d.morph_off + (size_t)by * d.Bx + bx];
+                const T mv = (d.shifting ? a.smorph : a.morph)[d.morph_off + (size_t)by * d.Bx + bx];
 #pragma unroll
                 for (int c = 0; c < SB_MAXC; ++c)
                     if (c < C) acc[c] += (T)sed[c] * mv;
@@ -357,6 +358,10 @@ template <typename T> struct UpdateArgs {
     int npix_max; // shared-memory array length
     int mode;     // 0 = update, 1 = gradients only
     double *g_sed, *g_morph, *g_center;
+    T *smorph;              // packed like morph: Fourier-shifted images of the shifting sources (what the model uses)
+    T *toep;                // [n_shift][8][toep_len]: Re/Im Toeplitz vectors of the shift along y and x and their d/ds
+    int toep_len;           // 2*Bmax-1
+    const int *shift_list;  // k_shift_apply: source index per CTA
     const int *work;        // generic kernel: source index per block (NULL: block index)
     // grouped fast path (k_update_fast): one 64-thread group per source, groups of a CTA share one operator table
     const int *fast_groups; // [n_cta][fast_G] source index or -1
@@ -539,6 +544,92 @@ template <typename T> __device__ void update_point(const UpdateArgs<T> &a, const
     point_planes<T>(a, d, cen[0], cen[1], fy, fx);
 }
 
+// ======================================================================================================
+// Sub-pixel shifted image morphologies: ImageMorphology(shifting=True) -> fft.shift (morphology.py:124-130, fft.py:399-428)
+//
+// The reference pads the image to a fast grid F, multiplies its rfftn by exp(-2 pi i (fftfreq_y s0 + rfftfreq_x s1)) and
+// transforms back.  Restricted to the B x B box this is EXACTLY   o = Re(Cy) u Re(Tx)^T - Im(Cy) u Im(Tx)^T   with the
+// Toeplitz vectors  Cy[d] = 1/Fy sum_k exp(2 pi i (k d - m_k s0)/Fy)  (m_k: signed frequency, complex inverse transform
+// along y) and  Tx[d] = 1/Fx sum_{k<=Fx/2} c_k exp(2 pi i k (d - s1)/Fx)  (c = 1,2,...,2,1: what the real inverse transform
+// along x does) -- including the non-Hermitian Nyquist row a fractional shift creates (checked against the reference's
+// fft.shift to 2e-15).  The vectors and their derivatives wrt the shift are rebuilt for the current shift by direct
+// summation in double precision (any F, no FFT), the products are small dense contractions in shared memory.
+// ======================================================================================================
+template <typename T> __device__ __forceinline__ T *toep_vec(const UpdateArgs<T> &a, const DevSource &d, int v) {
+    return a.toep + ((size_t)d.toep_off * 8 + v) * a.toep_len;
+}
+
+// vectors (0..7) = Re Cy, Im Cy, d/ds0 Re Cy, d/ds0 Im Cy, Re Tx, Im Tx, d/ds1 Re Tx, d/ds1 Im Tx; entry j <-> offset d = j-(B-1)
+template <typename T> __device__ void shift_vectors(const UpdateArgs<T> &a, const DevSource &d, double s0, double s1) {
+    const int By = d.By, Bx = d.Bx, ny = 2 * By - 1, nx = 2 * Bx - 1;
+    for (int idx = threadIdx.x; idx < ny + nx; idx += blockDim.x) {
+        const bool ydir = idx < ny;
+        const int F = ydir ? d.shift_Fy : d.shift_Fx, off = ydir ? idx - (By - 1) : idx - ny - (Bx - 1);
+        const double sh = ydir ? s0 : s1, w = 2.0 * M_PI / F;
+        double re = 0, im = 0, dre = 0, dim = 0;
+        if (ydir) {
+            for (int k = 0; k < F; ++k) {
+                const int m = k < (F + 1) / 2 ? k : k - F; // numpy.fft.fftfreq
+                double sn, cs;
+                sincos(w * ((double)k * off - (double)m * sh), &sn, &cs);
+                re += cs, im += sn;
+                const double f = -w * m; // d/ds0 of the phase
+                dre += -f * sn, dim += f * cs;
+            }
+        } else {
+            for (int k = 0; k <= F / 2; ++k) {
+                const double c = (k == 0 || 2 * k == F) ? 1.0 : 2.0;
+                double sn, cs;
+                sincos(w * k * ((double)off - sh), &sn, &cs);
+                re += c * cs, im += c * sn;
+                const double f = -w * k;
+                dre += -c * f * sn, dim += c * f * cs;
+            }
+        }
+        const int j = ydir ? idx : idx - ny, base = ydir ? 0 : 4;
+        toep_vec<T>(a, d, base + 0)[j] = (T)(re / F), toep_vec<T>(a, d, base + 1)[j] = (T)(im / F);
+        toep_vec<T>(a, d, base + 2)[j] = (T)(dre / F), toep_vec<T>(a, d, base + 3)[j] = (T)(dim / F);
+    }
+}
+
+// out[y',x'] = sum_{y,x} (Ay[y'-y] in[y,x] Bx[x'-x]) as two passes through the scratch image w (all in shared memory)
+// transpose = true applies the transposed operators (Ay[y-y'], Bx[x-x']): the vector-Jacobian product
+template <typename T, bool TRANSPOSE>
+__device__ void toeplitz_apply(const T *in, T *w, T *out, const T *Ay, const T *Bxv, int By, int Bx, bool accumulate, T sign) {
+    const int n = By * Bx;
+    for (int p = threadIdx.x; p < n; p += blockDim.x) { // along x
+        const int y = p / Bx, x1 = p - y * Bx;
+        T acc = T(0);
+        for (int x = 0; x < Bx; ++x) acc += in[y * Bx + x] * Bxv[(TRANSPOSE ? x - x1 : x1 - x) + Bx - 1];
+        w[p] = acc;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < n; p += blockDim.x) { // along y
+        const int y1 = p / Bx, x = p - y1 * Bx;
+        T acc = T(0);
+        for (int y = 0; y < By; ++y) acc += w[y * Bx + x] * Ay[(TRANSPOSE ? y - y1 : y1 - y) + By - 1];
+        out[p] = accumulate ? out[p] + sign * acc : sign * acc;
+    }
+    __syncthreads();
+}
+
+// one CTA per shifting source: Toeplitz vectors for the current shift, then smorph = shift(morph)
+template <typename T> __global__ void __launch_bounds__(128) k_shift_apply(const UpdateArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int k = a.shift_list[blockIdx.x];
+    const DevSource &d = a.src[k];
+    if (a.done[d.scene]) return;
+    const int n = d.By * d.Bx;
+    T *u = reinterpret_cast<T *>(smem), *w = u + a.npix_max, *o = w + a.npix_max;
+    shift_vectors<T>(a, d, a.center[2 * d.point_idx], a.center[2 * d.point_idx + 1]);
+    for (int p = threadIdx.x; p < n; p += blockDim.x) u[p] = a.morph[d.morph_off + p];
+    __threadfence_block();
+    __syncthreads();
+    toeplitz_apply<T, false>(u, w, o, toep_vec<T>(a, d, 0), toep_vec<T>(a, d, 4), d.By, d.Bx, false, T(1));
+    toeplitz_apply<T, false>(u, w, o, toep_vec<T>(a, d, 1), toep_vec<T>(a, d, 5), d.By, d.Bx, true, T(-1));
+    for (int p = threadIdx.x; p < n; p += blockDim.x) a.smorph[d.morph_off + p] = o[p];
+}
+
 template <typename T> __device__ void update_extended(const UpdateArgs<T> &a, const DevSource &d, int k, unsigned char *smem) {
     const int tid = threadIdx.x, nt = blockDim.x, C = a.C, s = d.scene, it = *a.it_ptr;
     const int n = d.By * d.Bx, Bx = d.Bx;
@@ -558,11 +649,49 @@ template <typename T> __device__ void update_extended(const UpdateArgs<T> &a, co
     const double alpha = d.morph_step;
     const bool upd = a.mode == 0 && !d.morph_fixed;
     double pmax = 0.0;
+    double gshift0 = 0.0, gshift1 = 0.0;
+    if (d.shifting) {
+        // the model holds the SHIFTED image: gather the gradient wrt it (zn), the spectrum gradient against it, then pull the
+        // gradient back to the image (xs) and to the shift through the transposed Toeplitz operators
+        const T *sm = a.smorph + d.morph_off;
+        for (int p = tid; p < n; p += nt) {
+            const int by = p / Bx, bx = p - by * Bx, y = d.oy + by, x = d.ox + bx;
+            double gm = 0.0;
+            if ((unsigned)y < (unsigned)a.Ny && (unsigned)x < (unsigned)a.Nx) {
+#pragma unroll
+                for (int c = 0; c < SB_MAXC; ++c) {
+                    if (c < C) {
+                        const double g = grad_at<T>(a, s, c, y, x);
+                        gm += sedv[c] * g;
+                        gs[c] += g * (double)sm[p];
+                    }
+                }
+            }
+            zn[p] = (T)gm;
+        }
+        __syncthreads();
+        const T *RCy = toep_vec<T>(a, d, 0), *ICy = toep_vec<T>(a, d, 1), *dRCy = toep_vec<T>(a, d, 2), *dICy = toep_vec<T>(a, d, 3);
+        const T *RTx = toep_vec<T>(a, d, 4), *ITx = toep_vec<T>(a, d, 5), *dRTx = toep_vec<T>(a, d, 6), *dITx = toep_vec<T>(a, d, 7);
+        toeplitz_apply<T, true>(zn, z, xs, RCy, RTx, d.By, d.Bx, false, T(1));  // d/d image
+        toeplitz_apply<T, true>(zn, z, xs, ICy, ITx, d.By, d.Bx, true, T(-1));
+        toeplitz_apply<T, true>(zn, z, ps, dRCy, RTx, d.By, d.Bx, false, T(1)); // d/d s0 = <image, dCy^T g Tx>
+        toeplitz_apply<T, true>(zn, z, ps, dICy, ITx, d.By, d.Bx, true, T(-1));
+        for (int p = tid; p < n; p += nt) gshift0 += (double)ps[p] * (double)mp[p];
+        __syncthreads();
+        toeplitz_apply<T, true>(zn, z, ps, RCy, dRTx, d.By, d.Bx, false, T(1)); // d/d s1
+        toeplitz_apply<T, true>(zn, z, ps, ICy, dITx, d.By, d.Bx, true, T(-1));
+        for (int p = tid; p < n; p += nt) gshift1 += (double)ps[p] * (double)mp[p];
+        __syncthreads();
+        gshift0 = block_sum(gshift0, red);
+        gshift1 = block_sum(gshift1, red);
+    }
     for (int p = tid; p < n; p += nt) {
         const int by = p / Bx, bx = p - by * Bx, y = d.oy + by, x = d.ox + bx;
         const T mval = mp[p];
         double gm = 0.0;
-        if ((unsigned)y < (unsigned)a.Ny && (unsigned)x < (unsigned)a.Nx) {
+        if (d.shifting) {
+            gm = (double)xs[p];
+        } else if ((unsigned)y < (unsigned)a.Ny && (unsigned)x < (unsigned)a.Nx) {
 #pragma unroll
             for (int c = 0; c < SB_MAXC; ++c) {
                 if (c < C) {
@@ -596,7 +725,20 @@ template <typename T> __device__ void update_extended(const UpdateArgs<T> &a, co
     if (a.mode == 1) {
         if (tid == 0 && a.g_sed)
             for (int c = 0; c < C; ++c) a.g_sed[(size_t)k * C + c] = gsum[c];
+        if (tid == 0 && d.shifting && a.g_center) a.g_center[2 * d.point_idx] = gshift0, a.g_center[2 * d.point_idx + 1] = gshift1;
         return;
+    }
+    if (tid == 0 && d.shifting && a.mode == 0) { // the shift itself: AMSGrad step, no constraint (morphology.py:672-675)
+        const double g2[2] = {gshift0, gshift1};
+        double *cen = a.center + 2 * d.point_idx, *m = a.cen_m + 2 * d.point_idx, *v = a.cen_v + 2 * d.point_idx,
+               *vh = a.cen_vhat + 2 * d.point_idx;
+        for (int i = 0; i < 2; ++i) {
+            double mm_ = m[i], vv = v[i], vvh = vh[i];
+            const double psi = amsgrad(g2[i], mm_, vv, vvh, it, a.fs);
+            m[i] = mm_, v[i] = vv, vh[i] = vvh;
+            cen[i] = cen[i] - d.shift_step * mm_ / psi;
+            if (!isfinite(cen[i])) atomicExch(a.status + s, SB_ERR_NONFINITE);
+        }
     }
     if (upd) {
         const double psimax = block_max(pmax, red);

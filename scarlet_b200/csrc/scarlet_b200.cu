@@ -240,7 +240,9 @@ template <typename T> struct PlanT : sb_plan {
     DevBuf<double> d_sed, d_sed_m, d_sed_v, d_sed_vhat, d_center, d_cen_m, d_cen_v, d_cen_vhat, d_loss, d_loss_const;
     DevBuf<double> d_gsed, d_gcenter, d_gmorph, d_stage;
     DevBuf<T> d_morph, d_morph_m, d_morph_v, d_morph_vhat, d_pmorph, d_model, d_rendered, d_scratch_x, d_scratch_ps;
-    DevBuf<int> d_work, d_fast_groups;
+    DevBuf<int> d_work, d_fast_groups, d_shift_list;
+    DevBuf<T> d_smorph, d_toep;
+    int n_shift = 0, toep_len = 1;
     int n_generic = 0, n_fast_cta = 0, fast_G = 0, fast_GT = 64, fast_npix = 0, fast_table_cap = 0;
     size_t fast_smem = 0;
     std::vector<HostMono> hmonos;
@@ -365,6 +367,13 @@ template <typename T> struct PlanT : sb_plan {
                         if (code != SB_OP_POSITIVITY && code != SB_OP_NORMALIZE)
                             return set_err(SB_ERR_ARG, "source %d: spectrum constraint op-code %d is not supported on a 1-D parameter", k, code);
                     }
+                if (d.kind == 0 && in.shifting) {
+                    if (in.shift_Fy < in.By || in.shift_Fx < in.Bx || (in.shift_Fx & 1))
+                        return set_err(SB_ERR_ARG, "source %d: bad shift grid %dx%d for a %dx%d image", k, in.shift_Fy, in.shift_Fx, in.By, in.Bx);
+                    d.shifting = 1, d.shift_Fy = in.shift_Fy, d.shift_Fx = in.shift_Fx, d.shift_step = in.shift_step;
+                    d.toep_off = n_shift++;
+                    toep_len = std::max(toep_len, 2 * std::max(in.By, in.Bx) - 1);
+                }
                 if (d.kind == 0) {
                     if (d.chain >= 0)
                         for (int i = 0; i < desc.chains[d.chain].n_ops; ++i) {
@@ -373,7 +382,7 @@ template <typename T> struct PlanT : sb_plan {
                                 return set_err(SB_ERR_ARG, "source %d: monotonic table size %d != box %dx%d", k, desc.mono[op.iarg].n_pix, d.By, d.Bx);
                         }
                     d.morph_off = n_morph;
-                    d.point_idx = -1;
+                    d.point_idx = d.shifting ? n_point++ : -1;
                     n_morph += (long long)d.By * d.Bx;
                     npix_max = std::max(npix_max, d.By * d.Bx);
                 } else if (d.kind == 1) {
@@ -410,6 +419,18 @@ template <typename T> struct PlanT : sb_plan {
         }
         SB_TRY(d_pmorph.alloc(std::max<long long>(n_pmorph, 1)));
         SB_TRY(d_pmorph.zero(stream));
+        if (n_shift) {
+            std::vector<int> sl;
+            for (int k = 0; k < n_src; ++k)
+                if (h_src[k].shifting) sl.push_back(k);
+            SB_TRY(d_shift_list.alloc(sl.size()));
+            SB_CUDA(cudaMemcpy(d_shift_list.p, sl.data(), sl.size() * sizeof(int), cudaMemcpyHostToDevice));
+            SB_TRY(d_smorph.alloc(std::max<long long>(n_morph, 1)));
+            SB_TRY(d_smorph.zero(stream));
+            SB_TRY(d_toep.alloc((size_t)n_shift * 8 * toep_len));
+            SB_TRY(d_toep.zero(stream));
+            SB_TRY(raise_smem((const void *)k_shift_apply<T>, (size_t)3 * npix_max * sizeof(T)));
+        }
         SB_TRY(d_done.alloc(S));
         SB_TRY(d_niter.alloc(S));
         SB_TRY(d_status.alloc(S));
@@ -574,7 +595,7 @@ template <typename T> struct PlanT : sb_plan {
         int npix = 0, cap = 0;
         for (int k = 0; k < n_src; ++k) {
             const DevSource &d = h_src[k];
-            bool fast = d.kind == 0 && d.chain >= 0 && C <= SB_FAST_MAXC;
+            bool fast = d.kind == 0 && d.chain >= 0 && C <= SB_FAST_MAXC && !d.shifting;
             int tasks = 0;
             if (fast) {
                 int n_mono_ops = 0;
@@ -829,7 +850,14 @@ template <typename T> struct PlanT : sb_plan {
             k_point_morph<T><<<n_src, 128, 0, stream>>>(ua, n_src);
             SB_CUDA(cudaGetLastError());
         }
+        if (which == 0 && n_shift) SB_TRY(launch_shift_apply());
         SB_CUDA(cudaStreamSynchronize(stream));
+        return SB_OK;
+    }
+    int launch_shift_apply() {
+        UpdateArgs<T> ua = update_args(0);
+        k_shift_apply<T><<<n_shift, 128, (size_t)3 * npix_max * sizeof(T), stream>>>(ua);
+        SB_CUDA(cudaGetLastError());
         return SB_OK;
     }
     int download_params(int which, double *sed, double *morph, double *center) override {
@@ -882,6 +910,7 @@ template <typename T> struct PlanT : sb_plan {
         a.g_sed = d_gsed.p, a.g_morph = d_gmorph.p, a.g_center = d_gcenter.p;
         a.work = nullptr, a.fast_groups = d_fast_groups.p, a.fast_G = fast_G, a.fast_npix = fast_npix, a.fast_table_cap = fast_table_cap;
         a.scratch_x = d_scratch_x.p, a.scratch_ps = d_scratch_ps.p;
+        a.smorph = d_smorph.p, a.toep = d_toep.p, a.toep_len = toep_len, a.shift_list = d_shift_list.p;
         return a;
     }
 
@@ -906,6 +935,7 @@ template <typename T> struct PlanT : sb_plan {
             RenderArgs<T> ra;
             memset(&ra, 0, sizeof ra);
             ra.src = d_src.p, ra.scene_src_start = d_start.p, ra.sed = d_sed.p, ra.morph = d_morph.p, ra.pmorph = d_pmorph.p;
+            ra.smorph = d_smorph.p;
             ra.C = C, ra.Ny = desc.Ny, ra.Nx = desc.Nx, ra.n_obs = (int)obs.size();
             for (size_t o = 0; o < obs.size(); ++o) ra.obs[o] = obs[o]->dev;
             ra.done = d_done.p;
@@ -923,6 +953,7 @@ template <typename T> struct PlanT : sb_plan {
             memset(&sa, 0, sizeof sa);
             sa.ob = ob.sdev, sa.Ny = desc.Ny, sa.Nx = desc.Nx, sa.Cm = C, sa.npair = ob.npair, sa.cb = ob.cb, sa.done = d_done.p;
             sa.src = d_src.p, sa.scene_src_start = d_start.p, sa.sed = d_sed.p, sa.morph = d_morph.p, sa.pmorph = d_pmorph.p;
+            sa.smorph = d_smorph.p;
             sa.model_out = model_out, sa.partials = ob.partials.p;
             sa.magic_nx = 0xffffffffu / (unsigned)desc.Nx + 1u, sa.max_cand = max_src_scene + 1;
             sa.rendered_out = ((int)o == rendered_obs) ? rendered_out : nullptr;
@@ -1034,6 +1065,10 @@ template <typename T> struct PlanT : sb_plan {
                     SB_CUDA(cudaGetLastError());
                     ++nk;
                 }
+            }
+            if (mode == 0 && n_shift) { // new shifts / images -> new shifted morphologies for the next render
+                SB_TRY(launch_shift_apply());
+                ++nk;
             }
         }
         mark();

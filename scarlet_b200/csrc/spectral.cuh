@@ -52,7 +52,7 @@ template <typename T> struct SpecArgs {
     const DevSource *src;
     const int *scene_src_start;
     const double *sed;
-    const T *morph, *pmorph;
+    const T *morph, *pmorph, *smorph; // smorph: Fourier-shifted images of the shifting sources
     T *model_out; // optional [S][Cm][Ny][Nx]
     // residual
     double *partials; // [S][gridDim.x]
@@ -206,7 +206,7 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
         rc.oy = d.oy, rc.ox = d.ox, rc.By = d.By, rc.Bx = d.Bx;
         const int plane = d.kind == 0 ? 0 : d.By * d.Bx;
         rc.plane = plane;
-        rc.mp = (d.kind == 0 ? a.morph : a.pmorph + (size_t)(ob.chan_off + c0) * plane) + d.morph_off;
+        rc.mp = (d.kind == 0 ? (d.shifting ? a.smorph : a.morph) : a.pmorph + (size_t)(ob.chan_off + c0) * plane) + d.morph_off;
         const double *sed = a.sed + (size_t)k * a.Cm + ob.chan_off + c0;
 #pragma unroll
         for (int c = 0; c < SB_SPEC_MAXCB; ++c) rc.sed[c] = c < Cb ? (T)sed[c] : T(0);

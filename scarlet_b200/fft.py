@@ -175,3 +175,20 @@ def convolve(image, kernel, padding=3, axes=(-2, -1), return_Fourier=True):
     if image.image.ndim == 2:
         out = out[0]
     return Fourier(out) if return_Fourier else out
+
+
+def shift(image, shift, fft_shape=None, axes=(-2, -1), return_Fourier=True):
+    """Sub-pixel translation by a Fourier phase ramp (scarlet/fft.py:399-428): centre-pad to the fast shape of
+    (image, image, padding 10), ifftshift, rfftn, multiply by exp(-2 pi i (fftfreq_y s0 + rfftfreq_x s1)), irfftn, fftshift,
+    centre-crop.  Host NumPy, for stand-alone ``get_model`` calls; inside the fitting loop the same linear map is evaluated on
+    the device from its Toeplitz form (csrc/kernels.cuh: k_shift_apply)."""
+    img = image.image if isinstance(image, Fourier) else np.asarray(image)
+    if img.ndim != 2 or tuple(a % 2 for a in axes) != (0, 1):
+        raise NotImplementedError("shift covers 2-D images")
+    if fft_shape is None:
+        fft_shape = _get_fft_shape(img, img, padding=10, axes=(0, 1))
+    spec = _as_fourier(np.asarray(img, dtype=np.float64)).fft(fft_shape, (0, 1))
+    ramp = np.exp(-2j * np.pi * np.fft.fftfreq(fft_shape[0]) * shift[0])[:, None] * \
+        np.exp(-2j * np.pi * np.fft.rfftfreq(fft_shape[1]) * shift[1])[None, :]
+    out = Fourier.from_fft(spec * ramp, fft_shape, img.shape, (0, 1))
+    return out if return_Fourier else np.real(out.image)

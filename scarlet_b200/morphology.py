@@ -48,7 +48,8 @@ class ImageMorphology(Morphology):
     """Free-form image.  ``resizing=True``: every 10 iterations ``Blend.fit`` calls ``update`` (host), which shrinks the
     box when its outer rings are empty or grows it when the optimiser keeps pulling flux towards an edge; the device
     loop is then re-planned with the new shapes and warm optimiser state (morphology.py:132-207, blend.py:196-198).
-    ``shifting`` (Fourier sub-pixel shift) is a 'next' row (SURVEY f-3)."""
+    ``shifting=True``: the model is the image translated by the free sub-pixel ``shift`` parameter (``fft.shift``); image
+    and shift are both fitted (SURVEY f-3)."""
 
     def __init__(self, frame, image, bbox=None, shifting=False, shift=None, resizing=True):
         if isinstance(image, Parameter):
@@ -74,9 +75,11 @@ class ImageMorphology(Morphology):
         super().__init__(frame, image, shift, bbox=bbox)
 
     def get_model(self, *parameters):
-        if self.shifting:
-            raise NotImplementedError("Fourier-shifted morphologies are a 'next' row (SURVEY f-3)")
-        return self.get_parameter(0, *parameters)
+        image = self.get_parameter(0, *parameters)
+        if self.shifting:  # morphology.py:124-130
+            from . import fft
+            return fft.shift(np.asarray(image), np.asarray(self.get_parameter(1, *parameters)), return_Fourier=False)
+        return image
 
     def _replace_image(self, old, data, m, v, vhat):
         """New image Parameter (private, contiguous copies: the old arrays may live in a plan's staging memory), step halved."""

@@ -108,7 +108,8 @@ def make_blend(scene, precision=32, device=None):
             B = s["morph"].shape[0]
             sources.append(sb.ExtendedSource(frame, s["center"], obs, spectrum=s["sed"].copy(), morphology=s["morph"].copy(),
                                              bbox=sb.Box((B, B), origin=s["origin"]), monotonic="angle",
-                                             symmetric=cfg["symmetric"], resizing=bool(cfg.get("resizing", False))))
+                                             symmetric=cfg["symmetric"], resizing=bool(cfg.get("resizing", False)),
+                                             shifting=bool(cfg.get("shifting", False))))
         else:
             sources.append(sb.PointSource(frame, s["center"], obs, spectrum=s["sed"].copy()))
     return sb.Blend(sources, obs, precision=precision, device=device)

@@ -606,6 +606,44 @@ def test_ragged_batch_and_many_channels():
             assert rel_peak(src.parameters[0], osrc.spectrum.x) < tol
 
 
+@pytest.mark.parametrize("precision,tol", [(64, 1e-9), (32, 2e-5)])
+def test_shifting_morphology_matches_oracle(precision, tol):
+    """ExtendedSource(shifting=True) -- the model uses fft.shift(image, shift) and both are fitted.  The oracle
+    shifts with the reference's literal FFT pipeline and differentiates it with torch autograd; the device evaluates the
+    equivalent Toeplitz operators.  One evaluation (model, loss, gradients wrt spectrum, image and shift), then a fit."""
+    from oracle import scenes
+    from scarlet_b200 import synthetic
+    scene = synthetic.make_scene(dict(C=3, N=40, n_ext=3, n_pt=1, psf="gaussian", P=15, B=15, symmetric=False, iters=10, config_id=31,
+                                      shifting=True), 0)
+    dtype = np.float32 if precision == 32 else np.float64
+    o = scenes.build_oracle(scene, frame_dtype=dtype)
+    blend = synthetic.make_blend(scene, precision=precision)
+    assert [p.name for p in blend.sources[0].parameters] == ["spectrum", "image", "shift"] and not blend.sources[0].parameters[2].fixed
+    plan = blend._get_plan()
+    plan.upload_parameters(state=False)
+    ev = plan.evaluate(want=("model", "loss", "grads"))
+    loss, grads = o.loss_and_grads()
+    assert rel_peak(ev["model"][0], o.get_model()) < tol
+    assert_allclose(ev["loss"][0], loss, rtol=max(tol, 1e-9))
+    gi = 0
+    n_ext = sum(1 for s in o.sources if s.kind == "extended")
+    for k, src in enumerate(o.sources):
+        assert rel_peak(ev["g_sed"][k], grads[gi]) < 20 * tol
+        if src.kind == "extended":
+            assert rel_peak(ev["g_morph"][k], grads[gi + 1]) < 20 * tol
+            assert_allclose(ev["g_center"][k], grads[gi + 2], rtol=200 * tol, atol=200 * tol * np.abs(grads[gi + 2]).max())
+        gi += len(src.parameters)
+    o.fit(max_iter=10, e_rel=1e-3, min_iter=10 ** 9)
+    n, _ = blend.fit(max_iter=10, e_rel=1e-3, min_iter=10 ** 9)
+    assert_allclose(np.array(blend.loss), np.array(o.loss), rtol=max(tol, 1e-9))
+    for src, osrc in zip(blend.sources, o.sources):
+        assert rel_peak(src.parameters[0], osrc.spectrum.x) < 10 * tol
+        if osrc.kind == "extended":
+            assert rel_peak(src.parameters[1], osrc.image.x) < 10 * tol
+            assert np.abs(np.asarray(src.parameters[2]) - osrc.shift.x).max() < 100 * tol
+    assert rel_peak(blend.get_model(), o.get_model()) < 10 * tol
+
+
 def test_nonfinite_raises_arithmetic_error():
     from scarlet_b200 import synthetic
     sc = synthetic.make_scene("tiny", 0)
