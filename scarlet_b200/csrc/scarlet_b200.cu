@@ -521,6 +521,10 @@ template <typename T> struct PlanT : sb_plan {
                     SB_TRY(raise_smem((const void *)ob.ky.column_fwd, ob.smem_col));
                     SB_TRY(raise_smem((const void *)ob.ky.column_inv, ob.smem_col));
                     SB_TRY(raise_smem((const void *)k_resample_lr<T>, (size_t)od.H * od.W * sizeof(T)));
+                    if ((size_t)Fy * SB_RS_ROWS * sizeof(cplx) > 200 * 1024 || (size_t)od.H * SB_RS_KY * sizeof(cplx) > 200 * 1024)
+                        return set_err(SB_ERR_ARG, "observation %d: resampling geometry too large", o);
+                    SB_TRY(raise_smem((const void *)k_resample_t1<T>, (size_t)Fy * SB_RS_ROWS * sizeof(cplx)));
+                    SB_TRY(raise_smem((const void *)k_resample_q<T>, (size_t)od.H * SB_RS_KY * sizeof(cplx)));
                 }
                 SB_TRY(ob.partials.alloc((size_t)S * ob.n_part));
                 SB_TRY(ob.partials.zero(stream));
@@ -965,15 +969,17 @@ template <typename T> struct PlanT : sb_plan {
             mark();
             if (ob.dev.kind == 2) { // resampling observation: M^ -> K^ conj(M^) -> Ey . -> LR, residual -> . Ex, Ey^T . -> K^ Q^ -> G
                 const SpecObs<T> &sd = ob.sdev;
-                const dim3 tgrid((sd.Fxc + 127) / 128, (sd.H + 7) / 8, S * sd.C), qgrid((sd.Fxc + 127) / 128, sd.Fy, S * sd.C);
+                const dim3 tgrid((sd.Fxc + 127) / 128, (sd.H + SB_RS_ROWS - 1) / SB_RS_ROWS, S * sd.C);
+                const dim3 qgrid((sd.Fxc + 127) / 128, (sd.Fy + SB_RS_KY - 1) / SB_RS_KY, S * sd.C);
+                const size_t t1_smem = (size_t)sd.Fy * SB_RS_ROWS * sizeof(cplx), q_smem = (size_t)sd.H * SB_RS_KY * sizeof(cplx);
                 ob.ky.column_fwd<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
-                k_resample_t1<T><<<tgrid, 128, 0, stream>>>(sa);
+                k_resample_t1<T><<<tgrid, 128, t1_smem, stream>>>(sa);
                 SB_CUDA(cudaGetLastError());
                 mark(), mark();
                 k_resample_lr<T><<<S * sd.C, 256, (size_t)sd.H * sd.W * sizeof(T), stream>>>(sa);
                 SB_CUDA(cudaGetLastError());
                 mark(), mark();
-                k_resample_q<T><<<qgrid, 128, 0, stream>>>(sa);
+                k_resample_q<T><<<qgrid, 128, q_smem, stream>>>(sa);
                 ob.ky.column_inv<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
                 SB_CUDA(cudaGetLastError());
                 mark();

@@ -510,31 +510,39 @@ template <typename T, int R1, int R2, int NB> __global__ void __launch_bounds__(
     }
 }
 
-// T1[img][i][kx] = sum_ky Ey[i][ky] P[img][ky][kx];  grid (ceil(Fxc/128), ceil(H/8), S*C), 128 threads
+// T1[img][i][kx] = sum_ky Ey[i][ky] P[img][ky][kx];  grid (ceil(Fxc/128), ceil(H/16), S*C), 128 threads: one kx per thread,
+// 16 low-resolution rows per CTA whose Ey rows are staged in shared memory (P is read ceil(H/16) times in total)
+#define SB_RS_ROWS 16
 template <typename T> __global__ void __launch_bounds__(128) k_resample_t1(const SpecArgs<T> a) {
     typedef typename Cx<T>::type C2;
+    extern __shared__ __align__(16) unsigned char smem[];
     const SpecObs<T> &ob = a.ob;
     const int img = blockIdx.z, s = img / ob.C;
     if (a.done[s]) return;
-    const int kx = blockIdx.x * 128 + threadIdx.x, i0 = blockIdx.y * 8;
+    const int kx = blockIdx.x * 128 + threadIdx.x, i0 = blockIdx.y * SB_RS_ROWS, ni = min(SB_RS_ROWS, ob.H - i0);
+    C2 *ey = reinterpret_cast<C2 *>(smem); // [ky][SB_RS_ROWS]
+    for (int idx = threadIdx.x; idx < ob.Fy * SB_RS_ROWS; idx += blockDim.x) {
+        const int ky = idx / SB_RS_ROWS, q = idx - ky * SB_RS_ROWS;
+        ey[idx] = q < ni ? ob.Ey[(size_t)(i0 + q) * ob.Fy + ky] : C2{T(0), T(0)};
+    }
+    __syncthreads();
     if (kx >= ob.Fxc) return;
-    C2 acc[8];
+    C2 acc[SB_RS_ROWS];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] = C2{T(0), T(0)};
+    for (int q = 0; q < SB_RS_ROWS; ++q) acc[q] = C2{T(0), T(0)};
     const C2 *Pc = ob.P + (size_t)img * ob.Fy * ob.Xp + kx;
     for (int ky = 0; ky < ob.Fy; ++ky) {
         const C2 p = Pc[(size_t)ky * ob.Xp];
+        const C2 *e = ey + ky * SB_RS_ROWS;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-            if (i0 + q < ob.H) {
-                const C2 e = ob.Ey[(size_t)(i0 + q) * ob.Fy + ky];
-                acc[q].x += e.x * p.x - e.y * p.y;
-                acc[q].y += e.x * p.y + e.y * p.x;
-            }
+        for (int q = 0; q < SB_RS_ROWS; ++q) {
+            acc[q].x += e[q].x * p.x - e[q].y * p.y;
+            acc[q].y += e[q].x * p.y + e[q].y * p.x;
+        }
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-        if (i0 + q < ob.H) ob.T1[((size_t)img * ob.H + i0 + q) * ob.Xp + kx] = acc[q];
+    for (int q = 0; q < SB_RS_ROWS; ++q)
+        if (q < ni) ob.T1[((size_t)img * ob.H + i0 + q) * ob.Xp + kx] = acc[q];
 }
 
 // one CTA per (scene, band): LR = h^2 sum_kx c_kx Re(Ex T1), residual r = w (LR - d), chi^2 partial, then U = r Ex -> T1
@@ -580,26 +588,51 @@ template <typename T> __global__ void __launch_bounds__(256) k_resample_lr(const
     if (tid == 0) a.partials[img] = part;
 }
 
-// P[img][ky][kx] = h^2 K^[ky][kx] sum_i Ey[i][ky] U[img][i][kx];  grid (ceil(Fxc/128), Fy, S*C)
+// P[img][ky][kx] = h^2 K^[ky][kx] sum_i Ey[i][ky] U[img][i][kx];  grid (ceil(Fxc/128), ceil(Fy/64), S*C), 128 threads: one kx
+// per thread, 64 ky per CTA; the U column of a thread is held in registers 16 rows at a time, Ey in shared memory
+#define SB_RS_KY 64
 template <typename T> __global__ void __launch_bounds__(128) k_resample_q(const SpecArgs<T> a) {
     typedef typename Cx<T>::type C2;
+    extern __shared__ __align__(16) unsigned char smem[];
     const SpecObs<T> &ob = a.ob;
     const int img = blockIdx.z, s = img / ob.C;
     if (a.done[s]) return;
-    const int kx = blockIdx.x * 128 + threadIdx.x, ky = blockIdx.y;
-    if (kx >= ob.Fxc) return;
-    C2 acc = C2{T(0), T(0)};
-    const C2 *U = ob.T1 + (size_t)img * ob.H * ob.Xp + kx;
-    for (int i = 0; i < ob.H; ++i) {
-        const C2 e = ob.Ey[(size_t)i * ob.Fy + ky], u = U[(size_t)i * ob.Xp];
-        acc.x += e.x * u.x - e.y * u.y;
-        acc.y += e.x * u.y + e.y * u.x;
+    const int kx = blockIdx.x * 128 + threadIdx.x, ky0 = blockIdx.y * SB_RS_KY, nky = min(SB_RS_KY, ob.Fy - ky0);
+    C2 *ey = reinterpret_cast<C2 *>(smem); // [H][SB_RS_KY]
+    for (int idx = threadIdx.x; idx < ob.H * SB_RS_KY; idx += blockDim.x) {
+        const int i = idx / SB_RS_KY, q = idx - i * SB_RS_KY;
+        ey[idx] = q < nky ? ob.Ey[(size_t)i * ob.Fy + ky0 + q] : C2{T(0), T(0)};
     }
-    const C2 k = ob.khat[((size_t)(ob.khat_shared ? img - s * ob.C : img) * ob.Fy + ky) * ob.Xp + kx];
-    C2 out;
-    out.x = ob.h2 * (k.x * acc.x - k.y * acc.y);
-    out.y = ob.h2 * (k.x * acc.y + k.y * acc.x);
-    ob.P[((size_t)img * ob.Fy + ky) * ob.Xp + kx] = out;
+    __syncthreads();
+    if (kx >= ob.Fxc) return;
+    const C2 *U = ob.T1 + (size_t)img * ob.H * ob.Xp + kx;
+    const C2 *K = ob.khat + ((size_t)(ob.khat_shared ? img - s * ob.C : img) * ob.Fy + ky0) * ob.Xp + kx;
+    C2 *Pout = ob.P + ((size_t)img * ob.Fy + ky0) * ob.Xp + kx;
+    for (int ib = 0; ib < ob.H; ib += SB_RS_ROWS) {
+        C2 u[SB_RS_ROWS];
+#pragma unroll
+        for (int q = 0; q < SB_RS_ROWS; ++q) u[q] = ib + q < ob.H ? U[(size_t)(ib + q) * ob.Xp] : C2{T(0), T(0)};
+        for (int q = 0; q < nky; ++q) {
+            C2 acc = C2{T(0), T(0)};
+#pragma unroll
+            for (int r = 0; r < SB_RS_ROWS; ++r) {
+                if (ib + r < ob.H) {
+                    const C2 e = ey[(ib + r) * SB_RS_KY + q];
+                    acc.x += e.x * u[r].x - e.y * u[r].y;
+                    acc.y += e.x * u[r].y + e.y * u[r].x;
+                }
+            }
+            const C2 k = K[(size_t)q * ob.Xp];
+            C2 out;
+            out.x = ob.h2 * (k.x * acc.x - k.y * acc.y);
+            out.y = ob.h2 * (k.x * acc.y + k.y * acc.x);
+            C2 *dst = Pout + (size_t)q * ob.Xp;
+            if (ib == 0)
+                *dst = out;
+            else
+                dst->x += out.x, dst->y += out.y;
+        }
+    }
 }
 
 // ---- dispatch table ----------------------------------------------------------------------------------
