@@ -18,7 +18,8 @@ from .parameter import Parameter, relative_step  # noqa: F401
 from .prior import Prior  # noqa: F401
 from .psf import PSF, GaussianPSF, ImagePSF  # noqa: F401
 from .renderer import ConvolutionRenderer, NullRenderer, Renderer  # noqa: F401
-from .source import ExtendedSource, PointSource  # noqa: F401
+from .source import (CompactExtendedSource, ExtendedSource, MultiExtendedSource, PointSource,  # noqa: F401
+                     SingleExtendedSource)
 from .spectrum import Spectrum, TabulatedSpectrum  # noqa: F401
 
 __version__ = "0.1.0"

@@ -291,8 +291,32 @@ def multires(sc):
     save("multires.npz", **out)
 
 
+def source_recipes(sc):
+    """The other branches of the reference's ``ExtendedSource`` factory on data/hsc_cosmos_35.npz: a two-component source
+    (K=2) and a compact one, initialised by the reference."""
+    d = np.load(os.path.join(REF_DATA, "hsc_cosmos_35.npz"))
+    images, variance, psfs = d["images"], d["variance"], d["psfs"]
+    channels = [str(f) for f in d["filters"]]
+    centers = [(float(s["y"]), float(s["x"])) for s in d["catalog"]][:3]
+    frame = sc.frame.Frame(images.shape, psf=sc.psf.GaussianPSF(sigma=(0.8,) * len(channels)), channels=channels)
+    obs = sc.observation.Observation(images, psf=sc.psf.ImagePSF(psfs.copy()), weights=1 / variance, channels=channels)
+    obs.match(frame)
+    out = dict(centers=np.array(centers))
+    multi = sc.source.ExtendedSource(frame, centers[1], obs, K=2)
+    for k, comp in enumerate(multi.children):
+        out["multi%d_spectrum" % k] = np.asarray(comp.parameters[0])
+        out["multi%d_image" % k] = np.asarray(comp.parameters[1])
+        out["multi%d_origin" % k] = np.array(comp.bbox.origin)
+        out["multi%d_spectrum_step" % k] = np.asarray(comp.parameters[0].step(comp.parameters[0], it=0))
+    compact = sc.source.ExtendedSource(frame, centers[2], obs, compact=True)
+    out.update(compact_spectrum=np.asarray(compact.parameters[0]), compact_image=np.asarray(compact.parameters[1]),
+               compact_origin=np.array(compact.bbox.origin))
+    save("source_recipes.npz", **out)
+
+
 if __name__ == "__main__":
     sc = ref_shim.install()
-    which = sys.argv[1:] or ["obs_render_loss", "hsc_cosmos_35", "point_extended", "prox_chain", "monotonic_weights", "multires"]
+    which = sys.argv[1:] or ["obs_render_loss", "hsc_cosmos_35", "point_extended", "prox_chain", "monotonic_weights", "multires",
+                             "source_recipes"]
     for name in which:
         globals()[name](sc)

@@ -246,6 +246,23 @@ def test_source_initialisation_vs_reference_fixture():
     pt = sb.PointSource(frame, tuple(g["centers"][0]), obs)
     peak = sb.ImagePSF(g["psfs"]).get_model().max(axis=(1, 2))
     assert_allclose(pt.parameters[0], g["images"][:, 33, 14] / peak, rtol=1e-6)
+    # the other branches of the factory (source.py:759-807): two stacked components, and a compact source
+    r = golden("source_recipes.npz")
+    multi = sb.ExtendedSource(frame, tuple(r["centers"][1]), obs, K=2)
+    assert isinstance(multi, sb.MultiExtendedSource) and len(multi.children) == 2
+    for k, comp in enumerate(multi.children):
+        assert comp.bbox.origin == tuple(r["multi%d_origin" % k])
+        assert_allclose(comp.parameters[0], r["multi%d_spectrum" % k], rtol=1e-6)
+        assert_allclose(comp.parameters[1], r["multi%d_image" % k], atol=1e-6)
+        assert_allclose(comp.parameters[0].step(comp.parameters[0], it=0), r["multi%d_spectrum_step" % k], rtol=1e-5)
+    compact = sb.ExtendedSource(frame, tuple(r["centers"][2]), obs, compact=True)
+    assert compact.bbox.origin == tuple(r["compact_origin"])
+    assert_allclose(compact.parameters[0], r["compact_spectrum"], rtol=1e-6)
+    assert_allclose(compact.parameters[1], r["compact_image"], atol=1e-12)
+    # a blend of all recipes fits on the device (CombinedComponent leaves are flattened into the plan)
+    blend = sb.Blend([multi, compact, pt], obs)
+    n, logL = blend.fit(12, e_rel=1e-4)
+    assert n == 12 and np.isfinite(logL) and blend.loss[-1] < blend.loss[0]
 
 
 @pytest.mark.parametrize("precision,tol", [(64, 1e-8), (32, 1e-4)])
