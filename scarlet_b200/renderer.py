@@ -76,8 +76,12 @@ class ConvolutionRenderer(Renderer):
     def __init__(self, data_frame, model_frame, *parameters, convolution_type="fft", padding=10, psf_shift=None):
         if psf_shift is not None:
             raise NotImplementedError("psf_shift is outside the device path (SURVEY 2.1: out of scope)")
-        if convolution_type != "fft":
-            raise NotImplementedError("real-space convolution is a 'next' row (SURVEY f-4)")
+        if convolution_type not in ("fft", "real"):
+            raise ValueError("`convolution` must be either 'real' or 'fft', got {}".format(convolution_type))
+        # "real" (renderer.py:97-127, operators_pybind11.cc:39-56: a sum of shifted, scaled copies of the image, zero outside
+        # the frame) and "fft" are the same linear map -- a "same"-size convolution with the difference kernel -- and the
+        # device evaluates that one map for both; only the floating-point summation order differs from the reference's
+        # real-space loop.
         super().__init__(data_frame, model_frame, *parameters)
         self._convolution_type = convolution_type
         self.slices, self.origin = _spatial_slices(data_frame, model_frame)
