@@ -661,6 +661,41 @@ def test_shifting_morphology_matches_oracle(precision, tol):
     assert rel_peak(blend.get_model(), o.get_model()) < 10 * tol
 
 
+def test_post_fit_api_pickle_render_measure():
+    """what users do around fit (quickstart cells 27-34): get_model, Observation.render, measure.*, pickle of the sources
+    with their optimiser state (Parameter.m / v / vhat / std live in the plan's packed host arrays until detached)"""
+    import pickle
+    import scarlet_b200 as sb
+    from scarlet_b200 import measure, synthetic
+    scene = synthetic.make_scene("tiny", 3)
+    blend = synthetic.make_blend(scene)
+    blend.fit(max_iter=8, e_rel=1e-4)
+    model = blend.get_model()
+    obs = blend.observations[0]
+    rendered = obs.render(model)
+    assert rendered.shape == obs.data.shape and np.isfinite(rendered).all()
+    plan = blend._get_plan()
+    plan.upload_parameters(state=False)
+    assert_allclose(obs.get_log_likelihood(model), -plan.evaluate(want=("loss",))["loss"][0], rtol=1e-5)  # host formula vs device loss
+    src = blend.sources[0]
+    assert measure.flux(src).shape == (3,) and measure.snr(src, obs) > 0
+    p = src.parameters[1]
+    assert p.m is not None and p.v.shape == p.shape and np.ma.isMaskedArray(p.std)
+    blob = pickle.dumps(blend.sources)
+    v_before = np.array(p.v)
+    blend._plan.close()  # frees the packed staging arrays: the parameters keep private copies of their state
+    assert_array_equal(np.array(p.v), v_before) and p.std is not None
+    restored = pickle.loads(blob)
+    q = restored[0].parameters[1]
+    assert_array_equal(np.asarray(q), np.asarray(p))
+    assert_array_equal(q.v, v_before)
+    assert_allclose(q.std, p.std)
+    # a second fit on the restored sources warm-starts from the pickled state
+    blend2 = sb.Blend(restored, obs)
+    n, _ = blend2.fit(max_iter=3, e_rel=1e-9)
+    assert n == 3 and np.isfinite(blend2.loss).all()
+
+
 def test_nonfinite_raises_arithmetic_error():
     from scarlet_b200 import synthetic
     sc = synthetic.make_scene("tiny", 0)
