@@ -228,6 +228,14 @@ int sb_fft_convolve_f32(const float *image, int C, int Ny, int Nx, const double 
 int sb_fft_convolve_f64(const double *image, int C, int Ny, int Nx, const double *khat, int Fy, int Fx,
                         int adjoint, double *out, int device);
 
+/* Same argument list as the reference binding apply_filter(image, values, y_start, y_end, x_start, x_end, result)
+ * (operators_pybind11.cc:39-56, bound at :248-249): result = sum_n values[n] * image shifted by tap n, zero outside the image;
+ * taps are accumulated per pixel in order n = 0..n_taps-1 with separate multiply and add, like the reference's loop. */
+int sb_apply_filter_f32(const float *image, int H, int W, const float *values, const int32_t *y_start, const int32_t *y_end,
+                        const int32_t *x_start, const int32_t *x_end, int n_taps, float *result, int device);
+int sb_apply_filter_f64(const double *image, int H, int W, const double *values, const int32_t *y_start, const int32_t *y_end,
+                        const int32_t *x_start, const int32_t *x_end, int n_taps, double *result, int device);
+
 #ifdef __cplusplus
 }
 #endif

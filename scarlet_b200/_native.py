@@ -96,6 +96,8 @@ SYMBOLS = {
     "sb_monotonic_f64": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int]),
     "sb_prox_chain_f32": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(sb_chain_desc), _P, C.c_int, C.c_int]),
     "sb_prox_chain_f64": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(sb_chain_desc), _P, C.c_int, C.c_int]),
+    "sb_apply_filter_f32": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int]),
+    "sb_apply_filter_f64": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int]),
     "sb_fft_convolve_f32": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int]),
     "sb_fft_convolve_f64": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int]),
 }

@@ -1321,6 +1321,20 @@ __global__ void k_embed_kernel(const double *ker, double *grid, int n_img, int P
         grid[(im * Fy + gy) * Fx + gx] = ker[i];
     }
 }
+// real-space filter of the reference's apply_filter (operators_pybind11.cc:39-56), gather form: one thread per output pixel
+template <typename T>
+__global__ void k_apply_filter(const T *img, int H, int W, const T *values, const int *ys, const int *ye, const int *xs, const int *xe,
+                               int n_taps, T *out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    T acc = T(0);
+    for (int n = 0; n < n_taps; ++n) {
+        const int r = y - ys[n], c = x - xs[n];
+        if (r >= 0 && c >= 0 && r < H - ys[n] - ye[n] && c < W - xs[n] - xe[n])
+            acc = add_rn(acc, mul_rn(values[n], img[(size_t)(r + ye[n]) * W + c + xe[n]]));
+    }
+    out[(size_t)y * W + x] = acc;
+}
 template <typename TI, typename TO> __global__ void k_cast(const TI *in, TO *out, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = (TO)in[i];

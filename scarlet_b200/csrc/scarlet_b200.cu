@@ -1521,3 +1521,39 @@ int sb_fft_convolve_f64(const double *image, int C, int Ny, int Nx, const double
 }
 
 } // extern "C"
+
+// ---- apply_filter ------------------------------------------------------------------------------------------------
+template <typename T>
+static int run_apply_filter(const T *image, int H, int W, const T *values, const int32_t *ys, const int32_t *ye, const int32_t *xs,
+                            const int32_t *xe, int n_taps, T *result, int device) {
+    if (!image || !values || !ys || !ye || !xs || !xe || !result || H <= 0 || W <= 0 || n_taps < 0) return set_err(SB_ERR_ARG, "bad argument");
+    SB_TRY(need_device(device));
+    SB_CUDA(cudaSetDevice(device));
+    DevBuf<T> dimg, dval, dout;
+    DevBuf<int> db[4];
+    const int32_t *hb[4] = {ys, ye, xs, xe};
+    SB_TRY(dimg.alloc((size_t)H * W));
+    SB_TRY(dout.alloc((size_t)H * W));
+    SB_TRY(dval.alloc(std::max(n_taps, 1)));
+    SB_CUDA(cudaMemcpy(dimg.p, image, (size_t)H * W * sizeof(T), cudaMemcpyHostToDevice));
+    if (n_taps) SB_CUDA(cudaMemcpy(dval.p, values, (size_t)n_taps * sizeof(T), cudaMemcpyHostToDevice));
+    for (int i = 0; i < 4; ++i) {
+        SB_TRY(db[i].alloc(std::max(n_taps, 1)));
+        if (n_taps) SB_CUDA(cudaMemcpy(db[i].p, hb[i], (size_t)n_taps * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8);
+    k_apply_filter<T><<<grid, block>>>(dimg.p, H, W, dval.p, db[0].p, db[1].p, db[2].p, db[3].p, n_taps, dout.p);
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaMemcpy(result, dout.p, (size_t)H * W * sizeof(T), cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+extern "C" {
+int sb_apply_filter_f32(const float *image, int H, int W, const float *values, const int32_t *y_start, const int32_t *y_end,
+                        const int32_t *x_start, const int32_t *x_end, int n_taps, float *result, int device) {
+    return run_apply_filter<float>(image, H, W, values, y_start, y_end, x_start, x_end, n_taps, result, device);
+}
+int sb_apply_filter_f64(const double *image, int H, int W, const double *values, const int32_t *y_start, const int32_t *y_end,
+                        const int32_t *x_start, const int32_t *x_end, int n_taps, double *result, int device) {
+    return run_apply_filter<double>(image, H, W, values, y_start, y_end, x_start, x_end, n_taps, result, device);
+}
+} // extern "C"

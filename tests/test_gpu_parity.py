@@ -74,6 +74,29 @@ def test_monotonic_batch_and_arbitrary_order():
     assert_array_equal(a, b)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_apply_filter_bit_exact(dtype):
+    """the reference's second native entry point (operators_pybind11.cc:39-56): real-space filter as a sum of shifted,
+    scaled blocks -- against the same loop in NumPy (separate multiply and add per tap, image dtype), bit for bit"""
+    from scarlet_b200.operators_pybind11 import apply_filter
+    rng = np.random.default_rng(9)
+    img = rng.standard_normal((23, 31)).astype(dtype)
+    ker = rng.standard_normal((5, 7)).astype(dtype)
+    dy, dx = np.mgrid[:5, :7]
+    dy, dx = (dy - 2).reshape(-1), (dx - 3).reshape(-1)
+    z = np.zeros(dy.size, dtype=int)
+    ys, ye, xs, xe = np.maximum(z, dy), -np.minimum(z, dy), np.maximum(z, dx), -np.minimum(z, dx)
+    ref = np.zeros_like(img)
+    for n, v in enumerate(ker.reshape(-1)):
+        rows, cols = img.shape[0] - ys[n] - ye[n], img.shape[1] - xs[n] - xe[n]
+        ref[ys[n]:ys[n] + rows, xs[n]:xs[n] + cols] += v * img[ye[n]:ye[n] + rows, xe[n]:xe[n] + cols]
+    out = np.full_like(img, np.nan)
+    apply_filter(img, ker.reshape(-1), ys, ye, xs, xe, out)
+    assert_array_equal(out, ref)
+    from scipy import signal
+    assert_allclose(out, signal.convolve2d(img.astype(np.float64), ker.astype(np.float64), mode="same"), atol=1e-4 if dtype == np.float32 else 1e-12)
+
+
 def test_native_errors_are_reported():
     from scarlet_b200 import _native
     from scarlet_b200.operators_pybind11 import prox_weighted_monotonic
