@@ -382,6 +382,20 @@ __device__ __forceinline__ double grad_at(const UpdateArgs<T> &a, int s, int c, 
     return g;
 }
 
+// The C band gradients at one pixel.  With a single observation the loads are issued back to back (straight-line code, no
+// loop over observations between them) so that one memory round trip serves all bands; otherwise band by band via grad_at.
+template <typename T, int CMAX>
+__device__ __forceinline__ void grad_bands(const UpdateArgs<T> &a, int s, int C, int y, int x, T (&v)[CMAX]) {
+    const DevObs<T> &ob = a.obs[0];
+    const size_t plane = (size_t)ob.Bh * ob.Bw;
+    const T *b = ob.B + ((size_t)s * ob.C * ob.Bh + y) * ob.Bw + x;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        const int co = c - ob.chan_off;
+        v[c] = (c < C && co >= 0 && co < ob.C) ? b[(size_t)co * plane] : T(0);
+    }
+}
+
 // AMSGrad moments (Reddi, Kale & Kumar 2018, no bias correction) -- proxmin's _amsgrad_phi_psi as restated
 // in oracle/scarlet_oracle.py:amsgrad_phi_psi.  Returns psi; m, v, vhat updated in place.
 __device__ __forceinline__ double amsgrad(double g, double &m, double &v, double &vhat, int it, const FitScalars &fs) {
@@ -812,6 +826,12 @@ template <typename T> __global__ void __launch_bounds__(128) k_update(const Upda
 // ======================================================================================================
 // GT = threads per group (64 or 128), a template parameter of everything below
 
+// Thread index inside a group.  Wavefront levels mostly hold fewer than 32 tasks, so only the warp with lt < 32 works during
+// the sweep; a warp's scheduler is (warp index mod 4), and with the plain numbering those leading warps would all sit on
+// schedulers 0 and 2 (GT = 64).  Every other pair of groups therefore numbers its warps the other way round.
+template <int GT> __device__ __forceinline__ int group_lane(int g) {
+    return GT == 64 ? (int)((threadIdx.x ^ (((unsigned)g >> 1 & 1u) << 5)) & 63u) : (int)(threadIdx.x & (GT - 1));
+}
 template <int GT> __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(GT) : "memory"); }
 
 struct GroupRed {
@@ -858,7 +878,7 @@ template <typename T> struct FastTable { // shared-memory image of a DevMono wit
 // (empty slots are trailing), which leaves the sum bit-identical.
 template <typename T, int GT> __device__ __forceinline__ void group_sweep(T *img, const FastTable<T> &t, T min_gradient, int g) {
     const T keep = T(1) - min_gradient;
-    const int lt = threadIdx.x & (GT - 1);
+    const int lt = group_lane<GT>(g);
     int beg = t.ls[0];
     for (int L = 0; L < t.n_levels; ++L) {
         const int end = t.ls[L + 1];
@@ -880,7 +900,7 @@ template <typename T, int GT> __device__ __forceinline__ void group_sweep(T *img
 
 template <typename T, int GT>
 __device__ void group_chain(T *a, int By, int Bx, const DevChain &ch, const FastTable<T> &tab, GroupRed &red) {
-    const int n = By * Bx, lt = threadIdx.x & (GT - 1), g = red.g;
+    const int n = By * Bx, g = red.g, lt = group_lane<GT>(g);
     for (int r = 0; r < ch.repeat; ++r) {
         for (int o = 0; o < ch.n_ops; ++o) {
             const sb_op op = ch.ops[o];
@@ -996,7 +1016,7 @@ __device__ inline FusedChain fused_chain_of(const DevChain &ch, int By, int Bx) 
 
 template <typename T, int GT> __global__ void __launch_bounds__(1024, 1) k_update_fast(const UpdateArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int G = a.fast_G, g = threadIdx.x / GT, lt = threadIdx.x & (GT - 1);
+    const int G = a.fast_G, g = threadIdx.x / GT, lt = group_lane<GT>(g);
     const int *mine = a.fast_groups + (size_t)blockIdx.x * G;
     // ---- shared memory carve-up: table (W4 | uint2 | int ls | u16 pix), reduction slots, G images
     const int cap = a.fast_table_cap;
@@ -1067,22 +1087,54 @@ template <typename T, int GT> __global__ void __launch_bounds__(1024, 1) k_updat
     for (int p0 = lt; p0 < n; p0 += PB * GT) {
         T mval[PB], m0[PB], v0[PB], vh0[PB];
         double gm[PB];
+        if (a.n_obs == 1) { // every load of the trip first, then the arithmetic
+            T gv[PB][SB_FAST_MAXC];
+            bool in[PB];
 #pragma unroll
-        for (int i = 0; i < PB; ++i) {
-            const int p = p0 + i * GT;
-            mval[i] = m0[i] = v0[i] = vh0[i] = T(0);
-            gm[i] = 0.0;
-            if (p < n) {
-                const int by = (int)__umulhi((unsigned)p, magic), bx = p - by * Bx, y = d.oy + by, x = d.ox + bx;
-                mval[i] = mp[p];
-                if (upd) m0[i] = mm[p], v0[i] = mv[p], vh0[i] = mvh[p];
-                if ((unsigned)y < (unsigned)a.Ny && (unsigned)x < (unsigned)a.Nx) {
+            for (int i = 0; i < PB; ++i) {
+                const int p = p0 + i * GT;
+                mval[i] = m0[i] = v0[i] = vh0[i] = T(0);
+                in[i] = false;
+                if (p < n) {
+                    const int by = (int)__umulhi((unsigned)p, magic), bx = p - by * Bx, y = d.oy + by, x = d.ox + bx;
+                    mval[i] = mp[p];
+                    if (upd) m0[i] = mm[p], v0[i] = mv[p], vh0[i] = mvh[p];
+                    in[i] = (unsigned)y < (unsigned)a.Ny && (unsigned)x < (unsigned)a.Nx;
+                    if (in[i]) grad_bands<T, SB_FAST_MAXC>(a, s, C, y, x, gv[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < PB; ++i) {
+                gm[i] = 0.0;
+                if (in[i]) {
 #pragma unroll
                     for (int c = 0; c < SB_FAST_MAXC; ++c) {
                         if (c < C) {
-                            const double gg = grad_at<T>(a, s, c, y, x);
+                            const double gg = 0.0 + (double)gv[i][c];
                             gm[i] += gsum[c] * gg;
                             gs[c] += (T)gg * mval[i];
+                        }
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PB; ++i) {
+                const int p = p0 + i * GT;
+                mval[i] = m0[i] = v0[i] = vh0[i] = T(0);
+                gm[i] = 0.0;
+                if (p < n) {
+                    const int by = (int)__umulhi((unsigned)p, magic), bx = p - by * Bx, y = d.oy + by, x = d.ox + bx;
+                    mval[i] = mp[p];
+                    if (upd) m0[i] = mm[p], v0[i] = mv[p], vh0[i] = mvh[p];
+                    if ((unsigned)y < (unsigned)a.Ny && (unsigned)x < (unsigned)a.Nx) {
+#pragma unroll
+                        for (int c = 0; c < SB_FAST_MAXC; ++c) {
+                            if (c < C) {
+                                const double gg = grad_at<T>(a, s, c, y, x);
+                                gm[i] += gsum[c] * gg;
+                                gs[c] += (T)gg * mval[i];
+                            }
                         }
                     }
                 }

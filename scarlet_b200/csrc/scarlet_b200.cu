@@ -223,7 +223,8 @@ struct sb_plan {
     virtual int spectral_mode() const = 0;
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side = nullptr; // runs the generic update kernel next to the grouped one
     int64_t dev_bytes = 0;
     int64_t launches = 0;
 };
@@ -297,7 +298,10 @@ template <typename T> struct PlanT : sb_plan {
         if (h_nactive) cudaFreeHost(h_nactive);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
         if (stream) cudaStreamDestroy(stream);
+        if (side) cudaStreamDestroy(side);
     }
 
     int64_t total_bytes() {
@@ -320,6 +324,9 @@ template <typename T> struct PlanT : sb_plan {
         SB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         SB_CUDA(cudaEventCreate(&ev0));
         SB_CUDA(cudaEventCreate(&ev1));
+        SB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        SB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        SB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         SB_CUDA(cudaHostAlloc((void **)&h_nactive, sizeof(int), cudaHostAllocDefault));
 
         // ---- constraint tables
@@ -1057,6 +1064,13 @@ template <typename T> struct PlanT : sb_plan {
                 SB_CUDA(cudaGetLastError());
                 ++nk;
             } else {
+                // The generic kernel works on other sources than the grouped one, which leaves room on every SM: fork it
+                // onto the side stream so that the two run concurrently (also inside a graph capture).
+                const bool fork = n_fast_cta && n_generic && !marks;
+                if (fork) {
+                    SB_CUDA(cudaEventRecord(ev_fork, stream));
+                    SB_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+                }
                 if (n_fast_cta) {
                     if (fast_GT == 128)
                         k_update_fast<T, 128><<<n_fast_cta, 128 * fast_G, fast_smem, stream>>>(ua);
@@ -1065,7 +1079,17 @@ template <typename T> struct PlanT : sb_plan {
                     SB_CUDA(cudaGetLastError());
                     ++nk;
                 }
-                if (n_generic) {
+                if (fork) { // launched second: the grouped kernel's one big CTA per SM goes in first, these fill the rest
+                    UpdateArgs<T> ug = ua;
+                    ug.work = d_work.p;
+                    k_update<T><<<n_generic, 128, update_smem(), side>>>(ug);
+                    SB_CUDA(cudaGetLastError());
+                    ++nk;
+                    SB_CUDA(cudaEventRecord(ev_join, side));
+                }
+                if (fork) {
+                    SB_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+                } else if (n_generic) {
                     ua.work = d_work.p;
                     k_update<T><<<n_generic, 128, update_smem(), stream>>>(ua);
                     SB_CUDA(cudaGetLastError());

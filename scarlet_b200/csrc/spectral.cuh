@@ -220,16 +220,40 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
 #pragma unroll
         for (int c = 0; c < SB_SPEC_MAXCB; ++c) acc[c] = T(0);
         if (y < Ny) {
+            // candidates four at a time: the morphology values of a chunk are fetched back to back, then accumulated in
+            // candidate order (one memory round trip per chunk instead of one per overlapping source)
 #pragma unroll 1
-            for (int i = 0; i < ncand; ++i) {
-                const SpecCand<T> &rc = recs[i];
-                const int by = y - rc.oy, bx = x - rc.ox;
-                if ((unsigned)by < (unsigned)rc.By && (unsigned)bx < (unsigned)rc.Bx) {
-                    const T *pm = rc.mp + by * rc.Bx + bx;
-                    const int plane = rc.plane; // 0: one morphology image for all bands; else per-band planes (point sources)
+            for (int i0 = 0; i0 < ncand; i0 += 4) {
+                const T *pm[4];
+                T v[4];
 #pragma unroll
-                    for (int c = 0; c < SB_SPEC_MAXCB; ++c)
-                        if (c < Cb) acc[c] += rc.sed[c] * pm[c * plane];
+                for (int j = 0; j < 4; ++j) {
+                    pm[j] = nullptr;
+                    v[j] = T(0);
+                    if (i0 + j < ncand) {
+                        const SpecCand<T> &rc = recs[i0 + j];
+                        const int by = y - rc.oy, bx = x - rc.ox;
+                        if ((unsigned)by < (unsigned)rc.By && (unsigned)bx < (unsigned)rc.Bx) {
+                            pm[j] = rc.mp + by * rc.Bx + bx;
+                            v[j] = pm[j][0];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (pm[j]) {
+                        const SpecCand<T> &rc = recs[i0 + j];
+                        const int plane = rc.plane; // 0: one morphology image for all bands; else per-band planes (point sources)
+                        if (plane == 0) {
+#pragma unroll
+                            for (int c = 0; c < SB_SPEC_MAXCB; ++c)
+                                if (c < Cb) acc[c] += rc.sed[c] * v[j];
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < SB_SPEC_MAXCB; ++c)
+                                if (c < Cb) acc[c] += rc.sed[c] * pm[j][c * plane];
+                        }
+                    }
                 }
             }
         }
@@ -299,19 +323,20 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
             const int dy0 = y - ob.oy, dy1 = dy0 + 1;
             const bool row0 = y < Ny && (unsigned)dy0 < (unsigned)ob.H, row1 = y + 1 < Ny && (unsigned)dy1 < (unsigned)ob.H;
             const size_t base0 = ((size_t)(s * Co + c) * ob.H + dy0) * ob.W, base1 = base0 + ob.W;
+            // (read-only loads: the optional rendered_out stores in between must not serialise them)
             sbfft::static_for<0, R1>([&](auto i) {
                 constexpr int n1 = decltype(i)::value;
                 const int x = n1 * R2 + n2, dx = x - ob.ox;
                 const bool col = x < Nx && (unsigned)dx < (unsigned)ob.W;
                 T r0 = T(0), r1 = T(0);
                 if (col && row0) {
-                    const T m = a_[n1].x, w = ob.weights[base0 + dx], diff = m - ob.data[base0 + dx];
+                    const T m = a_[n1].x, w = __ldg(ob.weights + base0 + dx), diff = m - __ldg(ob.data + base0 + dx);
                     r0 = w * diff;
                     part_t += r0 * diff;
                     if (a.rendered_out) a.rendered_out[base0 + dx] = m;
                 }
                 if (col && row1) {
-                    const T m = a_[n1].y, w = ob.weights[base1 + dx], diff = m - ob.data[base1 + dx];
+                    const T m = a_[n1].y, w = __ldg(ob.weights + base1 + dx), diff = m - __ldg(ob.data + base1 + dx);
                     r1 = w * diff;
                     part_t += r1 * diff;
                     if (a.rendered_out) a.rendered_out[base1 + dx] = m;
