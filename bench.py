@@ -9,8 +9,9 @@ A "step" is one fit of a batch of independent synthetic scenes for a FIXED numbe
 + gradient back-propagation + AMSGrad/proximal update of every parameter.
 
   value  : scene-iterations per second over all GPUs, inputs resident in HBM, CUDA-event timed (max over ranks)
-  e2e    : the same through the public API (BlendBatch.fit) with host buffers: pinned H2D copy of the observation
-           cubes, K^ and parameters, and D2H read-back of fitted parameters, optimiser state and losses, every step
+  e2e    : the same through the public API (BatchPipeline over BlendBatch objects) with host buffers: pinned H2D copy of
+           the observation cubes, kernel images and parameters, and D2H read-back of fitted parameters, optimiser state
+           and losses, every step; the copies of one batch overlap the device loop of the other
   roofline: dominant stage of an iteration, algorithmic bytes / CUDA-event time, against MEASURED_PEAKS.json
   cpu_baseline: the oracle restatement of the reference loop on one host core (rank 0, N=1, bounded sample)
 Multi-GPU: independent scenes are sharded across ranks (weak scaling, no collective inside the loop); NCCL is used
@@ -43,7 +44,9 @@ def parse():
     ap.add_argument("--precision", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-single", action="store_true")
-    ap.add_argument("--e2e-streams", type=int, default=3, help="plans/streams of the end-to-end leg (copy/compute overlap)")
+    ap.add_argument("--e2e-mode", default="pipeline", choices=["pipeline", "batch"],
+                    help="end-to-end leg: a stream of batches through BatchPipeline (default) or one BlendBatch.fit per step")
+    ap.add_argument("--e2e-streams", type=int, default=3, help="--e2e-mode batch: plans/streams of the BlendBatch (copy/compute overlap)")
     return ap.parse_args()
 
 
@@ -273,33 +276,58 @@ def run_b200(args):
     value = world * S * iters * args.steps / (ms_total / 1e3)
 
     # ---- end-to-end through the public API with host buffers (e2e) -------------------------------
-    # The same scenes as one BlendBatch split over a few plans/streams, so that the copies of one part overlap the loop of
-    # another; built here (the device-resident leg above keeps the single plan).
+    # A stream of batches through BatchPipeline: two BlendBatch objects (own host Parameters, own pinned staging, own device
+    # plan) take turns; while the device loops over one, the other copies its results out and the next step's observations,
+    # kernel images and parameters in.  Every step's H2D and D2H copies are inside the timed region.
+    # (--e2e-mode batch: one BlendBatch.fit per step, split over --e2e-streams plans.)
+    from scarlet_b200 import BatchPipeline
     h2d = d2h = 0
-    batch_e2e = BlendBatch(blends, precision=args.precision, device=local, n_streams=args.e2e_streams) if args.e2e_streams > 1 else batch
-    init_parts = [p.pack_current()[0] for p in batch_e2e.plans]
+    pipelined = args.e2e_mode == "pipeline"
+    if pipelined:
+        blends_b = [_make_blend(args.config, base[i % uniq], precision=args.precision, device=local) for i in range(S)]
+        batch_b = BlendBatch(blends_b, precision=args.precision, device=local)
+        turn_batches = [batch, batch_b]
+        batch_e2e = batch
+    else:
+        batch_e2e = BlendBatch(blends, precision=args.precision, device=local, n_streams=args.e2e_streams) if args.e2e_streams > 1 else batch
+        turn_batches = [batch_e2e]
+    init_parts = {id(b): [p.pack_current()[0] for p in b.plans] for b in turn_batches}
 
-    def e2e_step():
-        nonlocal h2d, d2h
-        # restore the host Parameters to their initial values and forget the optimiser state (host-side bookkeeping,
-        # outside the timed region)
-        for p, vals in zip(batch_e2e.plans, init_parts):
+    def restart(k, b):
+        # restore the host Parameters to their initial values and forget the optimiser state (host-side bookkeeping)
+        for p, vals in zip(b.plans, init_parts[id(b)]):
             p.forget_state(values=vals)
-        for b in blends:
-            b.loss.clear()
+        for bl in b.blends:
+            bl.loss.clear()
+
+    def e2e_steps(n):
+        nonlocal h2d, d2h
+        if not pipelined:
+            total = 0.0
+            for _ in range(n):
+                restart(0, batch_e2e)
+                barrier()
+                t0 = time.perf_counter()
+                # H2D: data, weights, difference kernels, parameters (pinned staging); the loop; D2H: parameters, state, losses
+                batch_e2e.fit(max_iter=iters, e_rel=1e-3, fixed_iterations=True, check_every=10 ** 6, upload_observations=True)
+                gather_results()
+                barrier()
+                total += time.perf_counter() - t0
+            h2d, d2h = batch_e2e.last_transfer_bytes
+            return total
         barrier()
         t0 = time.perf_counter()
-        # H2D: data, weights, difference kernels, parameters (pinned staging); the loop; D2H: parameters, state, losses
-        batch_e2e.fit(max_iter=iters, e_rel=1e-3, fixed_iterations=True, check_every=10 ** 6, upload_observations=True)
-        gather_results()
+        BatchPipeline(depth=2).run([turn_batches[k % 2] for k in range(n)], max_iter=iters, e_rel=1e-3, fixed_iterations=True,
+                                   check_every=10 ** 6, upload_observations=True, prepare=restart)
+        for _ in range(n):
+            gather_results()
         barrier()
         dt = time.perf_counter() - t0
-        h2d, d2h = batch_e2e.last_transfer_bytes
+        h2d, d2h = batch.last_transfer_bytes
         return dt
 
-    e2e_times = [e2e_step() for _ in range(max(1, min(args.warmup, 1)))]
-    e2e_times = [e2e_step() for _ in range(args.steps)]
-    e2e_local = float(np.sum(e2e_times))
+    e2e_steps(2 if pipelined else 1)
+    e2e_local = float(e2e_steps(args.steps))
     if world > 1:
         t = torch.tensor([e2e_local], device="cuda:%d" % local, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -409,7 +437,9 @@ def run_b200(args):
                              % (args.config, n_cpu, os.cpu_count() or 1)}
 
         conf = workload_config(args, cfg, S, iters)
-        conf.update({"e2e_streams": len(batch_e2e.plans), "fft_grid": list(fshape), "unique_scenes_per_gpu": uniq, "device_bytes_per_gpu": plan.device_bytes,
+        conf.update({"e2e": ("BatchPipeline(depth=2): two BlendBatch objects take turns, the copies of one overlap the loop of the other"
+                             if pipelined else "one BlendBatch.fit per step over %d plans/streams" % len(batch_e2e.plans)),
+                     "fft_grid": list(fshape), "unique_scenes_per_gpu": uniq, "device_bytes_per_gpu": plan.device_bytes,
                      "single_scene_iterations_per_sec": single,
                      "spectral": "fused row/column kernels" if fused else "cuFFT",
                      "cufft_execs_per_iteration": 0 if fused else 4 * len(plan.obs_meta),
@@ -427,6 +457,8 @@ def run_b200(args):
     barrier()
     if batch_e2e is not batch:
         batch_e2e.close()
+    if pipelined:
+        batch_b.close()
     plan.close()
     if world > 1:
         dist.destroy_process_group()

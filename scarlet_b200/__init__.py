@@ -5,7 +5,7 @@ hand-written CUDA (sm_100a) + cuFFT behind the C ABI in ``include/scarlet_b200.h
 """
 from . import fft, measure, operator  # noqa: F401
 from .bbox import Box, overlapped_slices  # noqa: F401
-from .blend import Blend, BlendBatch  # noqa: F401
+from .blend import BatchPipeline, Blend, BlendBatch  # noqa: F401
 from .cache import Cache  # noqa: F401
 from .component import CombinedComponent, Component, FactorizedComponent  # noqa: F401
 from .constraint import (CenterOnConstraint, Constraint, ConstraintChain, MonotonicityConstraint,  # noqa: F401

@@ -181,14 +181,23 @@ class BlendBatch:
         opts = _fit_options(max_iter, e_rel, min_iter, noise_factor, alg_kwargs, check_every)
 
         def one(i):
-            plan = self.plans[i]
-            h2d = plan.upload_observations() if upload_observations else 0
-            h2d += plan.upload_parameters(state=True)
-            n_iter, loss, status = plan.fit(opts)
-            d2h = plan.download_parameters(state=True) + n_iter.nbytes + status.nbytes + loss.nbytes
-            return n_iter, loss, status, h2d, d2h
+            h2d = self._copy_in(i, upload_observations)
+            out = self.plans[i].fit(opts)
+            return out + (h2d, self._copy_out(i, out))
 
-        outs = self._each(one)
+        return self._finish(self._each(one))
+
+    # the three stages of a fit, per plan (BatchPipeline interleaves them across batches)
+    def _copy_in(self, i, upload_observations):
+        plan = self.plans[i]
+        h2d = plan.upload_observations() if upload_observations else 0
+        return h2d + plan.upload_parameters(state=True)
+
+    def _copy_out(self, i, out):
+        n_iter, loss, status = out
+        return self.plans[i].download_parameters(state=True) + n_iter.nbytes + status.nbytes + loss.nbytes
+
+    def _finish(self, outs):
         self.last_transfer_bytes = (int(sum(o[3] for o in outs)), int(sum(o[4] for o in outs)))
         results = []
         for part, (n_iter, loss, status, _, _) in zip(self.parts, outs):
@@ -203,3 +212,73 @@ class BlendBatch:
     def close(self):
         for p in self.plans:
             p.close()
+
+
+class BatchPipeline:
+    """Fits a sequence of :class:`BlendBatch` objects back to back on one GPU as a three-stage pipeline: while the device
+    runs the loop of batch k (alone, so its kernels see the whole GPU), batch k+1 copies its observations and parameters in
+    and batch k-1 copies its results out.  ``depth`` batches are in flight; every batch brings its own device buffers (its
+    plans), and a batch object that appears several times in the sequence is fitted again each time, in order.
+
+    ``run`` returns the per-batch results of ``BlendBatch.fit`` in sequence order.  ``prepare(k, batch)`` (optional) runs
+    in the worker just before batch k's copy-in (e.g. to load the next set of observations into the host buffers)."""
+
+    def __init__(self, depth=2):
+        self.depth = max(1, int(depth))
+
+    def run(self, batches, max_iter=200, e_rel=1e-3, min_iter=1, noise_factor=0, upload_observations=True, prepare=None,
+            **alg_kwargs):
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        check_every = int(alg_kwargs.pop("check_every", 10))
+        opts = _fit_options(max_iter, e_rel, min_iter, noise_factor, alg_kwargs, check_every)
+        batches = list(batches)
+        cond = threading.Condition()
+        turn = {"in": 0, "loop": 0}
+        own = {id(b): threading.Lock() for b in batches}
+        failed = []
+
+        def take(stage, k):  # stages are entered in sequence order
+            with cond:
+                cond.wait_for(lambda: turn[stage] == k or bool(failed))
+
+        def give(stage):
+            with cond:
+                turn[stage] += 1
+                cond.notify_all()
+
+        def work(k):
+            b = batches[k]
+            idx = range(len(b.plans))
+            held = False
+            try:
+                take("in", k)
+                try:
+                    if failed:
+                        return None
+                    own[id(b)].acquire()  # inside the turn: an earlier use of the same batch object finishes first
+                    held = True
+                    if prepare is not None:
+                        prepare(k, b)
+                    h2d = [b._copy_in(i, upload_observations) for i in idx]
+                finally:
+                    give("in")
+                take("loop", k)
+                try:
+                    if failed:
+                        return None
+                    outs = b._each(lambda i: b.plans[i].fit(opts))
+                finally:
+                    give("loop")
+                return b._finish([outs[i] + (h2d[i], b._copy_out(i, outs[i])) for i in idx])
+            except BaseException as e:  # let the other workers drain instead of waiting for this turn forever
+                with cond:
+                    failed.append(e)
+                    cond.notify_all()
+                raise
+            finally:
+                if held:
+                    own[id(b)].release()
+
+        with ThreadPoolExecutor(self.depth) as pool:
+            return list(pool.map(work, range(len(batches))))

@@ -74,6 +74,30 @@ def test_monotonic_batch_and_arbitrary_order():
     assert_array_equal(a, b)
 
 
+def test_batch_pipeline_matches_plain_batches():
+    """BatchPipeline (copy-in / loop / copy-out of consecutive batches overlapped) gives exactly the results of fitting the
+    same batches one after the other, also when a batch object comes round a second time (warm restart)."""
+    from scarlet_b200 import BatchPipeline, BlendBatch, synthetic
+
+    def make(seed0):
+        return [synthetic.make_blend(synthetic.make_scene("tiny", seed0 + i)) for i in range(3)]
+
+    ref_a, ref_b = BlendBatch(make(10)), BlendBatch(make(20))
+    ref = [ref_a.fit(max_iter=12, e_rel=1e-6, upload_observations=True), ref_b.fit(max_iter=12, e_rel=1e-6, upload_observations=True),
+           ref_a.fit(max_iter=12, e_rel=1e-6, upload_observations=True)]
+    a, b = BlendBatch(make(10)), BlendBatch(make(20))
+    got = BatchPipeline(depth=2).run([a, b, a], max_iter=12, e_rel=1e-6)
+    assert got == ref
+    for x, y in ((a, ref_a), (b, ref_b)):
+        for bx, by in zip(x.blends, y.blends):
+            assert bx.loss == by.loss
+            for px, py in zip(bx.parameters, by.parameters):
+                assert_array_equal(np.asarray(px), np.asarray(py))
+                assert_array_equal(px.v, py.v)
+    for x in (a, b, ref_a, ref_b):
+        x.close()
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_apply_filter_bit_exact(dtype):
     """the reference's second native entry point (operators_pybind11.cc:39-56): real-space filter as a sum of shifted,

@@ -262,3 +262,88 @@ def test_measure_helpers():
     yy, xx = np.mgrid[:B, :B]
     assert_allclose(cen[1:], [(yy * s["morph"]).sum() / s["morph"].sum() + s["origin"][0], (xx * s["morph"]).sum() / s["morph"].sum() + s["origin"][1]], rtol=1e-6)
     assert_allclose(measure.flux(model), model.sum(axis=(1, 2)))
+
+
+def test_batch_pipeline_orders_stages_and_overlaps_copies():
+    """BatchPipeline (host logic, no GPU): copy-in and loop stages are entered in sequence order, one loop at a time; the
+    next batch's copy-in runs while the current loop is busy; a batch object used twice is finished before it is reused."""
+    import threading
+    import time
+    from scarlet_b200.blend import BatchPipeline
+    log, lock = [], threading.Lock()
+
+    def note(*ev):
+        with lock:
+            log.append(ev + (time.perf_counter(),))
+
+    class FakePlan:
+        def __init__(self, name):
+            self.name = name
+
+        def fit(self, opts):
+            note("loop+", self.name)
+            time.sleep(0.08)
+            note("loop-", self.name)
+            return (self.name, "loss", "status")
+
+    class FakeBatch:
+        def __init__(self, name):
+            self.name, self.plans, self.uses = name, [FakePlan(name)], 0
+
+        def _each(self, fn):
+            return [fn(0)]
+
+        def _copy_in(self, i, upload_observations):
+            note("in+", self.name)
+            time.sleep(0.03)
+            note("in-", self.name)
+            return 7
+
+        def _copy_out(self, i, out):
+            note("out+", self.name)
+            time.sleep(0.03)
+            note("out-", self.name)
+            return 5
+
+        def _finish(self, outs):
+            self.uses += 1
+            return (self.name, self.uses, outs[0][3], outs[0][4])
+
+    a, b = FakeBatch("a"), FakeBatch("b")
+    prepared = []
+    res = BatchPipeline(depth=2).run([a, b, a, b, a], max_iter=3, prepare=lambda k, batch: prepared.append((k, batch.name)))
+    assert res == [("a", 1, 7, 5), ("b", 1, 7, 5), ("a", 2, 7, 5), ("b", 2, 7, 5), ("a", 3, 7, 5)]
+    assert prepared == [(0, "a"), (1, "b"), (2, "a"), (3, "b"), (4, "a")]
+    order = [e[1] for e in log if e[0] == "loop+"]
+    assert order == ["a", "b", "a", "b", "a"]
+    # loops never overlap
+    depth = 0
+    for ev in log:
+        if ev[0] == "loop+":
+            depth += 1
+            assert depth == 1
+        elif ev[0] == "loop-":
+            depth -= 1
+    # the second batch copies in while the first one loops
+    t = {(e[0], i): e[2] for i, e in enumerate(log)}
+    first_loop_end = [e[2] for e in log if e[0] == "loop-"][0]
+    second_in_start = [e[2] for e in log if e[0] == "in+"][1]
+    assert second_in_start < first_loop_end
+    # a reused batch object: its next copy-in starts only after its previous copy-out ended
+    ins = [e[2] for e in log if e[0] == "in+" and e[1] == "a"]
+    outs = [e[2] for e in log if e[0] == "out-" and e[1] == "a"]
+    assert ins[1] > outs[0] and ins[2] > outs[1]
+
+
+def test_batch_pipeline_propagates_errors():
+    from scarlet_b200.blend import BatchPipeline
+
+    class Bad:
+        plans = [None]
+
+        def _copy_in(self, i, u):
+            raise RuntimeError("copy failed")
+
+    import pytest
+    with pytest.raises(RuntimeError, match="copy failed"):
+        BatchPipeline(depth=2).run([Bad(), Bad(), Bad()], max_iter=1)
