@@ -1186,22 +1186,34 @@ template <typename T, int GT> __global__ void __launch_bounds__(1024, 1) k_updat
                     group_sweep<T, GT>(zn, tab, (T)fc.mono_grad, g);
                     // pass A: symmetry (pairs p, n-1-p), positivity, centre floor, running maximum
                     T mx = -INFINITY;
-                    for (int p = lt; p <= half; p += GT) {
-                        const int q = n - 1 - p;
-                        T u = zn[p], v = zn[q];
-                        if (fc.has_sym) {
-                            const T un = hs * (u + v) + om * u, vn = hs * (v + u) + om * v;
-                            u = un, v = vn;
+                    for (int p0 = lt; p0 <= half; p0 += 2 * GT) { // two pairs per trip, their four loads first
+                        T uu[2], vv[2];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int p = p0 + i * GT;
+                            uu[i] = vv[i] = T(0);
+                            if (p <= half) uu[i] = zn[p], vv[i] = zn[n - 1 - p];
                         }
-                        u = u > zero ? u : zero;
-                        v = v > zero ? v : zero;
-                        if (p == half) {
-                            u = u > tiny ? u : tiny;
-                            v = u;
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int p = p0 + i * GT;
+                            if (p <= half) {
+                                T u = uu[i], v = vv[i];
+                                if (fc.has_sym) {
+                                    const T un = hs * (u + v) + om * u, vn = hs * (v + u) + om * v;
+                                    u = un, v = vn;
+                                }
+                                u = u > zero ? u : zero;
+                                v = v > zero ? v : zero;
+                                if (p == half) {
+                                    u = u > tiny ? u : tiny;
+                                    v = u;
+                                }
+                                zn[p] = u, zn[n - 1 - p] = v;
+                                mx = u > mx ? u : mx;
+                                mx = v > mx ? v : mx;
+                            }
                         }
-                        zn[p] = u, zn[q] = v;
-                        mx = u > mx ? u : mx;
-                        mx = v > mx ? v : mx;
                     }
                     const T den = group_max_t<T, GT>(red, mx); // barrier inside: pass A is complete for the whole group
                     // pass B: normalise, convergence sums, store z, next proximal argument

@@ -103,18 +103,32 @@ __device__ __forceinline__ void load_and_merge(const SpecArgs<T> &a, typename Cx
     typedef typename Cx<T>::type C2;
     typedef sbfft::Plan2<R1, R2> P;
     const SpecObs<T> &ob = a.ob;
-    const int Fxc = ob.Fxc, Fx = ob.Fx, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    constexpr int Fx = R1 * R2, Fxc = Fx / 2 + 1, TR = (Fxc + 31) / 32; // the row transform length is the template's
+    const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     for (int f = threadIdx.x >> 5; f < NB; f += nw) {
         const int p = f / Cb, c = c0 + f - p * Cb, y = y0 + 2 * p;
         C2 *z0 = fbuf + f * P::SF;
         const bool one = y < a.Ny, two = y + 1 < a.Ny;
         const C2 *row = ob.X + ((size_t)(s * ob.C + c) * a.Ny + (one ? y : 0)) * ob.Xp;
-        for (int k = lane; k < Fxc; k += 32) {
-            C2 A = {T(0), T(0)}, B = {T(0), T(0)};
-            if (one) A = row[k];
-            if (two) B = row[ob.Xp + k];
-            z0[k] = C2{A.x - B.y, A.y + B.x};
-            if (k > 0 && 2 * k < Fx) z0[Fx - k] = C2{A.x + B.y, B.x - A.y};
+        // every load of the two half spectra first (2 TR independent requests per lane), then the merge: with the loop
+        // rolled, each trip waited for its own two loads and a CTA spent most of its life in these round trips
+        C2 A[TR], B[TR];
+#pragma unroll
+        for (int t = 0; t < TR; ++t) {
+            const int k = lane + 32 * t;
+            A[t] = B[t] = C2{T(0), T(0)};
+            if (k < Fxc) {
+                if (one) A[t] = row[k];
+                if (two) B[t] = row[ob.Xp + k];
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < TR; ++t) {
+            const int k = lane + 32 * t;
+            if (k < Fxc) {
+                z0[k] = C2{A[t].x - B[t].y, A[t].y + B[t].x};
+                if (k > 0 && 2 * k < Fx) z0[Fx - k] = C2{A[t].x + B[t].y, B[t].x - A[t].y};
+            }
         }
     }
 }
