@@ -407,7 +407,7 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
 // ======================================================================================================
 // column pass: forward column FFT, x K^ (or conj K^), inverse column FFT; NB adjacent columns per CTA
 // ======================================================================================================
-template <typename T, int R1, int R2, int NB> __global__ void __launch_bounds__(NB *sbfft::Plan2<R1, R2>::RMAX, (sizeof(T) == 4 && sbfft::Plan2<R1, R2>::RMAX <= 20) ? 4 : 1) k_spec_column(const SpecArgs<T> a) {
+template <typename T, int R1, int R2, int NB> __global__ void __launch_bounds__(NB *sbfft::Plan2<R1, R2>::RMAX, (sizeof(T) == 4 && sbfft::Plan2<R1, R2>::RMAX <= 20) ? 3 : 1) k_spec_column(const SpecArgs<T> a) {
     typedef typename Cx<T>::type C2;
     typedef sbfft::Plan2<R1, R2> P;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -423,6 +423,10 @@ template <typename T, int R1, int R2, int NB> __global__ void __launch_bounds__(
     C2 *sm = fbuf + f * P::SF;
     C2 *X = ob.X + (size_t)img * Ny * ob.Xp + kx;
     const C2 *K = ob.khat + (size_t)(ob.khat_shared ? img - s * ob.C : img) * ob.Fy * ob.Xp + kx;
+    // the K^ column of this lane is requested first: its R2 loads are in flight during the X loads and the whole forward transform
+    C2 k_[R2];
+    if (j < R1 && col)
+        sbfft::static_for<0, R2>([&](auto i) { k_[decltype(i)::value] = K[(size_t)(j + R1 * decltype(i)::value) * ob.Xp]; });
     __syncthreads();
     C2 a_[R1];
     if (j < R2) {
@@ -440,12 +444,12 @@ template <typename T, int R1, int R2, int NB> __global__ void __launch_bounds__(
             if (a.conj)
                 sbfft::static_for<0, R2>([&](auto i) {
                     constexpr int k2 = decltype(i)::value;
-                    b_[k2] = sbfft::cmul_conj(b_[k2], K[(size_t)(j + R1 * k2) * ob.Xp]);
+                    b_[k2] = sbfft::cmul_conj(b_[k2], k_[k2]);
                 });
             else
                 sbfft::static_for<0, R2>([&](auto i) {
                     constexpr int k2 = decltype(i)::value;
-                    b_[k2] = sbfft::cmul(b_[k2], K[(size_t)(j + R1 * k2) * ob.Xp]);
+                    b_[k2] = sbfft::cmul(b_[k2], k_[k2]);
                 });
         }
     }
