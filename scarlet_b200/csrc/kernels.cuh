@@ -1014,7 +1014,9 @@ __device__ inline FusedChain fused_chain_of(const DevChain &ch, int By, int Bx) 
     return f;
 }
 
-template <typename T, int GT> __global__ void __launch_bounds__(1024, 1) k_update_fast(const UpdateArgs<T> a) {
+// MAXT: upper bound of the CTA size the launch will use (threads = GT x groups).  The kernel always runs one CTA per SM, so a
+// smaller bound hands the spare registers of the file to each thread (832 threads: 78 registers instead of 64).
+template <typename T, int GT, int MAXT = 1024> __global__ void __launch_bounds__(MAXT, 1) k_update_fast(const UpdateArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int G = a.fast_G, g = threadIdx.x / GT, lt = group_lane<GT>(g);
     const int *mine = a.fast_groups + (size_t)blockIdx.x * G;
@@ -1083,7 +1085,7 @@ template <typename T, int GT> __global__ void __launch_bounds__(1024, 1) k_updat
     const double alpha = d.morph_step;
     const bool upd = !d.morph_fixed;
     double pmax = 0.0;
-    constexpr int PB = 2; // pixels per trip: all loads first (see pass B below)
+    constexpr int PB = 2; // pixels per trip: all loads first (see pass B below); 3 is slower even with 78 registers
     for (int p0 = lt; p0 < n; p0 += PB * GT) {
         T mval[PB], m0[PB], v0[PB], vh0[PB];
         double gm[PB];

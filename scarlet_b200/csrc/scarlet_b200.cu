@@ -677,6 +677,7 @@ template <typename T> struct PlanT : sb_plan {
             SB_TRY(d_scratch_x.alloc(std::max<long long>(n_morph, 1)));
             SB_TRY(d_scratch_ps.alloc(std::max<long long>(n_morph, 1)));
             SB_TRY(raise_smem(fast_GT == 128 ? (const void *)k_update_fast<T, 128> : (const void *)k_update_fast<T, 64>, fast_smem));
+            SB_TRY(raise_smem((const void *)k_update_fast<T, 64, 832>, fast_smem));
         }
         return SB_OK;
     }
@@ -1074,6 +1075,8 @@ template <typename T> struct PlanT : sb_plan {
                 if (n_fast_cta) {
                     if (fast_GT == 128)
                         k_update_fast<T, 128><<<n_fast_cta, 128 * fast_G, fast_smem, stream>>>(ua);
+                    else if (64 * fast_G <= 832)
+                        k_update_fast<T, 64, 832><<<n_fast_cta, 64 * fast_G, fast_smem, stream>>>(ua);
                     else
                         k_update_fast<T, 64><<<n_fast_cta, 64 * fast_G, fast_smem, stream>>>(ua);
                     SB_CUDA(cudaGetLastError());
