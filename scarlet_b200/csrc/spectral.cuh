@@ -192,9 +192,10 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
     T *tile = reinterpret_cast<T *>(tw + R1 * R2);
     SpecCand<T> *recs = reinterpret_cast<SpecCand<T> *>(
         (reinterpret_cast<uintptr_t>(tile + (size_t)a.cb * rows * Nx) + 15) & ~(uintptr_t)15);
-    int *cand = reinterpret_cast<int *>(recs + a.max_cand);
     stage_twiddles<T, R1, R2>(tw, ob.tw_x);
-    // sources whose boxes intersect these rows, in scene order (deterministic accumulation order)
+    // Sources whose boxes intersect these rows, in scene order (deterministic accumulation order).  The first warp tests 32
+    // sources per trip and each lane with a hit writes its own compact record (everything the pixel loop needs) to shared
+    // memory: one pass over the source table, one barrier.
     const int k0 = a.scene_src_start[s], k1 = a.scene_src_start[s + 1];
     if (tid < 32) {
         int cnt = 0;
@@ -206,27 +207,24 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
                 ok = d.oy < y0 + rows && d.oy + d.By > y0;
             }
             const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (ok) cand[cnt + __popc(m & ((1u << tid) - 1u))] = k;
+            if (ok) {
+                const DevSource &d = a.src[k];
+                SpecCand<T> rc;
+                rc.oy = d.oy, rc.ox = d.ox, rc.By = d.By, rc.Bx = d.Bx;
+                const int plane = d.kind == 0 ? 0 : d.By * d.Bx;
+                rc.plane = plane;
+                rc.mp = (d.kind == 0 ? (d.shifting ? a.smorph : a.morph) : a.pmorph + (size_t)(ob.chan_off + c0) * plane) + d.morph_off;
+                const double *sed = a.sed + (size_t)k * a.Cm + ob.chan_off + c0;
+#pragma unroll
+                for (int c = 0; c < SB_SPEC_MAXCB; ++c) rc.sed[c] = c < Cb ? (T)sed[c] : T(0);
+                recs[cnt + __popc(m & ((1u << tid) - 1u))] = rc;
+            }
             cnt += __popc(m);
         }
         if (tid == 0) s_ncand = cnt;
     }
     __syncthreads();
     const int ncand = s_ncand;
-    for (int i = tid; i < ncand; i += nt) { // compact records: everything the pixel loop needs, in shared memory
-        const int k = cand[i];
-        const DevSource &d = a.src[k];
-        SpecCand<T> rc;
-        rc.oy = d.oy, rc.ox = d.ox, rc.By = d.By, rc.Bx = d.Bx;
-        const int plane = d.kind == 0 ? 0 : d.By * d.Bx;
-        rc.plane = plane;
-        rc.mp = (d.kind == 0 ? (d.shifting ? a.smorph : a.morph) : a.pmorph + (size_t)(ob.chan_off + c0) * plane) + d.morph_off;
-        const double *sed = a.sed + (size_t)k * a.Cm + ob.chan_off + c0;
-#pragma unroll
-        for (int c = 0; c < SB_SPEC_MAXCB; ++c) rc.sed[c] = c < Cb ? (T)sed[c] : T(0);
-        recs[i] = rc;
-    }
-    __syncthreads();
 #pragma unroll 1
     for (int idx = tid; idx < rows * Nx; idx += nt) {
         const int r = (int)__umulhi((unsigned)idx, a.magic_nx), x = idx - r * Nx, y = y0 + r;
