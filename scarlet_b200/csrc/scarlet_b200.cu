@@ -274,6 +274,10 @@ template <typename T> struct PlanT : sb_plan {
         int kchunk = 0;
         DevBuf<double> kimg, kgrid;
         DevBuf<double2> kspec;
+        // upload staging, kept between calls: cudaFree synchronises the whole device, which would make a copy-in wait for
+        // another plan's running loop (BatchPipeline)
+        DevBuf<float> stage_f;
+        DevBuf<double2> stage_z;
     };
     std::vector<std::unique_ptr<Obs>> obs;
     int loss_cap = 0;
@@ -714,8 +718,8 @@ template <typename T> struct PlanT : sb_plan {
         SB_CUDA(cudaSetDevice(device));
         Obs &ob = *obs[o];
         const size_t nd = ob.data.n;
-        DevBuf<float> stage;
-        if (sizeof(T) == 8 && (data || weights)) SB_TRY(stage.alloc(nd));
+        DevBuf<float> &stage = ob.stage_f;
+        if (sizeof(T) == 8 && (data || weights) && stage.n < nd) SB_TRY(stage.alloc(nd));
         const float *srcs[2] = {data, weights};
         T *dsts[2] = {ob.data.p, ob.weights.p};
         for (int i = 0; i < 2; ++i) {
@@ -729,9 +733,9 @@ template <typename T> struct PlanT : sb_plan {
             }
         }
         if (khat && (ob.dev.kind == 0 || ob.dev.kind == 2)) {
-            DevBuf<double2> ks;
+            DevBuf<double2> &ks = ob.stage_z;
             const size_t nk = (size_t)(ob.dev.khat_shared ? 1 : S) * ob.dev.C * ob.dev.Fy * ob.dev.Fxc;
-            SB_TRY(ks.alloc(nk));
+            if (ks.n < nk) SB_TRY(ks.alloc(nk));
             SB_CUDA(cudaMemcpyAsync(ks.p, khat, nk * sizeof(double2), cudaMemcpyHostToDevice, stream));
             const long long nrows = (long long)(ob.dev.khat_shared ? 1 : S) * ob.dev.C * ob.dev.Fy;
             k_cast_scale_cplx_pitched<T><<<grid_for(nrows * ob.dev.Fxc), 256, 0, stream>>>(ks.p, ob.khat.p, nrows, ob.dev.Fxc, ob.dev.Kp,
@@ -796,8 +800,8 @@ template <typename T> struct PlanT : sb_plan {
         Obs &ob = *obs[o];
         if (ob.dev.kind != 2 || !ey || !ex) return set_err(SB_ERR_ARG, "observation %d is not a resampling observation", o);
         SB_CUDA(cudaSetDevice(device));
-        DevBuf<double2> st;
-        SB_TRY(st.alloc(std::max(ob.Ey.n, ob.Ex.n)));
+        DevBuf<double2> &st = ob.stage_z;
+        if (st.n < std::max(ob.Ey.n, ob.Ex.n)) SB_TRY(st.alloc(std::max(ob.Ey.n, ob.Ex.n)));
         SB_CUDA(cudaMemcpyAsync(st.p, ey, ob.Ey.n * sizeof(double2), cudaMemcpyHostToDevice, stream));
         k_cast_scale_cplx<T><<<grid_for(ob.Ey.n), 256, 0, stream>>>(st.p, ob.Ey.p, (long long)ob.Ey.n, 1.0);
         SB_CUDA(cudaGetLastError());
@@ -806,8 +810,8 @@ template <typename T> struct PlanT : sb_plan {
         k_cast_scale_cplx<T><<<grid_for(ob.Ex.n), 256, 0, stream>>>(st.p, ob.Ex.p, (long long)ob.Ex.n, 1.0);
         SB_CUDA(cudaGetLastError());
         SB_CUDA(cudaStreamSynchronize(stream));
+        if (ob.sdev.h2 != (T)h2) have_graph = false; // h2 travels in the kernel arguments
         ob.sdev.h2 = (T)h2;
-        have_graph = false; // h2 travels in the kernel arguments
         return SB_OK;
     }
 
