@@ -866,12 +866,54 @@ template <int GT> __device__ __forceinline__ double group_max(GroupRed &r, doubl
 }
 
 template <typename T> struct FastTable { // shared-memory image of a DevMono with nb == 4
-    const uint2 *nbr;
+    const uint2 *nbr;          // four neighbours per task as 16-bit BYTE offsets into the image (index * sizeof(T))
     const W4<T> *w;
-    const unsigned short *pix;
+    const unsigned short *pix; // byte offset of the task's own pixel
     const int *ls;
     int n_levels;
 };
+
+// 32-bit shared-window addresses + ld/st.shared: the sweep touches shared memory only through these, which spares the
+// generic-to-shared address arithmetic the compiler otherwise redoes on every level (and one add per neighbour).
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int lds_i32(unsigned a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u16(unsigned a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u32x2(unsigned a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_real(unsigned a, float) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_real(unsigned a, double) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_real(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+__device__ __forceinline__ void sts_real(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
+__device__ __forceinline__ W4<float> lds_w4(unsigned a, float) {
+    W4<float> w;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.a), "=f"(w.b), "=f"(w.c), "=f"(w.d) : "r"(a));
+    return w;
+}
+__device__ __forceinline__ W4<double> lds_w4(unsigned a, double) {
+    W4<double> w;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(w.a), "=d"(w.b) : "r"(a));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(w.c), "=d"(w.d) : "r"(a + 16u));
+    return w;
+}
 
 // Empty neighbour slots of the shared-memory table point at a spare cell behind the image that always holds 0 and carry
 // weight 0, so the four products need no predicates: (+0) is added at the END of the reference's summation order
@@ -879,19 +921,20 @@ template <typename T> struct FastTable { // shared-memory image of a DevMono wit
 template <typename T, int GT> __device__ __forceinline__ void group_sweep(T *img, const FastTable<T> &t, T min_gradient, int g) {
     const T keep = T(1) - min_gradient;
     const int lt = group_lane<GT>(g);
-    int beg = t.ls[0];
+    const unsigned zb = smem_u32(img), a_nbr = smem_u32(t.nbr), a_w = smem_u32(t.w), a_pix = smem_u32(t.pix), a_ls = smem_u32(t.ls);
+    int beg = lds_i32(a_ls);
     for (int L = 0; L < t.n_levels; ++L) {
-        const int end = t.ls[L + 1];
+        const int end = lds_i32(a_ls + 4u * (unsigned)(L + 1));
         for (int j = beg + lt; j < end; j += GT) {
-            const uint2 nb = t.nbr[j];
-            const W4<T> w = t.w[j];
-            const int p = t.pix[j];
-            T ref = mul_rn(img[nb.x & 0xffffu], w.a);
-            ref = add_rn(ref, mul_rn(img[nb.x >> 16], w.b));
-            ref = add_rn(ref, mul_rn(img[nb.y & 0xffffu], w.c));
-            ref = add_rn(ref, mul_rn(img[nb.y >> 16], w.d));
+            const uint2 nb = lds_u32x2(a_nbr + 8u * (unsigned)j);
+            const W4<T> w = lds_w4(a_w + (unsigned)sizeof(W4<T>) * (unsigned)j, T(0));
+            const unsigned ap = zb + lds_u16(a_pix + 2u * (unsigned)j);
+            T ref = mul_rn(lds_real(zb + (nb.x & 0xffffu), T(0)), w.a);
+            ref = add_rn(ref, mul_rn(lds_real(zb + (nb.x >> 16), T(0)), w.b));
+            ref = add_rn(ref, mul_rn(lds_real(zb + (nb.y & 0xffffu), T(0)), w.c));
+            ref = add_rn(ref, mul_rn(lds_real(zb + (nb.y >> 16), T(0)), w.d));
             const T cap = mul_rn(ref, keep);
-            if (cap < img[p]) img[p] = cap;
+            if (cap < lds_real(ap, T(0))) sts_real(ap, cap);
         }
         beg = end;
         group_bar<GT>(g);
@@ -1047,14 +1090,13 @@ template <typename T, int GT, int MAXT = 1024> __global__ void __launch_bounds__
             const W4<T> *gw = reinterpret_cast<const W4<T> *>(mo.w);
             const unsigned spare = (unsigned)mo.n_pix; // index of the always-zero cell behind each image
             for (int j = threadIdx.x; j < mo.n_tasks; j += blockDim.x) {
-                uint2 v = gn[j];
-                if ((v.x & 0xffffu) == 0xffffu) v.x = (v.x & 0xffff0000u) | spare;
-                if ((v.x >> 16) == 0xffffu) v.x = (v.x & 0xffffu) | (spare << 16);
-                if ((v.y & 0xffffu) == 0xffffu) v.y = (v.y & 0xffff0000u) | spare;
-                if ((v.y >> 16) == 0xffffu) v.y = (v.y & 0xffffu) | (spare << 16);
-                s_nbr[j] = v;
+                const uint2 v = gn[j];
+                unsigned i0 = v.x & 0xffffu, i1 = v.x >> 16, i2 = v.y & 0xffffu, i3 = v.y >> 16;
+                i0 = (i0 == 0xffffu ? spare : i0) * (unsigned)sizeof(T), i1 = (i1 == 0xffffu ? spare : i1) * (unsigned)sizeof(T);
+                i2 = (i2 == 0xffffu ? spare : i2) * (unsigned)sizeof(T), i3 = (i3 == 0xffffu ? spare : i3) * (unsigned)sizeof(T);
+                s_nbr[j] = make_uint2(i0 | (i1 << 16), i2 | (i3 << 16)); // byte offsets (host: (n_pix + 1) sizeof(T) < 65536)
                 s_w[j] = gw[j];
-                s_pix[j] = (unsigned short)mo.pix[j];
+                s_pix[j] = (unsigned short)(mo.pix[j] * (int)sizeof(T));
             }
             for (int j = threadIdx.x; j <= mo.n_levels; j += blockDim.x) s_ls[j] = mo.level_start[j];
             tab.n_levels = mo.n_levels;

@@ -628,6 +628,8 @@ template <typename T> struct PlanT : sb_plan {
                 // must fit next to one image even with a single group per CTA
                 const size_t need = fast_smem_bytes(1, (d.By * d.Bx + 4) & ~3, (tasks + 7) & ~7);
                 if (need > 200 * 1024) fast = false;
+                // the shared-memory table addresses pixels by 16-bit byte offsets (spare cell included)
+                if ((size_t)(d.By * d.Bx + 1) * sizeof(T) > 65535) fast = false;
             }
             if (fast) {
                 by_chain[d.chain].push_back(k);
