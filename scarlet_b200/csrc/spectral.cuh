@@ -296,7 +296,7 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
 // ======================================================================================================
 // inverse row FFT -> residual + loss -> forward row FFT
 // ======================================================================================================
-template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) k_spec_residual(const SpecArgs<T> a) {
+template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256, 2) k_spec_residual(const SpecArgs<T> a) {
     typedef typename Cx<T>::type C2;
     typedef sbfft::Plan2<R1, R2> P;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -335,25 +335,45 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
             const int dy0 = y - ob.oy, dy1 = dy0 + 1;
             const bool row0 = y < Ny && (unsigned)dy0 < (unsigned)ob.H, row1 = y + 1 < Ny && (unsigned)dy1 < (unsigned)ob.H;
             const size_t base0 = ((size_t)(s * Co + c) * ob.H + dy0) * ob.W, base1 = base0 + ob.W;
-            // (read-only loads: the optional rendered_out stores in between must not serialise them)
-            sbfft::static_for<0, R1>([&](auto i) {
-                constexpr int n1 = decltype(i)::value;
-                const int x = n1 * R2 + n2, dx = x - ob.ox;
-                const bool col = x < Nx && (unsigned)dx < (unsigned)ob.W;
-                T r0 = T(0), r1 = T(0);
-                if (col && row0) {
-                    const T m = a_[n1].x, w = __ldg(ob.weights + base0 + dx), diff = m - __ldg(ob.data + base0 + dx);
-                    r0 = w * diff;
-                    part_t += r0 * diff;
-                    if (a.rendered_out) a.rendered_out[base0 + dx] = m;
-                }
-                if (col && row1) {
-                    const T m = a_[n1].y, w = __ldg(ob.weights + base1 + dx), diff = m - __ldg(ob.data + base1 + dx);
-                    r1 = w * diff;
-                    part_t += r1 * diff;
-                    if (a.rendered_out) a.rendered_out[base1 + dx] = m;
-                }
-                a_[n1] = C2{r0, r1};
+            // Four columns at a time: their (up to) sixteen data / weight values are requested first, then consumed.  Element
+            // by element, every pair of loads sat behind the branch (and the optional rendered_out store) of the previous
+            // element and a lane paid 2 R1 dependent round trips to L2.
+            constexpr int CH = 4;
+            sbfft::static_for<0, (R1 + CH - 1) / CH>([&](auto gi) {
+                constexpr int g0 = decltype(gi)::value * CH;
+                T wv[CH][2], dv[CH][2];
+                bool ok[CH][2];
+                sbfft::static_for<0, CH>([&](auto ui) {
+                    constexpr int u = decltype(ui)::value, n1 = g0 + u;
+                    if (n1 < R1) {
+                        const int x = n1 * R2 + n2, dx = x - ob.ox;
+                        const bool col = x < Nx && (unsigned)dx < (unsigned)ob.W;
+                        ok[u][0] = col && row0, ok[u][1] = col && row1;
+                        wv[u][0] = dv[u][0] = wv[u][1] = dv[u][1] = T(0);
+                        if (ok[u][0]) wv[u][0] = __ldg(ob.weights + base0 + dx), dv[u][0] = __ldg(ob.data + base0 + dx);
+                        if (ok[u][1]) wv[u][1] = __ldg(ob.weights + base1 + dx), dv[u][1] = __ldg(ob.data + base1 + dx);
+                    }
+                });
+                sbfft::static_for<0, CH>([&](auto ui) {
+                    constexpr int u = decltype(ui)::value, n1 = g0 + u;
+                    if (n1 < R1) {
+                        const int dx = n1 * R2 + n2 - ob.ox;
+                        T r0 = T(0), r1 = T(0);
+                        if (ok[u][0]) {
+                            const T m = a_[n1 < R1 ? n1 : 0].x, diff = m - dv[u][0];
+                            r0 = wv[u][0] * diff;
+                            part_t += r0 * diff;
+                            if (a.rendered_out) a.rendered_out[base0 + dx] = m;
+                        }
+                        if (ok[u][1]) {
+                            const T m = a_[n1 < R1 ? n1 : 0].y, diff = m - dv[u][1];
+                            r1 = wv[u][1] * diff;
+                            part_t += r1 * diff;
+                            if (a.rendered_out) a.rendered_out[base1 + dx] = m;
+                        }
+                        a_[n1 < R1 ? n1 : 0] = C2{r0, r1};
+                    }
+                });
             });
         }
     }
