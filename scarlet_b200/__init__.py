@@ -3,7 +3,7 @@
 The public names mirror the reference package for everything on that path; the per-iteration work runs in
 hand-written CUDA (sm_100a) + cuFFT behind the C ABI in ``include/scarlet_b200.h``.  No CPU fallback.
 """
-from . import fft, measure, operator  # noqa: F401
+from . import fft, initialization, measure, operator  # noqa: F401
 from .bbox import Box, overlapped_slices  # noqa: F401
 from .blend import BatchPipeline, Blend, BlendBatch  # noqa: F401
 from .cache import Cache  # noqa: F401

@@ -314,9 +314,50 @@ def source_recipes(sc):
     save("source_recipes.npz", **out)
 
 
+def init_helpers(sc):
+    """The reference's user-facing initialisation helpers on data/hsc_cosmos_35.npz: ``get_psf_spectrum`` (with SNR) at the
+    first five catalogue positions, the component count ``init_source`` settles on, and ``set_spectra_to_match`` applied to
+    three single-component sources (inputs: the rendered unit-spectrum models, outputs: the solved spectra)."""
+    d = np.load(os.path.join(REF_DATA, "hsc_cosmos_35.npz"))
+    images, variance, psfs = d["images"], d["variance"], d["psfs"]
+    channels = [str(f) for f in d["filters"]]
+    centers = [(float(s["y"]), float(s["x"])) for s in d["catalog"]][:5]
+    frame = sc.frame.Frame(images.shape, psf=sc.psf.GaussianPSF(sigma=(0.8,) * len(channels)), channels=channels)
+    weights = 1 / variance
+    weights[:, 5:9, 30:34] = 0  # a masked patch, so that the mask handling is exercised
+    obs = sc.observation.Observation(images, psf=sc.psf.ImagePSF(psfs.copy()), weights=weights, channels=channels)
+    obs.match(frame)
+    out = dict(centers=np.array(centers), weights=weights.astype(np.float32))
+    spec, snr = [], []
+    for c in centers:
+        a, b = sc.initialization.get_psf_spectrum(c, obs, compute_snr=True)
+        spec.append(a), snr.append(b)
+    out["psf_spectrum"], out["psf_snr"] = np.array(spec), np.array(snr)
+    out["edge_spectrum"] = sc.initialization.get_psf_spectrum((1.0, 2.0), obs)  # PSF box sticks out of the image
+    # component counts of init_source for a few min_snr values (the cap is floor(psf_snr / min_snr))
+    ks = []
+    for min_snr in (50, 200, 1000):
+        row = []
+        for c in centers[:3]:
+            src = sc.initialization.init_source(frame, c, obs, max_components=2, min_snr=min_snr)
+            row.append(len(src.children) if isinstance(src, sc.component.CombinedComponent) else
+                       (0 if type(src).__name__ == "CompactExtendedSource" else 1))
+        ks.append(row)
+    out["init_source_K"] = np.array(ks)
+    sources = [sc.source.ExtendedSource(frame, c, obs, resizing=False) for c in centers[:3]]
+    for k, src in enumerate(sources):
+        src.parameters[0][:] = 1
+        out["src%d_image" % k] = np.asarray(src.parameters[1])
+        out["src%d_origin" % k] = np.array(src.bbox.origin)
+    out["unit_rendered"] = np.stack([obs.render(src.get_model(frame=frame)) for src in sources]).astype(np.float32)
+    sc.initialization.set_spectra_to_match(sources, obs)
+    out["matched_spectra"] = np.stack([np.asarray(src.parameters[0]) for src in sources])
+    save("init_helpers.npz", **out)
+
+
 if __name__ == "__main__":
     sc = ref_shim.install()
     which = sys.argv[1:] or ["obs_render_loss", "hsc_cosmos_35", "point_extended", "prox_chain", "monotonic_weights", "multires",
-                             "source_recipes"]
+                             "source_recipes", "init_helpers"]
     for name in which:
         globals()[name](sc)

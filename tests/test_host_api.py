@@ -347,3 +347,122 @@ def test_batch_pipeline_propagates_errors():
     import pytest
     with pytest.raises(RuntimeError, match="copy failed"):
         BatchPipeline(depth=2).run([Bad(), Bad(), Bad()], max_iter=1)
+
+
+def _hsc_observation(weights=None):
+    import scarlet_b200 as sb
+    g = golden("hsc_cosmos_35.npz")
+    C = g["images"].shape[0]
+    frame = sb.Frame(g["images"].shape, psf=sb.GaussianPSF(sigma=(0.8,) * C), channels=list(range(C)))
+    obs = sb.Observation(g["images"].copy(), psf=sb.ImagePSF(g["psfs"].copy()), weights=(g["weights"] if weights is None else weights).copy(),
+                         channels=list(range(C)))
+    obs.match(frame)
+    return frame, obs
+
+
+def test_get_psf_spectrum_vs_reference_fixture():
+    """initialization.get_psf_spectrum (PSF-projected spectrum + matched-filter SNR, masked pixels left out, PSF box allowed
+    to stick out of the image) against the reference's own outputs on data/hsc_cosmos_35 (make_golden.py:init_helpers)"""
+    from scarlet_b200 import initialization as init
+    h = golden("init_helpers.npz")
+    frame, obs = _hsc_observation(weights=h["weights"])
+    for k, center in enumerate(h["centers"]):
+        spectrum, snr = init.get_psf_spectrum(tuple(center), obs, compute_snr=True)
+        assert_allclose(spectrum, h["psf_spectrum"][k], rtol=2e-6)
+        assert_allclose(snr, h["psf_snr"][k], rtol=2e-6)
+    assert_allclose(init.get_psf_spectrum((1.0, 2.0), obs), h["edge_spectrum"], rtol=2e-6)
+    per_obs = init.get_psf_spectrum(tuple(h["centers"][0]), (obs, obs), concat=False)
+    assert len(per_obs) == 2 and per_obs[0].shape == (5,)
+
+
+def test_init_source_component_count_and_fallback(monkeypatch):
+    """initialization.init_source / init_all_sources control flow (initialization.py:287-490): component count capped by
+    floor(psf_snr / min_snr), one component fewer after every ArithmeticError, compact source as the last resort, skipped
+    list -- the counts equal the reference's on data/hsc_cosmos_35 (source construction itself is stubbed: it needs the GPU)"""
+    import scarlet_b200.source as source_module
+    from scarlet_b200 import initialization as init
+    h = golden("init_helpers.npz")
+    frame, obs = _hsc_observation(weights=h["weights"])
+    calls = []
+
+    class Fake:
+        def __init__(self, K, compact, fail):
+            self.K, self.compact, self.fail = K, compact, fail
+
+        def check_parameters(self):
+            if self.fail:
+                raise ArithmeticError("not finite")
+
+    bad = set()
+
+    def fake_factory(model_frame, sky_coord, observations, K=1, compact=False, **kw):
+        calls.append((K, compact))
+        return Fake(K, compact, (0 if compact else K) in bad)
+
+    monkeypatch.setattr(source_module, "ExtendedSource", fake_factory)
+    for row, min_snr in zip(h["init_source_K"], (50, 200, 1000)):
+        got = [init.init_source(frame, tuple(c), obs, max_components=2, min_snr=min_snr).K for c in h["centers"][:3]]
+        assert got == list(row)
+    # fallback chain 2 -> 1 -> compact; without fallback the error propagates
+    bad.update({2, 1})
+    calls.clear()
+    src = init.init_source(frame, tuple(h["centers"][0]), obs, max_components=2)
+    assert src.compact and calls == [(2, False), (1, False), (1, True)]
+    bad.add(0)
+    assert init.init_source(frame, tuple(h["centers"][0]), obs, max_components=2) is None
+    with pytest.raises(ArithmeticError):
+        init.init_source(frame, tuple(h["centers"][0]), obs, max_components=2, fallback=False)
+    # init_all_sources: exceptions are collected when silent
+    def exploding(model_frame, sky_coord, observations, **kw):
+        if sky_coord == tuple(h["centers"][1]):
+            raise ValueError("boom")
+        return Fake(1, False, False)
+
+    monkeypatch.setattr(source_module, "ExtendedSource", exploding)
+    sources, skipped = init.init_all_sources(frame, [tuple(c) for c in h["centers"][:3]], obs, silent=True, set_spectra=False)
+    assert len(sources) == 2 and skipped == [1]
+    with pytest.raises(ValueError):
+        init.init_all_sources(frame, [tuple(c) for c in h["centers"][:3]], obs, silent=False, set_spectra=False)
+
+
+def test_set_spectra_to_match_vs_reference_fixture(monkeypatch):
+    """initialization.set_spectra_to_match: weighted linear least squares for the amplitudes of all components per channel,
+    given their unit-spectrum rendered models -- against the reference's result for three sources on data/hsc_cosmos_35 with
+    a masked patch.  Observation.render (device) is replaced by the reference's rendered models from the fixture; a duplicated
+    component shares its twin's spectrum."""
+    import scarlet_b200 as sb
+    from scarlet_b200 import initialization as init
+    from scarlet_b200.bbox import Box
+    h = golden("init_helpers.npz")
+    frame, obs = _hsc_observation(weights=h["weights"])
+    sources = []
+    for k in range(3):
+        img = h["src%d_image" % k]
+        oy, ox = (int(v) for v in h["src%d_origin" % k][-2:])
+        sources.append(sb.ExtendedSource(frame, tuple(h["centers"][k]), obs, spectrum=np.full(5, 3.0, dtype=np.float32), morphology=img,
+                                         bbox=Box(img.shape, origin=(oy, ox)), resizing=False))
+    for src in sources:  # the closing constraint projection runs on the device; the fixture's spectra are positive anyway
+        src.parameters[0].constraint = None
+    rendered = iter(h["unit_rendered"])
+    seen = []
+
+    def fake_render(model, *parameters):
+        seen.append(np.asarray(model))
+        return next(rendered).astype(np.float64)
+
+    monkeypatch.setattr(obs, "render", fake_render, raising=False)
+    init.set_spectra_to_match(sources, obs)
+    assert len(seen) == 3
+    for k, src in enumerate(sources):
+        # the models handed to the renderer carry a flat unit spectrum
+        assert_allclose(seen[k].sum(axis=(1, 2)), np.full(5, h["src%d_image" % k].sum()), rtol=1e-5)
+        assert_allclose(np.asarray(src.parameters[0]), h["matched_spectra"][k], rtol=2e-4)
+    # a duplicate of source 0 is left out of the solve and gets the same spectrum
+    twin = sb.ExtendedSource(frame, tuple(h["centers"][0]), obs, spectrum=np.ones(5, dtype=np.float32), morphology=h["src0_image"],
+                             bbox=sources[0].children[1].bbox.copy() if hasattr(sources[0].children[1].bbox, "copy") else None, resizing=False)
+    twin.parameters[0].constraint = None
+    rendered = iter(h["unit_rendered"])
+    seen.clear()
+    init.set_spectra_to_match(sources + [twin], obs)
+    assert len(seen) == 3
+    assert_allclose(np.asarray(twin.parameters[0]), np.asarray(sources[0].parameters[0]))
