@@ -16,7 +16,7 @@ from .morphology import ExtendedSourceMorphology, ImageMorphology, Morphology, P
 from .observation import Observation  # noqa: F401
 from .parameter import Parameter, relative_step  # noqa: F401
 from .prior import Prior  # noqa: F401
-from .psf import PSF, GaussianPSF, ImagePSF  # noqa: F401
+from .psf import PSF, FunctionPSF, GaussianPSF, ImagePSF, MoffatPSF  # noqa: F401
 from .renderer import ConvolutionRenderer, NullRenderer, Renderer  # noqa: F401
 from .source import (CompactExtendedSource, ExtendedSource, MultiExtendedSource, PointSource,  # noqa: F401
                      SingleExtendedSource)

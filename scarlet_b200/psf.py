@@ -1,5 +1,5 @@
 """PSF models (host setup).  Mirrors scarlet/psf.py: ``normalize`` 9-17, ``FunctionPSF`` 39-77,
-``GaussianPSF`` 80-142, ``ImagePSF`` 205-234.  PSF images are evaluated on the host once per scene to build
+``GaussianPSF`` 80-142, ``MoffatPSF`` 143-201, ``ImagePSF`` 205-234.  PSF images are evaluated on the host once per scene to build
 the difference kernel; the per-iteration evaluation of a point source's PSF image at a moving sub-pixel centre
 happens on the device (csrc/kernels.cuh: point_planes / update_point)."""
 import numpy as np
@@ -65,6 +65,28 @@ class GaussianPSF(FunctionPSF):
             return np.exp(-(X ** 2) / (2 * sigma ** 2))
         s2 = np.sqrt(2) * sigma
         return np.sqrt(np.pi / 2) * sigma * (1 - special.erfc((0.5 - X) / s2) + 1 - special.erfc((2 * X + 1) / (2 * s2)))
+
+
+class MoffatPSF(FunctionPSF):
+    """Circular Moffat profile ``(1 + r^2 / alpha^2)^-beta`` per band, sampled at the pixel centres (the reference has no
+    pixel-integrated form either, psf.py:143-201) and normalised to unit sum over its box.  Usable as the PSF of an
+    observation; the device code for point sources assumes a Gaussian MODEL-frame PSF."""
+
+    def __init__(self, alpha=4.7, beta=1.5, integrate=False, boxsize=None):
+        alpha = prepare_param(alpha, "alpha", fixed=True)
+        beta = prepare_param(beta, "beta", fixed=True)
+        assert len(alpha) == len(beta)
+        assert integrate is False, "In-pixel integration not implemented (yet)!"
+        if boxsize is None:
+            boxsize = int(np.ceil(5 * np.max(alpha)))
+        super().__init__(alpha, beta, integrate=integrate, boxsize=boxsize)
+
+    def get_model(self, *parameters, offset=None):
+        alpha, beta = self.get_parameter(0, *parameters), self.get_parameter(1, *parameters)
+        oy, ox = (0, 0) if offset is None else (offset[0], offset[1])
+        pairs = [(alpha[0], beta[0])] if self.is_same else list(zip(alpha, beta))  # "same" looks at alpha only, like the reference
+        r2 = (self._Y - oy)[:, None] ** 2 + (self._X - ox)[None, :] ** 2
+        return normalize(np.stack([(1 + r2 / a ** 2) ** -b for a, b in pairs], axis=0))
 
 
 class ImagePSF(PSF):

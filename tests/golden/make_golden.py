@@ -352,6 +352,11 @@ def init_helpers(sc):
     out["unit_rendered"] = np.stack([obs.render(src.get_model(frame=frame)) for src in sources]).astype(np.float32)
     sc.initialization.set_spectra_to_match(sources, obs)
     out["matched_spectra"] = np.stack([np.asarray(src.parameters[0]) for src in sources])
+    # functional PSF models (psf.py:80-201)
+    moffat = sc.psf.MoffatPSF(alpha=[4.7, 3.0, 2.2], beta=[1.5, 2.5, 3.0], boxsize=21)
+    out["moffat"], out["moffat_offset"] = moffat.get_model(), moffat.get_model(offset=(0.3, -0.2))
+    out["moffat_same"] = sc.psf.MoffatPSF(alpha=[2.0, 2.0], beta=[2.0, 2.0]).get_model()
+    out["gauss_offset"] = sc.psf.GaussianPSF(sigma=[0.8, 1.3], boxsize=11).get_model(offset=(0.25, -0.4))
     save("init_helpers.npz", **out)
 
 

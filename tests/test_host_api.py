@@ -466,3 +466,20 @@ def test_set_spectra_to_match_vs_reference_fixture(monkeypatch):
     init.set_spectra_to_match(sources + [twin], obs)
     assert len(seen) == 3
     assert_allclose(np.asarray(twin.parameters[0]), np.asarray(sources[0].parameters[0]))
+
+
+def test_function_psf_models_vs_reference_fixture():
+    """MoffatPSF / GaussianPSF images (centre-sampled Moffat, pixel-integrated Gaussian, sub-pixel offsets, the single-plane
+    form when all bands share a width) against the reference's own (psf.py:80-201)"""
+    import scarlet_b200 as sb
+    h = golden("init_helpers.npz")
+    moffat = sb.MoffatPSF(alpha=[4.7, 3.0, 2.2], beta=[1.5, 2.5, 3.0], boxsize=21)
+    assert moffat.bbox.shape == (3, 21, 21) and moffat.bbox.origin == (0, -10, -10)
+    assert_allclose(moffat.get_model(), h["moffat"], rtol=1e-12)
+    assert_allclose(moffat.get_model(offset=(0.3, -0.2)), h["moffat_offset"], rtol=1e-12)
+    same = sb.MoffatPSF(alpha=[2.0, 2.0], beta=[2.0, 2.0]).get_model()
+    assert same.shape == h["moffat_same"].shape == (1, 11, 11)
+    assert_allclose(same, h["moffat_same"], rtol=1e-12)
+    assert_allclose(sb.GaussianPSF(sigma=[0.8, 1.3], boxsize=11).get_model(offset=(0.25, -0.4)), h["gauss_offset"], rtol=1e-10)
+    with pytest.raises(AssertionError):
+        sb.MoffatPSF(integrate=True)
