@@ -1,6 +1,6 @@
 """Post-fit measurements on component models: the step right after the fitting path.
 
-Same call signatures as scarlet/measure.py (``max_pixel`` 6-21, ``flux`` 24-38, ``centroid`` 41-59, ``snr`` 62-104): each
+Same call signatures as scarlet/measure.py (``max_pixel`` 6-21, ``flux`` 24-38, ``centroid`` 41-59, ``snr`` 62-104, ``moments`` 108-150): each
 takes a component (anything with ``get_model()`` and ``bbox``) or a plain (C, Ny, Nx) cube.  Plain reductions over
 models that are already on the host after ``Blend.fit`` wrote the parameters back; ``snr`` renders through the
 observations (device convolution for ``ConvolutionRenderer``)."""
@@ -49,3 +49,27 @@ def snr(component, observations):
         signal += float((rendered * w).sum())
         weight2 += float((var[finite] * w[finite] ** 2).sum())
     return signal / np.sqrt(weight2)
+
+
+def moments(component, N=2, centroid=None, weight=None):
+    """Weighted image moments up to order ``N`` as a dict ``{(p, q): value per channel}`` (measure.py:108-150).
+
+    Conventions are the reference's, kept as they are so that numbers agree: the first key index ``p`` is the power of the
+    coordinate along the LAST image axis measured from ``centroid[0]``, the second, ``q``, the power of the coordinate along
+    the second-to-last axis measured from ``centroid[1]``; the default centroid is ``shape // 2`` of the whole array (for a
+    cube its first two entries are ``C // 2`` and ``Ny // 2``)."""
+    model = np.asarray(component.get_model() if hasattr(component, "get_model") else component)
+    if weight is None:
+        weight = 1
+    else:
+        assert model.shape == np.shape(weight)
+    if centroid is None:
+        centroid = np.array(model.shape) // 2
+    along_rows, along_cols = np.indices(model.shape[-2:], dtype=np.float64)
+    u = along_cols - centroid[0]
+    v = along_rows - centroid[1]
+    out = {}
+    for n in range(N + 1):
+        for p in range(n + 1):
+            out[p, n - p] = (u ** p * v ** (n - p) * model * weight).sum(axis=(-2, -1))
+    return out

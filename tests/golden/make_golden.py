@@ -357,6 +357,18 @@ def init_helpers(sc):
     out["moffat"], out["moffat_offset"] = moffat.get_model(), moffat.get_model(offset=(0.3, -0.2))
     out["moffat_same"] = sc.psf.MoffatPSF(alpha=[2.0, 2.0], beta=[2.0, 2.0]).get_model()
     out["gauss_offset"] = sc.psf.GaussianPSF(sigma=[0.8, 1.3], boxsize=11).get_model(offset=(0.25, -0.4))
+    # image moments (measure.py:108-150) of a small cube and of a single image
+    import importlib
+    ref_measure = importlib.import_module(sc.__name__ + ".measure")
+    rng = np.random.default_rng(108)
+    cube, wgt = rng.random((3, 9, 7)), rng.random((3, 9, 7))
+    out["mom_cube"], out["mom_weight"] = cube, wgt
+    for name, args in (("default", {}), ("centroid", dict(centroid=np.array([2.5, 4.25]))), ("weighted", dict(N=3, weight=wgt))):
+        M = ref_measure.moments(cube, **args)
+        out["mom_%s_keys" % name] = np.array(sorted(M))
+        out["mom_%s_vals" % name] = np.array([M[k] for k in sorted(M)])
+    M2 = ref_measure.moments(cube[0], N=1)
+    out["mom_image_vals"] = np.array([M2[k] for k in sorted(M2)])
     save("init_helpers.npz", **out)
 
 

@@ -483,3 +483,23 @@ def test_function_psf_models_vs_reference_fixture():
     assert_allclose(sb.GaussianPSF(sigma=[0.8, 1.3], boxsize=11).get_model(offset=(0.25, -0.4)), h["gauss_offset"], rtol=1e-10)
     with pytest.raises(AssertionError):
         sb.MoffatPSF(integrate=True)
+
+
+def test_measure_moments_vs_reference_fixture():
+    """measure.moments (same keys, same axis conventions, default centroid, explicit centroid, weight function, 2-D input)
+    against the reference's numbers"""
+    from scarlet_b200 import measure
+    h = golden("init_helpers.npz")
+    cube, wgt = h["mom_cube"], h["mom_weight"]
+    for name, args in (("default", {}), ("centroid", dict(centroid=np.array([2.5, 4.25]))), ("weighted", dict(N=3, weight=wgt))):
+        M = measure.moments(cube, **args)
+        assert [tuple(k) for k in h["mom_%s_keys" % name]] == sorted(M)
+        assert_allclose(np.array([M[k] for k in sorted(M)]), h["mom_%s_vals" % name], rtol=1e-12)
+    M2 = measure.moments(cube[0], N=1)
+    assert_allclose(np.array([M2[k] for k in sorted(M2)]), h["mom_image_vals"], rtol=1e-12)
+
+    class Fake:
+        def get_model(self):
+            return cube
+
+    assert_allclose(measure.moments(Fake(), N=0)[0, 0], cube.sum(axis=(1, 2)))
