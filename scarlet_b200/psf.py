@@ -102,6 +102,7 @@ class ImagePSF(PSF):
 
     def get_model(self, *parameters, offset=None):
         image = np.array(self.get_parameter(0, *parameters)._data if not parameters else parameters[0])
-        if offset is not None:
-            raise NotImplementedError("Fourier-shifted ImagePSF (fft.shift) is a 'next' row (SURVEY f-3)")
+        if offset is not None:  # band by band through the host Fourier shift (psf.py:228-234, fft.py:399-428)
+            from . import fft
+            image = np.stack([fft.shift(plane, offset, return_Fourier=False) for plane in image], axis=0)
         return image

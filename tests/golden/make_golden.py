@@ -356,6 +356,7 @@ def init_helpers(sc):
     moffat = sc.psf.MoffatPSF(alpha=[4.7, 3.0, 2.2], beta=[1.5, 2.5, 3.0], boxsize=21)
     out["moffat"], out["moffat_offset"] = moffat.get_model(), moffat.get_model(offset=(0.3, -0.2))
     out["moffat_same"] = sc.psf.MoffatPSF(alpha=[2.0, 2.0], beta=[2.0, 2.0]).get_model()
+    out["imagepsf_offset"] = sc.psf.ImagePSF(psfs.copy()).get_model(offset=(0.3, -0.45))
     out["gauss_offset"] = sc.psf.GaussianPSF(sigma=[0.8, 1.3], boxsize=11).get_model(offset=(0.25, -0.4))
     # image moments (measure.py:108-150) of a small cube and of a single image
     import importlib

@@ -483,6 +483,8 @@ def test_function_psf_models_vs_reference_fixture():
     assert_allclose(sb.GaussianPSF(sigma=[0.8, 1.3], boxsize=11).get_model(offset=(0.25, -0.4)), h["gauss_offset"], rtol=1e-10)
     with pytest.raises(AssertionError):
         sb.MoffatPSF(integrate=True)
+    g = golden("hsc_cosmos_35.npz")
+    assert_allclose(sb.ImagePSF(g["psfs"].copy()).get_model(offset=(0.3, -0.45)), h["imagepsf_offset"], atol=1e-12)
 
 
 def test_measure_moments_vs_reference_fixture():
