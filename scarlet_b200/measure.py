@@ -44,10 +44,11 @@ def snr(component, observations):
     for obs in observations:
         rendered = np.asarray(obs.render(model), dtype=np.float64)
         w = rendered / rendered.sum(axis=(-2, -1))[:, None, None]
-        var = np.asarray(np.ma.filled(obs.noise_rms, np.inf), dtype=np.float64) ** 2
-        finite = np.isfinite(var)
+        # like the reference, the variance of a zero-weight pixel is what lies underneath the mask of noise_rms (1: numpy.ma
+        # keeps the numerator of 1/sqrt(w) there) -- its np.concatenate of the masked arrays drops the masks
+        var = np.asarray(np.ma.getdata(obs.noise_rms), dtype=np.float64) ** 2
         signal += float((rendered * w).sum())
-        weight2 += float((var[finite] * w[finite] ** 2).sum())
+        weight2 += float((var * w ** 2).sum())
     return signal / np.sqrt(weight2)
 
 

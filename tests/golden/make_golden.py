@@ -333,6 +333,11 @@ def init_helpers(sc):
         a, b = sc.initialization.get_psf_spectrum(c, obs, compute_snr=True)
         spec.append(a), snr.append(b)
     out["psf_spectrum"], out["psf_snr"] = np.array(spec), np.array(snr)
+    # detection image of the first source with the masked patch in the weights (initialization.py:213-284)
+    pix_spectrum = sc.initialization.get_pixel_spectrum(centers[0], obs)
+    out["detect"], out["detect_std"] = (a.astype(np.float32) for a in sc.initialization.build_initialization_image(obs, spectra=pix_spectrum))
+    out["detect_flat"], out["detect_flat_std"] = (a.astype(np.float32) for a in sc.initialization.build_initialization_image(obs))
+    del obs._detect
     out["edge_spectrum"] = sc.initialization.get_psf_spectrum((1.0, 2.0), obs)  # PSF box sticks out of the image
     # component counts of init_source for a few min_snr values (the cap is floor(psf_snr / min_snr))
     ks = []
@@ -368,6 +373,13 @@ def init_helpers(sc):
         M = ref_measure.moments(cube, **args)
         out["mom_%s_keys" % name] = np.array(sorted(M))
         out["mom_%s_vals" % name] = np.array([M[k] for k in sorted(M)])
+    # matched-filter SNR of a model cube with zero-weight pixels under the source (measure.py:60-104)
+    snr_model = sources[0].get_model(frame=frame)
+    out["snr_rendered"] = np.asarray(obs.render(snr_model), dtype=np.float32)
+    out["snr_value"] = np.array(ref_measure.snr(snr_model, obs))
+    shifted = np.roll(snr_model, (-26, 18), axis=(1, 2))  # the same source moved onto the masked patch
+    out["snr_rendered_masked"] = np.asarray(obs.render(shifted), dtype=np.float32)
+    out["snr_value_masked"] = np.array(ref_measure.snr(shifted, obs))
     M2 = ref_measure.moments(cube[0], N=1)
     out["mom_image_vals"] = np.array([M2[k] for k in sorted(M2)])
     save("init_helpers.npz", **out)

@@ -505,3 +505,22 @@ def test_measure_moments_vs_reference_fixture():
             return cube
 
     assert_allclose(measure.moments(Fake(), N=0)[0, 0], cube.sum(axis=(1, 2)))
+
+
+def test_detection_image_and_snr_with_masked_pixels_vs_reference_fixture():
+    """build_initialization_image and measure.snr on data with a zero-weight patch: the reference lets such pixels in with
+    the value underneath the mask of noise_rms (unit variance); both functions follow it (fixture from the reference)."""
+    from scarlet_b200 import initialization as init, measure
+    h = golden("init_helpers.npz")
+    frame, obs = _hsc_observation(weights=h["weights"])
+    assert (h["weights"][:, 5:9, 30:34] == 0).all()
+    spectrum = init.get_pixel_spectrum(tuple(h["centers"][0]), obs)
+    detect, std = init.build_initialization_image(obs, spectra=spectrum)
+    assert_allclose(detect, h["detect"], rtol=1e-6, atol=1e-6 * np.abs(h["detect"]).max())
+    assert_allclose(std, h["detect_std"], rtol=1e-6)
+    detect, std = init.build_initialization_image(obs)
+    assert_allclose(detect, h["detect_flat"], rtol=1e-6, atol=1e-6 * np.abs(h["detect_flat"]).max())
+    assert_allclose(std, h["detect_flat_std"], rtol=1e-6)
+    for tag in ("", "_masked"):  # Observation.render (device) replaced by the reference's rendered model
+        obs.render = lambda model, rendered=h["snr_rendered" + tag]: rendered
+        assert_allclose(measure.snr(np.zeros(frame.shape), obs), float(h["snr_value" + tag]), rtol=1e-5)
