@@ -315,6 +315,7 @@ def source_recipes(sc):
 
 
 def init_helpers(sc):
+    import importlib
     """The reference's user-facing initialisation helpers on data/hsc_cosmos_35.npz: ``get_psf_spectrum`` (with SNR) at the
     first five catalogue positions, the component count ``init_source`` settles on, and ``set_spectra_to_match`` applied to
     three single-component sources (inputs: the rendered unit-spectrum models, outputs: the solved spectra)."""
@@ -363,8 +364,19 @@ def init_helpers(sc):
     out["moffat_same"] = sc.psf.MoffatPSF(alpha=[2.0, 2.0], beta=[2.0, 2.0]).get_model()
     out["imagepsf_offset"] = sc.psf.ImagePSF(psfs.copy()).get_model(offset=(0.3, -0.45))
     out["gauss_offset"] = sc.psf.GaussianPSF(sigma=[0.8, 1.3], boxsize=11).get_model(offset=(0.25, -0.4))
+    # off-centre symmetry operators of the source initialisation (operator.py:207-271)
+    ref_operator = importlib.import_module(sc.__name__ + ".operator")
+    rng = np.random.default_rng(207)
+    sym_cases = [((9, 11), None, None), ((9, 11), (2, 7), None), ((9, 11), (6, 3), 0.0), ((8, 10), (5, 2), None), ((8, 10), (1, 8), -1.0),
+                 ((7, 7), (3, 3), None)]
+    out["sym_shapes"] = np.array([c[0] for c in sym_cases])
+    out["sym_centers"] = np.array([(-1, -1) if c[1] is None else c[1] for c in sym_cases])
+    out["sym_fills"] = np.array([np.nan if c[2] is None else c[2] for c in sym_cases])
+    for i, (shape, center, fill) in enumerate(sym_cases):
+        X = rng.random(shape)
+        out["sym%d_in" % i] = X.copy()
+        out["sym%d_out" % i] = np.array(ref_operator.prox_uncentered_symmetry(X.copy(), 0, center=center, algorithm="sdss", fill=fill))
     # image moments (measure.py:108-150) of a small cube and of a single image
-    import importlib
     ref_measure = importlib.import_module(sc.__name__ + ".measure")
     rng = np.random.default_rng(108)
     cube, wgt = rng.random((3, 9, 7)), rng.random((3, 9, 7))

@@ -524,3 +524,18 @@ def test_detection_image_and_snr_with_masked_pixels_vs_reference_fixture():
     for tag in ("", "_masked"):  # Observation.render (device) replaced by the reference's rendered model
         obs.render = lambda model, rendered=h["snr_rendered" + tag]: rendered
         assert_allclose(measure.snr(np.zeros(frame.shape), obs), float(h["snr_value" + tag]), rtol=1e-5)
+
+
+def test_uncentered_symmetry_vs_reference_fixture():
+    """operator.prox_uncentered_symmetry(algorithm="sdss") -- minimum of 180-degree partners about the peak or an explicit
+    off-centre pixel, odd and even shapes, with and without fill -- against the reference's outputs"""
+    from scarlet_b200 import operator
+    h = golden("init_helpers.npz")
+    for i, (shape, center, fill) in enumerate(zip(h["sym_shapes"], h["sym_centers"], h["sym_fills"])):
+        X = h["sym%d_in" % i].copy()
+        assert X.shape == tuple(shape)
+        out = operator.prox_uncentered_symmetry(X, 0, center=None if center[0] < 0 else tuple(int(v) for v in center), algorithm="sdss",
+                                                fill=None if np.isnan(fill) else float(fill))
+        assert_allclose(out, h["sym%d_out" % i], rtol=0, atol=0)
+    with pytest.raises(NotImplementedError):
+        operator.prox_uncentered_symmetry(np.ones((5, 5)), 0, algorithm="kspace")
