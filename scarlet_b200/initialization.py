@@ -86,7 +86,7 @@ def build_initialization_image(observations, spectra=None):
 def trim_morphology(center_index, morph, bg_thresh=0, boxsize=None):
     """Zero everything at or below ``bg_thresh`` and cut the smallest allowed square box around ``center_index`` that holds
     what is left.  -> (morph in that box, 2-D Box)"""
-    morph[morph <= bg_thresh] = 0
+    morph[~(morph > bg_thresh)] = 0  # also clears NaN pixels
     support = Box.from_data(morph, min_value=0)
     size = 0
     if support.contains(center_index):

@@ -376,6 +376,16 @@ def init_helpers(sc):
         X = rng.random(shape)
         out["sym%d_in" % i] = X.copy()
         out["sym%d_out" % i] = np.array(ref_operator.prox_uncentered_symmetry(X.copy(), 0, center=center, algorithm="sdss", fill=fill))
+    # box trimming (initialization.py:173-210): blob near the centre index, explicit box size, centre outside the support, NaN
+    yy, xx = np.mgrid[:40, :46]
+    blob = np.exp(-((yy - 17) ** 2 / 30.0 + (xx - 25) ** 2 / 18.0))
+    blob[3, 4] = np.nan
+    trim_cases = [((17, 25), 0.01, None), ((17, 25), 0.2, None), ((16, 27), 1e-4, None), ((17, 25), 0.01, 11), ((2, 40), 0.5, None)]
+    out["trim_in"] = blob
+    out["trim_args"] = np.array([(c[0][0], c[0][1], c[1], -1 if c[2] is None else c[2]) for c in trim_cases])
+    for i, (ci, thr, bs) in enumerate(trim_cases):
+        m, bb = sc.initialization.trim_morphology(ci, blob.copy(), bg_thresh=thr, boxsize=bs)
+        out["trim%d_out" % i], out["trim%d_origin" % i] = m, np.array(bb.origin)
     # image moments (measure.py:108-150) of a small cube and of a single image
     ref_measure = importlib.import_module(sc.__name__ + ".measure")
     rng = np.random.default_rng(108)

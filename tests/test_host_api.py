@@ -539,3 +539,15 @@ def test_uncentered_symmetry_vs_reference_fixture():
         assert_allclose(out, h["sym%d_out" % i], rtol=0, atol=0)
     with pytest.raises(NotImplementedError):
         operator.prox_uncentered_symmetry(np.ones((5, 5)), 0, algorithm="kspace")
+
+
+def test_trim_morphology_vs_reference_fixture():
+    """initialization.trim_morphology / get_minimal_boxsize: threshold, smallest standard box around the centre index that
+    holds the support, explicit box size, centre outside the support, NaN pixels -- against the reference's outputs"""
+    from scarlet_b200 import initialization as init
+    h = golden("init_helpers.npz")
+    for i, (cy, cx, thr, bs) in enumerate(h["trim_args"]):
+        morph, box = init.trim_morphology((int(cy), int(cx)), h["trim_in"].copy(), bg_thresh=float(thr), boxsize=None if bs < 0 else int(bs))
+        assert box.origin == tuple(h["trim%d_origin" % i]) and morph.shape == h["trim%d_out" % i].shape
+        assert_array_equal(morph, h["trim%d_out" % i])
+    assert [init.get_minimal_boxsize(s) for s in (0, 21, 22, 31, 32, 100)] == [21, 21, 31, 31, 41, 101]
