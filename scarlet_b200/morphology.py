@@ -112,8 +112,9 @@ class ImageMorphology(Morphology):
                 size = max(bbox.shape)
                 newsize = get_minimal_boxsize(size + 1)
                 pad = (newsize - size) // 2
-                self._replace_image(image, np.pad(image._data, pad, mode="linear_ramp"), np.pad(image.m, pad, mode="constant"),
-                                    np.pad(image.v, pad, mode="constant"), np.pad(image.vhat, pad, mode="constant"))
+                def grown(a):
+                    return None if a is None else np.pad(a, pad, mode="constant")
+                self._replace_image(image, np.pad(image._data, pad, mode="linear_ramp"), grown(image.m), grown(image.v), grown(image.vhat))
                 self.bbox = Box((newsize, newsize), origin=tuple(o - pad for o in self.bbox.origin))
                 raise UpdateException
 

@@ -386,6 +386,37 @@ def init_helpers(sc):
     for i, (ci, thr, bs) in enumerate(trim_cases):
         m, bb = sc.initialization.trim_morphology(ci, blob.copy(), bg_thresh=thr, boxsize=bs)
         out["trim%d_out" % i], out["trim%d_origin" % i] = m, np.array(bb.origin)
+    # dynamic box of an image morphology (morphology.py:52-68,132-207): shrink, grow, stay
+    rng = np.random.default_rng(132)
+    yy, xx = np.mgrid[:31, :31]
+    def blob(sig):
+        return np.exp(-((yy - 15) ** 2 + (xx - 15) ** 2) / (2.0 * sig ** 2))
+    box_cases = []
+    small = blob(1.5)
+    small[small < 1e-3] = 0                       # empty outer rings -> shrink
+    box_cases.append((small, 1e-3 * rng.standard_normal((31, 31)), np.full((31, 31), 1e-2)))
+    wide = blob(9.0)                               # flux at the edges, optimiser pulling outwards -> grow
+    m_out = -np.ones((31, 31)) * 5.0
+    box_cases.append((wide, m_out, np.full((31, 31), 1e-4)))
+    mid = blob(4.0)                                # nothing to do
+    v_mid = np.full((31, 31), 1e-2)
+    v_mid[0, :] = 0                                # zero second moments are masked out of the edge statistics
+    box_cases.append((mid, 1e-3 * rng.standard_normal((31, 31)), v_mid))
+    for i, (img, m, v) in enumerate(box_cases):
+        par = sc.parameter.Parameter(img.copy(), name="image", step=1e-2, m=m.copy(), v=v.copy(), vhat=v.copy() * 2)
+        fr = sc.frame.Frame((1, 61, 61), channels=["r"])
+        morph = sc.morphology.ImageMorphology(fr, par, bbox=sc.bbox.Box((31, 31), origin=(10, 12)), resizing=True)
+        try:
+            morph.update()
+            changed = 0
+        except sc.model.UpdateException:
+            changed = 1
+        new = morph.parameters[0]
+        out["box%d_image" % i], out["box%d_m" % i], out["box%d_v" % i] = img, m, v
+        out["box%d_changed" % i] = np.array(changed)
+        out["box%d_new_image" % i], out["box%d_new_m" % i] = np.asarray(new), np.asarray(new.m)
+        out["box%d_new_v" % i], out["box%d_new_vhat" % i] = np.asarray(new.v), np.asarray(new.vhat)
+        out["box%d_new_origin" % i], out["box%d_new_step" % i] = np.array(morph.bbox.origin), np.array(float(new.step))
     # image moments (measure.py:108-150) of a small cube and of a single image
     ref_measure = importlib.import_module(sc.__name__ + ".measure")
     rng = np.random.default_rng(108)

@@ -551,3 +551,36 @@ def test_trim_morphology_vs_reference_fixture():
         assert box.origin == tuple(h["trim%d_origin" % i]) and morph.shape == h["trim%d_out" % i].shape
         assert_array_equal(morph, h["trim%d_out" % i])
     assert [init.get_minimal_boxsize(s) for s in (0, 21, 22, 31, 32, 100)] == [21, 21, 31, 31, 41, 101]
+
+
+def test_image_morphology_update_vs_reference_fixture():
+    """ImageMorphology.update (dynamic box): shrink when the outer rings are empty, grow by linear-ramp padding
+    when the next AMSGrad step pulls flux to an edge (zero second moments masked out), step halved, optimiser state cut /
+    zero-padded, UpdateException raised -- new image, m, v, vhat, box and step against the reference's own update"""
+    import warnings
+    import scarlet_b200 as sb
+    h = golden("init_helpers.npz")
+    frame = sb.Frame((1, 61, 61), channels=["r"])
+    for i in range(3):
+        img, m, v = h["box%d_image" % i], h["box%d_m" % i], h["box%d_v" % i]
+        par = sb.Parameter(img.copy(), name="image", step=1e-2, m=m.copy(), v=v.copy(), vhat=v.copy() * 2)
+        morph = sb.ImageMorphology(frame, par, bbox=sb.Box((31, 31), origin=(10, 12)), resizing=True)
+        changed = 0
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                morph.update()
+            except sb.UpdateException:
+                changed = 1
+        assert changed == int(h["box%d_changed" % i])
+        new = morph.parameters[0]
+        assert tuple(morph.bbox.origin) == tuple(h["box%d_new_origin" % i]) and morph.bbox.shape == h["box%d_new_image" % i].shape
+        assert float(new.step) == float(h["box%d_new_step" % i])
+        assert_allclose(np.asarray(new), h["box%d_new_image" % i], rtol=1e-12)
+        for key in ("m", "v", "vhat"):
+            assert_allclose(np.asarray(getattr(new, key)), h["box%d_new_%s" % (i, key)], rtol=1e-12)
+    # a fixed or non-resizing image never changes
+    par = sb.Parameter(h["box0_image"].copy(), name="image", step=1e-2)
+    still = sb.ImageMorphology(frame, par, bbox=sb.Box((31, 31), origin=(10, 12)), resizing=False)
+    still.update()
+    assert still.bbox.shape == (31, 31)
