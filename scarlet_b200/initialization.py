@@ -39,10 +39,12 @@ def get_pixel_spectrum(sky_coord, observations, correct_psf=False, models=None, 
     for obs, model in zip(observations, models):
         iy, ix = np.round(obs.get_pixel(sky_coord)).astype(int)
         spectrum = np.array(obs.data[:, iy, ix])
+        # in-place divisions, like the reference's: the spectrum keeps the dtype of the data (the device rounds a float32
+        # spectrum to float32 after every step, so the dtype is part of the result)
         if correct_psf and obs.psf is not None:
-            spectrum = spectrum / obs.psf.get_model().max(axis=(1, 2))
+            spectrum /= obs.psf.get_model().max(axis=(1, 2))
         elif model is not None:
-            spectrum = spectrum / np.asarray(model)[:, iy, ix]
+            spectrum /= np.asarray(model)[:, iy, ix]
         if np.any(spectrum <= 0):
             (logger.warning if np.all(spectrum <= 0) else logger.info)("Zero or negative spectrum %s at %s", spectrum, sky_coord)
         spectra.append(spectrum)

@@ -82,7 +82,8 @@ class CompactExtendedSource(FactorizedComponent):
         center = np.asarray(model_frame.get_pixel(sky_coord), dtype=np.float64)
         morphology = ExtendedSourceMorphology(model_frame, center, morph, bbox=bbox, monotonic="angle", symmetric=False, min_grad=0,
                                               shifting=shifting, resizing=resizing)
-        spectrum = init.get_pixel_spectrum(sky_coord, obs_list, correct_psf=True) / morph.sum()
+        spectrum = init.get_pixel_spectrum(sky_coord, obs_list, correct_psf=True)
+        spectrum /= morph.sum()  # in place: keeps the dtype of the data, like the reference
         super().__init__(model_frame, TabulatedSpectrum(model_frame, spectrum, min_step=_noise_rms(obs_list)), morphology)
         self.center = morphology.center
 

@@ -358,6 +358,15 @@ def init_helpers(sc):
     out["unit_rendered"] = np.stack([obs.render(src.get_model(frame=frame)) for src in sources]).astype(np.float32)
     sc.initialization.set_spectra_to_match(sources, obs)
     out["matched_spectra"] = np.stack([np.asarray(src.parameters[0]) for src in sources])
+    # spectra of the PSF-shaped recipes keep the dtype of the data (in-place divisions, initialization.py:58-67, source.py:119,302)
+    clean = sc.observation.Observation(images, psf=sc.psf.ImagePSF(psfs.copy()), weights=1 / variance, channels=channels)
+    clean.match(frame)
+    point = sc.source.PointSource(frame, centers[0], clean)
+    out["point_spectrum"], out["point_center"] = np.asarray(point.parameters[0]), np.asarray(point.parameters[1])
+    out["point_spectrum_step"] = np.asarray(point.parameters[0].step(point.parameters[0], it=0))
+    compact = sc.source.ExtendedSource(frame, centers[2], clean, compact=True)
+    out["compact_spectrum"], out["compact_image"] = np.asarray(compact.parameters[0]), np.asarray(compact.parameters[1])
+    out["compact_origin"] = np.array(compact.bbox.origin)
     # functional PSF models (psf.py:80-201)
     moffat = sc.psf.MoffatPSF(alpha=[4.7, 3.0, 2.2], beta=[1.5, 2.5, 3.0], boxsize=21)
     out["moffat"], out["moffat_offset"] = moffat.get_model(), moffat.get_model(offset=(0.3, -0.2))

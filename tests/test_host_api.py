@@ -584,3 +584,24 @@ def test_image_morphology_update_vs_reference_fixture():
     still = sb.ImageMorphology(frame, par, bbox=sb.Box((31, 31), origin=(10, 12)), resizing=False)
     still.update()
     assert still.bbox.shape == (31, 31)
+
+
+def test_psf_shaped_recipes_keep_the_data_dtype():
+    """PointSource and the compact ExtendedSource (both built on the host): spectra bit-equal to the reference's INCLUDING the
+    dtype -- the reference divides the float32 peak-pixel values in place, and a float32 spectrum is rounded to float32 after
+    every step of the fit"""
+    import scarlet_b200 as sb
+    h = golden("init_helpers.npz")
+    g = golden("hsc_cosmos_35.npz")
+    frame, obs = _hsc_observation()
+    point = sb.PointSource(frame, tuple(h["centers"][0]), obs)
+    assert point.parameters[0].dtype == h["point_spectrum"].dtype == np.float32
+    assert_array_equal(np.asarray(point.parameters[0]), h["point_spectrum"])
+    assert_array_equal(np.asarray(point.parameters[1]), h["point_center"])
+    assert_array_equal(point.parameters[0].step(point.parameters[0], it=0), h["point_spectrum_step"])
+    compact = sb.ExtendedSource(frame, tuple(h["centers"][2]), obs, compact=True)
+    assert compact.parameters[0].dtype == h["compact_spectrum"].dtype == np.float32
+    assert_array_equal(np.asarray(compact.parameters[0]), h["compact_spectrum"])
+    assert_allclose(np.asarray(compact.parameters[1]), h["compact_image"], rtol=1e-12)
+    assert tuple(compact.bbox.origin) == tuple(h["compact_origin"])
+    assert g["images"].dtype == np.float32
