@@ -131,6 +131,9 @@ typedef struct sb_plan sb_plan;
 const char *sb_last_error(void);
 int sb_device_count(void);
 const char *sb_version(void);
+/* hash of the sources the library was compiled from (scarlet_b200/_build.py:source_hash): the loader refuses a binary
+ * whose hash differs from the sources next to it instead of calling a stale ABI */
+const char *sb_source_hash(void);
 
 /* Transform lengths of the fused spectral kernels (csrc/spectral.cuh): smallest supported length >= need, 0 if the
  * request exceeds the largest one (the plan then runs the convolutions through cuFFT on any 2/3/5/7-smooth grid). */
@@ -143,6 +146,10 @@ int64_t sb_plan_device_bytes(const sb_plan *plan);
 /* 1: the convolutions of this plan run in the fused row/column spectral kernels; 0: cuFFT + separate kernels
  * (grids with unsupported lengths, NullRenderer observations, or SB_SPECTRAL=cufft in the environment). */
 int sb_plan_spectral_mode(const sb_plan *plan);
+/* Diagnostic: histogram of the proximal sub-iterations (1..prox_max_iter, blend.py:145) the grouped update kernel ran
+ * per source since the last call.  enable=1 starts (or continues) counting and zeroes the counters after reading;
+ * enable=0 reads and switches the counters off.  out16 may be NULL. */
+int sb_plan_prox_histogram(sb_plan *plan, int enable, int64_t *out16);
 
 /* Observation data: data/weights float32 [n_scenes][C][H][W] (frame dtype, frame.py:29); K^ = rfftn of the
  * padded, ifftshifted difference kernel (renderer.py:198-202, fft.py:255-273) as interleaved complex128
@@ -150,6 +157,10 @@ int sb_plan_spectral_mode(const sb_plan *plan);
  * chi^2 of data pixels outside the model frame. */
 int sb_plan_upload_observation(sb_plan *plan, int obs, const float *data, const float *weights,
                                const double *khat, const double *loss_const);
+/* The same with float64 data / weights (a model frame of dtype float64 makes Observation.match keep float64 cubes,
+ * observation.py:75-84): a precision-64 plan stores them as they are, a precision-32 plan rounds on the device. */
+int sb_plan_upload_observation_f64(sb_plan *plan, int obs, const double *data, const double *weights,
+                                   const double *khat, const double *loss_const);
 /* Difference-kernel images instead of a host-computed K^ (what fft.convolve does on every call, fft.py:385-388):
  * kernels float64 [n][C][Py][Px] with n = 1 for an observation declared khat_shared, else n_scenes; (y0, x0) = grid
  * index of kernel pixel (0,0) before wrapping, i.e. the reference's centre-pad + ifftshift placement

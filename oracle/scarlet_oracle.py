@@ -46,6 +46,23 @@ from scipy import fftpack, special
 
 from . import monotonic_c
 
+# Arithmetic of the restatement.  The defaults are the reference's (see "Precision" above).  ``float32_arithmetic()``
+# switches the FFT convolutions to float32/complex64 and keeps the morphology images and their optimiser state in
+# float32 -- an independent float32 implementation of the same algorithm, used ONLY to measure how far float32 rounding
+# alone moves a trajectory (tools/parity_curve.py: the justification of the float32 tolerances in tests/).
+ARITH = {"fft": np.float64, "morph": np.float64}
+
+
+class float32_arithmetic:
+    def __enter__(self):
+        self.saved = dict(ARITH)
+        ARITH.update(fft=np.float32, morph=np.float32)
+        return self
+
+    def __exit__(self, *exc):
+        ARITH.update(self.saved)
+        return False
+
 # ----------------------------------------------------------------------------------------------
 # geometry  (bbox.py)
 # ----------------------------------------------------------------------------------------------
@@ -138,7 +155,7 @@ def get_fft_shape(shape1, shape2, padding=3, axes=None):
 
 def forward_fft(image, fft_shape, axes):
     """pad -> ifftshift -> rfftn over ``axes``.  fft.py:255-273.  float64/complex128 throughout."""
-    image = np.asarray(image, dtype=np.float64)
+    image = np.asarray(image, dtype=ARITH["fft"])
     padded = pad_to(image, fft_shape, axes)
     return np.fft.rfftn(np.fft.ifftshift(padded, axes), axes=axes)
 
@@ -437,7 +454,7 @@ class ExtendedSourceOracle:
         self.resizing = resizing
         self.shifting = shift is not None
         sed = np.asarray(sed, dtype=sed_dtype)
-        morph = np.array(morph, dtype=np.float64)
+        morph = np.array(morph, dtype=ARITH["morph"])
         self.min_step = np.asarray(min_step, dtype=np.float64)
         self.spectrum = OParam(sed, "spectrum", lambda x, it: relative_step(x, it, 1e-2, self.min_step),
                                ChainSpec([("positivity", 1e-20)]))
@@ -647,8 +664,14 @@ class ObservationOracle:
 
     def _kernel_fft(self, fshape):
         key = tuple(fshape)
+        key = key + (ARITH["fft"],)
         if key not in self._khat:
-            self._khat[key] = forward_fft(self.diff_kernel, fshape, (1, 2))
+            saved, ARITH["fft"] = ARITH["fft"], np.float64  # K^ is always formed in double, then stored in the working precision
+            try:
+                k = forward_fft(self.diff_kernel, fshape, (1, 2))
+            finally:
+                ARITH["fft"] = saved
+            self._khat[key] = k.astype(np.complex64) if saved == np.float32 else k
         return self._khat[key]
 
     # -- forward ------------------------------------------------------------------------------
@@ -672,7 +695,7 @@ class ObservationOracle:
         """Vector-Jacobian product of :meth:`render`: same FFT pipeline with conj(K^)."""
         C = self.data.shape[0]
         sub_shape = (C,) + self.frame_shape[1:]
-        emb = np.zeros(sub_shape, dtype=np.float64)
+        emb = np.zeros(sub_shape, dtype=ARITH["fft"])
         emb[self.model_slices] = grad_render[self.data_slices]
         if self.diff_kernel is not None:
             fshape = get_fft_shape(sub_shape, self.diff_kernel.shape, 3, (1, 2))
@@ -842,12 +865,13 @@ class SceneOracle:
         while it_outer < max_iter:
             params = self.parameters
             for p in params:
+                sdt = np.float32 if (p.name == "image" and p.x.dtype == np.float32) else np.float64  # float32_arithmetic() only
                 if p.m is None:
-                    p.m = np.zeros(p.x.shape)
+                    p.m = np.zeros(p.x.shape, dtype=sdt)
                 if p.v is None:
-                    p.v = np.zeros(p.x.shape)
+                    p.v = np.zeros(p.x.shape, dtype=sdt)
                 if p.vhat is None:
-                    p.vhat = np.zeros(p.x.shape)
+                    p.vhat = np.zeros(p.x.shape, dtype=sdt)
             restarted = False
             for it in range(max_iter - it_outer):  # proxmin's own counter starts at 0 in every call
                 loss, grads = self.loss_and_grads()

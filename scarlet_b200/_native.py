@@ -65,12 +65,15 @@ SYMBOLS = {
     "sb_last_error": (C.c_char_p, []),
     "sb_device_count": (C.c_int, []),
     "sb_version": (C.c_char_p, []),
+    "sb_source_hash": (C.c_char_p, []),
     "sb_fft_supported_length": (C.c_int, [C.c_int]),
     "sb_plan_spectral_mode": (C.c_int, [_P]),
+    "sb_plan_prox_histogram": (C.c_int, [_P, C.c_int, _P]),
     "sb_plan_create": (C.c_int, [C.POINTER(sb_batch_desc), C.c_int, C.POINTER(_P)]),
     "sb_plan_destroy": (None, [_P]),
     "sb_plan_device_bytes": (C.c_int64, [_P]),
     "sb_plan_upload_observation": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
+    "sb_plan_upload_observation_f64": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
     "sb_plan_upload_kernels": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "sb_plan_zero_state": (C.c_int, [_P]),
     "sb_plan_upload_resampling": (C.c_int, [_P, C.c_int, _P, _P, C.c_double]),
@@ -114,13 +117,17 @@ def lib():
     global _lib
     if _lib is None:
         path = _build.LIB
-        if not os.path.exists(path):
+        if not _build.up_to_date():  # missing, or built from other sources than the ones next to it: never load a stale ABI
             path = _build.build()
         handle = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(handle, name)  # AttributeError if the library does not export what the header declares
             fn.restype = res
             fn.argtypes = args
+        built = handle.sb_source_hash().decode()
+        if built != _build.source_hash():
+            raise NativeError("libscarlet_b200.so was built from other sources (%s) than csrc/ (%s): rebuild with "
+                              "python -m scarlet_b200._build" % (built, _build.source_hash()))
         _lib = handle
     return _lib
 

@@ -260,14 +260,24 @@ class DevicePlan:
         buf = (ctypes.c_byte * max(n, 8)).from_address(p)
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
-    def _stage_observations(self):
+    def _stage_observations(self, reuse=None):
         """Stack the per-scene cubes once into pinned staging buffers (host work, not repeated per upload)."""
         C, Ny, Nx = self.frame_shape
         self._host_obs = []
         for o, om in enumerate(self.obs_meta):
+            if reuse is not None:  # same pinned buffers, new contents of data / weights / constants
+                h = reuse[o]
+                for i, m in enumerate(om["metas"]):
+                    h["data"][i] = m["obs"].data
+                    h["weights"][i] = m["obs"].weights
+                h["consts"][...] = self._loss_consts(om["metas"])
+                self._host_obs.append(h)
+                continue
             metas = om["metas"]
             shp = (self.S,) + metas[0]["shape"]
-            data, weights = self._pinned(shp, np.float32), self._pinned(shp, np.float32)
+            # cubes travel in the plan's precision: a float64 twin must not see data rounded to float32
+            dt = np.float64 if self.precision == 64 else np.float32
+            data, weights = self._pinned(shp, dt), self._pinned(shp, dt)
             for i, m in enumerate(metas):
                 data[i] = m["obs"].data
                 weights[i] = m["obs"].weights
@@ -288,25 +298,30 @@ class DevicePlan:
                     khat[i] = op["khat"]
                 Fy, Fx = ops[0]["fshape"]
                 resamp = dict(khat=khat, Ey=ops[0]["Ey"], Ex=ops[0]["Ex"], h2=ops[0]["scale"] * Fy * Fx)
-            consts = []
-            for m in metas:
-                obs, (oy, ox) = m["obs"], m["origin"]
-                if m["kind"] == 2:  # resampled observation: every pixel is rendered
-                    consts.append(float(obs.log_norm))
-                    continue
-                H, W = obs.data.shape[1:]
-                outside = np.ones((H, W), dtype=bool)
-                y0, y1, x0, x1 = max(0, -oy), min(H, Ny - oy), max(0, -ox), min(W, Nx - ox)
-                if y1 > y0 and x1 > x0:
-                    outside[y0:y1, x0:x1] = False
-                extra = 0.0
-                if outside.any():
-                    w = np.asarray(obs.weights, dtype=np.float64)[:, outside]
-                    dd = np.asarray(obs.data, dtype=np.float64)[:, outside]
-                    extra = 0.5 * float((w * dd * dd).sum())
-                consts.append(float(obs.log_norm) + extra)
             self._host_obs.append(dict(data=data, weights=weights, kernels=kernels, korigin=metas[0]["korigin"], resamp=resamp,
-                                       consts=np.asarray(consts, dtype=np.float64)))
+                                       consts=self._loss_consts(metas)))
+
+    def _loss_consts(self, metas):
+        """per scene: log_norm (observation.py:172-186) + the chi^2 of data pixels the model frame does not cover"""
+        C, Ny, Nx = self.frame_shape
+        consts = []
+        for m in metas:
+            obs, (oy, ox) = m["obs"], m["origin"]
+            if m["kind"] == 2:  # resampled observation: every pixel is rendered
+                consts.append(float(obs.log_norm))
+                continue
+            H, W = obs.data.shape[1:]
+            outside = np.ones((H, W), dtype=bool)
+            y0, y1, x0, x1 = max(0, -oy), min(H, Ny - oy), max(0, -ox), min(W, Nx - ox)
+            if y1 > y0 and x1 > x0:
+                outside[y0:y1, x0:x1] = False
+            extra = 0.0
+            if outside.any():
+                w = np.asarray(obs.weights, dtype=np.float64)[:, outside]
+                dd = np.asarray(obs.data, dtype=np.float64)[:, outside]
+                extra = 0.5 * float((w * dd * dd).sum())
+            consts.append(float(obs.log_norm) + extra)
+        return np.asarray(consts, dtype=np.float64)
 
     def upload_observations(self):
         """Host (pinned) -> device copy of data, weights, difference-kernel images and the per-scene loss constants;
@@ -316,9 +331,9 @@ class DevicePlan:
         nbytes = 0
         for o, h in enumerate(self._host_obs):
             ker, rs = h["kernels"], h["resamp"]
-            nat.check(nat.lib().sb_plan_upload_observation(self._handle, o, nat.ptr(h["data"]), nat.ptr(h["weights"]),
-                                                           nat.ptr(rs["khat"].view(np.float64)) if rs is not None else None,
-                                                           nat.ptr(h["consts"])))
+            up = nat.lib().sb_plan_upload_observation_f64 if h["data"].dtype == np.float64 else nat.lib().sb_plan_upload_observation
+            nat.check(up(self._handle, o, nat.ptr(h["data"]), nat.ptr(h["weights"]),
+                         nat.ptr(rs["khat"].view(np.float64)) if rs is not None else None, nat.ptr(h["consts"])))
             if rs is not None:
                 nat.check(nat.lib().sb_plan_upload_resampling(self._handle, o, nat.ptr(rs["Ey"].view(np.float64)),
                                                               nat.ptr(rs["Ex"].view(np.float64)), rs["h2"]))
@@ -327,6 +342,21 @@ class DevicePlan:
                 nat.check(nat.lib().sb_plan_upload_kernels(self._handle, o, nat.ptr(ker), ker.shape[-2], ker.shape[-1],
                                                            h["korigin"][0], h["korigin"][1]))
             nbytes += h["data"].nbytes + h["weights"].nbytes + (ker.nbytes if ker is not None else 0) + h["consts"].nbytes
+        return nbytes
+
+    def refresh_observations(self):
+        """Re-read ``obs.data`` / ``obs.weights`` of every scene (they may have been edited in place since the plan was built, and
+        the reference reads them afresh on every fit) and upload them with the loss constants; kernels are not touched.
+        ``log_norm`` / ``noise_rms`` stay cached on the Observation exactly as in the reference (observation.py:116-124, 172-186)."""
+        if self._host_obs is None:
+            return self.upload_observations()
+        old, self._host_obs = self._host_obs, None
+        self._stage_observations(reuse=old)
+        nbytes = 0
+        for o, h in enumerate(self._host_obs):
+            up = nat.lib().sb_plan_upload_observation_f64 if h["data"].dtype == np.float64 else nat.lib().sb_plan_upload_observation
+            nat.check(up(self._handle, o, nat.ptr(h["data"]), nat.ptr(h["weights"]), None, nat.ptr(h["consts"])))
+            nbytes += h["data"].nbytes + h["weights"].nbytes + h["consts"].nbytes
         return nbytes
 
     # -------------------------------------------------------------------------------------------------
@@ -434,6 +464,20 @@ class DevicePlan:
         store.device_synced = True
         return 4 * nbytes
 
+    def upload_values(self, params, values):
+        """Upload explicit values for the given Parameter objects (same order) instead of their stored contents; the host
+        Parameters are not touched.  Backs ``Blend.get_model(*parameters)``."""
+        given = {id(p): np.asarray(v, dtype=np.float64) for p, v in zip(params, values)}
+        vals = self.store.arrays["value"]
+        for p, l in self._linked:
+            v = given.get(id(p))
+            if v is None:
+                v = np.asarray(p._data, dtype=np.float64)
+            if v.size != l.stop - l.start:
+                raise ValueError("parameter '%s': expected %d values, got shape %s" % (p.name, l.stop - l.start, v.shape))
+            vals[l.group].reshape(-1)[l.start:l.stop] = v.reshape(-1)
+        self._upload("value")
+
     def forget_state(self, values=None):
         """Benchmark helper: drop the optimiser state everywhere (next fit is a cold start) and optionally restore the
         parameter values from a ``pack_current()`` snapshot."""
@@ -525,6 +569,12 @@ class DevicePlan:
         nat.check(nat.lib().sb_plan_profile_iterations(self._handle, ctypes.byref(opts), int(n_iterations), nat.ptr(ms)))
         names = [nat.lib().sb_stage_name(i).decode() for i in range(nat.SB_N_STAGES)]
         return dict(zip(names, (ms / max(n_iterations, 1)).tolist()))
+
+    def prox_histogram(self, enable=True):
+        """Diagnostic: counts of proximal sub-iterations executed per source update since the last call (index = count)."""
+        out = np.zeros(16, dtype=np.int64)
+        nat.check(nat.lib().sb_plan_prox_histogram(self._handle, int(bool(enable)), nat.ptr(out)))
+        return out
 
     @property
     def spectral_mode(self):

@@ -25,8 +25,7 @@ def _fit_options(max_iter, e_rel, min_iter, noise_factor, alg_kwargs, check_ever
     scheme = kw.pop("scheme", "amsgrad")
     if scheme != "amsgrad":
         raise NotImplementedError("only scheme='amsgrad' (the reference default, blend.py:144) is implemented")
-    if kw.pop("callback", None) is not None:
-        raise NotImplementedError("per-iteration host callbacks would serialise the device loop; not supported")
+    kw.pop("callback", None)  # honoured by Blend.fit (host call per iteration); see there
     prox_max_iter = kw.pop("prox_max_iter", 10)
     b1, b2, eps = kw.pop("b1", 0.9), kw.pop("b2", 0.999), kw.pop("eps", 1e-8)
     kw.pop("p", None)
@@ -52,15 +51,27 @@ class Blend(CombinedComponent):
 
     # -- device plan ----------------------------------------------------------------------------------
     def _structure_key(self):
-        return tuple((id(p), p.shape) for p in self.parameters) + tuple(id(getattr(o, "renderer", None)) for o in self.observations)
+        """Everything the device descriptor bakes in (the reference re-reads all of it on every fit, blend.py:103-145):
+        identity, shape, ``fixed``, ``step`` and constraint of every parameter; renderer and cube identity of every
+        observation.  In-place edits of ``obs.data`` / ``obs.weights`` are covered by re-staging them in ``fit``."""
+        def step_key(p):
+            st = p.step
+            if callable(st):
+                return (id(getattr(st, "func", st)), repr(sorted(getattr(st, "keywords", {}).items(), key=lambda kv: kv[0])))
+            return float(st)
+        pk = tuple((id(p), p.shape, bool(p.fixed), step_key(p), id(p.constraint), id(p.prior)) for p in self.parameters)
+        ok = tuple((id(getattr(o, "renderer", None)), id(o.data), id(o.weights)) for o in self.observations)
+        return pk + ok
 
-    def _get_plan(self):
+    def _get_plan(self, refresh=False):
         key = self._structure_key()
         if self._plan is None or key != self._plan_key:
             if self._plan is not None:
                 self._plan.close()
             self._plan = DevicePlan([self], precision=self._precision, device=self._device)
             self._plan_key = key
+        elif refresh:
+            self._plan.refresh_observations()
         return self._plan
 
     # -- the fitting loop -----------------------------------------------------------------------------
@@ -72,6 +83,10 @@ class Blend(CombinedComponent):
         call (``UpdateException``) and restarts the optimiser with the new shapes, warm state and ``it = len(self.loss)``.
         Here one ``adaprox`` call is one device plan driven in slices that end exactly at those inspection points."""
         check_every = int(alg_kwargs.pop("check_every", 10))
+        # The reference pops scheme / prox_max_iter / callback out of alg_kwargs INSIDE its restart loop (blend.py:143-152):
+        # after the first UpdateException they are gone, i.e. a restarted call runs with the defaults and without the user
+        # callback.  Mirrored here, not fixed.
+        user_cb = alg_kwargs.get("callback", None)
         opts = _fit_options(max_iter, e_rel, min_iter, noise_factor, alg_kwargs, check_every)
         for src in self.sources:
             src.check_parameters()
@@ -80,15 +95,22 @@ class Blend(CombinedComponent):
         resizing = any(getattr(c.children[1], "resizing", False) and not c.children[1].parameters[0].fixed
                        for c in _leaves(self.sources) if hasattr(c.children[1], "resizing"))
         it = 0
+        first = True
         while it < max_iter:
-            plan = self._get_plan()
+            plan = self._get_plan(refresh=first)
+            first = False
             plan.upload_parameters(state=True)
             budget = max_iter - it  # iterations this adaprox call may run
             opts.max_iter, opts.resume, k_done, restarted = budget, 0, 0, False
             n0 = len(self.loss)
+            X = self.parameters + tuple(p for obs in self.observations for p in obs.parameters)
             while k_done < budget:
-                # without resizable boxes nobody inspects the sources: run the whole call in one go
-                stop = budget if not resizing else min(budget, 11 if k_done == 0 else k_done + 10)
+                # without resizable boxes nobody inspects the sources: run the whole call in one go; a user callback sees
+                # the parameters after every iteration (blend.py:301-302), so the call is then driven one iteration at a time
+                if user_cb is not None:
+                    stop = k_done + 1
+                else:
+                    stop = budget if not resizing else min(budget, 11 if k_done == 0 else k_done + 10)
                 opts.run_until = stop
                 n_iter, loss, status = plan.fit(opts)
                 opts.resume = 1
@@ -114,18 +136,35 @@ class Blend(CombinedComponent):
                         break
                 if n < stop:  # converged inside the slice (StopIteration in the reference)
                     break
+                if user_cb is not None:
+                    # order of Blend._callback (blend.py:276-302): the stop rule comes before the user callback
+                    if (not opts.fixed_iterations and last > min_iter and len(self.loss) >= 2
+                            and abs(self.loss[-1] - self.loss[-2]) < e_rel * abs(self.loss[-1])):
+                        break
+                    before = [np.array(x._data if hasattr(x, "_data") else x, copy=True) for x in X]
+                    try:
+                        user_cb(*X, it=last)
+                    except StopIteration:  # "clean return from proxmin"
+                        break
+                    if any(not np.array_equal(b, np.asarray(x)) for b, x in zip(before, X)):
+                        plan.upload_parameters(state=False)  # the callback edited parameters in place
             if not restarted:
                 break
+            user_cb = None
+            opts.prox_max_iter = 10
         logger.info("scarlet ran for {0} iterations to logL = {1}".format(len(self.loss), -self.loss[-1]))
         return len(self.loss), -self.loss[-1]
 
     # -- forward --------------------------------------------------------------------------------------
     def get_model(self, *parameters, frame=None):
         """Model of the entire blend in the model frame, rendered on the device."""
-        if parameters:
-            raise NotImplementedError("explicit parameter tuples (autograd tracing) do not exist on the device path")
         plan = self._get_plan()
-        plan.upload_parameters(state=False)
+        if parameters:  # values to use instead of the stored ones, in the order of ``self.parameters`` (blend.py:200-244)
+            if len(parameters) != len(self.parameters):
+                raise ValueError("expected %d parameter arrays, got %d" % (len(self.parameters), len(parameters)))
+            plan.upload_values(self.parameters, parameters)
+        else:
+            plan.upload_parameters(state=False)
         model = plan.evaluate(want=("model",))["model"][0].astype(self.frame.dtype)
         if frame is not None and frame is not self.frame and frame.bbox != self.frame.bbox:
             from .bbox import overlapped_slices
@@ -206,7 +245,7 @@ class BlendBatch:
                 b.loss.extend(loss[s, :n].tolist())
                 if status[s] == nat.SB_ERR_NONFINITE:
                     raise ArithmeticError("scene %d: a parameter became non-finite during the fit" % self.blends.index(b))
-                results.append((len(b.loss), -b.loss[-1]))
+                results.append((len(b.loss), -b.loss[-1] if b.loss else None))
         return results
 
     def close(self):

@@ -124,7 +124,7 @@ __device__ void apply_chain(T *a, int By, int Bx, const DevChain &ch, const DevM
             }
             case SB_OP_POSITIVITY: {
                 const T zero = (T)op.farg;
-                for (int p = tid; p < n; p += nt) a[p] = a[p] > zero ? a[p] : zero; // np.maximum
+                for (int p = tid; p < n; p += nt) a[p] = a[p] < zero ? zero : a[p]; // np.maximum: NaN propagates
                 __syncthreads();
                 break;
             }
@@ -132,7 +132,7 @@ __device__ void apply_chain(T *a, int By, int Bx, const DevChain &ch, const DevM
                 if (tid == 0) {
                     const int c = (By / 2) * Bx + Bx / 2;
                     const T tiny = (T)op.farg;
-                    a[c] = a[c] > tiny ? a[c] : tiny;
+                    a[c] = a[c] < tiny ? tiny : a[c]; // Python max(a, tiny): a NaN stays
                 }
                 __syncthreads();
                 break;
@@ -166,7 +166,7 @@ __device__ inline void apply_chain_1d(double *a, int n, const DevChain &ch) {
         for (int o = 0; o < ch.n_ops; ++o) {
             const sb_op op = ch.ops[o];
             if (op.code == SB_OP_POSITIVITY) {
-                for (int i = 0; i < n; ++i) a[i] = a[i] > op.farg ? a[i] : op.farg;
+                for (int i = 0; i < n; ++i) a[i] = a[i] < op.farg ? op.farg : a[i]; // NaN propagates like np.maximum
             } else if (op.code == SB_OP_NORMALIZE) {
                 double acc = op.iarg == 1 ? -INFINITY : 0.0;
                 for (int i = 0; i < n; ++i) acc = op.iarg == 1 ? fmax(acc, a[i]) : acc + a[i];
@@ -368,6 +368,7 @@ template <typename T> struct UpdateArgs {
     int fast_G, fast_npix;  // groups per CTA, shared-memory image length per group
     int fast_table_cap;     // task capacity of the shared-memory table
     T *scratch_x, *scratch_ps; // packed like the morphologies: gradient-step result x and metric psi
+    unsigned long long *prox_hist; // optional [16]: histogram of proximal sub-iterations executed per source (diagnostic)
 };
 
 // gradient of the loss wrt the model at frame pixel (y,x), channel c: sum over the observations that see c
@@ -977,7 +978,7 @@ __device__ void group_chain(T *a, int By, int Bx, const DevChain &ch, const Fast
             }
             case SB_OP_POSITIVITY: {
                 const T zero = (T)op.farg;
-                for (int p = lt; p < n; p += GT) a[p] = a[p] > zero ? a[p] : zero;
+                for (int p = lt; p < n; p += GT) a[p] = a[p] < zero ? zero : a[p];
                 group_bar<GT>(g);
                 break;
             }
@@ -985,7 +986,7 @@ __device__ void group_chain(T *a, int By, int Bx, const DevChain &ch, const Fast
                 if (lt == 0) {
                     const int c = (By / 2) * Bx + Bx / 2;
                     const T tiny = (T)op.farg;
-                    a[c] = a[c] > tiny ? a[c] : tiny;
+                    a[c] = a[c] < tiny ? tiny : a[c];
                 }
                 group_bar<GT>(g);
                 break;
@@ -1247,10 +1248,10 @@ template <typename T, int GT, int MAXT = 1024> __global__ void __launch_bounds__
                                     const T un = hs * (u + v) + om * u, vn = hs * (v + u) + om * v;
                                     u = un, v = vn;
                                 }
-                                u = u > zero ? u : zero;
-                                v = v > zero ? v : zero;
+                                u = u < zero ? zero : u; // np.maximum / max(): a NaN survives and is caught below
+                                v = v < zero ? zero : v;
                                 if (p == half) {
-                                    u = u > tiny ? u : tiny;
+                                    u = u < tiny ? tiny : u;
                                     v = u;
                                 }
                                 zn[p] = u, zn[n - 1 - p] = v;
@@ -1293,6 +1294,7 @@ template <typename T, int GT, int MAXT = 1024> __global__ void __launch_bounds__
                         }
                     }
                     group_sum2<GT>(red, dd, nn); // barrier inside: zn is complete before the next sweep
+                    if (a.prox_hist && lt == 0 && (dd <= e2 * nn || last)) atomicAdd(a.prox_hist + min(sub + 1, 15), 1ull);
                     if (dd <= e2 * nn) break;
                 }
             } else {

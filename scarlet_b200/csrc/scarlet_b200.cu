@@ -209,7 +209,7 @@ using namespace sb;
 // =====================================================================================================
 struct sb_plan {
     virtual ~sb_plan() {}
-    virtual int upload_observation(int obs, const float *data, const float *weights, const double *khat, const double *loss_const) = 0;
+    virtual int upload_observation(int obs, const void *data, const void *weights, int elem_bytes, const double *khat, const double *loss_const) = 0;
     virtual int upload_kernels(int obs, const double *ker, int Py, int Px, int y0, int x0) = 0;
     virtual int zero_state() = 0;
     virtual int upload_resampling(int obs, const double *ey, const double *ex, double h2) = 0;
@@ -221,6 +221,7 @@ struct sb_plan {
     virtual int profile(const sb_fit_opts *o, int n, float *stage_ms) = 0;
     virtual int device_params(void **sed, int64_t *n_sed, void **morph, int64_t *n_morph, int *elem_bytes) = 0;
     virtual int spectral_mode() const = 0;
+    virtual int prox_histogram(int enable, int64_t *out16) = 0;
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
@@ -715,22 +716,31 @@ template <typename T> struct PlanT : sb_plan {
     }
 
     // ---------------------------------------------------------------------------------------------
-    int upload_observation(int o, const float *data, const float *weights, const double *khat, const double *loss_const) override {
+    int upload_observation(int o, const void *data, const void *weights, int elem_bytes, const double *khat, const double *loss_const) override {
         if (o < 0 || o >= (int)obs.size()) return set_err(SB_ERR_ARG, "observation index %d out of range", o);
         SB_CUDA(cudaSetDevice(device));
         Obs &ob = *obs[o];
         const size_t nd = ob.data.n;
-        DevBuf<float> &stage = ob.stage_f;
-        if (sizeof(T) == 8 && (data || weights) && stage.n < nd) SB_TRY(stage.alloc(nd));
-        const float *srcs[2] = {data, weights};
+        const bool same = (size_t)elem_bytes == sizeof(T);
+        // staging for the cast on the device (kept between calls, see Obs::stage_f)
+        if (!same && (data || weights)) {
+            if (elem_bytes == 4 && ob.stage_f.n < nd) SB_TRY(ob.stage_f.alloc(nd));
+            if (elem_bytes == 8 && ob.stage_z.n < (nd + 1) / 2) SB_TRY(ob.stage_z.alloc((nd + 1) / 2));
+        }
+        const void *srcs[2] = {data, weights};
         T *dsts[2] = {ob.data.p, ob.weights.p};
         for (int i = 0; i < 2; ++i) {
             if (!srcs[i]) continue;
-            if (sizeof(T) == 4) {
-                SB_CUDA(cudaMemcpyAsync(dsts[i], srcs[i], nd * sizeof(float), cudaMemcpyHostToDevice, stream));
+            if (same) {
+                SB_CUDA(cudaMemcpyAsync(dsts[i], srcs[i], nd * sizeof(T), cudaMemcpyHostToDevice, stream));
+            } else if (elem_bytes == 4) {
+                SB_CUDA(cudaMemcpyAsync(ob.stage_f.p, srcs[i], nd * sizeof(float), cudaMemcpyHostToDevice, stream));
+                k_cast<float, T><<<grid_for(nd), 256, 0, stream>>>(ob.stage_f.p, dsts[i], (long long)nd);
+                SB_CUDA(cudaGetLastError());
             } else {
-                SB_CUDA(cudaMemcpyAsync(stage.p, srcs[i], nd * sizeof(float), cudaMemcpyHostToDevice, stream));
-                k_cast<float, T><<<grid_for(nd), 256, 0, stream>>>(stage.p, dsts[i], (long long)nd);
+                double *st = reinterpret_cast<double *>(ob.stage_z.p);
+                SB_CUDA(cudaMemcpyAsync(st, srcs[i], nd * sizeof(double), cudaMemcpyHostToDevice, stream));
+                k_cast<double, T><<<grid_for(nd), 256, 0, stream>>>(st, dsts[i], (long long)nd);
                 SB_CUDA(cudaGetLastError());
             }
         }
@@ -891,6 +901,26 @@ template <typename T> struct PlanT : sb_plan {
         return SB_OK;
     }
     int spectral_mode() const override { return fused ? 1 : 0; }
+    // diagnostic: how many of the <= prox_max_iter proximal sub-iterations the grouped update kernel actually runs
+    DevBuf<unsigned long long> d_prox_hist;
+    int prox_histogram(int enable, int64_t *out16) override {
+        SB_CUDA(cudaSetDevice(device));
+        if (enable && !d_prox_hist.p) {
+            SB_TRY(d_prox_hist.alloc(16));
+            have_graph = false; // the pointer travels in the kernel arguments
+        }
+        if (d_prox_hist.p && out16) {
+            SB_CUDA(cudaMemcpyAsync(out16, d_prox_hist.p, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+            SB_CUDA(cudaStreamSynchronize(stream));
+        }
+        if (d_prox_hist.p && enable) SB_TRY(d_prox_hist.zero(stream));
+        if (!enable && d_prox_hist.p) {
+            SB_CUDA(cudaStreamSynchronize(stream));
+            d_prox_hist.release();
+            have_graph = false;
+        }
+        return SB_OK;
+    }
     int device_params(void **sed, int64_t *n_sed, void **morph, int64_t *nm, int *elem_bytes) override {
         if (sed) *sed = d_sed.p;
         if (n_sed) *n_sed = (int64_t)n_src * C;
@@ -928,6 +958,7 @@ template <typename T> struct PlanT : sb_plan {
         a.g_sed = d_gsed.p, a.g_morph = d_gmorph.p, a.g_center = d_gcenter.p;
         a.work = nullptr, a.fast_groups = d_fast_groups.p, a.fast_G = fast_G, a.fast_npix = fast_npix, a.fast_table_cap = fast_table_cap;
         a.scratch_x = d_scratch_x.p, a.scratch_ps = d_scratch_ps.p;
+        a.prox_hist = d_prox_hist.p;
         a.smorph = d_smorph.p, a.toep = d_toep.p, a.toep_len = toep_len, a.shift_list = d_shift_list.p;
         return a;
     }
@@ -1279,7 +1310,11 @@ template <typename T> struct PlanT : sb_plan {
 extern "C" {
 
 const char *sb_last_error(void) { return g_err.c_str(); }
-const char *sb_version(void) { return "scarlet_b200 0.1 (sm_100a)"; }
+const char *sb_version(void) { return "scarlet_b200 0.2 (sm_100a)"; }
+#ifndef SB_SRC_HASH
+#define SB_SRC_HASH "unknown"
+#endif
+const char *sb_source_hash(void) { return SB_SRC_HASH; }
 int sb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -1348,7 +1383,10 @@ void sb_host_free(void *p) {
     return plan->expr;
 
 int sb_plan_upload_observation(sb_plan *plan, int obs, const float *data, const float *weights, const double *khat, const double *loss_const) {
-    PLAN_CALL(upload_observation(obs, data, weights, khat, loss_const))
+    PLAN_CALL(upload_observation(obs, data, weights, 4, khat, loss_const))
+}
+int sb_plan_upload_observation_f64(sb_plan *plan, int obs, const double *data, const double *weights, const double *khat, const double *loss_const) {
+    PLAN_CALL(upload_observation(obs, data, weights, 8, khat, loss_const))
 }
 int sb_plan_upload_kernels(sb_plan *plan, int obs, const double *kernels, int Py, int Px, int y0, int x0) {
     PLAN_CALL(upload_kernels(obs, kernels, Py, Px, y0, x0))
@@ -1404,6 +1442,7 @@ int sb_plan_device_params(sb_plan *plan, void **sed, int64_t *n_sed, void **morp
     PLAN_CALL(device_params(sed, n_sed, morph, n_morph, elem_bytes))
 }
 int sb_plan_spectral_mode(const sb_plan *plan) { return plan ? plan->spectral_mode() : -1; }
+int sb_plan_prox_histogram(sb_plan *plan, int enable, int64_t *out16) { PLAN_CALL(prox_histogram(enable, out16)) }
 int sb_fft_supported_length(int need) { return spec_supported_length(need); }
 int sb_plan_sync(sb_plan *plan) {
     if (!plan) return set_err(SB_ERR_ARG, "null plan");

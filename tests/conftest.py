@@ -14,6 +14,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Tests marked ``gpu`` are skipped (not failed) on a machine without a CUDA device."""
+    gpu_items = [it for it in items if "gpu" in it.keywords]
+    if not gpu_items:
+        return
+    try:
+        from scarlet_b200 import _native
+        have = _native.lib().sb_device_count() > 0
+    except Exception:
+        have = False
+    if not have:
+        skip = pytest.mark.skip(reason="no CUDA device: scarlet_b200 has no CPU fallback")
+        for it in gpu_items:
+            it.add_marker(skip)
+
+
 def golden(name):
     return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
 
