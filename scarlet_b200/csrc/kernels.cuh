@@ -355,7 +355,8 @@ template <typename T> struct UpdateArgs {
     FitScalars fs;
     int psf_b;
     double psf_sigma[SB_MAXC];
-    int npix_max; // shared-memory array length
+    int npix_max;   // shared-memory image length (largest box, padded)
+    int npix_shift; // ... of the largest box of a shifting source (0: none): three more scratch images
     int mode;     // 0 = update, 1 = gradients only
     double *g_sed, *g_morph, *g_center;
     T *smorph;              // packed like morph: Fourier-shifted images of the shifting sources (what the model uses)
@@ -635,7 +636,7 @@ template <typename T> __global__ void __launch_bounds__(128) k_shift_apply(const
     const DevSource &d = a.src[k];
     if (a.done[d.scene]) return;
     const int n = d.By * d.Bx;
-    T *u = reinterpret_cast<T *>(smem), *w = u + a.npix_max, *o = w + a.npix_max;
+    T *u = reinterpret_cast<T *>(smem), *w = u + a.npix_shift, *o = w + a.npix_shift;
     shift_vectors<T>(a, d, a.center[2 * d.point_idx], a.center[2 * d.point_idx + 1]);
     for (int p = threadIdx.x; p < n; p += blockDim.x) u[p] = a.morph[d.morph_off + p];
     __threadfence_block();
@@ -645,13 +646,19 @@ template <typename T> __global__ void __launch_bounds__(128) k_shift_apply(const
     for (int p = threadIdx.x; p < n; p += blockDim.x) a.smorph[d.morph_off + p] = o[p];
 }
 
+// Generic per-source update (one CTA per source): any box that fits one image in shared memory, any constraint chain.
+// Only the image being projected (zn) lives in shared memory -- the sweep and the symmetry partner need random access;
+// the gradient-step result x, the metric psi and the running iterate z (= the morphology array itself) are streamed
+// through global memory, each element always by the same thread.  Shifting sources additionally use three scratch
+// images in shared memory for the Toeplitz products.
 template <typename T> __device__ void update_extended(const UpdateArgs<T> &a, const DevSource &d, int k, unsigned char *smem) {
     const int tid = threadIdx.x, nt = blockDim.x, C = a.C, s = d.scene, it = *a.it_ptr;
     const int n = d.By * d.Bx, Bx = d.Bx;
-    T *xs = reinterpret_cast<T *>(smem);
-    T *z = xs + a.npix_max, *zn = z + a.npix_max, *ps = zn + a.npix_max;
-    double *red = reinterpret_cast<double *>(ps + a.npix_max);
+    T *zn = reinterpret_cast<T *>(smem);
+    double *red = reinterpret_cast<double *>(zn + a.npix_max);
     double *gsum = red + 40;
+    T *t0 = reinterpret_cast<T *>(gsum + SB_MAXC); // shifting sources only: three more images (a.npix_shift each)
+    T *t1 = t0 + a.npix_shift, *t2 = t1 + a.npix_shift;
 
     double sedv[SB_MAXC], gs[SB_MAXC];
 #pragma unroll
@@ -660,14 +667,14 @@ template <typename T> __device__ void update_extended(const UpdateArgs<T> &a, co
         gs[c] = 0.0;
     }
     T *mp = a.morph + d.morph_off, *mm = a.morph_m + d.morph_off, *mv = a.morph_v + d.morph_off,
-      *mvh = a.morph_vhat + d.morph_off;
+      *mvh = a.morph_vhat + d.morph_off, *gx = a.scratch_x + d.morph_off, *gp = a.scratch_ps + d.morph_off;
     const double alpha = d.morph_step;
     const bool upd = a.mode == 0 && !d.morph_fixed;
     double pmax = 0.0;
     double gshift0 = 0.0, gshift1 = 0.0;
     if (d.shifting) {
         // the model holds the SHIFTED image: gather the gradient wrt it (zn), the spectrum gradient against it, then pull the
-        // gradient back to the image (xs) and to the shift through the transposed Toeplitz operators
+        // gradient back to the image (t0) and to the shift through the transposed Toeplitz operators
         const T *sm = a.smorph + d.morph_off;
         for (int p = tid; p < n; p += nt) {
             const int by = p / Bx, bx = p - by * Bx, y = d.oy + by, x = d.ox + bx;
@@ -687,15 +694,15 @@ template <typename T> __device__ void update_extended(const UpdateArgs<T> &a, co
         __syncthreads();
         const T *RCy = toep_vec<T>(a, d, 0), *ICy = toep_vec<T>(a, d, 1), *dRCy = toep_vec<T>(a, d, 2), *dICy = toep_vec<T>(a, d, 3);
         const T *RTx = toep_vec<T>(a, d, 4), *ITx = toep_vec<T>(a, d, 5), *dRTx = toep_vec<T>(a, d, 6), *dITx = toep_vec<T>(a, d, 7);
-        toeplitz_apply<T, true>(zn, z, xs, RCy, RTx, d.By, d.Bx, false, T(1));  // d/d image
-        toeplitz_apply<T, true>(zn, z, xs, ICy, ITx, d.By, d.Bx, true, T(-1));
-        toeplitz_apply<T, true>(zn, z, ps, dRCy, RTx, d.By, d.Bx, false, T(1)); // d/d s0 = <image, dCy^T g Tx>
-        toeplitz_apply<T, true>(zn, z, ps, dICy, ITx, d.By, d.Bx, true, T(-1));
-        for (int p = tid; p < n; p += nt) gshift0 += (double)ps[p] * (double)mp[p];
+        toeplitz_apply<T, true>(zn, t1, t0, RCy, RTx, d.By, d.Bx, false, T(1));  // d/d image
+        toeplitz_apply<T, true>(zn, t1, t0, ICy, ITx, d.By, d.Bx, true, T(-1));
+        toeplitz_apply<T, true>(zn, t1, t2, dRCy, RTx, d.By, d.Bx, false, T(1)); // d/d s0 = <image, dCy^T g Tx>
+        toeplitz_apply<T, true>(zn, t1, t2, dICy, ITx, d.By, d.Bx, true, T(-1));
+        for (int p = tid; p < n; p += nt) gshift0 += (double)t2[p] * (double)mp[p];
         __syncthreads();
-        toeplitz_apply<T, true>(zn, z, ps, RCy, dRTx, d.By, d.Bx, false, T(1)); // d/d s1
-        toeplitz_apply<T, true>(zn, z, ps, ICy, dITx, d.By, d.Bx, true, T(-1));
-        for (int p = tid; p < n; p += nt) gshift1 += (double)ps[p] * (double)mp[p];
+        toeplitz_apply<T, true>(zn, t1, t2, RCy, dRTx, d.By, d.Bx, false, T(1)); // d/d s1
+        toeplitz_apply<T, true>(zn, t1, t2, ICy, dITx, d.By, d.Bx, true, T(-1));
+        for (int p = tid; p < n; p += nt) gshift1 += (double)t2[p] * (double)mp[p];
         __syncthreads();
         gshift0 = block_sum(gshift0, red);
         gshift1 = block_sum(gshift1, red);
@@ -705,7 +712,7 @@ template <typename T> __device__ void update_extended(const UpdateArgs<T> &a, co
         const T mval = mp[p];
         double gm = 0.0;
         if (d.shifting) {
-            gm = (double)xs[p];
+            gm = (double)t0[p];
         } else if ((unsigned)y < (unsigned)a.Ny && (unsigned)x < (unsigned)a.Nx) {
 #pragma unroll
             for (int c = 0; c < SB_MAXC; ++c) {
@@ -720,11 +727,12 @@ template <typename T> __device__ void update_extended(const UpdateArgs<T> &a, co
             double m_ = (double)mm[p], v_ = (double)mv[p], vh_ = (double)mvh[p];
             const double psi = amsgrad(gm, m_, v_, vh_, it, a.fs);
             mm[p] = (T)m_, mv[p] = (T)v_, mvh[p] = (T)vh_;
-            xs[p] = (T)((double)mval - alpha * m_ / psi);
-            ps[p] = (T)psi;
+            const T xn = (T)((double)mval - alpha * m_ / psi);
+            gx[p] = xn;
+            mp[p] = xn; // z0 = x
+            zn[p] = xn; // first proximal argument: z0 - psi/max(psi) (z0 - x) = x exactly
+            gp[p] = (T)psi;
             pmax = fmax(pmax, psi);
-        } else {
-            xs[p] = mval;
         }
         if (a.mode == 1 && a.g_morph) a.g_morph[d.morph_off + p] = gm;
     }
@@ -757,45 +765,37 @@ template <typename T> __device__ void update_extended(const UpdateArgs<T> &a, co
     }
     if (upd) {
         const double psimax = block_max(pmax, red);
+        bool bad = false;
         if (d.chain >= 0) {
             const DevChain &ch = a.chains[d.chain];
             const double gamma = alpha / psimax;
             const double fac = gamma / alpha;
-            for (int p = tid; p < n; p += nt) z[p] = xs[p];
             for (int sub = 0; sub < a.fs.prox_max_iter; ++sub) {
-                for (int p = tid; p < n; p += nt) {
-                    const double zz = (double)z[p];
-                    zn[p] = (T)(zz - fac * (double)ps[p] * (zz - (double)xs[p]));
+                if (sub > 0) {
+                    for (int p = tid; p < n; p += nt) {
+                        const double zz = (double)mp[p];
+                        zn[p] = (T)(zz - fac * (double)gp[p] * (zz - (double)gx[p]));
+                    }
                 }
                 __syncthreads();
                 apply_chain<T>(zn, d.By, d.Bx, ch, a.monos, red);
                 double dd = 0.0, nn = 0.0;
+                bad = false;
                 for (int p = tid; p < n; p += nt) {
-                    const double zo = (double)z[p], zv = (double)zn[p];
+                    const double zo = (double)mp[p], zv = (double)zn[p];
                     dd += (zv - zo) * (zv - zo);
                     nn += zo * zo;
-                    z[p] = zn[p];
+                    mp[p] = zn[p];
+                    bad |= !isfinite(zv);
                 }
                 dd = block_sum(dd, red);
                 nn = block_sum(nn, red);
                 if (dd <= a.fs.e_rel * a.fs.e_rel * nn) break;
             }
-            bool bad = false;
-            for (int p = tid; p < n; p += nt) {
-                const T r = z[p];
-                mp[p] = r;
-                bad |= !isfinite((double)r);
-            }
-            if (bad) atomicExch(a.status + s, SB_ERR_NONFINITE);
         } else {
-            bool bad = false;
-            for (int p = tid; p < n; p += nt) {
-                const T r = xs[p];
-                mp[p] = r;
-                bad |= !isfinite((double)r);
-            }
-            if (bad) atomicExch(a.status + s, SB_ERR_NONFINITE);
+            for (int p = tid; p < n; p += nt) bad |= !isfinite((double)mp[p]);
         }
+        if (bad) atomicExch(a.status + s, SB_ERR_NONFINITE);
     }
     if (tid == 0 && !d.sed_fixed) sed_update<T>(a, d, k, gsum, it);
 }
@@ -830,10 +830,22 @@ template <typename T> __global__ void __launch_bounds__(128) k_update(const Upda
 // Thread index inside a group.  Wavefront levels mostly hold fewer than 32 tasks, so only the warp with lt < 32 works during
 // the sweep; a warp's scheduler is (warp index mod 4), and with the plain numbering those leading warps would all sit on
 // schedulers 0 and 2 (GT = 64).  Every other pair of groups therefore numbers its warps the other way round.
+// GT = 32: one warp per source -- no named barrier at all (__syncwarp orders the shared-memory traffic of the lanes), no idle
+// second warp during the sweep, reductions by shuffles only.
 template <int GT> __device__ __forceinline__ int group_lane(int g) {
     return GT == 64 ? (int)((threadIdx.x ^ (((unsigned)g >> 1 & 1u) << 5)) & 63u) : (int)(threadIdx.x & (GT - 1));
 }
-template <int GT> __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(GT) : "memory"); }
+template <int GT> __device__ __forceinline__ void group_bar(int g) {
+    if constexpr (GT == 32)
+        __syncwarp();
+    else
+        asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(GT) : "memory");
+}
+__device__ __forceinline__ double warp_sum_all(double v) { // every lane gets the sum (fixed butterfly order)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 
 struct GroupRed {
     double *slot; // [2 parities][2 values][GT/32 warps]
@@ -841,6 +853,12 @@ struct GroupRed {
 };
 template <int GT> __device__ __forceinline__ void group_sum2(GroupRed &r, double &a, double &b) {
     constexpr int NW = GT / 32;
+    if constexpr (GT == 32) {
+        a = warp_sum_all(a);
+        b = warp_sum_all(b);
+        __syncwarp();
+        return;
+    }
     a = warp_sum(a);
     b = warp_sum(b);
     const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & (NW - 1);
@@ -854,6 +872,12 @@ template <int GT> __device__ __forceinline__ void group_sum2(GroupRed &r, double
 }
 template <int GT> __device__ __forceinline__ double group_max(GroupRed &r, double a) {
     constexpr int NW = GT / 32;
+    if constexpr (GT == 32) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+        __syncwarp();
+        return a;
+    }
     a = warp_max(a);
     const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & (NW - 1);
     double *s = r.slot + r.par * 2 * NW;
@@ -1019,6 +1043,15 @@ __device__ void group_chain(T *a, int By, int Bx, const DevChain &ch, const Fast
 // group-wide maximum in the image type (exact: a maximum needs no extra precision)
 template <typename T, int GT> __device__ __forceinline__ T group_max_t(GroupRed &r, T a) {
     constexpr int NW = GT / 32;
+    if constexpr (GT == 32) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const T b = __shfl_xor_sync(0xffffffffu, a, o);
+            a = b > a ? b : a;
+        }
+        __syncwarp();
+        return a;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const T b = __shfl_down_sync(0xffffffffu, a, o);

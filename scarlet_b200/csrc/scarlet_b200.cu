@@ -233,7 +233,7 @@ struct sb_plan {
 template <typename T> struct PlanT : sb_plan {
     typedef typename Cx<T>::type cplx;
     sb_batch_desc desc;
-    int S = 0, C = 0, n_src = 0, n_point = 0, npix_max = 0;
+    int S = 0, C = 0, n_src = 0, n_point = 0, npix_max = 0, npix_shift = 0;
     long long n_morph = 0, n_pmorph = 0;
     std::vector<DevSource> h_src;
     std::vector<int> h_start;
@@ -385,6 +385,7 @@ template <typename T> struct PlanT : sb_plan {
                     d.shifting = 1, d.shift_Fy = in.shift_Fy, d.shift_Fx = in.shift_Fx, d.shift_step = in.shift_step;
                     d.toep_off = n_shift++;
                     toep_len = std::max(toep_len, 2 * std::max(in.By, in.Bx) - 1);
+                    npix_shift = std::max(npix_shift, (in.By * in.Bx + 3) & ~3);
                 }
                 if (d.kind == 0) {
                     if (d.chain >= 0)
@@ -441,7 +442,9 @@ template <typename T> struct PlanT : sb_plan {
             SB_TRY(d_smorph.zero(stream));
             SB_TRY(d_toep.alloc((size_t)n_shift * 8 * toep_len));
             SB_TRY(d_toep.zero(stream));
-            SB_TRY(raise_smem((const void *)k_shift_apply<T>, (size_t)3 * npix_max * sizeof(T)));
+            if ((size_t)3 * npix_shift * sizeof(T) > 220 * 1024)
+                return set_err(SB_ERR_ARG, "largest box of a shifting source (%d px) does not fit in shared memory", npix_shift);
+            SB_TRY(raise_smem((const void *)k_shift_apply<T>, (size_t)3 * npix_shift * sizeof(T)));
         }
         SB_TRY(d_done.alloc(S));
         SB_TRY(d_niter.alloc(S));
@@ -646,7 +649,7 @@ template <typename T> struct PlanT : sb_plan {
         fast_G = 0;
         {
             const char *gt = getenv("SB_UPDATE_GROUP");
-            fast_GT = (gt && atoi(gt) == 128) ? 128 : 64;
+            fast_GT = (gt && atoi(gt) == 128) ? 128 : (gt && atoi(gt) == 32) ? 32 : 64;
             size_t n_fast = 0;
             for (auto &kv : by_chain) n_fast += kv.second.size();
             int sms = 148;
@@ -680,10 +683,12 @@ template <typename T> struct PlanT : sb_plan {
         SB_TRY(d_fast_groups.alloc(std::max<size_t>(groups.size(), 1)));
         if (!generic.empty()) SB_CUDA(cudaMemcpy(d_work.p, generic.data(), generic.size() * sizeof(int), cudaMemcpyHostToDevice));
         if (!groups.empty()) SB_CUDA(cudaMemcpy(d_fast_groups.p, groups.data(), groups.size() * sizeof(int), cudaMemcpyHostToDevice));
+        SB_TRY(d_scratch_x.alloc(std::max<long long>(n_morph, 1))); // both update kernels stream x and psi through these
+        SB_TRY(d_scratch_ps.alloc(std::max<long long>(n_morph, 1)));
         if (n_fast_cta) {
-            SB_TRY(d_scratch_x.alloc(std::max<long long>(n_morph, 1)));
-            SB_TRY(d_scratch_ps.alloc(std::max<long long>(n_morph, 1)));
             SB_TRY(raise_smem(fast_GT == 128 ? (const void *)k_update_fast<T, 128> : (const void *)k_update_fast<T, 64>, fast_smem));
+            SB_TRY(raise_smem((const void *)k_update_fast<T, 32, 448>, fast_smem));
+            SB_TRY(raise_smem((const void *)k_update_fast<T, 32>, fast_smem));
             SB_TRY(raise_smem((const void *)k_update_fast<T, 64, 832>, fast_smem));
         }
         return SB_OK;
@@ -693,7 +698,7 @@ template <typename T> struct PlanT : sb_plan {
                (size_t)((cap + 7) & ~7) * sizeof(unsigned short) + (size_t)G * npix * sizeof(T);
     }
 
-    size_t update_smem() const { return (size_t)4 * npix_max * sizeof(T) + (40 + SB_MAXC) * sizeof(double); }
+    size_t update_smem() const { return ((size_t)npix_max + 3 * (size_t)npix_shift) * sizeof(T) + (40 + SB_MAXC) * sizeof(double); }
 
     int ensure_loss_cap(int cap) {
         if (cap <= loss_cap) return SB_OK;
@@ -884,7 +889,7 @@ template <typename T> struct PlanT : sb_plan {
     }
     int launch_shift_apply() {
         UpdateArgs<T> ua = update_args(0);
-        k_shift_apply<T><<<n_shift, 128, (size_t)3 * npix_max * sizeof(T), stream>>>(ua);
+        k_shift_apply<T><<<n_shift, 128, (size_t)3 * npix_shift * sizeof(T), stream>>>(ua);
         SB_CUDA(cudaGetLastError());
         return SB_OK;
     }
@@ -954,7 +959,7 @@ template <typename T> struct PlanT : sb_plan {
         a.fs = cur_fs;
         a.psf_b = desc.psf_boxsize;
         memcpy(a.psf_sigma, desc.psf_sigma, sizeof a.psf_sigma);
-        a.npix_max = npix_max, a.mode = mode;
+        a.npix_max = npix_max, a.npix_shift = npix_shift, a.mode = mode;
         a.g_sed = d_gsed.p, a.g_morph = d_gmorph.p, a.g_center = d_gcenter.p;
         a.work = nullptr, a.fast_groups = d_fast_groups.p, a.fast_G = fast_G, a.fast_npix = fast_npix, a.fast_table_cap = fast_table_cap;
         a.scratch_x = d_scratch_x.p, a.scratch_ps = d_scratch_ps.p;
@@ -1110,7 +1115,11 @@ template <typename T> struct PlanT : sb_plan {
                     SB_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
                 }
                 if (n_fast_cta) {
-                    if (fast_GT == 128)
+                    if (fast_GT == 32 && 32 * fast_G <= 448)
+                        k_update_fast<T, 32, 448><<<n_fast_cta, 32 * fast_G, fast_smem, stream>>>(ua);
+                    else if (fast_GT == 32)
+                        k_update_fast<T, 32><<<n_fast_cta, 32 * fast_G, fast_smem, stream>>>(ua);
+                    else if (fast_GT == 128)
                         k_update_fast<T, 128><<<n_fast_cta, 128 * fast_G, fast_smem, stream>>>(ua);
                     else if (64 * fast_G <= 832)
                         k_update_fast<T, 64, 832><<<n_fast_cta, 64 * fast_G, fast_smem, stream>>>(ua);

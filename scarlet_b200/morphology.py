@@ -13,27 +13,33 @@ from .psf import PSF
 
 
 class Morphology(Model):
+    """A spatial model confined to ``bbox`` of the model frame."""
+
     def __init__(self, frame, *parameters, bbox=None):
-        assert isinstance(frame, Frame)
-        self.frame = frame
-        if bbox is None:
-            bbox = frame.bbox
-        assert isinstance(bbox, Box)
-        self.bbox = bbox
+        if not isinstance(frame, Frame):
+            raise AssertionError("frame must be a Frame")
+        box = frame.bbox if bbox is None else bbox
+        if not isinstance(box, Box):
+            raise AssertionError("bbox must be a Box")
+        self.frame, self.bbox = frame, box
         super().__init__(*parameters)
 
     def shrink_box(self, image, thresh=0):
-        """Peel the onion: drop outer rings that are entirely <= thresh, down to the next allowed box size
-        (morphology.py:52-68)."""
+        """Count the complete outer rings of ``image`` that hold nothing above ``thresh`` and cut the (square) box down to
+        the smallest allowed size that still contains the rest (morphology.py:52-68).  Only ``self.bbox`` changes."""
         size = max(image.shape)
-        dist = 0
-        while (np.all(image[dist, :] <= thresh) and np.all(image[-dist - 1, :] <= thresh)
-               and np.all(image[:, dist] <= thresh) and np.all(image[:, -dist - 1] <= thresh)):
-            dist += 1
-        newsize = get_minimal_boxsize(size - 2 * dist)
-        if newsize < size:
-            dist = (size - newsize) // 2
-            self.bbox = Box((newsize, newsize), origin=tuple(o + dist for o in self.bbox.origin))
+
+        def ring_is_empty(d):
+            edges = (image[d, :], image[-d - 1, :], image[:, d], image[:, -d - 1])
+            return all(np.all(e <= thresh) for e in edges)
+
+        empty_rings = 0
+        while ring_is_empty(empty_rings):
+            empty_rings += 1
+        target = get_minimal_boxsize(size - 2 * empty_rings)
+        if target < size:
+            trim = (size - target) // 2
+            self.bbox = Box((target, target), origin=tuple(o + trim for o in self.bbox.origin))
 
 
 def get_minimal_boxsize(size, min_size=21, increment=10):
@@ -52,26 +58,28 @@ class ImageMorphology(Morphology):
     and shift are both fitted (SURVEY f-3)."""
 
     def __init__(self, frame, image, bbox=None, shifting=False, shift=None, resizing=True):
-        if isinstance(image, Parameter):
-            assert image.name == "image"
-        else:
+        if not isinstance(image, Parameter):  # bare array: positive image with a step relative to its mean
             image = Parameter(image, name="image", step=relative_step, constraint=PositivityConstraint())
-        if bbox is None:
-            assert frame.bbox[1:].shape == image.shape
+        elif image.name != "image":
+            raise AssertionError("the image parameter must be named 'image'")
+        if bbox is None:  # the image then has to cover the whole frame
             bbox = Box(image.shape)
-        else:
-            assert bbox.shape == image.shape
-        self.resizing = resizing
-        self.shifting = shifting
+            if frame.bbox[1:].shape != image.shape:
+                raise AssertionError("an image without a box must have the shape of the frame")
+        elif bbox.shape != image.shape:
+            raise AssertionError("box and image shapes differ")
+        self.resizing, self.shifting = resizing, shifting
+        # The second parameter always exists: the reference also creates a free 'shift' that nothing reads when
+        # shifting=False (morphology.py:112-113); it keeps the parameter tuple aligned with the reference's.
         if shift is None:
-            # the reference creates this free-but-unused parameter too (morphology.py:112-113)
             shift = Parameter(np.zeros(2), name="shift", step=1e-2, fixed=self.shifting)
+        elif isinstance(shift, Parameter):
+            if shift.name != "shift" or shift.shape != (2,):
+                raise AssertionError("the shift parameter must be named 'shift' and hold (dy, dx)")
         else:
-            assert shift.shape == (2,)
-            if isinstance(shift, Parameter):
-                assert shift.name == "shift"
-            else:
-                shift = Parameter(shift, name="shift", step=1e-2)
+            shift = Parameter(np.asarray(shift), name="shift", step=1e-2)
+            if shift.shape != (2,):
+                raise AssertionError("shift must hold (dy, dx)")
         super().__init__(frame, image, shift, bbox=bbox)
 
     def get_model(self, *parameters):
@@ -145,17 +153,13 @@ class ExtendedSourceMorphology(ImageMorphology):
 
     def __init__(self, frame, center, image, bbox=None, monotonic="angle", symmetric=False, min_grad=0,
                  shifting=False, resizing=True):
-        constraints = []
-        if monotonic is True:
-            monotonic = "angle"
-        elif monotonic is False:
-            monotonic = None
-        if monotonic is not None:
-            constraints.append(MonotonicityConstraint(neighbor_weight=monotonic, min_gradient=min_grad))
+        # projection order of morphology.py:644-669: monotonic -> [symmetric] -> positive -> centre floor -> peak = 1
+        weighting = "angle" if monotonic is True else (None if monotonic is False else monotonic)
+        chain = [MonotonicityConstraint(neighbor_weight=weighting, min_gradient=min_grad)] if weighting is not None else []
         if symmetric:
-            constraints.append(SymmetryConstraint())
-        constraints += [PositivityConstraint(), CenterOnConstraint(), NormalizationConstraint("max")]
-        image = Parameter(image, name="image", step=1e-2, constraint=ConstraintChain(*constraints))
+            chain.append(SymmetryConstraint())
+        chain.extend((PositivityConstraint(), CenterOnConstraint(), NormalizationConstraint("max")))
+        image = Parameter(image, name="image", step=1e-2, constraint=ConstraintChain(*chain))
         self.pixel_center = np.round(center).astype("int")
         shift = Parameter(center - self.pixel_center, name="shift", step=1e-1) if shifting else None
         self.shift = shift
