@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--precision", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-single", action="store_true")
+    ap.add_argument("--only-headline", action="store_true", help="skip the sub-records of the other BASELINE configurations")
     ap.add_argument("--e2e-mode", default="pipeline", choices=["pipeline", "batch"],
                     help="end-to-end leg: a stream of batches through BatchPipeline (default) or one BlendBatch.fit per step")
     ap.add_argument("--e2e-streams", type=int, default=3, help="--e2e-mode batch: plans/streams of the BlendBatch (copy/compute overlap)")
@@ -153,7 +154,7 @@ def run_reference(args):
         return
     import multiprocessing as mp
     from oracle import monotonic_c
-    monotonic_c.build()
+    monotonic_c._load()  # in the parent, before the fork: the workers inherit the mapped library (and the driver sees it loaded)
     cores = os.cpu_count() or 1
     iters = cpu_iters_for(args.config)
     ctx = mp.get_context("fork")
@@ -167,21 +168,25 @@ def run_reference(args):
         times = [step(args.warmup + k) for k in range(args.steps)]
     total = float(np.sum(times))
     value = cores * iters * args.steps / total
-    sample = "%d scenes (one per host thread) x %d iterations per step, %s" % (cores, iters, args.config)
+    sample = ("bounded sample of the workload named in config: %d scenes (one per host thread) x %d iterations per step, %s; "
+              "the metric is per scene-iteration" % (cores, iters, args.config))
     from scarlet_b200 import synthetic
     line = {"impl": "reference", "metric": "pgm_scene_iterations_per_sec", "value": value, "unit": "scene-iterations/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, _config_dict(args.config), cores, iters),
+            "config": workload_config(args.config, _config_dict(args.config), args.scenes or DEFAULT_SCENES[args.config],
+                                      args.iters or DEFAULT_ITERS[args.config]),
             "cpu_baseline": {"value": value, "unit": "scene-iterations/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "scene-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, cfg, scenes_per_unit, iters):
+def workload_config(config, cfg, scenes_per_unit, iters):
+    """The keys that NAME the workload -- identical in both arms (the reference arm times a bounded sample of it and says so in
+    ``cpu_baseline.sample``)."""
     return {"workload": "%s: %d-band %dx%d scene, %d ExtendedSource + %d PointSource, %s PSF %dx%d, box %d, %s"
-                        % (args.config, cfg["C"], cfg["N"], cfg["N"], cfg["n_ext"], cfg["n_pt"], cfg["psf"], cfg["P"], cfg["P"], cfg["B"],
+                        % (config, cfg["C"], cfg["N"], cfg["N"], cfg["n_ext"], cfg["n_pt"], cfg["psf"], cfg["P"], cfg["P"], cfg["B"],
                            "monotonic+symmetry" if cfg["symmetric"] else "monotonic"),
             "scenes_per_gpu": scenes_per_unit, "iterations_per_step": iters, "stop_rule": "disabled (fixed iterations)",
             "l2_policy": "inputs larger than L2 (per-GPU working set reported as device_bytes)"}
@@ -190,41 +195,51 @@ def workload_config(args, cfg, scenes_per_unit, iters):
 # ---------------------------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------------------------
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-    from scarlet_b200 import BlendBatch, _native, synthetic
+class Env:
+    """process-group plumbing shared by the per-config measurements"""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if _native.lib().sb_device_count() <= 0:
-        raise SystemExit("bench.py: no CUDA device -- scarlet_b200 has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        # NCCL prints its version banner on stdout when the communicator is first used: route stdout to stderr until then,
-        # so that rank 0's stdout carries exactly one JSON line
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            # NCCL prints its version banner on stdout when the communicator is first used: route stdout to stderr until
+            # then, so that rank 0's stdout carries exactly one JSON line
             sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+                dist.barrier()
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
 
-    cfg = _config_dict(args.config)
-    S = args.scenes or DEFAULT_SCENES[args.config]
-    iters = args.iters or DEFAULT_ITERS[args.config]
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], device="cuda:%d" % self.local, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def measure(env, args, config, S, iters, steps, warmup, headline):
+    """Device-resident value, end-to-end value, per-stage profile and roofline of one BASELINE configuration."""
+    from scarlet_b200 import BatchPipeline, BlendBatch, _native, synthetic
+    torch, dist, rank, world, local = env.torch, env.dist, env.rank, env.world, env.local
+    cfg = _config_dict(config)
     uniq = min(S, args.unique)
-    base = [_make_scene(args.config, rank * 100000 + i) for i in range(uniq)]
-    blends = [_make_blend(args.config, base[i % uniq], precision=args.precision, device=local) for i in range(S)]
+    base = [_make_scene(config, rank * 100000 + i) for i in range(uniq)]
+    blends = [_make_blend(config, base[i % uniq], precision=args.precision, device=local) for i in range(S)]
     batch = BlendBatch(blends, precision=args.precision, device=local)
     plan = batch.plan
-    fshape = plan.obs_meta[0]["metas"][0]["fshape"]
+    fshape = plan.obs_meta[-1]["metas"][0]["fshape"]
     opts = _native.fit_opts(max_iter=iters, e_rel=1e-3, min_iter=1, prox_max_iter=10, check_every=10 ** 6, fixed_iterations=True)
     init = plan.pack_current()[0]  # initial parameter values (sed, morph, center); the optimiser state starts at zero
 
@@ -247,44 +262,40 @@ def run_b200(args):
         from scarlet_b200.distributed import gather_device_parameters
         return gather_device_parameters(plan, local)[2]
 
-    # ---- device-resident timing (value) ----------------------------------------------------------
+    # ---- device-resident timing (value): the loop AND the final NCCL gather of the fitted parameters ----------
     def device_step():
         reset()
         barrier()
+        t0 = time.perf_counter()
         plan.timer_start()
         plan.fit_enqueue(opts, iters)
-        ms = plan.timer_stop()
-        gather_results()
+        ms = plan.timer_stop()  # CUDA events on the plan's stream around the loop
+        t1 = time.perf_counter()
+        gather_results()         # NCCL all-gather (N > 1); timed on the host clock between two device syncs
         barrier()
-        return ms
+        return ms + (1e3 * (time.perf_counter() - t1) if world > 1 else 0.0)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         device_step()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(local) if (headline and rank == 0) else None
+    if sampler:
         sampler.start()
     launches0 = plan.kernel_launches
-    ms_steps = [device_step() for _ in range(args.steps)]
+    ms_steps = [device_step() for _ in range(steps)]
     launches = plan.kernel_launches - launches0
-    ms_local = float(np.sum(ms_steps))
-    if world > 1:
-        t = torch.tensor([ms_local], device="cuda:%d" % local, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    else:
-        ms_total = ms_local
-    value = world * S * iters * args.steps / (ms_total / 1e3)
+    ms_total = env.max_over_ranks(float(np.sum(ms_steps)))
+    value = world * S * iters * steps / (ms_total / 1e3)
 
     # ---- end-to-end through the public API with host buffers (e2e) -------------------------------
     # A stream of batches through BatchPipeline: two BlendBatch objects (own host Parameters, own pinned staging, own device
     # plan) take turns; while the device loops over one, the other copies its results out and the next step's observations,
     # kernel images and parameters in.  Every step's H2D and D2H copies are inside the timed region.
     # (--e2e-mode batch: one BlendBatch.fit per step, split over --e2e-streams plans.)
-    from scarlet_b200 import BatchPipeline
     h2d = d2h = 0
     pipelined = args.e2e_mode == "pipeline"
+    batch_b = None
     if pipelined:
-        blends_b = [_make_blend(args.config, base[i % uniq], precision=args.precision, device=local) for i in range(S)]
+        blends_b = [_make_blend(config, base[i % uniq], precision=args.precision, device=local) for i in range(S)]
         batch_b = BlendBatch(blends_b, precision=args.precision, device=local)
         turn_batches = [batch, batch_b]
         batch_e2e = batch
@@ -330,18 +341,12 @@ def run_b200(args):
         return dt
 
     e2e_steps(2 if pipelined else 1)
-    e2e_local = float(e2e_steps(args.steps))
-    if world > 1:
-        t = torch.tensor([e2e_local], device="cuda:%d" % local, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_total = float(t.item())
-    else:
-        e2e_total = e2e_local
-    e2e_value = world * S * iters * args.steps / e2e_total
-    clocks = sampler.stop() if rank == 0 else None
+    e2e_total = env.max_over_ranks(float(e2e_steps(steps)))
+    e2e_value = world * S * iters * steps / e2e_total
+    clocks = sampler.stop() if sampler else None
 
     # ---- per-stage CUDA-event profile + roofline (rank 0) -----------------------------------------
-    line = None
+    rec = None
     if rank == 0:
         reset()
         plan.profile(opts, 3)
@@ -376,25 +381,30 @@ def run_b200(args):
             "fft_fwd_resid": eb * C * Fy * Fx + 2 * eb * C * Fc,
             "kmul_conj": 3 * 2 * eb * C * Fc,
             "fft_inv_grad": eb * C * Fy * Fx + 2 * eb * C * Fc,
-            "source_update": eb * src_px * (C + 8),
+            "source_update": eb * src_px * (C + 14),  # SURVEY 8(d) per-source term: B^2 (14 + C)
             "advance": 16,
         }
         stage_bytes.update(fused_bytes)
-        own = {k: v for k, v in stages.items() if not k.startswith("fft_") and stage_bytes.get(k, 0) > 0}
-        dom = max(own, key=own.get)
-        dom_ms = stages[dom]
-        achieved = stage_bytes[dom] * S / (dom_ms / 1e3) / 1e9
-        iter_ms = sum(stages.values())
-        alg_iter = synthetic.algorithmic_bytes(cfg, fshape, eb)
-        if args.config == "cfg4":  # two observations on different grids: only the per-source kernel has a closed-form byte count here
+        if config == "cfg4":  # two observations on different grids: only the per-source kernel has a closed-form byte count here
             for k in list(stage_bytes):
                 if k not in ("source_update", "advance"):
                     stage_bytes[k] = 0
-        whole = alg_iter * S / (ms_total / args.steps / iters / 1e3) / 1e9
+            alg_iter = synthetic.algorithmic_bytes_multires(cfg, eb)
+        else:
+            alg_iter = synthetic.algorithmic_bytes(cfg, fshape, eb)
+        own = {k: v for k, v in stages.items() if not k.startswith("fft_") and stage_bytes.get(k, 0) > 0}
+        # the kernel furthest below its roofline (lowest algorithmic GB/s) among those that matter (>= 5 % of the iteration)
+        iter_ms = sum(stages.values())
+        gbs = {k: stage_bytes[k] * S / (v / 1e3) / 1e9 for k, v in own.items() if v > 0}
+        cand = [k for k in gbs if stages[k] >= 0.05 * iter_ms] or list(gbs)
+        dom = min(cand, key=lambda k: gbs[k])
+        dom_ms = stages[dom]
+        achieved = gbs[dom]
+        whole = alg_iter * S / (ms_total / steps / iters / 1e3) / 1e9
         # DRAM bytes of the same kernel from the committed `ncu --set full` capture of this workload (per launch)
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_%s_s%d.json" % (args.config, S))
-        kname = {"source_update": "k_update_fast", "spec_render": "k_spec_render", "spec_column": "k_spec_column",
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_%s_s%d.json" % (config, S))
+        kname = {"source_update": "k_update_warp", "spec_render": "k_spec_render", "spec_column": "k_spec_column",
                  "spec_column_adj": "k_spec_column", "spec_residual": "k_spec_residual", "spec_grad": "k_spec_grad"}.get(dom)
         if args.precision == 32 and fused and kname and os.path.exists(tpath):
             try:
@@ -407,17 +417,15 @@ def run_b200(args):
                     "algorithmic_bytes_per_launch": stage_bytes[dom] * S,
                     "kernel_ms": dom_ms, "kernel_share_of_iteration": dom_ms / iter_ms,
                     "iteration": {"algorithmic_bytes_per_scene": alg_iter, "achieved": whole, "frac": whole / peak,
-                                  "note": "SURVEY.md 8(d) whole-iteration accounting incl. cuFFT stages"},
+                                  "note": "SURVEY.md 8(d) whole-iteration accounting (cuFFT-pipeline byte model), device-resident value"},
                     "stages_ms": stages,
                     "stages_gbs": {k: (stage_bytes[k] * S / (v / 1e3) / 1e9 if v > 0 and stage_bytes.get(k, 0) > 0 else None)
                                    for k, v in stages.items()}}
-        if args.config == "cfg4":
-            roofline["iteration"] = None
 
         # single-scene latency (the 200 it/s target of the north star is a per-scene figure)
         single = None
-        if not args.no_single:
-            one = BlendBatch([_make_blend(args.config, base[0], precision=args.precision, device=local)], precision=args.precision, device=local)
+        if headline and not args.no_single:
+            one = BlendBatch([_make_blend(config, base[0], precision=args.precision, device=local)], precision=args.precision, device=local)
             o1 = _native.fit_opts(max_iter=200, e_rel=1e-3, fixed_iterations=True, check_every=10 ** 6)
             for _ in range(3):
                 one.plan.forget_state()
@@ -428,43 +436,69 @@ def run_b200(args):
             single = 200 / (ms1 / 1e3)
             one.plan.close()
 
+        details = {"e2e": ("BatchPipeline(depth=2): two BlendBatch objects take turns, the copies of one overlap the loop of the other"
+                           if pipelined else "one BlendBatch.fit per step over %d plans/streams" % len(batch_e2e.plans)),
+                   "fft_grid": list(fshape), "unique_scenes_per_gpu": uniq, "device_bytes_per_gpu": plan.device_bytes,
+                   "single_scene_iterations_per_sec": single,
+                   "spectral": "fused row/column kernels" if fused else "cuFFT",
+                   "cufft_execs_per_iteration": 0 if fused else 4 * len(plan.obs_meta),
+                   "kernels_per_iteration": launches // max(steps * iters, 1), "precision": args.precision,
+                   "per_scene_psf": config != "cfg4",
+                   "value_includes": "the proximal-gradient loop (CUDA events) + the final NCCL gather of fitted parameters (N > 1)"}
+        if cfg.get("note"):
+            details["observations"] = cfg["note"]
+        rec = {"value": value, "unit": "scene-iterations/s", "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,
+               "config": workload_config(config, cfg, S, iters), "details": details, "clocks": clocks,
+               "e2e": {"value": e2e_value, "unit": "scene-iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "ms_per_step": 1e3 * e2e_total / steps},
+               "gpu_launches": int(launches), "roofline": roofline}
+    barrier()
+    if batch_e2e is not batch:
+        batch_e2e.close()
+    if batch_b is not None:
+        batch_b.close()
+    plan.close()
+    return rec
+
+
+def run_b200(args):
+    from scarlet_b200 import _native
+    if _native.lib().sb_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device -- scarlet_b200 has no CPU fallback")
+    env = Env()
+    S = args.scenes or DEFAULT_SCENES[args.config]
+    iters = args.iters or DEFAULT_ITERS[args.config]
+    head = measure(env, args, args.config, S, iters, args.steps, args.warmup, headline=True)
+    # the other BASELINE configurations, a few steps each, as sub-records of the same line (device value, e2e, roofline)
+    others = {}
+    if args.config == "cfg3" and not args.only_headline:
+        for c in ("cfg5", "cfg2", "cfg4"):
+            rec = measure(env, args, c, DEFAULT_SCENES[c], DEFAULT_ITERS[c], min(args.steps, 5), 3, headline=False)
+            if rec is not None:
+                others[c] = {"value": rec["value"], "unit": rec["unit"], "ms_per_step": rec["ms_per_step"], "steps": rec["steps"],
+                             "config": rec["config"], "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"],
+                             "roofline": {"iteration": rec["roofline"]["iteration"], "kernel": rec["roofline"]["kernel"],
+                                          "frac": rec["roofline"]["frac"], "stages_ms": rec["roofline"]["stages_ms"]},
+                             "fft_grid": rec["details"]["fft_grid"], "device_bytes_per_gpu": rec["details"]["device_bytes_per_gpu"]}
+    line = None
+    if env.rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if env.world == 1 and not args.no_cpu_baseline:
             from oracle import monotonic_c
-            monotonic_c.build()
+            monotonic_c._load()
             n_cpu = cpu_iters_for(args.config)
             _ref_worker((args.config, 0, 2))
             dt = _ref_worker((args.config, 0, n_cpu))
             cpu = {"value": n_cpu / dt, "unit": "scene-iterations/s", "cores": 1, "kind": "port",
                    "sample": "1 %s scene x %d iterations on one host core (oracle restatement, NumPy f64 + C sweep); host has %d cores"
                              % (args.config, n_cpu, os.cpu_count() or 1)}
-
-        conf = workload_config(args, cfg, S, iters)
-        conf.update({"e2e": ("BatchPipeline(depth=2): two BlendBatch objects take turns, the copies of one overlap the loop of the other"
-                             if pipelined else "one BlendBatch.fit per step over %d plans/streams" % len(batch_e2e.plans)),
-                     "fft_grid": list(fshape), "unique_scenes_per_gpu": uniq, "device_bytes_per_gpu": plan.device_bytes,
-                     "single_scene_iterations_per_sec": single,
-                     "spectral": "fused row/column kernels" if fused else "cuFFT",
-                     "cufft_execs_per_iteration": 0 if fused else 4 * len(plan.obs_meta),
-                     "kernels_per_iteration": launches // max(args.steps * iters, 1), "precision": args.precision,
-                     "per_scene_psf": args.config != "cfg4"})
-        if cfg.get("note"):
-            conf["observations"] = cfg["note"]
-        line = {"metric": "pgm_scene_iterations_per_sec", "value": value, "unit": "scene-iterations/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        line = {"metric": "pgm_scene_iterations_per_sec", "value": head["value"], "unit": head["unit"], "n_gpus": env.world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic",
-                "config": conf, "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "scene-iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": 1e3 * e2e_total / args.steps},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
-    barrier()
-    if batch_e2e is not batch:
-        batch_e2e.close()
-    if pipelined:
-        batch_b.close()
-    plan.close()
-    if world > 1:
-        dist.destroy_process_group()
+                "config": head["config"], "details": head["details"], "clocks": head["clocks"], "e2e": head["e2e"],
+                "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "cpu_baseline": cpu, "configs": others}
+    if env.world > 1:
+        env.dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
 

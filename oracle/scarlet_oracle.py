@@ -484,7 +484,7 @@ class ExtendedSourceOracle:
 
     def _new_image(self, data, m, v, vhat, origin_shift):
         old = self.image
-        self.image = OParam(np.array(data, dtype=np.float64), "image", old.step / 2, old.prox, old.fixed)
+        self.image = OParam(np.array(data, dtype=ARITH["morph"]), "image", old.step / 2, old.prox, old.fixed)
         self.image.m, self.image.v, self.image.vhat = np.array(m), np.array(v), np.array(vhat)
         C = self.bbox.shape[0]
         oy, ox = self.bbox.origin[1] + origin_shift, self.bbox.origin[2] + origin_shift

@@ -13,6 +13,7 @@
 
 #include "kernels.cuh"
 #include "spectral.cuh"
+#include "update_warp.cuh"
 
 namespace sb {
 
@@ -247,6 +248,14 @@ template <typename T> struct PlanT : sb_plan {
     int n_shift = 0, toep_len = 1;
     int n_generic = 0, n_fast_cta = 0, fast_G = 0, fast_GT = 64, fast_npix = 0, fast_table_cap = 0;
     size_t fast_smem = 0;
+    // warp-per-source kernel (update_warp.cuh)
+    static constexpr int WARP_NPT = 56, WARP_MAXT = sizeof(T) == 4 ? 448 : 256;
+    DevBuf<int> d_warp_groups;
+    DevBuf<XP<T>> d_xp;
+    int n_warp_cta = 0, warp_G = 0, warp_npix = 0, warp_cap = 0;
+    size_t warp_smem = 0;
+    cudaStream_t side2 = nullptr;
+    cudaEvent_t ev_join2 = nullptr;
     std::vector<HostMono> hmonos;
     DevBuf<float> d_stage_f;
     DevBuf<DevChain> d_chains;
@@ -305,8 +314,10 @@ template <typename T> struct PlanT : sb_plan {
         if (ev1) cudaEventDestroy(ev1);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
+        if (ev_join2) cudaEventDestroy(ev_join2);
         if (stream) cudaStreamDestroy(stream);
         if (side) cudaStreamDestroy(side);
+        if (side2) cudaStreamDestroy(side2);
     }
 
     int64_t total_bytes() {
@@ -332,6 +343,8 @@ template <typename T> struct PlanT : sb_plan {
         SB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
         SB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         SB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        SB_CUDA(cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking));
+        SB_CUDA(cudaEventCreateWithFlags(&ev_join2, cudaEventDisableTiming));
         SB_CUDA(cudaHostAlloc((void **)&h_nactive, sizeof(int), cudaHostAllocDefault));
 
         // ---- constraint tables
@@ -607,15 +620,36 @@ template <typename T> struct PlanT : sb_plan {
         return SB_OK;
     }
 
-    // Split the sources between the grouped fast kernel (k_update_fast) and the generic one (k_update).
+    // The ExtendedSource chain Monotonicity -> [Symmetry] -> Positivity -> CenterOn -> Normalization("max") (fused_chain_of)
+    bool chain_is_fused(int chain, int By, int Bx) const {
+        const sb_chain_desc &ch = desc.chains[chain];
+        if (ch.repeat != 1 || !(By & 1) || !(Bx & 1)) return false;
+        int i = 0;
+        if (i >= ch.n_ops || ch.ops[i].code != SB_OP_MONOTONIC) return false;
+        ++i;
+        if (i < ch.n_ops && ch.ops[i].code == SB_OP_SYMMETRY) ++i;
+        if (i >= ch.n_ops || ch.ops[i++].code != SB_OP_POSITIVITY) return false;
+        if (i >= ch.n_ops || ch.ops[i++].code != SB_OP_CENTER_ON) return false;
+        if (i >= ch.n_ops || ch.ops[i].code != SB_OP_NORMALIZE || ch.ops[i].iarg != 1) return false;
+        return i + 1 == ch.n_ops;
+    }
+    // cap = 32 (trips + 2) table entries (update_warp.cuh: table by trips)
+    static size_t warp_smem_bytes(int G, int npix, int cap) {
+        return (size_t)cap * (sizeof(W4<T>) + sizeof(uint2) + sizeof(unsigned short)) + 1024 * sizeof(int) +
+               (size_t)G * SB_FAST_MAXC * sizeof(double) + (size_t)G * npix * sizeof(T) + 16;
+    }
+
+    // Split the sources between the warp-per-source kernel (k_update_warp), the grouped kernel (k_update_fast) and the generic
+    // one (k_update).
     int plan_fast_path() {
-        std::map<int, std::vector<int>> by_chain;
+        std::map<int, std::vector<int>> by_chain, warp_chain;
         std::vector<int> generic;
-        int npix = 0, cap = 0;
+        int npix = 0, cap = 0, wnpix = 0, wcap = 0;
+        const bool use_warp = getenv("SB_NO_WARP_UPDATE") == nullptr;
         for (int k = 0; k < n_src; ++k) {
             const DevSource &d = h_src[k];
             bool fast = d.kind == 0 && d.chain >= 0 && C <= SB_FAST_MAXC && !d.shifting;
-            int tasks = 0;
+            int tasks = 0, trips = 0;
             if (fast) {
                 int n_mono_ops = 0;
                 const sb_chain_desc &ch = desc.chains[d.chain];
@@ -624,6 +658,7 @@ template <typename T> struct PlanT : sb_plan {
                         const HostMono &h = hmonos[ch.ops[i].iarg];
                         ++n_mono_ops;
                         tasks = h.n_tasks;
+                        for (int L = 0; L < h.n_levels; ++L) trips += (h.level_start[L + 1] - h.level_start[L] + 31) / 32;
                         if (h.nb != 4 || h.n_levels + 1 > 512) fast = false;
                     }
                 if (n_mono_ops > 1) fast = false;
@@ -635,7 +670,13 @@ template <typename T> struct PlanT : sb_plan {
                 // the shared-memory table addresses pixels by 16-bit byte offsets (spare cell included)
                 if ((size_t)(d.By * d.Bx + 1) * sizeof(T) > 65535) fast = false;
             }
-            if (fast) {
+            const bool warp = fast && use_warp && chain_is_fused(d.chain, d.By, d.Bx) && d.By * d.Bx <= 32 * WARP_NPT && trips <= 1020 &&
+                              warp_smem_bytes(4, (d.By * d.Bx + 4) & ~3, 32 * (trips + 2)) <= 200 * 1024;
+            if (warp) {
+                warp_chain[d.chain].push_back(k);
+                wnpix = std::max(wnpix, (d.By * d.Bx + 4) & ~3);
+                wcap = std::max(wcap, 32 * (trips + 2));
+            } else if (fast) {
                 by_chain[d.chain].push_back(k);
                 npix = std::max(npix, (d.By * d.Bx + 4) & ~3); // + the spare zero cell of group_sweep
                 cap = std::max(cap, (tasks + 7) & ~7);
@@ -643,35 +684,58 @@ template <typename T> struct PlanT : sb_plan {
                 generic.push_back(k);
         }
         fast_npix = npix, fast_table_cap = std::max(cap, 8);
-        // Every SM gets the same number of groups (= sources): the kernel is bound by the latency of the per-source
-        // proximal loop, so balance matters more than occupancy.  One CTA per SM (64 registers x 1024 threads fill the
-        // register file): up to 16 groups of GT = 64 threads (default), or 8 groups of 128 (SB_UPDATE_GROUP=128).
+        warp_npix = wnpix, warp_cap = std::max(wcap, 8);
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        // Every SM gets the same number of groups (= sources): the kernels are bound by the latency of the per-source
+        // proximal loop, so balance matters more than occupancy.  One CTA per SM.
+        auto pick_G = [&](size_t n_items, int gmax, auto smem_of) {
+            if (!n_items) return 0;
+            const size_t slots = (size_t)sms;
+            const int waves = (int)((n_items + slots * gmax - 1) / (slots * gmax));
+            int G = (int)((n_items + slots * waves - 1) / (slots * waves));
+            G = std::max(1, std::min(gmax, G));
+            while (G > 1 && smem_of(G) > (size_t)220 * 1024) --G;
+            return smem_of(G) <= (size_t)220 * 1024 ? G : 0;
+        };
+        auto make_groups = [](const std::map<int, std::vector<int>> &chains, int G, std::vector<int> &groups) {
+            for (auto &kv : chains) {
+                const std::vector<int> &v = kv.second;
+                for (size_t i = 0; i < v.size(); i += G)
+                    for (int j = 0; j < G; ++j) groups.push_back(i + j < v.size() ? v[i + j] : -1);
+            }
+        };
+        // ---- warp-per-source kernel: up to WARP_MAXT / 32 warps per CTA (register-resident iterate)
+        {
+            size_t n_warp = 0;
+            for (auto &kv : warp_chain) n_warp += kv.second.size();
+            warp_G = pick_G(n_warp, WARP_MAXT / 32, [&](int G) { return warp_smem_bytes(G, warp_npix, warp_cap); });
+            std::vector<int> groups;
+            if (warp_G)
+                make_groups(warp_chain, warp_G, groups);
+            else
+                for (auto &kv : warp_chain) by_chain[kv.first].insert(by_chain[kv.first].end(), kv.second.begin(), kv.second.end());
+            n_warp_cta = warp_G ? (int)(groups.size() / warp_G) : 0;
+            warp_smem = warp_G ? warp_smem_bytes(warp_G, warp_npix, warp_cap) : 0;
+            SB_TRY(d_warp_groups.alloc(std::max<size_t>(groups.size(), 1)));
+            if (!groups.empty()) SB_CUDA(cudaMemcpy(d_warp_groups.p, groups.data(), groups.size() * sizeof(int), cudaMemcpyHostToDevice));
+            if (n_warp_cta) {
+                SB_TRY(d_xp.alloc(std::max<long long>(n_morph, 1)));
+                SB_TRY(raise_smem((const void *)k_update_warp<T, WARP_NPT, WARP_MAXT>, warp_smem));
+            }
+        }
+        // ---- grouped kernel: up to 16 groups of GT = 64 threads (default), or 8 groups of 128 (SB_UPDATE_GROUP=128)
         fast_G = 0;
         {
             const char *gt = getenv("SB_UPDATE_GROUP");
             fast_GT = (gt && atoi(gt) == 128) ? 128 : (gt && atoi(gt) == 32) ? 32 : 64;
             size_t n_fast = 0;
             for (auto &kv : by_chain) n_fast += kv.second.size();
-            int sms = 148;
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-            const int ctas_per_sm = 1, gmax = 1024 / fast_GT;
-            const size_t smem_cap = (size_t)220 * 1024;
-            if (n_fast) {
-                const size_t slots = (size_t)sms * ctas_per_sm;
-                const int waves = (int)((n_fast + slots * gmax - 1) / (slots * gmax));
-                int G = (int)((n_fast + slots * waves - 1) / (slots * waves));
-                G = std::max(1, std::min(gmax, G));
-                while (G > 1 && fast_smem_bytes(G, fast_npix, fast_table_cap) > smem_cap) --G;
-                if (fast_smem_bytes(G, fast_npix, fast_table_cap) <= (size_t)220 * 1024) fast_G = G;
-            }
+            fast_G = pick_G(n_fast, 1024 / fast_GT, [&](int G) { return fast_smem_bytes(G, fast_npix, fast_table_cap); });
         }
         std::vector<int> groups;
         if (fast_G) {
-            for (auto &kv : by_chain) {
-                const std::vector<int> &v = kv.second;
-                for (size_t i = 0; i < v.size(); i += fast_G)
-                    for (int j = 0; j < fast_G; ++j) groups.push_back(i + j < v.size() ? v[i + j] : -1);
-            }
+            make_groups(by_chain, fast_G, groups);
         } else {
             for (auto &kv : by_chain) generic.insert(generic.end(), kv.second.begin(), kv.second.end());
             std::sort(generic.begin(), generic.end());
@@ -1107,43 +1171,49 @@ template <typename T> struct PlanT : sb_plan {
                 SB_CUDA(cudaGetLastError());
                 ++nk;
             } else {
-                // The generic kernel works on other sources than the grouped one, which leaves room on every SM: fork it
-                // onto the side stream so that the two run concurrently (also inside a graph capture).
-                const bool fork = n_fast_cta && n_generic && !marks;
-                if (fork) {
-                    SB_CUDA(cudaEventRecord(ev_fork, stream));
-                    SB_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+                // The three update kernels work on disjoint sources: the warp-per-source kernel goes first on the main stream
+                // (one big CTA per SM), the grouped and the generic kernel fill the rest of the machine from side streams
+                // (also inside a graph capture).
+                const int n_kinds = (n_warp_cta > 0) + (n_fast_cta > 0) + (n_generic > 0);
+                const bool fork = n_kinds > 1 && !marks;
+                if (fork) SB_CUDA(cudaEventRecord(ev_fork, stream));
+                cudaStream_t s_fast = stream, s_gen = stream;
+                if (fork && n_warp_cta && n_fast_cta) s_fast = side2;
+                if (fork && (n_warp_cta || n_fast_cta) && n_generic) s_gen = side;
+                if (n_warp_cta) {
+                    WarpArgs<T> wa;
+                    wa.groups = d_warp_groups.p, wa.G = warp_G, wa.npix = warp_npix, wa.table_cap = warp_cap, wa.xp = d_xp.p;
+                    k_update_warp<T, WARP_NPT, WARP_MAXT><<<n_warp_cta, 32 * warp_G, warp_smem, stream>>>(ua, wa);
+                    SB_CUDA(cudaGetLastError());
+                    ++nk;
                 }
                 if (n_fast_cta) {
+                    if (s_fast != stream) SB_CUDA(cudaStreamWaitEvent(s_fast, ev_fork, 0));
                     if (fast_GT == 32 && 32 * fast_G <= 448)
-                        k_update_fast<T, 32, 448><<<n_fast_cta, 32 * fast_G, fast_smem, stream>>>(ua);
+                        k_update_fast<T, 32, 448><<<n_fast_cta, 32 * fast_G, fast_smem, s_fast>>>(ua);
                     else if (fast_GT == 32)
-                        k_update_fast<T, 32><<<n_fast_cta, 32 * fast_G, fast_smem, stream>>>(ua);
+                        k_update_fast<T, 32><<<n_fast_cta, 32 * fast_G, fast_smem, s_fast>>>(ua);
                     else if (fast_GT == 128)
-                        k_update_fast<T, 128><<<n_fast_cta, 128 * fast_G, fast_smem, stream>>>(ua);
+                        k_update_fast<T, 128><<<n_fast_cta, 128 * fast_G, fast_smem, s_fast>>>(ua);
                     else if (64 * fast_G <= 832)
-                        k_update_fast<T, 64, 832><<<n_fast_cta, 64 * fast_G, fast_smem, stream>>>(ua);
+                        k_update_fast<T, 64, 832><<<n_fast_cta, 64 * fast_G, fast_smem, s_fast>>>(ua);
                     else
-                        k_update_fast<T, 64><<<n_fast_cta, 64 * fast_G, fast_smem, stream>>>(ua);
+                        k_update_fast<T, 64><<<n_fast_cta, 64 * fast_G, fast_smem, s_fast>>>(ua);
                     SB_CUDA(cudaGetLastError());
                     ++nk;
+                    if (s_fast != stream) SB_CUDA(cudaEventRecord(ev_join2, s_fast));
                 }
-                if (fork) { // launched second: the grouped kernel's one big CTA per SM goes in first, these fill the rest
+                if (n_generic) {
+                    if (s_gen != stream) SB_CUDA(cudaStreamWaitEvent(s_gen, ev_fork, 0));
                     UpdateArgs<T> ug = ua;
                     ug.work = d_work.p;
-                    k_update<T><<<n_generic, 128, update_smem(), side>>>(ug);
+                    k_update<T><<<n_generic, 128, update_smem(), s_gen>>>(ug);
                     SB_CUDA(cudaGetLastError());
                     ++nk;
-                    SB_CUDA(cudaEventRecord(ev_join, side));
+                    if (s_gen != stream) SB_CUDA(cudaEventRecord(ev_join, s_gen));
                 }
-                if (fork) {
-                    SB_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
-                } else if (n_generic) {
-                    ua.work = d_work.p;
-                    k_update<T><<<n_generic, 128, update_smem(), stream>>>(ua);
-                    SB_CUDA(cudaGetLastError());
-                    ++nk;
-                }
+                if (s_fast != stream) SB_CUDA(cudaStreamWaitEvent(stream, ev_join2, 0));
+                if (s_gen != stream) SB_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
             }
             if (mode == 0 && n_shift) { // new shifts / images -> new shifted morphologies for the next render
                 SB_TRY(launch_shift_apply());

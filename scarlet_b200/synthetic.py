@@ -208,6 +208,31 @@ def make_multires_scene(scene_id=0, config=None):
     return scene
 
 
+def algorithmic_bytes_multires(cfg, elem=4, frame=(8, 228, 228), fft_shape=(240, 240)):
+    """SURVEY.md 8(d) accounting extended to cfg4 (two observations of one model frame): every logical stage reads its
+    inputs and writes its outputs once.
+
+    high-resolution observation (ConvolutionRenderer, 3 bands, 200 x 200): the single-observation formula --
+        6 real-grid passes + 3 image passes + 6 complex passes;
+    low-resolution observation (ResolutionRenderer, 5 bands, 30 x 30; renderer.py:262-547 as the Parseval form of
+    csrc/spectral.cuh): forward  = padded model write + read (2 real), M^ write + read + K^ read (3 complex),
+                                   row-resampled spectrum T1 write + read (2 x C H Fxc complex), rendered + data + weights (3 images);
+                        adjoint  = U write + read (2 x C H Fxc complex), K^ Q^ write + read + K^ read (3 complex),
+                                   gradient grid write + read (2 real);
+    per source: B^2 (14 + C_model) as in the single-observation formula."""
+    c = dict(CFG4)
+    c.update(cfg if "hr_n" in cfg else {})
+    Cm, Ny, Nx = frame
+    Fy, Fx = fft_shape
+    Fxc = Fx // 2 + 1
+    Fc = Fy * Fxc
+    hr_C, lr_C, H, W = 3, 5, c["hr_n"], c["lr_n"]
+    hr = elem * (6 * hr_C * Fy * Fx + 3 * hr_C * H * H) + 2 * elem * (6 * hr_C * Fc)
+    lr = elem * (4 * lr_C * Fy * Fx + 3 * lr_C * W * W) + 2 * elem * (6 * lr_C * Fc + 4 * lr_C * W * Fxc)
+    src = elem * c["n_ext"] * c["B"] ** 2 * (14 + Cm)
+    return hr + lr + src
+
+
 def make_multires_blend(scene, precision=32, device=None):
     """scarlet_b200 objects of a cfg4 scene: -> Blend over [low-resolution, high-resolution] observations."""
     import scarlet_b200 as sb

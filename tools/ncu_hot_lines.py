@@ -1,8 +1,16 @@
 #!/usr/bin/env python
-"""Top source lines of a kernel by warp-stall samples:  ncu -i X.ncu-rep --page source --csv --print-source cuda,sass > src.csv;
-python tools/ncu_hot_lines.py src.csv [N]"""
+"""Top source lines of a kernel by warp-stall samples and by executed instructions:
+ncu -i X.ncu-rep --page source --csv --print-source cuda,sass > src.csv;  python tools/ncu_hot_lines.py src.csv [N]"""
 import csv
 import sys
+
+
+def num(x):
+    try:
+        return int(x)
+    except (TypeError, ValueError):
+        return 0
+
 
 rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
@@ -14,10 +22,15 @@ for r in rows:
         hdr = r
     elif len(r) > 6 and r[0].isdigit():
         d = dict(zip(hdr, r))
-        out.append((int(d["# Samples"] or 0), cur, int(r[0]), r[1][:100], d.get("stall_long_sb"), d.get("stall_barrier"),
-                    d.get("stall_short_sb"), d.get("stall_wait"), d.get("Instructions Executed")))
-tot = sum(o[0] for o in out) or 1
-print("# total samples %d" % tot)
-print("# samples share file:line long_sb barrier short_sb wait inst | source")
-for o in sorted(out, reverse=True)[:top]:
-    print("%6d %5.1f%% %s:%d lsb=%s bar=%s ssb=%s wait=%s inst=%s | %s" % (o[0], 100 * o[0] / tot, o[1], o[2], o[4], o[5], o[6], o[7], o[8], o[3]))
+        out.append(dict(samples=num(d["# Samples"]), file=cur, line=int(r[0]), src=r[1][:110], lsb=num(d.get("stall_long_sb")),
+                        bar=num(d.get("stall_barrier")), ssb=num(d.get("stall_short_sb")), wait=num(d.get("stall_wait")),
+                        inst=num(d.get("Instructions Executed")), wf=num(d.get("L1 Wavefronts Shared")),
+                        wfx=num(d.get("L1 Wavefronts Shared Excessive"))))
+tot = sum(o["samples"] for o in out) or 1
+ti = sum(o["inst"] for o in out) or 1
+print("# total samples %d, total warp instructions %d" % (tot, ti))
+print("# samples share | inst share | file:line long_sb barrier short_sb wait smem_wavefronts(excess) | source")
+for o in sorted(out, key=lambda o: -o["samples"])[:top]:
+    print("%6d %5.1f%% | %9d %5.1f%% | %s:%d lsb=%d bar=%d ssb=%d wait=%d wf=%d(%d) | %s" % (
+        o["samples"], 100 * o["samples"] / tot, o["inst"], 100 * o["inst"] / ti, o["file"], o["line"], o["lsb"], o["bar"], o["ssb"],
+        o["wait"], o["wf"], o["wfx"], o["src"]))
