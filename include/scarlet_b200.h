@@ -124,7 +124,19 @@ typedef struct sb_fit_opts { /* Blend.fit / proxmin.adaprox arguments, blend.py:
     int32_t run_until; /* stop this call when the iteration counter reaches run_until (0: max_iter) */
     double e_rel;
     double b1, b2, eps;
+    int32_t pause_every; /* > 0: a scene whose adaprox iteration counter is a positive multiple of this pauses after that
+                            iteration (state SB_SCENE_PAUSED) so that the host can inspect its sources -- Blend._callback's
+                            src.update() every 10 iterations (blend.py:284-292).  0: never */
+    int32_t _pad1;
 } sb_fit_opts;
+
+/* per-scene run state (sb_plan_scene_status); distinct bits */
+#define SB_SCENE_RUN 0
+#define SB_SCENE_CONVERGED 1   /* the stop rule fired (blend.py:294-299) */
+#define SB_SCENE_PAUSED 2      /* inspection point reached; | SB_SCENE_CONV_PENDING if the stop rule also fired there */
+#define SB_SCENE_EXHAUSTED 4   /* loss history reached the scene's limit (max_iter) */
+#define SB_SCENE_FAILED 8      /* non-finite parameter */
+#define SB_SCENE_CONV_PENDING 16
 
 typedef struct sb_plan sb_plan;
 
@@ -150,6 +162,25 @@ int sb_plan_spectral_mode(const sb_plan *plan);
  * per source since the last call.  enable=1 starts (or continues) counting and zeroes the counters after reading;
  * enable=0 reads and switches the counters off.  out16 may be NULL. */
 int sb_plan_prox_histogram(sb_plan *plan, int enable, int64_t *out16);
+
+/* ---- batches whose scenes restart independently (dynamic boxes: every scene is its own sequence of proxmin.adaprox calls,
+ * blend.py:99-198).  Each scene carries its own iteration counter of the running call (proxmin's ``it``), the length of its
+ * loss history in this fit, an iteration budget and a run flag.  All arrays have n_scenes entries; NULL leaves a table as is.
+ *   it_local  : counter of the running adaprox call (0 after a restart)
+ *   loss_len  : entries of the loss history written so far (the next loss goes to column loss_len)
+ *   limit     : the scene stops (SB_SCENE_EXHAUSTED) when loss_len reaches limit
+ *   active    : 1 = run, 0 = skip (also clears the error flags)
+ *   prox_iter : per-scene prox_max_iter (a restarted call runs with the default 10, blend.py:143-145)
+ * sb_plan_run launches iterations (no reset of anything) until no scene is running or max_launches is reached; the number
+ * of running scenes is polled every opts->check_every launches. */
+int sb_plan_scene_control(sb_plan *plan, const int32_t *it_local, const int32_t *loss_len, const int32_t *limit,
+                          const int32_t *active, const int32_t *prox_iter);
+int sb_plan_scene_status(sb_plan *plan, int32_t *it_local, int32_t *loss_len, int32_t *state);
+int sb_plan_run(sb_plan *plan, const sb_fit_opts *opts, int max_launches, int32_t *launched);
+/* loss histories [n_scenes][n_cols] (n_cols <= the capacity set by the largest max_iter seen so far) */
+int sb_plan_download_loss(sb_plan *plan, double *loss, int n_cols);
+/* ... and back (a re-planned batch continues its histories: the stop rule compares with the previous entry) */
+int sb_plan_upload_loss(sb_plan *plan, const double *loss, int n_cols);
 
 /* Observation data: data/weights float32 [n_scenes][C][H][W] (frame dtype, frame.py:29); K^ = rfftn of the
  * padded, ifftshifted difference kernel (renderer.py:198-202, fft.py:255-273) as interleaved complex128

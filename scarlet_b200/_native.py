@@ -15,6 +15,7 @@ SB_MAX_CHANNELS = 16
 SB_MAX_OBS = 4
 SB_N_STAGES = 10
 SB_ERR_NONFINITE = -4
+SCENE_RUN, SCENE_CONVERGED, SCENE_PAUSED, SCENE_EXHAUSTED, SCENE_FAILED, SCENE_CONV_PENDING = 0, 1, 2, 4, 8, 16
 
 OP_MONOTONIC, OP_SYMMETRY, OP_POSITIVITY, OP_CENTER_ON, OP_NORMALIZE = 1, 2, 3, 4, 5
 
@@ -56,7 +57,7 @@ class sb_fit_opts(C.Structure):
     _fields_ = [("max_iter", C.c_int32), ("min_iter", C.c_int32), ("prox_max_iter", C.c_int32), ("check_every", C.c_int32),
                 ("fixed_iterations", C.c_int32), ("overwrite_vhat_at_it0", C.c_int32), ("resume", C.c_int32),
                 ("run_until", C.c_int32), ("e_rel", C.c_double),
-                ("b1", C.c_double), ("b2", C.c_double), ("eps", C.c_double)]
+                ("b1", C.c_double), ("b2", C.c_double), ("eps", C.c_double), ("pause_every", C.c_int32), ("_pad1", C.c_int32)]
 
 
 # every symbol declared in include/scarlet_b200.h: (restype, argtypes)
@@ -69,6 +70,11 @@ SYMBOLS = {
     "sb_fft_supported_length": (C.c_int, [C.c_int]),
     "sb_plan_spectral_mode": (C.c_int, [_P]),
     "sb_plan_prox_histogram": (C.c_int, [_P, C.c_int, _P]),
+    "sb_plan_scene_control": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "sb_plan_scene_status": (C.c_int, [_P, _P, _P, _P]),
+    "sb_plan_run": (C.c_int, [_P, C.POINTER(sb_fit_opts), C.c_int, _P]),
+    "sb_plan_download_loss": (C.c_int, [_P, _P, C.c_int]),
+    "sb_plan_upload_loss": (C.c_int, [_P, _P, C.c_int]),
     "sb_plan_create": (C.c_int, [C.POINTER(sb_batch_desc), C.c_int, C.POINTER(_P)]),
     "sb_plan_destroy": (None, [_P]),
     "sb_plan_device_bytes": (C.c_int64, [_P]),
@@ -151,10 +157,10 @@ def default_device():
 
 
 def fit_opts(max_iter=200, e_rel=1e-3, min_iter=1, prox_max_iter=10, check_every=10, fixed_iterations=False,
-             b1=0.9, b2=0.999, eps=1e-8, overwrite_vhat_at_it0=True, resume=False, run_until=0):
+             b1=0.9, b2=0.999, eps=1e-8, overwrite_vhat_at_it0=True, resume=False, run_until=0, pause_every=0):
     return sb_fit_opts(int(max_iter), int(min_iter), int(prox_max_iter), int(check_every), int(bool(fixed_iterations)),
                        int(bool(overwrite_vhat_at_it0)), int(bool(resume)), int(run_until), float(e_rel), float(b1), float(b2),
-                       float(eps))
+                       float(eps), int(pause_every), 0)
 
 
 def as_array(x, dtype):

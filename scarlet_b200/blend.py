@@ -193,17 +193,18 @@ class BlendBatch:
     def __init__(self, blends, precision=32, device=None, n_streams=1):
         from .distributed import shard_bounds
         self.blends = list(blends)
-        for b in self.blends:
-            for c in _leaves(b.sources):
-                morph = c.children[1]
-                if getattr(morph, "resizing", False) and not morph.parameters[0].fixed:
-                    raise NotImplementedError("BlendBatch fits fixed boxes: build the sources with resizing=False (dynamic boxes "
-                                              "re-plan a scene every few iterations; use Blend.fit for those)")
-        n_streams = max(1, min(int(n_streams), len(self.blends)))
+        self.precision, self.device = precision, device
+        # Dynamic boxes (``resizing=True``, the reference default): every scene is its own sequence of optimiser calls that
+        # restart whenever one of its boxes changes (blend.py:99-198), so the scenes of a batch drift apart.  The device keeps
+        # per-scene iteration counters and pause flags for that; the batch is then driven as ONE plan (``_fit_dynamic``).
+        self.dynamic = any(getattr(c.children[1], "resizing", False) and not c.children[1].parameters[0].fixed
+                           for b in self.blends for c in _leaves(b.sources))
+        n_streams = 1 if self.dynamic else max(1, min(int(n_streams), len(self.blends)))
         self.parts = [self.blends[a:b] for a, b in shard_bounds(len(self.blends), n_streams)]
         self.plans = [DevicePlan(part, precision=precision, device=device) for part in self.parts]
         self.plan = self.plans[0]
         self.last_transfer_bytes = (0, 0)
+        self.replans = 0
 
     def _each(self, fn):
         if len(self.plans) == 1:
@@ -217,7 +218,11 @@ class BlendBatch:
 
     def fit(self, max_iter=200, e_rel=1e-3, min_iter=1, noise_factor=0, upload_observations=False, **alg_kwargs):
         check_every = int(alg_kwargs.pop("check_every", 10))
+        if alg_kwargs.get("callback") is not None:
+            raise NotImplementedError("user callbacks are honoured by Blend.fit (one scene); a batch has no common iteration")
         opts = _fit_options(max_iter, e_rel, min_iter, noise_factor, alg_kwargs, check_every)
+        if self.dynamic:
+            return self._fit_dynamic(opts, max_iter, e_rel, min_iter, upload_observations)
 
         def one(i):
             h2d = self._copy_in(i, upload_observations)
@@ -225,6 +230,91 @@ class BlendBatch:
             return out + (h2d, self._copy_out(i, out))
 
         return self._finish(self._each(one))
+
+    def _fit_dynamic(self, opts, max_iter, e_rel, min_iter, upload_observations):
+        """Batch fit with dynamic boxes: equals ``Blend.fit`` of every scene on its own, bit for bit.
+
+        The device runs all scenes until each one has either converged, spent its budget, failed, or reached an inspection
+        point of ITS OWN optimiser call (iterations 10, 20, ... of that call, blend.py:284-292) where it pauses.  The host then
+        runs ``src.update()`` on the paused scenes; a scene whose boxes changed restarts (``it = len(loss)``, warm state, its
+        ``scheme`` / ``prox_max_iter`` back at the defaults exactly like the reference's restart loop, blend.py:143-152), the
+        others resume.  Box changes re-plan the batch (new shapes, new operator tables); state travels through the host."""
+        import ctypes
+        S = len(self.blends)
+        for b in self.blends:
+            for src in b.sources:
+                src.check_parameters()
+        if max_iter <= 0:
+            return [(len(b.loss), (-b.loss[-1] if b.loss else None)) for b in self.blends]
+        prev_len = np.array([len(b.loss) for b in self.blends], dtype=np.int64)
+        it_local = np.zeros(S, dtype=np.int32)
+        loss_len = np.zeros(S, dtype=np.int32)
+        limit = np.full(S, max_iter, dtype=np.int32)
+        prox = np.full(S, opts.prox_max_iter, dtype=np.int32)
+        finished = np.zeros(S, dtype=bool)
+        loss = np.zeros((S, int(max_iter)))  # this fit's loss histories (host copy; re-uploaded to a re-planned batch)
+        opts.max_iter, opts.pause_every = int(max_iter), 10
+        opts.check_every = min(opts.check_every, 10)
+        h2d = d2h = 0
+        need_plan, first = False, True
+        lib = nat.lib()
+        while not finished.all():
+            if need_plan or self.plan._handle is None:
+                self.plan.close()
+                self.plan = DevicePlan(self.blends, precision=self.precision, device=self.device)
+                self.plans, self.parts = [self.plan], [self.blends]
+                self.replans += 1
+                need_plan = False
+                nat.check(lib.sb_plan_upload_loss(self.plan._handle, nat.ptr(loss), int(max_iter)))
+            elif first and upload_observations:
+                h2d += self.plan.upload_observations()
+            first = False
+            plan = self.plan
+            h2d += plan.upload_parameters(state=True)
+            active = (~finished).astype(np.int32)
+            nat.check(lib.sb_plan_scene_control(plan._handle, nat.ptr(it_local), nat.ptr(loss_len), nat.ptr(limit), nat.ptr(active),
+                                                nat.ptr(prox)))
+            launched = ctypes.c_int32()
+            nat.check(lib.sb_plan_run(plan._handle, ctypes.byref(opts), int(max_iter) + 1, ctypes.byref(launched)))
+            state = np.zeros(S, dtype=np.int32)
+            nat.check(lib.sb_plan_scene_status(plan._handle, nat.ptr(it_local), nat.ptr(loss_len), nat.ptr(state)))
+            nat.check(lib.sb_plan_download_loss(plan._handle, nat.ptr(loss), int(max_iter)))
+            d2h += plan.download_parameters(state=True) + loss.nbytes
+            for s, b in enumerate(self.blends):
+                if finished[s]:
+                    continue
+                st = int(state[s])
+                if st == nat.SCENE_FAILED:
+                    b.loss.extend(loss[s, :loss_len[s]].tolist())
+                    for src in b.sources:
+                        src.check_parameters()  # raises ArithmeticError naming the parameter (model.py:153-165)
+                    raise ArithmeticError("scene %d: a parameter became non-finite during the fit" % s)
+                if st & nat.SCENE_PAUSED:
+                    changed = False
+                    for src in b.sources:
+                        try:
+                            src.update()
+                        except UpdateException:
+                            changed = True
+                    if changed:  # blend.py:196-198: restart with it = len(loss); the popped keywords are gone (defaults)
+                        need_plan = True
+                        it_local[s], prox[s] = 0, 10
+                        limit[s] = max_iter - prev_len[s]
+                        finished[s] = loss_len[s] >= limit[s]
+                    elif st & nat.SCENE_CONV_PENDING:
+                        finished[s] = True
+                    else:
+                        finished[s] = loss_len[s] >= limit[s]
+                elif st in (nat.SCENE_CONVERGED, nat.SCENE_EXHAUSTED):
+                    finished[s] = True
+                elif st == nat.SCENE_RUN and launched.value >= max_iter + 1:
+                    finished[s] = True  # cannot happen (budget >= launches); guards an endless loop
+        self.last_transfer_bytes = (int(h2d), int(d2h))
+        results = []
+        for s, b in enumerate(self.blends):
+            b.loss.extend(loss[s, :loss_len[s]].tolist())
+            results.append((len(b.loss), -b.loss[-1] if b.loss else None))
+        return results
 
     # the three stages of a fit, per plan (BatchPipeline interleaves them across batches)
     def _copy_in(self, i, upload_observations):

@@ -96,7 +96,7 @@ template <typename T> struct DevObs {
 };
 
 struct FitScalars {
-    int prox_max_iter, min_iter, fixed_iterations, overwrite_vhat_at_it0;
+    int prox_max_iter, min_iter, fixed_iterations, overwrite_vhat_at_it0, pause_every, _pad;
     double e_rel, b1, b2, eps;
 };
 

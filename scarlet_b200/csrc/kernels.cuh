@@ -349,7 +349,8 @@ template <typename T> struct UpdateArgs {
     T *pmorph;
     const DevChain *chains;
     const DevMono *monos;
-    const int *it_ptr;
+    const int *it_ptr; // [S] per-scene iteration counter of the running adaprox call (proxmin's ``it``)
+    const int *prox_iter; // optional [S]: per-scene prox_max_iter (a restarted scene falls back to the default, blend.py:143-145)
     const int *done;
     int *status;
     FitScalars fs;
@@ -398,6 +399,10 @@ __device__ __forceinline__ void grad_bands(const UpdateArgs<T> &a, int s, int C,
     }
 }
 
+template <typename T> __device__ __forceinline__ int prox_max_iter_of(const UpdateArgs<T> &a, int scene) {
+    return a.prox_iter ? a.prox_iter[scene] : a.fs.prox_max_iter;
+}
+
 // AMSGrad moments (Reddi, Kale & Kumar 2018, no bias correction) -- proxmin's _amsgrad_phi_psi as restated
 // in oracle/scarlet_oracle.py:amsgrad_phi_psi.  Returns psi; m, v, vhat updated in place.
 __device__ __forceinline__ double amsgrad(double g, double &m, double &v, double &vhat, int it, const FitScalars &fs) {
@@ -434,7 +439,7 @@ __device__ void sed_update(const UpdateArgs<T> &a, const DevSource &d, int k, co
     if (d.sed_chain >= 0) {
         const DevChain &ch = a.chains[d.sed_chain];
         for (int c = 0; c < C; ++c) z[c] = xn[c];
-        for (int sub = 0; sub < a.fs.prox_max_iter; ++sub) {
+        for (int sub = 0; sub < prox_max_iter_of(a, d.scene); ++sub) {
             for (int c = 0; c < C; ++c) {
                 const double gamma = alpha[c] / psimax;
                 zn[c] = z[c] - gamma / alpha[c] * psi[c] * (z[c] - xn[c]);
@@ -493,7 +498,7 @@ template <typename T> __global__ void __launch_bounds__(128) k_point_morph(const
 
 template <typename T> __device__ void update_point(const UpdateArgs<T> &a, const DevSource &d, int k, double *red) {
     __shared__ double fy[16], fx[16], dfy[16], dfx[16], gsed[SB_MAXC];
-    const int b = d.By, tid = threadIdx.x, nt = blockDim.x, C = a.C, s = d.scene, it = *a.it_ptr;
+    const int b = d.By, tid = threadIdx.x, nt = blockDim.x, C = a.C, s = d.scene, it = a.it_ptr[d.scene];
     double *cen = a.center + 2 * d.point_idx;
     const double cy = cen[0], cx = cen[1];
     const double offy = cy - (d.oy + b / 2.0), offx = cx - (d.ox + b / 2.0);
@@ -652,7 +657,7 @@ template <typename T> __global__ void __launch_bounds__(128) k_shift_apply(const
 // through global memory, each element always by the same thread.  Shifting sources additionally use three scratch
 // images in shared memory for the Toeplitz products.
 template <typename T> __device__ void update_extended(const UpdateArgs<T> &a, const DevSource &d, int k, unsigned char *smem) {
-    const int tid = threadIdx.x, nt = blockDim.x, C = a.C, s = d.scene, it = *a.it_ptr;
+    const int tid = threadIdx.x, nt = blockDim.x, C = a.C, s = d.scene, it = a.it_ptr[d.scene];
     const int n = d.By * d.Bx, Bx = d.Bx;
     T *zn = reinterpret_cast<T *>(smem);
     double *red = reinterpret_cast<double *>(zn + a.npix_max);
@@ -770,7 +775,7 @@ template <typename T> __device__ void update_extended(const UpdateArgs<T> &a, co
             const DevChain &ch = a.chains[d.chain];
             const double gamma = alpha / psimax;
             const double fac = gamma / alpha;
-            for (int sub = 0; sub < a.fs.prox_max_iter; ++sub) {
+            for (int sub = 0; sub < prox_max_iter_of(a, d.scene); ++sub) {
                 if (sub > 0) {
                     for (int p = tid; p < n; p += nt) {
                         const double zz = (double)mp[p];
@@ -1143,7 +1148,7 @@ template <typename T, int GT, int MAXT = 1024> __global__ void __launch_bounds__
     const int s = d.scene;
     if (a.done[s]) return;
 
-    const int it = *a.it_ptr, C = a.C, n = d.By * d.Bx, Bx = d.Bx;
+    const int it = a.it_ptr[s], C = a.C, n = d.By * d.Bx, Bx = d.Bx;
     const unsigned magic = 0xffffffffu / (unsigned)Bx + 1u; // p / Bx == umulhi(p, magic) for p, Bx < 65536
     T *zn = s_img + (size_t)g * a.fast_npix;
     GroupRed red;
@@ -1260,7 +1265,7 @@ template <typename T, int GT, int MAXT = 1024> __global__ void __launch_bounds__
             if (fc.ok) {
                 const T hs = (T)(0.5 * fc.sym), om = (T)(1.0 - fc.sym), zero = (T)fc.zero, tiny = (T)fc.tiny;
                 const int half = (n - 1) >> 1; // centre pixel index (odd x odd box): its 180-degree partner is itself
-                for (int sub = 0; sub < a.fs.prox_max_iter; ++sub) {
+                for (int sub = 0; sub < prox_max_iter_of(a, d.scene); ++sub) {
                     group_sweep<T, GT>(zn, tab, (T)fc.mono_grad, g);
                     // pass A: symmetry (pairs p, n-1-p), positivity, centre floor, running maximum
                     T mx = -INFINITY;
@@ -1297,7 +1302,7 @@ template <typename T, int GT, int MAXT = 1024> __global__ void __launch_bounds__
                     // pass B: normalise, convergence sums, store z, next proximal argument
                     double dd = 0.0, nn = 0.0;
                     bad = false;
-                    const bool last = sub + 1 == a.fs.prox_max_iter;
+                    const bool last = sub + 1 == prox_max_iter_of(a, d.scene);
                     // (loads of a batch are issued before its stores: the compiler cannot reorder them itself because
                     // mp, ps and xs may alias as far as it knows, and one L2 round trip per pixel would dominate)
                     for (int p0 = lt; p0 < n; p0 += 4 * GT) {
@@ -1331,7 +1336,7 @@ template <typename T, int GT, int MAXT = 1024> __global__ void __launch_bounds__
                     if (dd <= e2 * nn) break;
                 }
             } else {
-                for (int sub = 0; sub < a.fs.prox_max_iter; ++sub) {
+                for (int sub = 0; sub < prox_max_iter_of(a, d.scene); ++sub) {
                     if (sub > 0) {
                         for (int p = lt; p < n; p += GT) {
                             const double zz = (double)mp[p];
@@ -1365,6 +1370,9 @@ template <typename T, int GT, int MAXT = 1024> __global__ void __launch_bounds__
 // ======================================================================================================
 // K7  per-scene loss reduction + stop rule + iteration counter      reference: blend.py:264-274, 276-302
 // ======================================================================================================
+// per-scene run state (device array, read by the host between slices of a fit)
+enum { SB_RUN = 0, SB_CONVERGED = 1, SB_PAUSED = 2, SB_EXHAUSTED = 4, SB_FAILED = 8, SB_CONV_PENDING = 16 }; // distinct bits
+
 struct LossArgs {
     int n_obs;
     const double *partials[SB_MAX_OBS]; // per observation: [S][n_part[o]]
@@ -1373,17 +1381,21 @@ struct LossArgs {
     double *loss;             // [S][cap]
     int cap;
     int *done, *n_iter, *n_active_next;
-    const int *it_ptr;
+    int *it_arr;              // [S] iteration counter of the running adaprox call; advanced here (last kernel of an iteration)
+    const int *limit;         // [S] optional: stop when the loss history reaches this length (max_iter of the scene's fit)
+    int *state;               // [S] SB_RUN ... (| SB_CONV_PENDING)
     const int *status;
+    int advance;              // 0: evaluate only (counters untouched)
     FitScalars fs;
 };
 
-// one block per scene: fixed-order reduction of the chi^2 partials -> loss[s][it], then the stop rule
+// one block per scene: fixed-order reduction of the chi^2 partials -> loss[s][len], then Blend._callback's decisions
+// (blend.py:276-302): non-finite parameters, inspection of the sources every ``pause_every`` iterations (the host runs
+// src.update() on a paused scene and either restarts or resumes it), the stop rule, the iteration budget.
 __global__ void __launch_bounds__(128) k_loss_stop(const LossArgs a) {
     __shared__ double red[40];
     const int s = blockIdx.x;
     if (a.done[s]) return;
-    const int it = *a.it_ptr;
     double acc = 0.0;
     for (int o = 0; o < a.n_obs; ++o) {
         const double *p = a.partials[o] + (size_t)s * a.n_part[o];
@@ -1391,23 +1403,38 @@ __global__ void __launch_bounds__(128) k_loss_stop(const LossArgs a) {
     }
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) {
+        const int it = a.it_arr[s], idx = a.n_iter[s]; // idx: length of this fit's loss history so far
         const double l1 = a.loss_const[s] + 0.5 * acc;
-        a.loss[(size_t)s * a.cap + it] = l1;
-        a.n_iter[s] = it + 1;
-        bool stop = a.status[s] != 0;
-        if (!a.fs.fixed_iterations && it > 0 && it > a.fs.min_iter) {
-            const double l0 = a.loss[(size_t)s * a.cap + it - 1];
-            if (fabs(l1 - l0) < a.fs.e_rel * fabs(l1)) stop = true;
+        a.loss[(size_t)s * a.cap + idx] = l1;
+        if (!a.advance) {
+            a.n_iter[s] = idx + 1;
+            return;
         }
-        if (stop)
+        a.n_iter[s] = idx + 1;
+        a.it_arr[s] = it + 1;
+        bool conv = false;
+        if (!a.fs.fixed_iterations && it > 0 && it > a.fs.min_iter && idx > 0) {
+            const double l0 = a.loss[(size_t)s * a.cap + idx - 1];
+            conv = fabs(l1 - l0) < a.fs.e_rel * fabs(l1);
+        }
+        int st = SB_RUN;
+        if (a.status[s] != 0)
+            st = SB_FAILED;
+        else if (a.fs.pause_every > 0 && it > 0 && it % a.fs.pause_every == 0)
+            st = SB_PAUSED | (conv ? SB_CONV_PENDING : 0);
+        else if (conv)
+            st = SB_CONVERGED;
+        else if (a.limit && idx + 1 >= a.limit[s])
+            st = SB_EXHAUSTED;
+        a.state[s] = st;
+        if (st != SB_RUN)
             a.done[s] = 1;
         else
             atomicAdd(a.n_active_next, 1);
     }
 }
 
-__global__ void k_tick(int *it_ptr, int *n_active, int *n_active_next) {
-    *it_ptr += 1;
+__global__ void k_tick(int *n_active, int *n_active_next) {
     *n_active = *n_active_next;
     *n_active_next = 0;
 }

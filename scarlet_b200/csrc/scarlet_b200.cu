@@ -223,6 +223,11 @@ struct sb_plan {
     virtual int device_params(void **sed, int64_t *n_sed, void **morph, int64_t *n_morph, int *elem_bytes) = 0;
     virtual int spectral_mode() const = 0;
     virtual int prox_histogram(int enable, int64_t *out16) = 0;
+    virtual int scene_control(const int32_t *it_local, const int32_t *loss_len, const int32_t *limit, const int32_t *active, const int32_t *prox_iter) = 0;
+    virtual int scene_status(int32_t *it_local, int32_t *loss_len, int32_t *state) = 0;
+    virtual int run(const sb_fit_opts *o, int max_launches, int32_t *launched) = 0;
+    virtual int download_loss(double *loss, int n_cols) = 0;
+    virtual int upload_loss(const double *loss, int n_cols) = 0;
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
@@ -239,7 +244,8 @@ template <typename T> struct PlanT : sb_plan {
     std::vector<DevSource> h_src;
     std::vector<int> h_start;
     DevBuf<DevSource> d_src;
-    DevBuf<int> d_start, d_done, d_niter, d_status, d_it, d_nactive, d_nactive_next;
+    DevBuf<int> d_start, d_done, d_niter, d_status, d_it, d_nactive, d_nactive_next, d_state, d_limit, d_prox_iter;
+    bool use_limit = false, use_prox_iter = false;
     DevBuf<double> d_sed, d_sed_m, d_sed_v, d_sed_vhat, d_center, d_cen_m, d_cen_v, d_cen_vhat, d_loss, d_loss_const;
     DevBuf<double> d_gsed, d_gcenter, d_gmorph, d_stage;
     DevBuf<T> d_morph, d_morph_m, d_morph_v, d_morph_vhat, d_pmorph, d_model, d_rendered, d_scratch_x, d_scratch_ps;
@@ -462,7 +468,10 @@ template <typename T> struct PlanT : sb_plan {
         SB_TRY(d_done.alloc(S));
         SB_TRY(d_niter.alloc(S));
         SB_TRY(d_status.alloc(S));
-        SB_TRY(d_it.alloc(1));
+        SB_TRY(d_it.alloc(S));
+        SB_TRY(d_state.alloc(S));
+        SB_TRY(d_limit.alloc(S));
+        SB_TRY(d_prox_iter.alloc(S));
         SB_TRY(d_nactive.alloc(1));
         SB_TRY(d_nactive_next.alloc(1));
         SB_TRY(d_loss_const.alloc(S));
@@ -774,11 +783,18 @@ template <typename T> struct PlanT : sb_plan {
         return SB_OK;
     }
 
+    // the optional per-scene tables (sb_plan_scene_control) travel in the kernel arguments: plain fits run without them
+    void drop_scene_tables() {
+        if (use_limit || use_prox_iter) have_graph = false;
+        use_limit = use_prox_iter = false;
+    }
+
     int reset_counters() {
         SB_TRY(d_done.zero(stream));
         SB_TRY(d_niter.zero(stream));
         SB_TRY(d_status.zero(stream));
         SB_TRY(d_it.zero(stream));
+        SB_TRY(d_state.zero(stream));
         SB_TRY(d_nactive_next.zero(stream));
         SB_CUDA(cudaMemcpyAsync(d_nactive.p, &S, sizeof(int), cudaMemcpyHostToDevice, stream));
         return SB_OK;
@@ -1005,6 +1021,7 @@ template <typename T> struct PlanT : sb_plan {
         memset(&f, 0, sizeof f);
         f.prox_max_iter = o->prox_max_iter, f.min_iter = o->min_iter, f.fixed_iterations = o->fixed_iterations;
         f.overwrite_vhat_at_it0 = o->overwrite_vhat_at_it0;
+        f.pause_every = o->pause_every;
         f.e_rel = o->e_rel, f.b1 = o->b1, f.b2 = o->b2, f.eps = o->eps;
         return f;
     }
@@ -1020,6 +1037,7 @@ template <typename T> struct PlanT : sb_plan {
         a.center = d_center.p, a.cen_m = d_cen_m.p, a.cen_v = d_cen_v.p, a.cen_vhat = d_cen_vhat.p;
         a.pmorph = d_pmorph.p, a.chains = d_chains.p, a.monos = d_monos.p;
         a.it_ptr = d_it.p, a.done = d_done.p, a.status = d_status.p;
+        a.prox_iter = use_prox_iter ? d_prox_iter.p : nullptr;
         a.fs = cur_fs;
         a.psf_b = desc.psf_boxsize;
         memcpy(a.psf_sigma, desc.psf_sigma, sizeof a.psf_sigma);
@@ -1227,13 +1245,13 @@ template <typename T> struct PlanT : sb_plan {
             la.n_obs = (int)obs.size();
             for (size_t o = 0; o < obs.size(); ++o) la.partials[o] = obs[o]->partials.p, la.n_part[o] = obs[o]->n_part;
             la.loss_const = d_loss_const.p, la.loss = d_loss.p, la.cap = loss_cap, la.done = d_done.p, la.n_iter = d_niter.p;
-            la.n_active_next = d_nactive_next.p, la.it_ptr = d_it.p, la.status = d_status.p, la.fs = cur_fs;
-            if (mode == 1) la.fs.fixed_iterations = 1;
+            la.n_active_next = d_nactive_next.p, la.it_arr = d_it.p, la.status = d_status.p, la.fs = cur_fs;
+            la.state = d_state.p, la.limit = use_limit ? d_limit.p : nullptr, la.advance = mode == 0;
             k_loss_stop<<<S, 128, 0, stream>>>(la);
             SB_CUDA(cudaGetLastError());
             ++nk;
             if (mode == 0) {
-                k_tick<<<1, 1, 0, stream>>>(d_it.p, d_nactive.p, d_nactive_next.p);
+                k_tick<<<1, 1, 0, stream>>>(d_nactive.p, d_nactive_next.p);
                 SB_CUDA(cudaGetLastError());
                 ++nk;
             }
@@ -1278,6 +1296,7 @@ template <typename T> struct PlanT : sb_plan {
         SB_TRY(check_opts(o));
         SB_CUDA(cudaSetDevice(device));
         SB_TRY(ensure_loss_cap(std::max(n, 1)));
+        drop_scene_tables();
         SB_TRY(ensure_graph(o));
         SB_TRY(reset_counters());
         for (int i = 0; i < n; ++i) SB_CUDA(cudaGraphLaunch(graph, stream));
@@ -1291,6 +1310,7 @@ template <typename T> struct PlanT : sb_plan {
         SB_TRY(check_opts(o));
         SB_CUDA(cudaSetDevice(device));
         SB_TRY(ensure_loss_cap(std::max(o->max_iter, 1)));
+        if (!o->resume) drop_scene_tables();
         SB_TRY(ensure_graph(o));
         if (!o->resume) {
             SB_TRY(reset_counters());
@@ -1317,12 +1337,89 @@ template <typename T> struct PlanT : sb_plan {
         return SB_OK;
     }
 
+    // ---- per-scene control of a running fit (batches whose scenes restart independently: dynamic boxes) ------------------
+    // Every scene carries its own adaprox iteration counter, loss-history length, iteration budget and run flag; `run`
+    // launches iterations until no scene is running any more (converged, paused for inspection, budget spent, failed).
+    int scene_control(const int32_t *it_local, const int32_t *loss_len, const int32_t *limit, const int32_t *active, const int32_t *prox_iter) override {
+        SB_CUDA(cudaSetDevice(device));
+        if (it_local) SB_CUDA(cudaMemcpyAsync(d_it.p, it_local, S * sizeof(int), cudaMemcpyHostToDevice, stream));
+        if (loss_len) SB_CUDA(cudaMemcpyAsync(d_niter.p, loss_len, S * sizeof(int), cudaMemcpyHostToDevice, stream));
+        if (limit) {
+            SB_CUDA(cudaMemcpyAsync(d_limit.p, limit, S * sizeof(int), cudaMemcpyHostToDevice, stream));
+            if (!use_limit) have_graph = false;
+            use_limit = true;
+        }
+        if (prox_iter) {
+            SB_CUDA(cudaMemcpyAsync(d_prox_iter.p, prox_iter, S * sizeof(int), cudaMemcpyHostToDevice, stream));
+            if (!use_prox_iter) have_graph = false;
+            use_prox_iter = true;
+        }
+        if (active) {
+            std::vector<int> done(S), state(S);
+            int n = 0;
+            for (int s = 0; s < S; ++s) done[s] = active[s] ? 0 : 1, n += active[s] ? 1 : 0;
+            SB_CUDA(cudaMemcpyAsync(d_done.p, done.data(), S * sizeof(int), cudaMemcpyHostToDevice, stream));
+            SB_CUDA(cudaMemcpyAsync(d_nactive.p, &n, sizeof(int), cudaMemcpyHostToDevice, stream));
+            SB_TRY(d_nactive_next.zero(stream));
+            SB_TRY(d_status.zero(stream));
+            SB_CUDA(cudaStreamSynchronize(stream)); // host vectors die here
+        }
+        SB_CUDA(cudaStreamSynchronize(stream));
+        return SB_OK;
+    }
+    int scene_status(int32_t *it_local, int32_t *loss_len, int32_t *state) override {
+        SB_CUDA(cudaSetDevice(device));
+        if (it_local) SB_CUDA(cudaMemcpyAsync(it_local, d_it.p, S * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        if (loss_len) SB_CUDA(cudaMemcpyAsync(loss_len, d_niter.p, S * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        if (state) SB_CUDA(cudaMemcpyAsync(state, d_state.p, S * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        SB_CUDA(cudaStreamSynchronize(stream));
+        return SB_OK;
+    }
+    int run(const sb_fit_opts *o, int max_launches, int32_t *launched) override {
+        SB_TRY(check_opts(o));
+        SB_CUDA(cudaSetDevice(device));
+        SB_TRY(ensure_loss_cap(std::max(o->max_iter, 1)));
+        SB_TRY(ensure_graph(o));
+        int n = 0;
+        while (n < max_launches) {
+            SB_CUDA(cudaGraphLaunch(graph, stream));
+            ++n;
+            if (n % o->check_every == 0 || n == max_launches) {
+                SB_CUDA(cudaMemcpyAsync(h_nactive, d_nactive.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                SB_CUDA(cudaStreamSynchronize(stream));
+                if (*h_nactive == 0) break;
+            }
+        }
+        launches += (int64_t)n * kernels_per_iter;
+        if (launched) *launched = n;
+        return SB_OK;
+    }
+    int download_loss(double *loss, int n_cols) override {
+        SB_CUDA(cudaSetDevice(device));
+        if (!loss || n_cols <= 0 || n_cols > loss_cap) return set_err(SB_ERR_ARG, "download_loss: %d columns requested, capacity %d", n_cols, loss_cap);
+        SB_CUDA(cudaMemcpy2DAsync(loss, (size_t)n_cols * sizeof(double), d_loss.p, (size_t)loss_cap * sizeof(double),
+                                  (size_t)n_cols * sizeof(double), S, cudaMemcpyDeviceToHost, stream));
+        SB_CUDA(cudaStreamSynchronize(stream));
+        return SB_OK;
+    }
+
+    int upload_loss(const double *loss, int n_cols) override {
+        SB_CUDA(cudaSetDevice(device));
+        if (!loss || n_cols <= 0) return set_err(SB_ERR_ARG, "upload_loss: bad argument");
+        SB_TRY(ensure_loss_cap(n_cols));
+        SB_CUDA(cudaMemcpy2DAsync(d_loss.p, (size_t)loss_cap * sizeof(double), loss, (size_t)n_cols * sizeof(double),
+                                  (size_t)n_cols * sizeof(double), S, cudaMemcpyHostToDevice, stream));
+        SB_CUDA(cudaStreamSynchronize(stream));
+        return SB_OK;
+    }
+
     int profile(const sb_fit_opts *o, int n, float *stage_ms) override {
         SB_TRY(check_opts(o));
         SB_CUDA(cudaSetDevice(device));
         SB_TRY(ensure_loss_cap(std::max(n, 1)));
         cur_fs = scalars(o);
         have_graph = false;
+        drop_scene_tables();
         SB_TRY(reset_counters());
         for (int i = 0; i < SB_N_STAGES; ++i) stage_ms[i] = 0.f;
         for (int i = 0; i < n; ++i) {
@@ -1354,6 +1451,7 @@ template <typename T> struct PlanT : sb_plan {
         SB_CUDA(cudaSetDevice(device));
         if (o < 0 || o >= (int)obs.size()) return set_err(SB_ERR_ARG, "observation index %d out of range", o);
         SB_TRY(ensure_loss_cap(1));
+        drop_scene_tables();
         SB_TRY(reset_counters());
         const size_t nmodel = (size_t)S * C * desc.Ny * desc.Nx, nrend = obs[o]->data.n;
         if (model) {
@@ -1522,6 +1620,14 @@ int sb_plan_device_params(sb_plan *plan, void **sed, int64_t *n_sed, void **morp
 }
 int sb_plan_spectral_mode(const sb_plan *plan) { return plan ? plan->spectral_mode() : -1; }
 int sb_plan_prox_histogram(sb_plan *plan, int enable, int64_t *out16) { PLAN_CALL(prox_histogram(enable, out16)) }
+int sb_plan_scene_control(sb_plan *plan, const int32_t *it_local, const int32_t *loss_len, const int32_t *limit, const int32_t *active,
+                          const int32_t *prox_iter) {
+    PLAN_CALL(scene_control(it_local, loss_len, limit, active, prox_iter))
+}
+int sb_plan_scene_status(sb_plan *plan, int32_t *it_local, int32_t *loss_len, int32_t *state) { PLAN_CALL(scene_status(it_local, loss_len, state)) }
+int sb_plan_run(sb_plan *plan, const sb_fit_opts *opts, int max_launches, int32_t *launched) { PLAN_CALL(run(opts, max_launches, launched)) }
+int sb_plan_download_loss(sb_plan *plan, double *loss, int n_cols) { PLAN_CALL(download_loss(loss, n_cols)) }
+int sb_plan_upload_loss(sb_plan *plan, const double *loss, int n_cols) { PLAN_CALL(upload_loss(loss, n_cols)) }
 int sb_fft_supported_length(int need) { return spec_supported_length(need); }
 int sb_plan_sync(sb_plan *plan) {
     if (!plan) return set_err(SB_ERR_ARG, "null plan");

@@ -176,7 +176,7 @@ template <typename T, int NPT, int MAXT> __global__ void __launch_bounds__(MAXT,
 
     WarpTable<T> tab;
     tab.nbr = smem_u32(s_nbr + lane), tab.w = smem_u32(s_w + lane), tab.pix = smem_u32(s_pix + lane), tab.n_trips = s_ntrips;
-    const int it = *a.it_ptr, C = a.C, n = d.By * d.Bx, Bx = d.Bx;
+    const int it = a.it_ptr[s], C = a.C, n = d.By * d.Bx, Bx = d.Bx;
     const unsigned magic = 0xffffffffu / (unsigned)Bx + 1u; // p / Bx == umulhi(p, magic) for p, Bx < 65536
     T *zn = s_img + (size_t)wid * wa.npix;
     const unsigned zb = smem_u32(zn);
@@ -271,7 +271,7 @@ template <typename T, int NPT, int MAXT> __global__ void __launch_bounds__(MAXT,
         }
         int nsub = 0;
 #pragma unroll 1
-        for (int sub = 0; sub < a.fs.prox_max_iter; ++sub) {
+        for (int sub = 0; sub < prox_max_iter_of(a, s); ++sub) {
             warp_sweep<T>(zb, tab, keep);
             // ---- pass A: [symmetry] + positivity + centre floor, written back only when pixels are mixed; running maximum
             T mx = -INFINITY;
@@ -318,7 +318,7 @@ template <typename T, int NPT, int MAXT> __global__ void __launch_bounds__(MAXT,
             const T den = warp_max_all_t<T>(mx);
             const T inv = T(1) / den;
             // ---- pass B: normalise, convergence sums against the register-resident previous iterate, next argument
-            const bool last = sub + 1 == a.fs.prox_max_iter;
+            const bool last = sub + 1 == prox_max_iter_of(a, s);
             T dd = T(0), nn = T(0);
             constexpr int LB = 4; // x / psi of a batch are requested before the batch's arithmetic
             static_assert(NPT % LB == 0, "NPT must be a multiple of the load batch");

@@ -954,3 +954,59 @@ def test_full_length_float64_twin(config, n_iter, scene_id):
     """The float64 twin against the float64 oracle over the same trajectories: algorithmic identity of the CUDA path."""
     from scarlet_b200 import synthetic
     _compare_fit(synthetic.make_scene(config, scene_id), n_iter, 64, 1e-8, 1e-9, tol_model=1e-9)
+
+
+def test_generic_kernel_takes_boxes_beyond_grouped_limit():
+    """a 129 x 129 box is beyond the 16-bit byte offsets of the grouped / warp kernels (and beyond the
+    register-resident iterate), so the generic kernel (one shared-memory image, x / psi / z streamed) takes it."""
+    from scarlet_b200 import synthetic
+    cfg = dict(synthetic.CONFIGS["cfg2"], B=129, N=160, n_ext=2, config_id=12)
+    scene = synthetic.make_scene(cfg, 0)
+    _compare_fit(scene, 5, 64, 1e-9, 1e-9)
+    _compare_fit(scene, 5, 32, 1e-5, 1e-5)
+
+
+def _many_resizing_scenes(n):
+    """variants of the resizing scene: amplitudes, widths and noise differ, so the scenes resize at different iterations"""
+    out = []
+    for i in range(n):
+        rng = np.random.default_rng(100 + i)
+        scene = _resizing_scene()
+        scene["images"] = (scene["images"] * rng.uniform(0.6, 1.4) + rng.standard_normal(scene["images"].shape) * 0.5).astype(np.float32)
+        for s in scene["sources"]:
+            s["sed"] = (s["sed"] * rng.uniform(0.7, 1.3)).astype(np.float32)
+        if i % 3 == 1:  # a scene whose second box starts large enough: fewer restarts
+            y, x = np.mgrid[:41, :41] - 20
+            m = np.exp(-np.hypot(y, x) / 1.5) * (np.hypot(y, x) < 6)
+            s = scene["sources"][1]
+            s["morph"], s["origin"] = m / m.max(), (s["center"][0] - 20, s["center"][1] - 20)
+        out.append(scene)
+    return out
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+def test_dynamic_batch_equals_individual_fits(precision):
+    """a batch of 32 scenes with dynamic boxes (the reference default) equals 32 single ``Blend.fit`` runs bit
+    for bit -- per-scene iteration counters, pause at each scene's own inspection points, restart with warm state."""
+    from scarlet_b200 import BlendBatch, synthetic
+    scenes_ = _many_resizing_scenes(32)
+    singles = [synthetic.make_blend(sc, precision=precision) for sc in scenes_]
+    res_single = [b.fit(max_iter=45, e_rel=1e-4) for b in singles]
+    batch_blends = [synthetic.make_blend(sc, precision=precision) for sc in scenes_]
+    batch = BlendBatch(batch_blends, precision=precision)
+    assert batch.dynamic
+    res_batch = batch.fit(max_iter=45, e_rel=1e-4)
+    assert batch.replans >= 2
+    sizes = set()
+    for k, (a, b) in enumerate(zip(singles, batch_blends)):
+        assert res_single[k][0] == res_batch[k][0], k
+        assert a.loss == b.loss, k
+        for pa, pb in zip(a.parameters, b.parameters):
+            assert pa.shape == pb.shape and np.array_equal(np.asarray(pa), np.asarray(pb)), (k, pa.name)
+            if pa.m is not None and pb.m is not None:
+                assert np.array_equal(np.asarray(pa.m), np.asarray(pb.m)) and np.array_equal(np.asarray(pa.v), np.asarray(pb.v))
+        assert [s.bbox for s in a.sources] == [s.bbox for s in b.sources]
+        sizes.add(tuple(s.parameters[1].shape[0] for s in b.sources))
+        sizes.add(len(b.loss))
+    assert len(sizes) > 3  # the scenes really went different ways
+    batch.close()
