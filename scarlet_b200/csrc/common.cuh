@@ -77,6 +77,11 @@ struct DevMono {
     const unsigned *code;     // [n_tasks] 4 bits per slot: offset index, 15 = empty
     const void *w;            // T [nb][n_tasks]
     const int *level_start;   // [n_levels+1]
+    // the same operator laid out by TRIPS for the warp-per-source kernel (update_warp.cuh), nb == 4 only: every level cut
+    // into trips of exactly 32 slots, dummy tasks in the unused slots, one dummy trip behind the last; one byte image
+    // [W4<T> x w_cap | uint2 x w_cap | u16 x w_cap] that the kernel pulls into shared memory with bulk async copies
+    const void *wtab;
+    int w_trips, w_cap;       // trips (even), entries = 32 (w_trips + 1)
 };
 
 struct DevChain {

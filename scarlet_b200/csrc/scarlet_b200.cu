@@ -136,6 +136,7 @@ template <typename T> struct MonoDevice {
     DevBuf<int> pix, level_start;
     DevBuf<uint2> nbr;
     DevBuf<W4<T>> w;
+    DevBuf<unsigned char> wtab;
     DevMono dev;
     int upload(const HostMono &h, cudaStream_t st) {
         const int n = h.n_tasks, groups = h.nb / 4;
@@ -168,6 +169,40 @@ template <typename T> struct MonoDevice {
         dev.n_pix = h.n_pix, dev.n_tasks = n, dev.n_levels = h.n_levels, dev.nb = h.nb;
         for (int i = 0; i < 8; ++i) dev.off[i] = h.off[i];
         dev.pix = pix.p, dev.code = reinterpret_cast<const unsigned *>(nbr.p), dev.w = w.p, dev.level_start = level_start.p;
+        dev.wtab = nullptr, dev.w_trips = 0, dev.w_cap = 0;
+        if (h.nb == 4 && (size_t)(h.n_pix + 1) * sizeof(T) <= 65535) { // table by trips (see DevMono::wtab)
+            int trips = 0;
+            for (int L = 0; L < h.n_levels; ++L) trips += (h.level_start[L + 1] - h.level_start[L] + 31) / 32;
+            trips += trips & 1;
+            const int cap = 32 * (trips + 1);
+            const unsigned spare = (unsigned)h.n_pix * (unsigned)sizeof(T); // byte offset of the always-zero cell behind the image
+            std::vector<unsigned char> img((size_t)cap * (sizeof(W4<T>) + sizeof(uint2) + sizeof(unsigned short)));
+            W4<T> *tw = reinterpret_cast<W4<T> *>(img.data());
+            uint2 *tn = reinterpret_cast<uint2 *>(tw + cap);
+            unsigned short *tp = reinterpret_cast<unsigned short *>(tn + cap);
+            for (int q = 0; q < cap; ++q) {
+                tw[q] = W4<T>{T(0), T(0), T(0), T(0)};
+                tn[q] = make_uint2(spare | (spare << 16), spare | (spare << 16));
+                tp[q] = (unsigned short)spare;
+            }
+            int t = 0;
+            for (int L = 0; L < h.n_levels; ++L)
+                for (int b = h.level_start[L]; b < h.level_start[L + 1]; b += 32, ++t)
+                    for (int l = 0; l < 32 && b + l < h.level_start[L + 1]; ++l) {
+                        const int j = b + l, q = 32 * t + l;
+                        unsigned o[4];
+                        for (int i = 0; i < 4; ++i) {
+                            const unsigned v = h.nbr[(size_t)i * n + j];
+                            o[i] = v == 0xffffu ? spare : v * (unsigned)sizeof(T);
+                        }
+                        tn[q] = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+                        tw[q] = W4<T>{(T)h.w[j], (T)h.w[(size_t)n + j], (T)h.w[(size_t)2 * n + j], (T)h.w[(size_t)3 * n + j]};
+                        tp[q] = (unsigned short)((unsigned)h.pix[j] * (unsigned)sizeof(T));
+                    }
+            SB_TRY(wtab.alloc(img.size()));
+            SB_CUDA(cudaMemcpy(wtab.p, img.data(), img.size(), cudaMemcpyHostToDevice));
+            dev.wtab = wtab.p, dev.w_trips = trips, dev.w_cap = cap;
+        }
         return SB_OK;
     }
 };
@@ -256,6 +291,7 @@ template <typename T> struct PlanT : sb_plan {
     size_t fast_smem = 0;
     // warp-per-source kernel (update_warp.cuh)
     static constexpr int WARP_NPT = 56, WARP_MAXT = sizeof(T) == 4 ? 448 : 256;
+    static constexpr size_t WARP_RING = XpRing<T>::BYTES;
     DevBuf<int> d_warp_groups;
     DevBuf<XP<T>> d_xp;
     int n_warp_cta = 0, warp_G = 0, warp_npix = 0, warp_cap = 0;
@@ -642,10 +678,10 @@ template <typename T> struct PlanT : sb_plan {
         if (i >= ch.n_ops || ch.ops[i].code != SB_OP_NORMALIZE || ch.ops[i].iarg != 1) return false;
         return i + 1 == ch.n_ops;
     }
-    // cap = 32 (trips + 2) table entries (update_warp.cuh: table by trips)
+    // cap = table entries (DevMono::w_cap); per warp: image, x/psi ring (WARP_RING bytes), spectrum-gradient slots, mbarriers
     static size_t warp_smem_bytes(int G, int npix, int cap) {
-        return (size_t)cap * (sizeof(W4<T>) + sizeof(uint2) + sizeof(unsigned short)) + 1024 * sizeof(int) +
-               (size_t)G * SB_FAST_MAXC * sizeof(double) + (size_t)G * npix * sizeof(T) + 16;
+        return (size_t)cap * (sizeof(W4<T>) + sizeof(uint2) + sizeof(unsigned short)) + 64 +
+               (size_t)G * (SB_FAST_MAXC * sizeof(double) + (size_t)npix * sizeof(T) + WARP_RING + 64);
     }
 
     // Split the sources between the warp-per-source kernel (k_update_warp), the grouped kernel (k_update_fast) and the generic
@@ -680,11 +716,11 @@ template <typename T> struct PlanT : sb_plan {
                 if ((size_t)(d.By * d.Bx + 1) * sizeof(T) > 65535) fast = false;
             }
             const bool warp = fast && use_warp && chain_is_fused(d.chain, d.By, d.Bx) && d.By * d.Bx <= 32 * WARP_NPT && trips <= 1020 &&
-                              warp_smem_bytes(4, (d.By * d.Bx + 4) & ~3, 32 * (trips + 2)) <= 200 * 1024;
+                              warp_smem_bytes(4, (d.By * d.Bx + 4) & ~3, 32 * (trips + (trips & 1) + 1)) <= 200 * 1024;
             if (warp) {
                 warp_chain[d.chain].push_back(k);
                 wnpix = std::max(wnpix, (d.By * d.Bx + 4) & ~3);
-                wcap = std::max(wcap, 32 * (trips + 2));
+                wcap = std::max(wcap, 32 * (trips + (trips & 1) + 1));
             } else if (fast) {
                 by_chain[d.chain].push_back(k);
                 npix = std::max(npix, (d.By * d.Bx + 4) & ~3); // + the spare zero cell of group_sweep
@@ -729,7 +765,7 @@ template <typename T> struct PlanT : sb_plan {
             SB_TRY(d_warp_groups.alloc(std::max<size_t>(groups.size(), 1)));
             if (!groups.empty()) SB_CUDA(cudaMemcpy(d_warp_groups.p, groups.data(), groups.size() * sizeof(int), cudaMemcpyHostToDevice));
             if (n_warp_cta) {
-                SB_TRY(d_xp.alloc(std::max<long long>(n_morph, 1)));
+                SB_TRY(d_xp.alloc((size_t)n_warp_cta * warp_G * (32 * WARP_NPT))); // one padded, 16-byte aligned slot per warp
                 SB_TRY(raise_smem((const void *)k_update_warp<T, WARP_NPT, WARP_MAXT>, warp_smem));
             }
         }
@@ -1201,6 +1237,8 @@ template <typename T> struct PlanT : sb_plan {
                 if (n_warp_cta) {
                     WarpArgs<T> wa;
                     wa.groups = d_warp_groups.p, wa.G = warp_G, wa.npix = warp_npix, wa.table_cap = warp_cap, wa.xp = d_xp.p;
+                    wa.use_ring = getenv("SB_NO_XP_RING") == nullptr;
+                    wa.bulk_table = getenv("SB_NO_BULK_TABLE") == nullptr;
                     k_update_warp<T, WARP_NPT, WARP_MAXT><<<n_warp_cta, 32 * warp_G, warp_smem, stream>>>(ua, wa);
                     SB_CUDA(cudaGetLastError());
                     ++nk;

@@ -24,12 +24,51 @@ namespace sb {
 
 template <typename T> struct XP { T x, psi; }; // gradient-step result and AMSGrad metric of one pixel, interleaved
 
+// ---- bulk asynchronous copies (the copy engine behind TMA: cp.async.bulk, SASS UBLKCP) + mbarrier completion ----------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n"
+                 "}" ::"r"(bar),
+                 "r"(parity)
+                 : "memory");
+}
+// generic-proxy writes (st.global / st.shared) -> visible to the asynchronous proxy that executes the bulk copies
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// x / psi of one source travel from global memory (L2) to the proximal loop through a small shared-memory ring that a
+// bulk asynchronous copy fills XP_AHEAD chunks ahead of the consumer: no registers, no exposed L2 latency.
+template <typename T> struct XpRing {
+    static constexpr int TRIPS = 4;                             // trips (of 32 pixels) per chunk = the load batch of pass B
+    static constexpr int STAGES = 2;                            // power of two; 2 KB per warp keeps 14 warps per CTA at 41 x 41
+    static constexpr int CHUNK = TRIPS * 32 * (int)sizeof(XP<T>); // bytes per chunk
+    static constexpr int BYTES = STAGES * CHUNK;
+};
+
 template <typename T> struct WarpArgs {
     const int *groups;   // [n_cta][G] source index or -1
     int G;               // warps (= sources) per CTA
     int npix;            // shared-memory image length per warp (largest box + spare cell, padded)
     int table_cap;       // task capacity of the shared-memory table
-    XP<T> *xp;           // packed like the morphologies
+    XP<T> *xp;           // one padded slot of 32 NPT entries per warp
+    int bulk_table;      // 1: operator table by bulk asynchronous copy; 0: copied by all threads (diagnostic switch)
+    int use_ring;        // 1: x / psi reach pass B through the bulk-copy ring; 0: plain global loads (diagnostic switch)
 };
 
 __device__ __forceinline__ float warp_sum_all_t(float v) {
@@ -114,15 +153,17 @@ template <typename T, int NPT, int MAXT> __global__ void __launch_bounds__(MAXT,
     extern __shared__ __align__(16) unsigned char smem[];
     const int G = wa.G, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int *mine = wa.groups + (size_t)blockIdx.x * G;
-    // ---- shared memory: table by trips (W4 | uint2 | u16 pix, table_cap = 32 (n_trips + 1) entries each), trip list, G images
+    // ---- shared memory: table by trips (W4 | uint2 | u16 pix, table_cap entries each), barriers, then per warp: spectrum
+    // gradient, image, x/psi ring
+    typedef XpRing<T> Ring;
     const int cap = wa.table_cap;
     W4<T> *s_w = reinterpret_cast<W4<T> *>(smem);
     uint2 *s_nbr = reinterpret_cast<uint2 *>(s_w + cap);
-    unsigned *s_ts = reinterpret_cast<unsigned *>(s_nbr + cap); // [1024] first task | count << 16 of every trip
-    unsigned short *s_pix = reinterpret_cast<unsigned short *>(s_ts + 1024);
-    double *s_gsum = reinterpret_cast<double *>(s_pix + cap); // [G][SB_FAST_MAXC]
+    unsigned short *s_pix = reinterpret_cast<unsigned short *>(s_nbr + cap);
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_pix + cap); // [1 + G * STAGES] (cap is a multiple of 32)
+    double *s_gsum = reinterpret_cast<double *>(s_bar + 1 + (size_t)G * Ring::STAGES + ((1 + G * Ring::STAGES) & 1)); // 16-byte aligned
     T *s_img = reinterpret_cast<T *>(s_gsum + (size_t)G * SB_FAST_MAXC);
-    __shared__ int s_ntrips;
+    unsigned char *s_ring = reinterpret_cast<unsigned char *>(s_img + (size_t)G * wa.npix);
 
     int k0 = -1;
     for (int i = 0; i < G; ++i)
@@ -132,56 +173,55 @@ template <typename T, int NPT, int MAXT> __global__ void __launch_bounds__(MAXT,
         }
     const DevChain &ch = a.chains[a.src[k0].chain];
     const DevMono &mo = a.monos[ch.ops[0].iarg]; // host: the chain starts with the monotonic operator (fused pattern)
-    if (threadIdx.x == 0) { // levels -> trips of at most 32 tasks (host: n_trips + 2 <= 1024, 32 (n_trips + 2) <= table_cap)
-        int nt = 0;
-        for (int L = 0; L < mo.n_levels; ++L) {
-            const int b = mo.level_start[L], e = mo.level_start[L + 1];
-            for (int q = b; q < e; q += 32) s_ts[nt++] = (unsigned)q | ((unsigned)min(32, e - q) << 16);
-        }
-        if (nt & 1) s_ts[nt++] = 0u; // even trip count
-        s_ts[nt] = 0u;               // the dummy trip the last prefetch of the sweep reads
-        s_ntrips = nt;
+    // The CTA's operator table: three bulk asynchronous copies issued by one thread, complete on s_bar[0]; every warp waits for
+    // them only right before its first sweep, i.e. the copy runs under the gradient gather of phase 1.
+    const unsigned bar_tab = smem_u32(s_bar);
+    if (threadIdx.x == 0) {
+        mbar_init(bar_tab, 1);
+        for (int i = 0; i < G * Ring::STAGES; ++i) mbar_init(bar_tab + 8u * (unsigned)(1 + i), 1);
+        mbar_fence_init();
     }
-    __syncthreads();
-    {
-        const uint2 *gn = reinterpret_cast<const uint2 *>(mo.code);
-        const W4<T> *gw = reinterpret_cast<const W4<T> *>(mo.w);
-        const unsigned spare = (unsigned)mo.n_pix * (unsigned)sizeof(T); // the always-zero cell behind each image
-        const int n_slots = 32 * (s_ntrips + 1);
-        for (int q = threadIdx.x; q < n_slots; q += blockDim.x) {
-            const unsigned e = s_ts[q >> 5], l = (unsigned)q & 31u;
-            uint2 nb = make_uint2(spare | (spare << 16), spare | (spare << 16));
-            W4<T> w = W4<T>{T(0), T(0), T(0), T(0)};
-            unsigned pix = spare;
-            if (l < (e >> 16)) {
-                const int j = (int)((e & 0xffffu) + l);
-                const uint2 v = gn[j];
-                unsigned i0 = v.x & 0xffffu, i1 = v.x >> 16, i2 = v.y & 0xffffu, i3 = v.y >> 16;
-                i0 = i0 == 0xffffu ? spare : i0 * (unsigned)sizeof(T), i1 = i1 == 0xffffu ? spare : i1 * (unsigned)sizeof(T);
-                i2 = i2 == 0xffffu ? spare : i2 * (unsigned)sizeof(T), i3 = i3 == 0xffffu ? spare : i3 * (unsigned)sizeof(T);
-                nb = make_uint2(i0 | (i1 << 16), i2 | (i3 << 16)); // byte offsets (host: (n_pix + 1) sizeof(T) < 65536)
-                w = gw[j];
-                pix = (unsigned)mo.pix[j] * (unsigned)sizeof(T);
-            }
-            s_nbr[q] = nb, s_w[q] = w, s_pix[q] = (unsigned short)pix;
+    // every warp looks at its own source (one dependent chain per warp, all in parallel); barrier + OR
+    const int k_mine = wid < G ? mine[wid] : -1;
+    const bool live_mine = k_mine >= 0 && !a.done[a.src[k_mine].scene];
+    if (!__syncthreads_or(live_mine ? 1 : 0)) return; // every scene of this CTA has stopped: nothing is copied
+    if (wa.bulk_table) {
+        if (threadIdx.x == 0) {
+            const unsigned n = (unsigned)mo.w_cap;
+            const unsigned char *src = static_cast<const unsigned char *>(mo.wtab);
+            mbar_expect_tx(bar_tab, n * (unsigned)(sizeof(W4<T>) + sizeof(uint2) + sizeof(unsigned short)));
+            bulk_g2s(smem_u32(s_w), src, n * (unsigned)sizeof(W4<T>), bar_tab);
+            bulk_g2s(smem_u32(s_nbr), src + (size_t)n * sizeof(W4<T>), n * (unsigned)sizeof(uint2), bar_tab);
+            bulk_g2s(smem_u32(s_pix), src + (size_t)n * (sizeof(W4<T>) + sizeof(uint2)), n * (unsigned)sizeof(unsigned short), bar_tab);
         }
+    } else { // diagnostic: the same precomputed table copied by all threads
+        const unsigned n = (unsigned)mo.w_cap;
+        const uint4 *src = static_cast<const uint4 *>(mo.wtab);
+        uint4 *dw = reinterpret_cast<uint4 *>(s_w), *dn = reinterpret_cast<uint4 *>(s_nbr), *dp = reinterpret_cast<uint4 *>(s_pix);
+        const unsigned nw = n * (unsigned)sizeof(W4<T>) / 16u, nn2 = n * 8u / 16u, np = n * 2u / 16u;
+        for (unsigned i = threadIdx.x; i < nw; i += blockDim.x) dw[i] = src[i];
+        for (unsigned i = threadIdx.x; i < nn2; i += blockDim.x) dn[i] = src[nw + i];
+        for (unsigned i = threadIdx.x; i < np; i += blockDim.x) dp[i] = src[nw + nn2 + i];
+        __syncthreads();
+        if (threadIdx.x == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tab) : "memory");
     }
-    __syncthreads();
-    if (wid >= G) return;
-    const int k = mine[wid];
-    if (k < 0) return;
+    // (a warp without work still waits for the table copies: shared memory must not be released under them)
+    const int k = k_mine;
+    if (!live_mine) {
+        mbar_wait(bar_tab, 0u);
+        return;
+    }
     const DevSource &d = a.src[k];
     const int s = d.scene;
-    if (a.done[s]) return;
 
     WarpTable<T> tab;
-    tab.nbr = smem_u32(s_nbr + lane), tab.w = smem_u32(s_w + lane), tab.pix = smem_u32(s_pix + lane), tab.n_trips = s_ntrips;
+    tab.nbr = smem_u32(s_nbr + lane), tab.w = smem_u32(s_w + lane), tab.pix = smem_u32(s_pix + lane), tab.n_trips = mo.w_trips;
     const int it = a.it_ptr[s], C = a.C, n = d.By * d.Bx, Bx = d.Bx;
     const unsigned magic = 0xffffffffu / (unsigned)Bx + 1u; // p / Bx == umulhi(p, magic) for p, Bx < 65536
     T *zn = s_img + (size_t)wid * wa.npix;
     const unsigned zb = smem_u32(zn);
     T *mp = a.morph + d.morph_off, *mm = a.morph_m + d.morph_off, *mv = a.morph_v + d.morph_off, *mvh = a.morph_vhat + d.morph_off;
-    XP<T> *xp = wa.xp + d.morph_off;
+    XP<T> *xp = wa.xp + (size_t)(blockIdx.x * G + wid) * (32 * NPT); // this warp's padded, 16-byte aligned slot
     const bool upd = !d.morph_fixed;
     const T alpha = (T)d.morph_step;
 
@@ -269,9 +309,36 @@ template <typename T, int NPT, int MAXT> __global__ void __launch_bounds__(MAXT,
             const int p = lane + 32 * i;
             zold[i] = p < n ? zn[p] : T(0);
         }
+        // ---- x / psi stream: chunk g of the stream (pass g / nch, chunk g % nch of the source's slot) lands in ring stage
+        // g % STAGES; lane 0 keeps STAGES chunks in flight, speculating that the next pass happens (passes 0 .. prox_max - 2
+        // read x / psi; what was requested but never consumed is drained before the warp leaves)
+        const int prox_max = prox_max_iter_of(a, s);
+        const int nch = (((n + 31) >> 5) + Ring::TRIPS - 1) / Ring::TRIPS; // chunks per pass
+        const int g_end = nch * (prox_max - 1);                            // chunks of the whole stream
+        const unsigned ring = smem_u32(s_ring + (size_t)wid * Ring::BYTES), bar_ring = bar_tab + 8u * (unsigned)(1 + wid * Ring::STAGES);
+        // producer side (lane 0 issues; every lane keeps the same counters): stage, chunk within the pass, chunks left to request
+        int iss_stage = 0, iss_chunk = 0, iss_left = g_end > 0 ? g_end : 0;
+        // consumer side: stage, its phase parity, requested-but-unconsumed chunks
+        int use_stage = 0, n_flight = 0;
+        unsigned use_parity = 0u;
+        auto issue = [&]() {
+            if (lane == 0) {
+                mbar_expect_tx(bar_ring + 8u * (unsigned)iss_stage, (unsigned)Ring::CHUNK);
+                bulk_g2s(ring + (unsigned)(iss_stage * Ring::CHUNK), reinterpret_cast<const unsigned char *>(xp) + (size_t)iss_chunk * Ring::CHUNK,
+                         (unsigned)Ring::CHUNK, bar_ring + 8u * (unsigned)iss_stage);
+            }
+            iss_stage = (iss_stage + 1) & (Ring::STAGES - 1);
+            iss_chunk = iss_chunk + 1 == nch ? 0 : iss_chunk + 1;
+            --iss_left, ++n_flight;
+        };
+        fence_proxy_async(); // this lane's st.global of x / psi -> visible to the bulk copies
+        __syncwarp();
+        if (!wa.use_ring) iss_left = 0;
+        while (n_flight < Ring::STAGES && iss_left > 0) issue();
+        mbar_wait(bar_tab, 0u); // the operator table has landed
         int nsub = 0;
 #pragma unroll 1
-        for (int sub = 0; sub < prox_max_iter_of(a, s); ++sub) {
+        for (int sub = 0; sub < prox_max; ++sub) {
             warp_sweep<T>(zb, tab, keep);
             // ---- pass A: [symmetry] + positivity + centre floor, written back only when pixels are mixed; running maximum
             T mx = -INFINITY;
@@ -318,38 +385,55 @@ template <typename T, int NPT, int MAXT> __global__ void __launch_bounds__(MAXT,
             const T den = warp_max_all_t<T>(mx);
             const T inv = T(1) / den;
             // ---- pass B: normalise, convergence sums against the register-resident previous iterate, next argument
-            const bool last = sub + 1 == prox_max_iter_of(a, s);
+            const bool last = sub + 1 == prox_max;
             T dd = T(0), nn = T(0);
-            constexpr int LB = 4; // x / psi of a batch are requested before the batch's arithmetic
-            static_assert(NPT % LB == 0, "NPT must be a multiple of the load batch");
+            constexpr int LB = Ring::TRIPS; // one ring chunk = the x / psi of LB trips
+            static_assert(NPT % LB == 0, "NPT must be a multiple of the chunk length");
 #pragma unroll
             for (int i0 = 0; i0 < NPT; i0 += LB) {
-                XP<T> q[LB];
+                if (32 * i0 < n) { // warp-uniform: chunk i0 / LB exists for this box
+                    XP<T> q[LB];
 #pragma unroll
-                for (int u = 0; u < LB; ++u) {
-                    const int p = lane + 32 * (i0 + u);
-                    q[u] = XP<T>{T(0), T(0)};
-                    if (p < n && !last) q[u] = xp[p];
-                }
+                    for (int u = 0; u < LB; ++u) q[u] = XP<T>{T(0), T(0)};
+                    if (!last && !wa.use_ring) {
 #pragma unroll
-                for (int u = 0; u < LB; ++u) {
-                    const int i = i0 + u, p = lane + 32 * i;
-                    if (p < n) {
-                        T z = zn[p];
-                        if (!fc.has_sym) {
-                            z = z < zero ? zero : z;
-                            if (p == half) z = z < tiny ? tiny : z;
+                        for (int u = 0; u < LB; ++u) {
+                            const int p = lane + 32 * (i0 + u);
+                            if (p < n) q[u] = xp[p];
                         }
-                        T r;
-                        if constexpr (sizeof(T) == 4)
-                            r = z == den ? T(1) : z * inv;
-                        else
-                            r = z / den;
-                        const T zo = zold[i], df = r - zo;
-                        dd += df * df;
-                        nn += zo * zo;
-                        zold[i] = r;
-                        if (!last) zn[p] = r - (fac * q[u].psi) * (r - q[u].x);
+                    } else if (!last) {
+                        mbar_wait(bar_ring + 8u * (unsigned)use_stage, use_parity);
+                        const XP<T> *rq = reinterpret_cast<const XP<T> *>(s_ring + (size_t)wid * Ring::BYTES + (size_t)use_stage * Ring::CHUNK);
+#pragma unroll
+                        for (int u = 0; u < LB; ++u) q[u] = rq[32 * u + lane];
+                    }
+#pragma unroll
+                    for (int u = 0; u < LB; ++u) {
+                        const int i = i0 + u, p = lane + 32 * i;
+                        if (p < n) {
+                            T z = zn[p];
+                            if (!fc.has_sym) {
+                                z = z < zero ? zero : z;
+                                if (p == half) z = z < tiny ? tiny : z;
+                            }
+                            T r;
+                            if constexpr (sizeof(T) == 4)
+                                r = z == den ? T(1) : z * inv;
+                            else
+                                r = z / den;
+                            const T zo = zold[i], df = r - zo;
+                            dd += df * df;
+                            nn += zo * zo;
+                            zold[i] = r;
+                            if (!last) zn[p] = r - (fac * q[u].psi) * (r - q[u].x);
+                        }
+                    }
+                    if (!last && wa.use_ring) { // the chunk's values have been consumed by every lane: refill its stage
+                        __syncwarp();
+                        use_stage = (use_stage + 1) & (Ring::STAGES - 1);
+                        use_parity ^= use_stage == 0 ? 1u : 0u;
+                        --n_flight;
+                        if (iss_left > 0) issue();
                     }
                 }
             }
@@ -358,6 +442,11 @@ template <typename T, int NPT, int MAXT> __global__ void __launch_bounds__(MAXT,
             __syncwarp(); // zn is complete before the next sweep
             nsub = sub + 1;
             if (dd <= e2 * nn) break;
+        }
+        for (; n_flight > 0; --n_flight) { // requested for a pass that never came: let the copies land before the warp leaves
+            mbar_wait(bar_ring + 8u * (unsigned)use_stage, use_parity);
+            use_stage = (use_stage + 1) & (Ring::STAGES - 1);
+            use_parity ^= use_stage == 0 ? 1u : 0u;
         }
         if (a.prox_hist && lane == 0) atomicAdd(a.prox_hist + min(nsub, 15), 1ull);
         // ---- the projected image -> morphology; a non-finite pixel poisons the sum
@@ -373,6 +462,7 @@ template <typename T, int NPT, int MAXT> __global__ void __launch_bounds__(MAXT,
         chk = warp_sum_all_t(chk);
         if (lane == 0 && !isfinite((double)chk)) atomicExch(a.status + s, SB_ERR_NONFINITE);
     }
+    if (!upd) mbar_wait(bar_tab, 0u); // nobody leaves while the table copies are in flight
     if (lane == 0 && !d.sed_fixed) sed_update<T>(a, d, k, gsum, it);
 }
 
