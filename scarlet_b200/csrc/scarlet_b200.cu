@@ -231,6 +231,34 @@ static int raise_smem_limit(int device, const void *fn, size_t bytes) {
     return SB_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link dependency on libcuda)
+typedef CUresult (*tensor_map_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                         const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tensor_map_encode_fn tensor_map_encoder() {
+    static tensor_map_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<tensor_map_encode_fn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+// 2-D map over a row-major [rows][pitch] array of 8-byte elements (complex64), box = [box_rows][box_cols]
+static bool make_tensor_map_c64(CUtensorMap *map, void *base, uint64_t rows, uint64_t pitch, uint32_t box_rows, uint32_t box_cols) {
+    tensor_map_encode_fn enc = tensor_map_encoder();
+    if (!enc || box_rows > 256 || box_cols > 256 || (pitch * 8) % 16 != 0) return false;
+    const cuuint64_t dims[2] = {pitch, rows}, strides[1] = {pitch * 8};
+    const cuuint32_t box[2] = {box_cols, box_rows}, estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static inline int grid_for(long long n, int block = 256, int cap = 148 * 16) {
     long long g = (n + block - 1) / block;
     return (int)std::max<long long>(1, std::min<long long>(g, cap));
@@ -319,7 +347,9 @@ template <typename T> struct PlanT : sb_plan {
         DevBuf<cplx> X, tw_x, tw_y, Pbuf, T1buf, Ey, Ex; // Pbuf..Ex: resampling observations (kind 2) only
         DevBuf<T> G;
         int npair = 1, cb = 1, row_threads = 0;
-        size_t smem_render = 0, smem_row = 0, smem_col = 0;
+        size_t smem_render = 0, smem_row = 0, smem_col = 0, smem_col_tma = 0;
+        bool use_tma = false; // column pass through the Tensor Memory Accelerator (float, Ny <= 256)
+        CUtensorMap tmX, tmK;
         // kernel-image -> K^ (double precision, chunked over scenes)
         cufftHandle kplan = 0;
         bool have_kplan = false;
@@ -579,6 +609,15 @@ template <typename T> struct PlanT : sb_plan {
                 SB_TRY(raise_smem((const void *)ob.kx.residual, ob.smem_row));
                 SB_TRY(raise_smem((const void *)ob.kx.grad, ob.smem_row));
                 SB_TRY(raise_smem((const void *)ob.ky.column, ob.smem_col));
+                if (sizeof(T) == 4 && od.kind == 0 && ob.ky.column_tma && desc.Ny <= 256 && Fy % 2 == 0 && Fy / 2 <= 256 &&
+                    getenv("SB_NO_TMA") == nullptr) {
+                    const int NB = ob.ky.NBcol;
+                    ob.smem_col_tma = 128 + ((size_t)(desc.Ny + Fy) * NB + Fy) * sizeof(cplx) + 16;
+                    ob.use_tma = ob.smem_col_tma <= 227 * 1024 &&
+                                 make_tensor_map_c64(&ob.tmX, ob.X.p, (uint64_t)S * od.C * desc.Ny, Xp, desc.Ny, NB) &&
+                                 make_tensor_map_c64(&ob.tmK, ob.khat.p, (uint64_t)(od.khat_shared ? 1 : S) * od.C * Fy, Xp, Fy / 2, NB);
+                    if (ob.use_tma) SB_TRY(raise_smem((const void *)ob.ky.column_tma, ob.smem_col_tma));
+                }
                 ob.n_part = ((desc.Ny + 2 * ob.npair - 1) / (2 * ob.npair)) * ((od.C + ob.cb - 1) / ob.cb);
                 if (od.kind == 2) {
                     ob.n_part = od.C;
@@ -1158,14 +1197,20 @@ template <typename T> struct PlanT : sb_plan {
                 continue;
             }
             sa.conj = 0;
-            ob.ky.column<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
+            if (ob.use_tma)
+                ob.ky.column_tma<<<cgrid, cthreads, ob.smem_col_tma, stream>>>(sa, ob.tmX, ob.tmK);
+            else
+                ob.ky.column<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
             SB_CUDA(cudaGetLastError());
             mark(), mark();
             ob.kx.residual<<<rgrid, ob.row_threads, ob.smem_row, stream>>>(sa);
             SB_CUDA(cudaGetLastError());
             mark(), mark();
             sa.conj = 1;
-            ob.ky.column<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
+            if (ob.use_tma)
+                ob.ky.column_tma<<<cgrid, cthreads, ob.smem_col_tma, stream>>>(sa, ob.tmX, ob.tmK);
+            else
+                ob.ky.column<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
             SB_CUDA(cudaGetLastError());
             mark();
             ob.kx.grad<<<rgrid, ob.row_threads, ob.smem_row, stream>>>(sa);

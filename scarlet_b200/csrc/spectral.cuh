@@ -18,6 +18,8 @@
 //
 // X: [S][C][Ny][Xp] complex, G: [S][C][Ny][Nx] real.  All transforms are unnormalised; 1/(Fy Fx) is folded into K^.
 #pragma once
+#include <cuda.h> // CUtensorMap
+
 #include "common.cuh"
 #include "fft_core.cuh"
 
@@ -484,6 +486,121 @@ template <typename T, int R1, int R2, int NB> __global__ void __launch_bounds__(
     }
 }
 
+// ---- the same column pass with the tiles moved by the Tensor Memory Accelerator ------------------------------------------
+// One thread issues three tensor copies (cp.async.bulk.tensor.2d, SASS UTMALDG): the [Ny x NB] tile of X and the [Fy x NB]
+// tile of K^ (two boxes of Fy/2 rows: a box dimension is limited to 256) land in shared memory and complete on an mbarrier;
+// the transformed tile goes back with one tensor store (UTMASTG).  No thread computes a global address or issues a global
+// load / store; columns beyond the pitch are zero-filled on load and clipped on store by the copy engine.  The exchange
+// buffer of the two-stage FFT aliases the tiles (they are dead once every thread holds its elements in registers), so a CTA
+// needs (Ny + Fy) NB sizeof(complex) bytes: three CTAs per SM at 288 x 288, whose copies overlap each other's arithmetic.
+namespace tma {
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void wait(unsigned bar, unsigned parity) {
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "W_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra D_%=;\n"
+                 "bra W_%=;\n"
+                 "D_%=:\n"
+                 "}" ::"r"(bar),
+                 "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ void load_2d(unsigned dst, const CUtensorMap *map, int x, int y, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(map), "r"(x), "r"(y), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void store_2d(const CUtensorMap *map, int x, int y, unsigned src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x), "r"(y), "r"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void commit_and_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+} // namespace tma
+
+template <typename T, int R1, int R2, int NB>
+__global__ void __launch_bounds__(NB *sbfft::Plan2<R1, R2>::RMAX, (sizeof(T) == 4 && sbfft::Plan2<R1, R2>::RMAX <= 20) ? 3 : 1)
+    k_spec_column_tma(const SpecArgs<T> a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmK) {
+    typedef typename Cx<T>::type C2;
+    typedef sbfft::Plan2<R1, R2> P;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const SpecObs<T> &ob = a.ob;
+    const int img = blockIdx.y, s = img / ob.C;
+    if (a.done[s]) return;
+    const int Ny = a.Ny, Fy = ob.Fy, tid = threadIdx.x;
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    C2 *tileX = reinterpret_cast<C2 *>(smem);                 // [Ny][NB]
+    C2 *tileK = tileX + (size_t)Ny * NB;                      // [Fy][NB]
+    C2 *tw = tileK + (size_t)Fy * NB;                         // [R1 R2]
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(tw + R1 * R2);
+    C2 *fbuf = tileX;                                         // exchange buffer: aliases the tiles (see above)
+    const unsigned bar_a = tma::smem_addr(bar);
+    const int kx0 = blockIdx.x * NB, kimg = ob.khat_shared ? img - s * ob.C : img;
+    if (tid == 0) {
+        tma::mbar_init(bar_a, 1);
+        tma::fence_barrier_init();
+        tma::expect_tx(bar_a, (unsigned)((Ny + Fy) * NB * sizeof(C2)));
+        tma::load_2d(tma::smem_addr(tileX), &tmX, kx0, img * Ny, bar_a);
+        tma::load_2d(tma::smem_addr(tileK), &tmK, kx0, kimg * Fy, bar_a);
+        tma::load_2d(tma::smem_addr(tileK + (size_t)(Fy / 2) * NB), &tmK, kx0, kimg * Fy + Fy / 2, bar_a);
+    }
+    stage_twiddles<T, R1, R2>(tw, ob.tw_y);
+    __syncthreads(); // the barrier is initialised for everybody, the twiddles are staged
+    tma::wait(bar_a, 0u);
+    const int f = tid % NB, j = tid / NB;
+    C2 *sm = fbuf + f * P::SF;
+    C2 k_[R2], a_[R1];
+    if (j < R1) sbfft::static_for<0, R2>([&](auto i) { k_[decltype(i)::value] = tileK[(size_t)(j + R1 * decltype(i)::value) * NB + f]; });
+    if (j < R2)
+        sbfft::static_for<0, R1>([&](auto i) {
+            const int n = decltype(i)::value * R2 + j;
+            a_[decltype(i)::value] = n < Ny ? tileX[(size_t)n * NB + f] : C2{T(0), T(0)};
+        });
+    __syncthreads(); // every element sits in a register: the tiles may be overwritten by the exchange buffer
+    if (j < R2) sbfft::fwd_stage_a<R1, R2>(a_, j, tw, sm);
+    __syncthreads();
+    C2 b_[R2];
+    if (j < R1) {
+        sbfft::fwd_stage_b<R1, R2>(b_, j, sm);
+        if (a.conj)
+            sbfft::static_for<0, R2>([&](auto i) {
+                constexpr int k2 = decltype(i)::value;
+                b_[k2] = sbfft::cmul_conj(b_[k2], k_[k2]);
+            });
+        else
+            sbfft::static_for<0, R2>([&](auto i) {
+                constexpr int k2 = decltype(i)::value;
+                b_[k2] = sbfft::cmul(b_[k2], k_[k2]);
+            });
+    }
+    __syncthreads();
+    if (j < R1) sbfft::inv_stage_b<R1, R2>(b_, j, tw, sm);
+    __syncthreads();
+    if (j < R2) sbfft::inv_stage_a<R1, R2>(a_, j, sm);
+    __syncthreads(); // the exchange buffer is dead: the result tile takes its place
+    if (j < R2)
+        sbfft::static_for<0, R1>([&](auto i) {
+            const int n = decltype(i)::value * R2 + j;
+            if (n < Ny) tileX[(size_t)n * NB + f] = a_[decltype(i)::value];
+        });
+    tma::fence_proxy_async_smem(); // st.shared -> visible to the copy engine
+    __syncthreads();
+    if (tid == 0) {
+        tma::store_2d(&tmX, kx0, img * Ny, tma::smem_addr(tileX));
+        tma::commit_and_wait_read(); // shared memory stays alive until the engine has read the tile
+    }
+}
+
 // ======================================================================================================
 // Resampling observation (ResolutionRenderer, scarlet/renderer.py:262-547).  With Parseval's theorem the reference's
 // "Fourier-shift the kernel to every low-resolution row, Fourier-shift the model to every low-resolution column,
@@ -704,7 +821,9 @@ template <typename T> __global__ void __launch_bounds__(128) k_resample_q(const 
 template <typename T> struct SpecKernels {
     typedef void (*fn)(const SpecArgs<T>);
     int R1 = 0, R2 = 0, NBcol = 0;
+    typedef void (*fn_tma)(const SpecArgs<T>, const CUtensorMap, const CUtensorMap);
     fn render = nullptr, residual = nullptr, grad = nullptr, column = nullptr, column_fwd = nullptr, column_inv = nullptr;
+    fn_tma column_tma = nullptr; // float only
     size_t sf = 0; // Plan2::SF
 };
 template <typename T> struct SpecColNB { static const int value = sizeof(T) == 4 ? 16 : 8; };
