@@ -73,6 +73,12 @@ typedef struct sb_obs_desc {
     int32_t oy, ox;   /* position of data pixel (0,0) in the model frame (translation only) */
     int32_t Fy, Fx;   /* FFT grid (fft.py:116-167) */
     int32_t khat_shared; /* 1: one K^ for all scenes, 0: one per scene */
+    int32_t psf_shift;   /* kind 0 only: ConvolutionRenderer(psf_shift=...) (renderer.py:172-177, 220-227): the difference kernel
+                            is moved by a fitted (dy, dx) with fft.shift before every convolution; the parameter travels in the
+                            centre arrays behind the sources' entries: observation-major, one slot per scene */
+    int32_t shift_Fy, shift_Fx; /* the reference's fast grid of that shift: _get_fft_shape(kernel, kernel, padding=10) */
+    int32_t shift_fixed;
+    double shift_step;   /* 1e-2 (renderer.py:176) */
 } sb_obs_desc;
 
 /* One FactorizedComponent (component.py:119-193). */

@@ -632,7 +632,9 @@ class ObservationOracle:
     observation's channels inside the model frame (channel map = slice, renderer.py:26-51);
     ``origin`` the (y,x) position of the data's pixel (0,0) in the model frame (pure translation)."""
 
-    def __init__(self, data, weights, psf, frame_dtype=np.float32, channel_offset=0, origin=(0, 0)):
+    def __init__(self, data, weights, psf, frame_dtype=np.float32, channel_offset=0, origin=(0, 0), psf_shift=None):
+        # renderer parameter of ConvolutionRenderer(psf_shift=...) (renderer.py:172-177): a free (dy, dx), step 1e-2, no constraint
+        self.psf_shift = None if psf_shift is None else OParam(np.array(psf_shift, dtype=np.float64), "psf_shift", 1e-2, None)
         self.data = np.asarray(data, dtype=frame_dtype)
         self.weights = (np.ones(self.data.shape, dtype=frame_dtype) if weights is None
                         else np.asarray(weights, dtype=frame_dtype))
@@ -662,7 +664,18 @@ class ObservationOracle:
         self.data_slices, self.model_slices = overlapped_slices(data_box, frame_box)
         return self
 
+    @property
+    def parameters(self):
+        return () if self.psf_shift is None else (self.psf_shift,)
+
+    def shifted_kernel(self, shift=None):
+        """renderer.py:220-227: the difference kernel moved by ``psf_shift`` with ``fft.shift`` (per band, axes (-2, -1))."""
+        sh = self.psf_shift.x if shift is None else shift
+        return np.stack([fourier_shift(k, sh) for k in self.diff_kernel])
+
     def _kernel_fft(self, fshape):
+        if self.psf_shift is not None:  # the kernel changes with the parameter: transformed on every call (as fft.convolve does)
+            return forward_fft(self.shifted_kernel(), fshape, (1, 2))
         key = tuple(fshape)
         key = key + (ARITH["fft"],)
         if key not in self._khat:
@@ -731,6 +744,26 @@ class ObservationOracle:
         if not want_grad:
             return nll
         return nll, self.render_adjoint(w * diff)
+
+    def param_grads(self, model):
+        """Gradient of the negative log-likelihood wrt the renderer parameters (``psf_shift``): the render is linear in the
+        shifted kernel K_s -- rendered[y, x] = sum_uv K_s[u, v] M[y - u + P//2, x - v + P//2] ("same" convolution) -- so
+        dL/dK_s is the correlation of the residual with the model, pulled back to the shift through ``fourier_shift``."""
+        if self.psf_shift is None:
+            return ()
+        from scipy import signal
+        C = self.data.shape[0]
+        sub = np.asarray(model[self.channel_offset:self.channel_offset + C], dtype=np.float64)
+        diff = self.render(model).astype(np.float64) - self.data
+        r = np.zeros(sub.shape)
+        r[self.model_slices] = (self.weights * diff)[self.data_slices]
+        P = self.diff_kernel.shape[-1]
+        g = np.zeros(2)
+        for c in range(C):
+            mp = np.pad(sub[c], P // 2)
+            gk = np.ascontiguousarray(signal.correlate(mp, r[c], mode="valid", method="fft")[::-1, ::-1])
+            g += fourier_shift_vjp(self.diff_kernel[c], self.psf_shift.x, gk)[2]
+        return (g,)
 
 
 class ResolutionObservationOracle(ObservationOracle):
@@ -816,7 +849,8 @@ class SceneOracle:
 
     @property
     def parameters(self):
-        return tuple(p for s in self.sources for p in s.parameters)
+        """blend.py:103-105: the sources' parameters, then the observations' (renderer) parameters."""
+        return tuple(p for s in self.sources for p in s.parameters) + tuple(p for o in self.observations for p in getattr(o, "parameters", ()))
 
     def get_model(self, values=None):
         """Sum of the boxed source models inside the frame.  blend.py:200-244, 17-27."""
@@ -850,6 +884,9 @@ class SceneOracle:
             gbox = np.zeros(src.bbox.shape, dtype=np.float64)
             gbox[ms] = g_model[fs]
             grads.extend(src.param_grads(gbox, vals))
+        for obs in self.observations:
+            if getattr(obs, "parameters", ()):
+                grads.extend(obs.param_grads(model))
         return total, grads
 
     def loss_only(self, values=None):

@@ -35,7 +35,9 @@ class sb_mono_desc(C.Structure):
 
 class sb_obs_desc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("chan_off", C.c_int32),
-                ("oy", C.c_int32), ("ox", C.c_int32), ("Fy", C.c_int32), ("Fx", C.c_int32), ("khat_shared", C.c_int32)]
+                ("oy", C.c_int32), ("ox", C.c_int32), ("Fy", C.c_int32), ("Fx", C.c_int32), ("khat_shared", C.c_int32),
+                ("psf_shift", C.c_int32), ("shift_Fy", C.c_int32), ("shift_Fx", C.c_int32), ("shift_fixed", C.c_int32),
+                ("shift_step", C.c_double)]
 
 
 class sb_source_desc(C.Structure):

@@ -107,8 +107,16 @@ class DevicePlan:
                         (m0["kind"], m0["shape"], m0["chan_off"], m0["origin"], m0["fshape"], m0["korigin"], m0["kshape"]):
                     raise ValueError("all scenes of a batch need identically shaped observations")
             shared = all(m["renderer"] is m0["renderer"] for m in metas)
+            has_shift = m0["psf_shift"] is not None
+            if any((m["psf_shift"] is not None) != has_shift or m["shift_grid"] != m0["shift_grid"] for m in metas):
+                raise ValueError("all scenes of a batch need the same renderer structure (psf_shift)")
+            if has_shift and shared and self.S > 1:
+                raise ValueError("psf_shift is fitted per scene: give every scene its own ConvolutionRenderer")
             desc.obs[o] = nat.sb_obs_desc(m0["kind"], m0["shape"][0], m0["shape"][1], m0["shape"][2], m0["chan_off"],
-                                          m0["origin"][0], m0["origin"][1], m0["fshape"][0], m0["fshape"][1], int(shared))
+                                          m0["origin"][0], m0["origin"][1], m0["fshape"][0], m0["fshape"][1], int(shared),
+                                          int(has_shift), m0["shift_grid"][0], m0["shift_grid"][1],
+                                          int(bool(m0["psf_shift"].fixed)) if has_shift else 0,
+                                          _const_step(m0["psf_shift"]) if has_shift else 0.0)
             self.obs_meta.append(dict(metas=metas, shared=shared))
 
         # ---- sources -----------------------------------------------------------------------------
@@ -199,6 +207,10 @@ class DevicePlan:
         self.C = C
         self.ext = [s for s in self.slots if s["kind"] == 0]
         self.pts = [s for s in self.slots if s.get("center") is not None]  # point-source centres and image shifts
+        for om in self.obs_meta:  # renderer parameters (psf_shift): behind the sources', observation-major, one per scene
+            for m in om["metas"]:
+                if m["psf_shift"] is not None:
+                    self.pts.append(dict(center=m["psf_shift"]))
         self.morph_sizes = [s["image"].size for s in self.ext]
         self.morph_offsets = np.concatenate([[0], np.cumsum(self.morph_sizes)]).astype(np.int64)
         self.n_morph = int(self.morph_offsets[-1])
@@ -244,11 +256,17 @@ class DevicePlan:
         else:
             raise TypeError("renderer %s is not on the device path (ConvolutionRenderer / NullRenderer / ResolutionRenderer)"
                             % type(r).__name__)
+        psf_shift = None
         if r.parameters:
-            raise NotImplementedError("parameterised renderers (psf_shift) are not on the device path")
+            if kind != 0 or len(r.parameters) != 1 or r.parameters[0].name != "psf_shift":
+                raise NotImplementedError("renderer parameters other than ConvolutionRenderer's psf_shift are not on the device path")
+            psf_shift = r.parameters[0]
+            if psf_shift.constraint is not None or psf_shift.prior is not None or psf_shift.shape != (2,):
+                raise TypeError("psf_shift must be an unconstrained (dy, dx) parameter")
         return dict(kind=kind, shape=tuple(obs.data.shape), chan_off=r.channel_offset, origin=tuple(r.origin),
                     fshape=tuple(int(f) for f in fshape), kernel=kernel, korigin=tuple(korigin),
-                    kshape=None if kernel is None else kernel.shape, obs=obs, renderer=r, operator=operator)
+                    kshape=None if kernel is None else kernel.shape, obs=obs, renderer=r, operator=operator, psf_shift=psf_shift,
+                    shift_grid=r.shift_grid() if psf_shift is not None else (0, 0))
 
     def _pinned(self, shape, dtype):
         """numpy view of pinned host memory (sb_host_alloc) -- staging for asynchronous H2D copies."""

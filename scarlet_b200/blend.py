@@ -60,7 +60,8 @@ class Blend(CombinedComponent):
                 return (id(getattr(st, "func", st)), repr(sorted(getattr(st, "keywords", {}).items(), key=lambda kv: kv[0])))
             return float(st)
         pk = tuple((id(p), p.shape, bool(p.fixed), step_key(p), id(p.constraint), id(p.prior)) for p in self.parameters)
-        ok = tuple((id(getattr(o, "renderer", None)), id(o.data), id(o.weights)) for o in self.observations)
+        ok = tuple((id(getattr(o, "renderer", None)), id(o.data), id(o.weights)) + tuple((id(p), bool(p.fixed), float(p.step)) for p in o.parameters)
+                   for o in self.observations)
         return pk + ok
 
     def _get_plan(self, refresh=False):

@@ -14,6 +14,7 @@
 #include "kernels.cuh"
 #include "spectral.cuh"
 #include "update_warp.cuh"
+#include "psf_shift.cuh"
 
 namespace sb {
 
@@ -350,6 +351,12 @@ template <typename T> struct PlanT : sb_plan {
         size_t smem_render = 0, smem_row = 0, smem_col = 0, smem_col_tma = 0;
         bool use_tma = false; // column pass through the Tensor Memory Accelerator (float, Ny <= 256)
         CUtensorMap tmX, tmK;
+        // ConvolutionRenderer(psf_shift=...): fitted kernel offset (psf_shift.cuh)
+        bool psf_shift = false, have_kernel = false;
+        int slot0 = 0, Py = 0, Px = 0, ky0 = 0, kx0 = 0, shift_Fy = 0, shift_Fx = 0, shift_fixed = 0;
+        double shift_step = 0;
+        DevBuf<double> ks, kd0, kd1, gk;
+        DevBuf<T> resid;
         // kernel-image -> K^ (double precision, chunked over scenes)
         cufftHandle kplan = 0;
         bool have_kplan = false;
@@ -494,6 +501,13 @@ template <typename T> struct PlanT : sb_plan {
             }
         }
         npix_max = (npix_max + 3) & ~3;
+        // renderer parameters (psf_shift) take centre slots behind the sources': observation-major, one per scene
+        std::vector<int> psf_slot0(desc.n_obs, -1);
+        for (int o = 0; o < desc.n_obs; ++o)
+            if (desc.obs[o].psf_shift) {
+                psf_slot0[o] = n_point;
+                n_point += S;
+            }
         SB_TRY(plan_fast_path());
         SB_TRY(d_src.alloc(std::max(n_src, 1)));
         SB_TRY(d_start.alloc(S + 1));
@@ -561,6 +575,8 @@ template <typename T> struct PlanT : sb_plan {
             Obs &ob = *obs.back();
             if (od.C <= 0 || od.chan_off < 0 || od.chan_off + od.C > C) return set_err(SB_ERR_ARG, "observation %d: channels outside the model frame", o);
             if (od.kind != 0 && od.kind != 1 && od.kind != 2) return set_err(SB_ERR_ARG, "observation %d: unsupported renderer kind %d", o, od.kind);
+            if (od.psf_shift && !fused)
+                return set_err(SB_ERR_ARG, "observation %d: psf_shift needs FFT lengths of the fused spectral kernels (got %dx%d)", o, od.Fy, od.Fx);
             if (od.kind == 2 && !fused)
                 return set_err(SB_ERR_ARG, "observation %d: a resampling observation needs FFT lengths of the fused spectral kernels "
                                            "(got %dx%d) and no NullRenderer observation in the same plan", o, od.Fy, od.Fx);
@@ -637,6 +653,17 @@ template <typename T> struct PlanT : sb_plan {
                         return set_err(SB_ERR_ARG, "observation %d: resampling geometry too large", o);
                     SB_TRY(raise_smem((const void *)k_resample_t1<T>, (size_t)Fy * SB_RS_ROWS * sizeof(cplx)));
                     SB_TRY(raise_smem((const void *)k_resample_q<T>, (size_t)od.H * SB_RS_KY * sizeof(cplx)));
+                }
+                if (od.psf_shift) {
+                    if (od.kind != 0) return set_err(SB_ERR_ARG, "observation %d: psf_shift needs a ConvolutionRenderer", o);
+                    if (od.khat_shared && S > 1) return set_err(SB_ERR_ARG, "observation %d: psf_shift needs one renderer (kernel) per scene", o);
+                    if (od.shift_Fx <= 0 || od.shift_Fy <= 0 || (od.shift_Fx & 1)) return set_err(SB_ERR_ARG, "observation %d: bad psf_shift grid %dx%d", o, od.shift_Fy, od.shift_Fx);
+                    ob.psf_shift = true, ob.slot0 = psf_slot0[o], ob.shift_Fy = od.shift_Fy, ob.shift_Fx = od.shift_Fx;
+                    ob.shift_step = od.shift_step, ob.shift_fixed = od.shift_fixed;
+                    SB_TRY(ob.resid.alloc((size_t)S * od.C * desc.Ny * desc.Nx));
+                    SB_TRY(ob.resid.zero(stream));
+                    if (d_model.n < (size_t)S * C * desc.Ny * desc.Nx) SB_TRY(d_model.alloc((size_t)S * C * desc.Ny * desc.Nx));
+                    SB_TRY(d_model.zero(stream));
                 }
                 SB_TRY(ob.partials.alloc((size_t)S * ob.n_part));
                 SB_TRY(ob.partials.zero(stream));
@@ -950,12 +977,35 @@ template <typename T> struct PlanT : sb_plan {
         }
         if (ob.kimg.n < (size_t)nk * d.C * per_img) SB_TRY(ob.kimg.alloc((size_t)nk * d.C * per_img));
         SB_CUDA(cudaMemcpyAsync(ob.kimg.p, ker, (size_t)nk * d.C * per_img * sizeof(double), cudaMemcpyHostToDevice, stream));
+        ob.Py = Py, ob.Px = Px, ob.ky0 = y0, ob.kx0 = x0, ob.have_kernel = true;
+        if (ob.psf_shift) { // K^ follows the fitted offset: shifted kernel (and its derivatives) for the current parameter
+            const size_t nimg = (size_t)S * d.C * per_img;
+            if (ob.ks.n < nimg) {
+                SB_TRY(ob.ks.alloc(nimg));
+                SB_TRY(ob.kd0.alloc(nimg));
+                SB_TRY(ob.kd1.alloc(nimg));
+                SB_TRY(ob.gk.alloc(nimg));
+            }
+            const size_t smem = (size_t)(8 * (Py + Px) + 3 * Py * Px) * sizeof(double);
+            if (smem > 200 * 1024) return set_err(SB_ERR_ARG, "psf_shift: kernel image %dx%d too large", Py, Px);
+            SB_TRY(raise_smem((const void *)k_psf_kernel<T>, smem));
+            SB_TRY(refresh_psf(o));
+        } else
+            SB_TRY(khat_from_images(ob, ob.kimg.p, nk));
+        SB_CUDA(cudaStreamSynchronize(stream));
+        return SB_OK;
+    }
+
+    // kernel images [n][C][Py][Px] (device, double) -> K^/(Fy Fx) in the plan's precision (pad, wrap, transform in double)
+    int khat_from_images(Obs &ob, const double *img, int nk) {
+        const DevObs<T> &d = ob.dev;
+        const size_t per_img = (size_t)ob.Py * ob.Px, per_spec = (size_t)d.Fy * d.Fxc;
         for (int s0 = 0; s0 < nk; s0 += ob.kchunk) {
             const int nb = std::min(ob.kchunk, nk - s0);
             SB_TRY(ob.kgrid.zero(stream));
             const long long nimg = (long long)nb * d.C * per_img;
-            k_embed_kernel<<<grid_for(nimg), 256, 0, stream>>>(ob.kimg.p + (size_t)s0 * d.C * per_img, ob.kgrid.p, nb * d.C, Py, Px,
-                                                             d.Fy, d.Fx, y0, x0);
+            k_embed_kernel<<<grid_for(nimg), 256, 0, stream>>>(img + (size_t)s0 * d.C * per_img, ob.kgrid.p, nb * d.C, ob.Py, ob.Px, d.Fy, d.Fx,
+                                                             ob.ky0, ob.kx0);
             SB_CUDA(cudaGetLastError());
             SB_CUFFT(cufftExecD2Z(ob.kplan, ob.kgrid.p, ob.kspec.p));
             const long long nspec = (long long)nb * d.C * per_spec, nrows = (long long)nb * d.C * d.Fy;
@@ -963,7 +1013,31 @@ template <typename T> struct PlanT : sb_plan {
                                                                             d.Fxc, d.Kp, 1.0 / ((double)d.Fy * d.Fx));
             SB_CUDA(cudaGetLastError());
         }
-        SB_CUDA(cudaStreamSynchronize(stream));
+        return SB_OK;
+    }
+
+    PsfShiftArgs<T> psf_args(int o, int mode) {
+        Obs &ob = *obs[o];
+        PsfShiftArgs<T> a;
+        memset(&a, 0, sizeof a);
+        a.S = S, a.C = ob.dev.C, a.Py = ob.Py, a.Px = ob.Px, a.Fy = ob.shift_Fy, a.Fx = ob.shift_Fx;
+        a.Ny = desc.Ny, a.Nx = desc.Nx, a.chan_off = ob.dev.chan_off, a.Cm = C, a.slot0 = ob.slot0;
+        a.kernel_shared = ob.dev.khat_shared, a.fixed = ob.shift_fixed, a.mode = mode, a.step = ob.shift_step;
+        a.kimg = ob.kimg.p, a.ks = ob.ks.p, a.kd0 = ob.kd0.p, a.kd1 = ob.kd1.p, a.gk = ob.gk.p;
+        a.model = d_model.p, a.resid = ob.resid.p;
+        a.center = d_center.p, a.cen_m = d_cen_m.p, a.cen_v = d_cen_v.p, a.cen_vhat = d_cen_vhat.p, a.g_center = d_gcenter.p;
+        a.it_ptr = d_it.p, a.done = d_done.p, a.status = d_status.p, a.fs = cur_fs;
+        return a;
+    }
+    // shifted kernel for the current offsets -> K^ (every scene has its own kernel: psf_shift plans are never khat_shared for S > 1)
+    int refresh_psf(int o) {
+        Obs &ob = *obs[o];
+        if (!ob.have_kernel) return SB_OK;
+        PsfShiftArgs<T> pa = psf_args(o, 0);
+        const size_t smem = (size_t)(8 * (ob.Py + ob.Px) + 3 * ob.Py * ob.Px) * sizeof(double);
+        k_psf_kernel<T><<<S * ob.dev.C, 128, smem, stream>>>(pa);
+        SB_CUDA(cudaGetLastError());
+        SB_TRY(khat_from_images(ob, ob.ks.p, S));
         return SB_OK;
     }
 
@@ -1039,6 +1113,9 @@ template <typename T> struct PlanT : sb_plan {
             SB_CUDA(cudaGetLastError());
         }
         if (which == 0 && n_shift) SB_TRY(launch_shift_apply());
+        if (which == 0 && center)
+            for (size_t o = 0; o < obs.size(); ++o)
+                if (obs[o]->psf_shift) SB_TRY(refresh_psf((int)o));
         SB_CUDA(cudaStreamSynchronize(stream));
         return SB_OK;
     }
@@ -1165,7 +1242,8 @@ template <typename T> struct PlanT : sb_plan {
             sa.ob = ob.sdev, sa.Ny = desc.Ny, sa.Nx = desc.Nx, sa.Cm = C, sa.npair = ob.npair, sa.cb = ob.cb, sa.done = d_done.p;
             sa.src = d_src.p, sa.scene_src_start = d_start.p, sa.sed = d_sed.p, sa.morph = d_morph.p, sa.pmorph = d_pmorph.p;
             sa.smorph = d_smorph.p;
-            sa.model_out = model_out, sa.partials = ob.partials.p;
+            sa.model_out = ob.psf_shift ? d_model.p : model_out, sa.partials = ob.partials.p;
+            sa.resid_out = ob.psf_shift ? ob.resid.p : nullptr;
             sa.magic_nx = 0xffffffffu / (unsigned)desc.Nx + 1u, sa.max_cand = max_src_scene + 1;
             sa.rendered_out = ((int)o == rendered_obs) ? rendered_out : nullptr;
             const dim3 rgrid((desc.Ny + 2 * ob.npair - 1) / (2 * ob.npair), S, (ob.sdev.C + ob.cb - 1) / ob.cb);
@@ -1315,6 +1393,19 @@ template <typename T> struct PlanT : sb_plan {
                 }
                 if (s_fast != stream) SB_CUDA(cudaStreamWaitEvent(stream, ev_join2, 0));
                 if (s_gen != stream) SB_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+            }
+            for (size_t o = 0; fused && o < obs.size(); ++o) { // fitted kernel offsets: gradient, step, new K^ for the next render
+                Obs &ob = *obs[o];
+                if (!ob.psf_shift) continue;
+                PsfShiftArgs<T> pa = psf_args((int)o, mode);
+                k_psf_corr<T><<<dim3(ob.Py, ob.dev.C, S), 256, 0, stream>>>(pa);
+                k_psf_update<T><<<S, 128, 0, stream>>>(pa);
+                SB_CUDA(cudaGetLastError());
+                nk += 2;
+                if (mode == 0 && !ob.shift_fixed) {
+                    SB_TRY(refresh_psf((int)o));
+                    nk += 3;
+                }
             }
             if (mode == 0 && n_shift) { // new shifts / images -> new shifted morphologies for the next render
                 SB_TRY(launch_shift_apply());

@@ -59,6 +59,7 @@ template <typename T> struct SpecArgs {
     // residual
     double *partials; // [S][gridDim.x]
     T *rendered_out;  // optional [S][C][H][W]
+    T *resid_out;     // optional [S][C][Ny][Nx]: w (rendered - data) in the model frame (psf_shift gradient)
     int conj;         // column kernel: multiply by conj(K^)
     unsigned magic_nx; // 2^32 / Nx + 1: idx / Nx == umulhi(idx, magic_nx)
     int max_cand;      // capacity of the render kernel's candidate list (largest number of sources in a scene)
@@ -374,6 +375,14 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
                             if (a.rendered_out) a.rendered_out[base1 + dx] = m;
                         }
                         a_[n1 < R1 ? n1 : 0] = C2{r0, r1};
+                        if (a.resid_out) {
+                            const int x = n1 * R2 + n2;
+                            if (x < Nx && y < Ny) {
+                                T *ro = a.resid_out + ((size_t)(s * Co + c) * Ny + y) * Nx + x;
+                                ro[0] = r0;
+                                if (y + 1 < Ny) ro[Nx] = r1;
+                            }
+                        }
                     }
                 });
             });
@@ -538,7 +547,8 @@ __global__ void __launch_bounds__(NB *sbfft::Plan2<R1, R2>::RMAX, (sizeof(T) == 
     const int img = blockIdx.y, s = img / ob.C;
     if (a.done[s]) return;
     const int Ny = a.Ny, Fy = ob.Fy, tid = threadIdx.x;
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    // (aligned by an offset, not through an integer cast: the compiler keeps the shared address space and emits LDS / STS)
+    unsigned char *smem = smem_raw + ((128u - (tma::smem_addr(smem_raw) & 127u)) & 127u);
     C2 *tileX = reinterpret_cast<C2 *>(smem);                 // [Ny][NB]
     C2 *tileK = tileX + (size_t)Ny * NB;                      // [Fy][NB]
     C2 *tw = tileK + (size_t)Fy * NB;                         // [R1 R2]

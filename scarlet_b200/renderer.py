@@ -75,7 +75,15 @@ class NullRenderer(Renderer):
 class ConvolutionRenderer(Renderer):
     def __init__(self, data_frame, model_frame, *parameters, convolution_type="fft", padding=10, psf_shift=None):
         if psf_shift is not None:
-            raise NotImplementedError("psf_shift is outside the device path (SURVEY 2.1: out of scope)")
+            # a fitted offset of the PSF difference kernel (astrometric mismatch between observations): renderer parameter
+            # with step 1e-2 and no constraint (renderer.py:175-177); it joins the optimiser's parameter tuple behind the
+            # sources' parameters (blend.py:103-105).  On the device: csrc/psf_shift.cuh.
+            from .parameter import Parameter
+            if not isinstance(psf_shift, Parameter):
+                psf_shift = Parameter(np.asarray(psf_shift, dtype=np.float64), name="psf_shift", step=1.0e-2)
+            elif psf_shift.name != "psf_shift":
+                raise AssertionError("the renderer parameter must be named 'psf_shift'")
+            parameters = (*parameters, psf_shift)
         if convolution_type not in ("fft", "real"):
             raise ValueError("`convolution` must be either 'real' or 'fft', got {}".format(convolution_type))
         # "real" (renderer.py:97-127, operators_pybind11.cc:39-56: a sum of shifted, scaled copies of the image, zero outside
@@ -104,13 +112,29 @@ class ConvolutionRenderer(Renderer):
         fshape, origin = fft.device_grid(sub_shape, ker.shape, padding=3)
         return fshape, origin, ker
 
+    def shifted_kernel(self, psf_shift):
+        """The difference kernel moved by ``psf_shift`` (renderer.py:220-227: ``fft.shift`` per band on the fast grid of
+        (kernel, kernel, padding 10), cropped back to the kernel box)."""
+        return np.stack([fft.shift(k, psf_shift, return_Fourier=False) for k in np.asarray(self.diff_kernel.image, dtype=np.float64)])
+
+    def shift_grid(self):
+        """fast grid of ``fft.shift`` for the kernel image"""
+        ker = np.asarray(self.diff_kernel.image)
+        return tuple(int(f) for f in fft._get_fft_shape(ker[0], ker[0], padding=10, axes=(0, 1)))
+
     def convolve(self, model, convolution_type=None, psf_shift=None):
-        fshape, khat = self.kernel_transform()
+        if psf_shift is not None:
+            sub_shape = (self.data_frame.C,) + tuple(self.model_frame.shape[1:])
+            fshape, khat = fft.kernel_transform(self.shifted_kernel(np.asarray(psf_shift)), sub_shape, padding=3)
+        else:
+            fshape, khat = self.kernel_transform()
         return fft.device_convolve(np.asarray(model), khat, fshape)
 
     def get_model(self, *parameters):
-        def transform(model):
-            return match_shape(self.convolve(self.map_channels(model)), self.data_frame, self.slices)
+        shift = self.get_parameter("psf_shift", *parameters)
+
+        def transform(model, *ignored):
+            return match_shape(self.convolve(self.map_channels(model), psf_shift=shift), self.data_frame, self.slices)
         return transform
 
 

@@ -17,6 +17,8 @@ What is written (all values produced by reference code, float64 unless the refer
 * ``prox_chain.npz``       -- constraint-chain outputs (monotonic angle/flat/nearest x symmetric on/off) on seeded
                              random 41x41 / 21x21 / 20x31 images.
 * ``monotonic_weights.npz``-- ``getRadialMonotonicWeights`` for several shapes / kinds / centres.
+* ``psf_shift.npz``        -- ``ConvolutionRenderer(psf_shift=...)``: shifted difference kernel, render, logL and finite
+                             differences of logL wrt the shift, for two shifts.
 """
 import os
 import sys
@@ -447,9 +449,54 @@ def init_helpers(sc):
     save("init_helpers.npz", **out)
 
 
+def psf_shift(sc):
+    """``ConvolutionRenderer(psf_shift=...)`` (renderer.py:172-177, 220-227, 252-254; fft.shift fft.py:399-428) through the
+    reference's own code: the shifted difference kernel, the rendered model, logL and central differences of logL wrt the shift
+    (float64 frame, as in ``_finite_diff``)."""
+    rng = np.random.default_rng(21)
+    C, Ny, Nx, P = 3, 34, 30, 15
+    channels = list(range(C))
+    model_psf = sc.psf.GaussianPSF(sigma=(0.8,) * C)
+    frame = sc.frame.Frame((C, Ny, Nx), psf=model_psf, channels=channels, dtype=np.float64)
+    y, x = np.mgrid[:P, :P] - P // 2
+    psfs = np.stack([(1 + (x * x + 1.3 * y * y + 0.4 * x * y) / (1.1 + 0.25 * c) ** 2) ** -2.5 for c in range(C)])
+    psfs /= psfs.sum(axis=(1, 2))[:, None, None]
+    model = np.zeros((C, Ny, Nx))
+    seds, morphs = [], []
+    for k in range(4):
+        cy, cx = rng.uniform(6, Ny - 6), rng.uniform(6, Nx - 6)
+        yy, xx = np.mgrid[:Ny, :Nx]
+        seds.append(rng.uniform(5, 50, C))
+        morphs.append(np.exp(-np.hypot(yy - cy, xx - cx) / rng.uniform(1.0, 2.5)))
+        model += seds[-1][:, None, None] * morphs[-1][None]
+    images = rng.standard_normal((C, Ny, Nx)) + model * 0.9
+    weights = rng.uniform(0.5, 2.0, (C, Ny, Nx))
+    out = dict(psfs=psfs, model=model, images=images, weights=weights, model_sigma=0.8, seds=np.array(seds), morphs=np.array(morphs))
+    for tag, shift in (("a", (0.3, -0.45)), ("b", (-1.2, 0.8))):
+        obs = sc.observation.Observation(images.copy(), psf=sc.psf.ImagePSF(psfs.copy()), weights=weights.copy(), channels=channels)
+        renderer = sc.renderer.ConvolutionRenderer(obs, frame, psf_shift=np.array(shift))
+        obs.match(frame, renderer=renderer)
+        sh = renderer.parameters[0]
+        kernel = sc.fft.shift(renderer.diff_kernel.image, np.asarray(sh), fft_shape=None, axes=(-2, -1), return_Fourier=True).image
+        rendered = obs.render(model, *obs.parameters)
+        logL = obs.get_log_likelihood(model, *obs.parameters)
+        fd = []
+        for j in range(2):
+            vals = []
+            for sgn in (+1, -1):
+                sh[j] = shift[j] + sgn * 1e-4  # the renderer reads its own Parameter (model.py:71-110)
+                vals.append(-obs.get_log_likelihood(model, *obs.parameters))
+            sh[j] = shift[j]
+            fd.append((vals[0] - vals[1]) / 2e-4)
+        out.update({"shift_" + tag: np.array(shift), "kernel_" + tag: np.asarray(kernel), "rendered_" + tag: np.asarray(rendered),
+                    "logL_" + tag: logL, "dloss_dshift_" + tag: np.array(fd), "step_" + tag: float(sh.step)})
+        out["diff_kernel"] = np.asarray(renderer.diff_kernel.image)
+    save("psf_shift.npz", **out)
+
+
 if __name__ == "__main__":
     sc = ref_shim.install()
     which = sys.argv[1:] or ["obs_render_loss", "hsc_cosmos_35", "point_extended", "prox_chain", "monotonic_weights", "multires",
-                             "source_recipes", "init_helpers"]
+                             "source_recipes", "init_helpers", "psf_shift"]
     for name in which:
         globals()[name](sc)

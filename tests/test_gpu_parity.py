@@ -1010,3 +1010,84 @@ def test_dynamic_batch_equals_individual_fits(precision):
         sizes.add(len(b.loss))
     assert len(sizes) > 3  # the scenes really went different ways
     batch.close()
+
+
+# --------------------------------------------------------------------------------------------------
+# ConvolutionRenderer(psf_shift=...)  (renderer.py:172-177, 220-227, 252-254)
+# --------------------------------------------------------------------------------------------------
+def _psf_shift_blend(g, shift, precision, fit_sources=False):
+    """the fixture scene as product objects: 4 full-frame components (spectrum x image), one observation whose renderer
+    carries the fitted kernel offset"""
+    import scarlet_b200 as sb
+    C = g["images"].shape[0]
+    channels = list(range(C))
+    dtype = np.float32 if precision == 32 else np.float64
+    frame = sb.Frame(g["images"].shape, psf=sb.GaussianPSF(sigma=(float(g["model_sigma"]),) * C), channels=channels, dtype=dtype)
+    obs = sb.Observation(g["images"].copy(), psf=sb.ImagePSF(g["psfs"].copy()), weights=g["weights"].copy(), channels=channels)
+    renderer = sb.renderer.ConvolutionRenderer(obs, frame, psf_shift=np.array(shift, dtype=np.float64))
+    obs.match(frame, renderer=renderer)
+    comps = []
+    for sed, morph in zip(g["seds"], g["morphs"]):
+        spectrum = sb.TabulatedSpectrum(frame, sb.Parameter(sed.copy(), name="spectrum", step=1e-2, fixed=not fit_sources,
+                                                            constraint=sb.PositivityConstraint()))
+        image = sb.Parameter(morph.copy(), name="image", step=1e-2, fixed=not fit_sources, constraint=sb.PositivityConstraint())
+        comps.append(sb.FactorizedComponent(frame, spectrum, sb.ImageMorphology(frame, image, resizing=False)))
+    return sb.Blend(comps, obs, precision=precision), obs, renderer
+
+
+def _psf_shift_oracle(g, shift, fit_sources=False, frame_dtype=np.float64):
+    from oracle import scarlet_oracle as so
+    C = g["images"].shape[0]
+    obs = so.ObservationOracle(g["images"], g["weights"], so.ImagePSFOracle(g["psfs"]), frame_dtype=frame_dtype, psf_shift=shift)
+    mpsf = so.GaussianPSFOracle((float(g["model_sigma"]),) * C)
+    srcs = []
+    for sed, morph in zip(g["seds"], g["morphs"]):
+        s = so.ExtendedSourceOracle(sed, morph, (0, 0), sed_dtype=np.float64)
+        s.spectrum = so.OParam(np.array(sed, dtype=np.float64), "spectrum", 1e-2, so.ChainSpec([("positivity", 0.0)]), fixed=not fit_sources)
+        s.image = so.OParam(np.array(morph, dtype=np.float64), "image", 1e-2, so.ChainSpec([("positivity", 0.0)]), fixed=not fit_sources)
+        s.shift.fixed = True
+        srcs.append(s)
+    return so.SceneOracle(g["images"].shape, mpsf, srcs, [obs], frame_dtype=frame_dtype)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_psf_shift_forward_and_gradient_vs_reference_fixture(tag):
+    """render, logL and d logL / d psf_shift against the reference's own outputs (tests/golden/make_golden.py:psf_shift)"""
+    g = golden("psf_shift.npz")
+    for precision, tol in ((64, 1e-9), (32, 2e-5)):
+        blend, obs, renderer = _psf_shift_blend(g, g["shift_" + tag], precision)
+        plan = blend._get_plan()
+        plan.upload_parameters(state=False)
+        ev = plan.evaluate(want=("model", "rendered", "loss", "grads"))
+        assert rel_peak(ev["model"][0], g["model"]) < max(tol, 1e-7)
+        assert rel_peak(ev["rendered"][0], g["rendered_" + tag]) < tol
+        assert_allclose(-ev["loss"][0], float(g["logL_" + tag]), rtol=max(tol, 1e-9))
+        gs = ev["g_center"][-1]  # the renderer parameter sits behind the sources' entries
+        assert_allclose(gs, g["dloss_dshift_" + tag], rtol=1e-6 if precision == 64 else 2e-3)
+        # the host-side render (what users call around a fit) follows the parameter too
+        assert rel_peak(obs.render(g["model"].astype(blend.frame.dtype), *obs.parameters), g["rendered_" + tag]) < tol
+        # (float32 frame: the difference kernel itself is formed from float32 PSF images, renderer.py:198-202)
+        assert_allclose(renderer.shifted_kernel(g["shift_" + tag]), g["kernel_" + tag], atol=1e-13 if precision == 64 else 5e-6)
+
+
+@pytest.mark.parametrize("fit_sources", [False, True])
+def test_psf_shift_fit_matches_oracle(fit_sources):
+    """the offset is fitted by the same AMSGrad step as every other parameter (blend.py:103-105: renderer parameters close
+    the parameter tuple); started away from the truth it moves, alone or together with the sources"""
+    g = golden("psf_shift.npz")
+    start = np.array([0.6, -0.2])
+    for precision, tol in ((64, 1e-8), (32, 1e-4)):
+        o = _psf_shift_oracle(g, start, fit_sources, frame_dtype=np.float64 if precision == 64 else np.float32)
+        o.fit(max_iter=12, e_rel=1e-3, min_iter=10 ** 9)
+        blend, obs, renderer = _psf_shift_blend(g, start, precision, fit_sources)
+        n, logL = blend.fit(max_iter=12, e_rel=1e-3, min_iter=10 ** 9)
+        assert n == 12
+        assert_allclose(np.array(blend.loss), np.array(o.loss), rtol=max(tol, 1e-9))
+        shift = np.asarray(renderer.parameters[0])
+        assert np.abs(shift - o.observations[0].psf_shift.x).max() < tol
+        assert np.abs(shift - start).max() > 0.05  # it really moved
+        assert renderer.parameters[0].m is not None
+        if fit_sources:
+            for comp, osrc in zip(blend.sources, o.sources):
+                assert rel_peak(comp.parameters[0], osrc.spectrum.x) < tol
+                assert rel_peak(comp.parameters[1], osrc.image.x) < tol

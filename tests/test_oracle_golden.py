@@ -222,3 +222,19 @@ def test_resolution_oracle_vs_reference_fixture():
     hr.match(tuple(g["frame_shape64"]), so.ImagePSFOracle(g["model_psf64"]))
     assert_allclose(hr.render(g["model64"]), g["hr_rendered64"], atol=1e-12 * np.abs(g["hr_rendered64"]).max())
     assert_allclose(-hr.neg_log_likelihood(g["model64"]), float(g["hr_logL64"]), rtol=1e-12)
+
+
+def test_psf_shift_oracle_vs_reference_fixture():
+    """``ConvolutionRenderer(psf_shift=...)`` (renderer.py:172-177, 220-227): the oracle's shifted kernel, render and logL equal
+    the reference's own outputs, its hand gradient wrt the shift equals central differences of the reference's logL."""
+    from oracle import scarlet_oracle as so
+    g = golden("psf_shift.npz")
+    C = g["images"].shape[0]
+    for tag in "ab":
+        obs = so.ObservationOracle(g["images"], g["weights"], so.ImagePSFOracle(g["psfs"]), frame_dtype=np.float64, psf_shift=g["shift_" + tag])
+        obs.match(g["model"].shape, so.GaussianPSFOracle((float(g["model_sigma"]),) * C))
+        assert_allclose(obs.diff_kernel, g["diff_kernel"], atol=1e-14)
+        assert_allclose(obs.shifted_kernel(), g["kernel_" + tag], atol=1e-14)
+        assert_allclose(obs.render(g["model"]), g["rendered_" + tag], atol=1e-11)
+        assert_allclose(-obs.neg_log_likelihood(g["model"]), float(g["logL_" + tag]), rtol=1e-13)
+        assert_allclose(obs.param_grads(g["model"])[0], g["dloss_dshift_" + tag], rtol=1e-6)
