@@ -461,6 +461,39 @@ def measure(env, args, config, S, iters, steps, warmup, headline):
     return rec
 
 
+def measure_dynamic(env, args, S=64, iters=50):
+    """cfg2-shaped scenes with dynamic boxes ON (``resizing=True``, the reference default): one ``BlendBatch.fit`` through the
+    public API with host buffers; every scene inspects its sources every 10 iterations of its own optimiser call, boxes that
+    changed re-plan the batch (scarlet_b200/blend.py:_fit_dynamic).  The boxes start at 31 x 31 around sources that want 41 x 41
+    and more, so the early inspections do resize.  Host-driven, hence end-to-end only."""
+    from scarlet_b200 import BlendBatch, synthetic
+    cfg = dict(synthetic.CONFIGS["cfg2"], B=31, resizing=True, config_id=22)
+    uniq = min(S, args.unique)
+    base = [synthetic.make_scene(cfg, env.rank * 100000 + i) for i in range(uniq)]
+
+    def run():
+        blends = [synthetic.make_blend(base[i % uniq], precision=args.precision, device=env.local) for i in range(S)]
+        batch = BlendBatch(blends, precision=args.precision, device=env.local)
+        env.torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = batch.fit(max_iter=iters, e_rel=1e-9, upload_observations=True)
+        env.torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out = (dt, sum(r[0] for r in res), batch.replans, batch.last_transfer_bytes,
+               sorted(set(int(src.parameters[1].shape[0]) for b in blends for src in b.sources)))
+        batch.close()
+        return out
+
+    run()
+    dt, n_it, replans, (h2d, d2h), sizes = run()
+    dt = env.max_over_ranks(dt)
+    return {"value": None, "unit": "scene-iterations/s", "config": workload_config("cfg2 with dynamic boxes (resizing=True, start 31x31)", cfg, S, iters),
+            "e2e": {"value": env.world * n_it / dt, "unit": "scene-iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * dt},
+            "replans": replans, "final_box_sizes": sizes,
+            "note": "host-driven inspection + re-plan; no device-resident figure"}
+
+
 def run_b200(args):
     from scarlet_b200 import _native
     if _native.lib().sb_device_count() <= 0:
@@ -480,6 +513,10 @@ def run_b200(args):
                              "roofline": {"iteration": rec["roofline"]["iteration"], "kernel": rec["roofline"]["kernel"],
                                           "frac": rec["roofline"]["frac"], "stages_ms": rec["roofline"]["stages_ms"]},
                              "fft_grid": rec["details"]["fft_grid"], "device_bytes_per_gpu": rec["details"]["device_bytes_per_gpu"]}
+    if args.config == "cfg3" and not args.only_headline:
+        dyn = measure_dynamic(env, args)
+        if env.rank == 0:
+            others["cfg2_dynamic"] = dyn
     line = None
     if env.rank == 0:
         cpu = None

@@ -623,6 +623,7 @@ template <typename T> struct PlanT : sb_plan {
                     return set_err(SB_ERR_ARG, "observation %d: frame too wide for the fused spectral kernels", o);
                 SB_TRY(raise_smem((const void *)ob.kx.render, ob.smem_render));
                 SB_TRY(raise_smem((const void *)ob.kx.residual, ob.smem_row));
+                SB_TRY(raise_smem((const void *)ob.kx.residual_r, ob.smem_row));
                 SB_TRY(raise_smem((const void *)ob.kx.grad, ob.smem_row));
                 SB_TRY(raise_smem((const void *)ob.ky.column, ob.smem_col));
                 if (sizeof(T) == 4 && od.kind == 0 && ob.ky.column_tma && desc.Ny <= 256 && Fy % 2 == 0 && Fy / 2 <= 256 &&
@@ -1281,7 +1282,7 @@ template <typename T> struct PlanT : sb_plan {
                 ob.ky.column<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
             SB_CUDA(cudaGetLastError());
             mark(), mark();
-            ob.kx.residual<<<rgrid, ob.row_threads, ob.smem_row, stream>>>(sa);
+            (ob.psf_shift ? ob.kx.residual_r : ob.kx.residual)<<<rgrid, ob.row_threads, ob.smem_row, stream>>>(sa);
             SB_CUDA(cudaGetLastError());
             mark(), mark();
             sa.conj = 1;

@@ -299,7 +299,10 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
 // ======================================================================================================
 // inverse row FFT -> residual + loss -> forward row FFT
 // ======================================================================================================
-template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256, 2) k_spec_residual(const SpecArgs<T> a) {
+// WITH_RESID: also write the residual in the model frame (SpecArgs::resid_out; psf_shift plans only -- a separate instantiation
+// keeps the extra stores and their predicates out of the hot kernel)
+template <typename T, int R1, int R2, bool WITH_RESID = false>
+__global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256, 2) k_spec_residual(const SpecArgs<T> a) {
     typedef typename Cx<T>::type C2;
     typedef sbfft::Plan2<R1, R2> P;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -375,7 +378,7 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
                             if (a.rendered_out) a.rendered_out[base1 + dx] = m;
                         }
                         a_[n1 < R1 ? n1 : 0] = C2{r0, r1};
-                        if (a.resid_out) {
+                        if constexpr (WITH_RESID) {
                             const int x = n1 * R2 + n2;
                             if (x < Nx && y < Ny) {
                                 T *ro = a.resid_out + ((size_t)(s * Co + c) * Ny + y) * Nx + x;
@@ -832,7 +835,7 @@ template <typename T> struct SpecKernels {
     typedef void (*fn)(const SpecArgs<T>);
     int R1 = 0, R2 = 0, NBcol = 0;
     typedef void (*fn_tma)(const SpecArgs<T>, const CUtensorMap, const CUtensorMap);
-    fn render = nullptr, residual = nullptr, grad = nullptr, column = nullptr, column_fwd = nullptr, column_inv = nullptr;
+    fn render = nullptr, residual = nullptr, residual_r = nullptr, grad = nullptr, column = nullptr, column_fwd = nullptr, column_inv = nullptr;
     fn_tma column_tma = nullptr; // float only
     size_t sf = 0; // Plan2::SF
 };

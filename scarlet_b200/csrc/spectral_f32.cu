@@ -8,7 +8,8 @@ bool spec_kernels_f32(int L, SpecKernels<float> *out) {
     if (L == (A) * (B)) {                                                         \
         out->R1 = A, out->R2 = B, out->NBcol = SpecColNB<float>::value;           \
         out->render = k_spec_render<float, A, B>;                                 \
-        out->residual = k_spec_residual<float, A, B>;                             \
+        out->residual = k_spec_residual<float, A, B>;                                 \
+        out->residual_r = k_spec_residual<float, A, B, true>;                             \
         out->grad = k_spec_grad<float, A, B>;                                     \
         out->column = k_spec_column<float, A, B, SpecColNB<float>::value>;        \
         out->column_tma = k_spec_column_tma<float, A, B, SpecColNB<float>::value>; \

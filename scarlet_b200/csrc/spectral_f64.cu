@@ -8,7 +8,8 @@ bool spec_kernels_f64(int L, SpecKernels<double> *out) {
     if (L == (A) * (B)) {                                                         \
         out->R1 = A, out->R2 = B, out->NBcol = SpecColNB<double>::value;           \
         out->render = k_spec_render<double, A, B>;                                 \
-        out->residual = k_spec_residual<double, A, B>;                             \
+        out->residual = k_spec_residual<double, A, B>;                                 \
+        out->residual_r = k_spec_residual<double, A, B, true>;                             \
         out->grad = k_spec_grad<double, A, B>;                                     \
         out->column = k_spec_column<double, A, B, SpecColNB<double>::value>;        \
         out->column_fwd = k_spec_column_fwd<double, A, B, SpecColNB<double>::value>; \
