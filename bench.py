@@ -51,7 +51,7 @@ def parse():
     return ap.parse_args()
 
 
-DEFAULT_SCENES = {"cfg2": 256, "cfg3": 96, "cfg4": 64, "cfg5": 512, "tiny": 64}
+DEFAULT_SCENES = {"cfg2": 256, "cfg3": 192, "cfg4": 64, "cfg5": 512, "tiny": 64}
 DEFAULT_ITERS = {"cfg2": 50, "cfg3": 50, "cfg4": 50, "cfg5": 50, "tiny": 20}
 
 
