@@ -93,7 +93,8 @@ typedef struct sb_source_desc {
     int32_t shifting;       /* kind 0 only: the model uses fft.shift(image, shift) (morphology.py:124-130, fft.py:399-428); the
                                free ``shift`` parameter then travels in the centre arrays like a point-source centre */
     int32_t shift_Fy, shift_Fx; /* the reference's fast grid of that shift: _get_fft_shape(image, image, padding=10) */
-    int32_t _pad0;
+    int32_t resizing;       /* kind 0 only: the box adapts during the fit (ImageMorphology(resizing=True), morphology.py:132-207);
+                               sb_plan_inspect evaluates the shrink / grow rules for such sources */
     double shift_step;      /* constant step of the shift parameter (1e-1, morphology.py:672-675) */
     double morph_step;      /* constant step of the image / center parameter */
     double sed_step_factor; /* relative_step factor (parameter.py:126-129); <0: constant step = sed_step_min[0] */
@@ -184,6 +185,15 @@ int sb_plan_scene_control(sb_plan *plan, const int32_t *it_local, const int32_t 
 int sb_plan_scene_status(sb_plan *plan, int32_t *it_local, int32_t *loss_len, int32_t *state);
 int sb_plan_run(sb_plan *plan, const sb_fit_opts *opts, int max_launches, int32_t *launched);
 /* loss histories [n_scenes][n_cols] (n_cols <= the capacity set by the largest max_iter seen so far) */
+/* Dynamic boxes: for every source of a PAUSED scene that is marked `resizing`, evaluate ImageMorphology.update's rules on the
+ * device (morphology.py:52-68, 132-207): action[k] = new box size (shrink: outer rings entirely <= 0; grow: the next gradient
+ * update pulls more than 0.1 of the peak towards an edge), 0 = keep, -1 = too close to a threshold to call (the host decides).
+ * action has n_sources entries.  The host only has to look at sources with action != 0. */
+int sb_plan_inspect(sb_plan *plan, int32_t *action);
+/* Replace the sources of a plan (same scenes, frame and observations; new boxes / chains / tables): everything on the
+ * observation side -- data, weights, K^, spectral buffers, tensor maps -- stays where it is.  Parameters and optimiser state
+ * are NOT carried over: upload them afterwards.  desc->obs must equal the plan's. */
+int sb_plan_set_sources(sb_plan *plan, const sb_batch_desc *desc);
 int sb_plan_download_loss(sb_plan *plan, double *loss, int n_cols);
 /* ... and back (a re-planned batch continues its histories: the stop rule compares with the previous entry) */
 int sb_plan_upload_loss(sb_plan *plan, const double *loss, int n_cols);

@@ -44,7 +44,7 @@ class sb_source_desc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("By", C.c_int32), ("Bx", C.c_int32), ("oy", C.c_int32), ("ox", C.c_int32),
                 ("chain", C.c_int32), ("sed_chain", C.c_int32), ("sed_is_f32", C.c_int32), ("morph_fixed", C.c_int32),
                 ("sed_fixed", C.c_int32), ("shifting", C.c_int32), ("shift_Fy", C.c_int32), ("shift_Fx", C.c_int32),
-                ("_pad0", C.c_int32), ("shift_step", C.c_double), ("morph_step", C.c_double),
+                ("resizing", C.c_int32), ("shift_step", C.c_double), ("morph_step", C.c_double),
                 ("sed_step_factor", C.c_double), ("sed_step_min", C.c_double * SB_MAX_CHANNELS)]
 
 
@@ -76,6 +76,8 @@ SYMBOLS = {
     "sb_plan_scene_status": (C.c_int, [_P, _P, _P, _P]),
     "sb_plan_run": (C.c_int, [_P, C.POINTER(sb_fit_opts), C.c_int, _P]),
     "sb_plan_download_loss": (C.c_int, [_P, _P, C.c_int]),
+    "sb_plan_inspect": (C.c_int, [_P, _P]),
+    "sb_plan_set_sources": (C.c_int, [_P, C.POINTER(sb_batch_desc)]),
     "sb_plan_upload_loss": (C.c_int, [_P, _P, C.c_int]),
     "sb_plan_create": (C.c_int, [C.POINTER(sb_batch_desc), C.c_int, C.POINTER(_P)]),
     "sb_plan_destroy": (None, [_P]),

@@ -119,7 +119,33 @@ class DevicePlan:
                                           _const_step(m0["psf_shift"]) if has_shift else 0.0)
             self.obs_meta.append(dict(metas=metas, shared=shared))
 
-        # ---- sources -----------------------------------------------------------------------------
+        self._desc = desc
+        self._describe_sources(desc)
+        handle = ctypes.c_void_p()
+        nat.check(nat.lib().sb_plan_create(ctypes.byref(desc), self.device, ctypes.byref(handle)))
+        self._handle = handle
+        self._build_store()
+        self.upload_observations()
+
+    def replace_sources(self):
+        """Dynamic boxes: the sources of the same scenes changed shape (``ImageMorphology.update``).  Only the source side of
+        the device plan is rebuilt (``sb_plan_set_sources``); data, weights, K^ and every spectral buffer stay on the device.
+        Parameters and optimiser state travel through the host: upload them afterwards."""
+        self._detach_store()
+        for p in getattr(self, "_store_ptrs", []):  # back to the pool (still owned by the plan, freed in close())
+            self._pinned_pool.append((p, self._pinned_sizes[p]))
+        self._store_ptrs = []
+        self._describe_sources(self._desc)
+        nat.check(nat.lib().sb_plan_set_sources(self._handle, ctypes.byref(self._desc)))
+        self._replanning = True
+        try:
+            self._build_store()
+        finally:
+            self._replanning = False
+
+    def _describe_sources(self, desc):
+        """Walk the sources of every scene -> flat source / chain / table descriptors inside ``desc`` (kept alive in ``_keep``)."""
+        C, Ny, Nx = self.frame_shape
         tables = MonoTables()
         chains, chain_keys = [], {}
 
@@ -187,6 +213,7 @@ class DevicePlan:
                     d.chain = chain_index(img.constraint, img.shape)
                     d.morph_step = _const_step(img)
                     d.morph_fixed = int(bool(img.fixed))
+                    d.resizing = int(bool(getattr(morph, "resizing", False)) and not img.fixed)
                     shift = morph.parameters[1] if len(morph.parameters) > 1 else None
                     if morph.shifting:  # the shift is a fitted parameter: it travels in the centre arrays
                         from . import fft
@@ -195,11 +222,12 @@ class DevicePlan:
                         fshape = fft._get_fft_shape(img._data, img._data, padding=10, axes=(0, 1))
                         d.shifting, d.shift_Fy, d.shift_Fx = 1, int(fshape[0]), int(fshape[1])
                         d.shift_step = 0.0 if shift.fixed else _const_step(shift)
-                        slot.update(kind=0, image=img, shift=None, center=shift)
+                        slot.update(kind=0, image=img, shift=None, center=shift, morph=morph)
                     else:
-                        slot.update(kind=0, image=img, shift=shift)
+                        slot.update(kind=0, image=img, shift=shift, morph=morph)
                 else:
                     raise TypeError("morphology model %s is not on the device path" % type(morph).__name__)
+                slot["scene"] = len(starts) - 1
                 src_descs.append(d)
                 self.slots.append(slot)
             starts.append(len(src_descs))
@@ -228,11 +256,13 @@ class DevicePlan:
         desc.chains = ctypes.addressof(chain_arr)
         desc.mono = ctypes.addressof(mono_arr)
         self._keep = [src_arr, chain_arr, mono_arr, start_arr, tables]
-        handle = ctypes.c_void_p()
-        nat.check(nat.lib().sb_plan_create(ctypes.byref(desc), self.device, ctypes.byref(handle)))
-        self._handle = handle
-        self._build_store()
-        self.upload_observations()
+
+    def inspect(self):
+        """Dynamic boxes: the device's reading of ``ImageMorphology.update``'s rules for every source of a paused scene ->
+        int32 array over the sources: new box size, 0 = keep, -1 = the host has to decide."""
+        action = np.zeros(max(self.n_src, 1), dtype=np.int32)
+        nat.check(nat.lib().sb_plan_inspect(self._handle, nat.ptr(action)))
+        return action[:self.n_src]
 
     # -------------------------------------------------------------------------------------------------
     @staticmethod
@@ -269,12 +299,24 @@ class DevicePlan:
                     shift_grid=r.shift_grid() if psf_shift is not None else (0, 0))
 
     def _pinned(self, shape, dtype):
-        """numpy view of pinned host memory (sb_host_alloc) -- staging for asynchronous H2D copies."""
+        """numpy view of pinned host memory (sb_host_alloc) -- staging for asynchronous H2D copies.  Buffers returned to the
+        pool by ``replace_sources`` are reused when large enough (cudaHostAlloc costs milliseconds)."""
         n = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        p = nat.lib().sb_host_alloc(max(n, 8))
-        if not p:
-            raise MemoryError("sb_host_alloc(%d) failed" % n)
-        self._pinned_ptrs.append(p)
+        pool = self.__dict__.setdefault("_pinned_pool", [])
+        fit = [i for i, (q, size) in enumerate(pool) if size >= max(n, 8)]
+        if fit:
+            i = min(fit, key=lambda j: pool[j][1])
+            p, size = pool.pop(i)
+            self.__dict__.setdefault("_pinned_sizes", {})[p] = size
+        else:
+            size = max(n, 8)
+            if self.__dict__.get("_replanning"):
+                size = int(size * 1.25)  # a re-planned batch: boxes tend to grow, leave headroom for the next re-plan
+            p = nat.lib().sb_host_alloc(size)
+            if not p:
+                raise MemoryError("sb_host_alloc(%d) failed" % size)
+            self._pinned_ptrs.append(p)
+            self.__dict__.setdefault("_pinned_sizes", {})[p] = size
         buf = (ctypes.c_byte * max(n, 8)).from_address(p)
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
@@ -409,6 +451,7 @@ class DevicePlan:
             else:
                 self._tables[group] = None
         self._param_refs = [p for p, _ in self._linked]  # keep the arrays (and their addresses) alive
+        self._store_ptrs = [a.ctypes.data for key in _HostStore.KEYS for a in self.store.arrays[key].values()]
 
     def _gather_values(self):
         vals = self.store.arrays["value"]

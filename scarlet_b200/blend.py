@@ -257,48 +257,76 @@ class BlendBatch:
         opts.max_iter, opts.pause_every = int(max_iter), 10
         opts.check_every = min(opts.check_every, 10)
         h2d = d2h = 0
-        need_plan, first = False, True
         lib = nat.lib()
+        if self.plan._handle is None:
+            self.plan = DevicePlan(self.blends, precision=self.precision, device=self.device)
+            self.plans, self.parts = [self.plan], [self.blends]
+        elif upload_observations:
+            h2d += self.plan.upload_observations()
+        plan = self.plan
+        # which leaf component (device source index) belongs to which scene / source object
+        host_current = True   # the host Parameters hold what the device holds
+        need_upload = True    # ... and the device has to be told (first round, or after a re-plan)
         while not finished.all():
-            if need_plan or self.plan._handle is None:
-                self.plan.close()
-                self.plan = DevicePlan(self.blends, precision=self.precision, device=self.device)
-                self.plans, self.parts = [self.plan], [self.blends]
-                self.replans += 1
-                need_plan = False
-                nat.check(lib.sb_plan_upload_loss(self.plan._handle, nat.ptr(loss), int(max_iter)))
-            elif first and upload_observations:
-                h2d += self.plan.upload_observations()
-            first = False
-            plan = self.plan
-            h2d += plan.upload_parameters(state=True)
+            if need_upload:
+                h2d += plan.upload_parameters(state=True)
+                need_upload = False
             active = (~finished).astype(np.int32)
             nat.check(lib.sb_plan_scene_control(plan._handle, nat.ptr(it_local), nat.ptr(loss_len), nat.ptr(limit), nat.ptr(active),
                                                 nat.ptr(prox)))
             launched = ctypes.c_int32()
             nat.check(lib.sb_plan_run(plan._handle, ctypes.byref(opts), int(max_iter) + 1, ctypes.byref(launched)))
+            host_current = False
             state = np.zeros(S, dtype=np.int32)
             nat.check(lib.sb_plan_scene_status(plan._handle, nat.ptr(it_local), nat.ptr(loss_len), nat.ptr(state)))
-            nat.check(lib.sb_plan_download_loss(plan._handle, nat.ptr(loss), int(max_iter)))
-            d2h += plan.download_parameters(state=True) + loss.nbytes
+            paused = (state & nat.SCENE_PAUSED) != 0
+            # the device reads ImageMorphology.update's rules for every source of a paused scene; only sources it flags (box
+            # change, or too close to a threshold to call) need the host -- and only then do parameters travel
+            action = plan.inspect() if paused.any() else np.zeros(plan.n_src, dtype=np.int32)
+            flagged = [k for k in np.nonzero(action)[0]]
+            if flagged or (state & nat.SCENE_FAILED).any():
+                d2h += plan.download_parameters(state=True)
+                host_current = True
+            changed_scene = np.zeros(S, dtype=bool)
+            flagged_comps = {id(plan.slots[k]["comp"]) for k in flagged}
+
+            def update(node):
+                """``src.update()`` restricted to the leaves the device flagged (the others would return unchanged): a
+                multi-component source stops at its first child that changed and re-derives its box (component.py:173-181,
+                262-273)."""
+                if isinstance(node, CombinedComponent):
+                    for child in node.children:
+                        try:
+                            update(child)
+                        except UpdateException:
+                            box = node.children[0].bbox.copy()
+                            for c in node.children[1:]:
+                                box = box | c.bbox
+                            node.bbox = box
+                            raise
+                elif id(node) in flagged_comps:
+                    node.update()
+
+            for s in sorted({plan.slots[k]["scene"] for k in flagged}):
+                if not paused[s]:
+                    continue
+                for src in self.blends[s].sources:
+                    try:
+                        update(src)
+                    except UpdateException:
+                        changed_scene[s] = True
             for s, b in enumerate(self.blends):
                 if finished[s]:
                     continue
                 st = int(state[s])
-                if st == nat.SCENE_FAILED:
+                if st & nat.SCENE_FAILED:
+                    nat.check(lib.sb_plan_download_loss(plan._handle, nat.ptr(loss), int(max_iter)))
                     b.loss.extend(loss[s, :loss_len[s]].tolist())
                     for src in b.sources:
                         src.check_parameters()  # raises ArithmeticError naming the parameter (model.py:153-165)
                     raise ArithmeticError("scene %d: a parameter became non-finite during the fit" % s)
                 if st & nat.SCENE_PAUSED:
-                    changed = False
-                    for src in b.sources:
-                        try:
-                            src.update()
-                        except UpdateException:
-                            changed = True
-                    if changed:  # blend.py:196-198: restart with it = len(loss); the popped keywords are gone (defaults)
-                        need_plan = True
+                    if changed_scene[s]:  # blend.py:196-198: restart with it = len(loss); the popped keywords are gone (defaults)
                         it_local[s], prox[s] = 0, 10
                         limit[s] = max_iter - prev_len[s]
                         finished[s] = loss_len[s] >= limit[s]
@@ -306,10 +334,18 @@ class BlendBatch:
                         finished[s] = True
                     else:
                         finished[s] = loss_len[s] >= limit[s]
-                elif st in (nat.SCENE_CONVERGED, nat.SCENE_EXHAUSTED):
+                elif st & (nat.SCENE_CONVERGED | nat.SCENE_EXHAUSTED):
                     finished[s] = True
                 elif st == nat.SCENE_RUN and launched.value >= max_iter + 1:
                     finished[s] = True  # cannot happen (budget >= launches); guards an endless loop
+            if changed_scene.any():
+                plan.replace_sources()  # new boxes / tables; observations stay on the device
+                self.replans += 1
+                need_upload = True
+        if not host_current:
+            d2h += plan.download_parameters(state=True)
+        nat.check(lib.sb_plan_download_loss(plan._handle, nat.ptr(loss), int(max_iter)))
+        d2h += loss.nbytes
         self.last_transfer_bytes = (int(h2d), int(d2h))
         results = []
         for s, b in enumerate(self.blends):

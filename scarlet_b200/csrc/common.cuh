@@ -60,7 +60,7 @@ template <> struct Cx<double> {
 struct DevSource {
     int kind, By, Bx, oy, ox, chain, sed_chain, sed_is_f32, morph_fixed, sed_fixed;
     int scene, point_idx; // point_idx: slot in the centre arrays (point-source centre, or sub-pixel shift of a shifting image)
-    int shifting, shift_Fy, shift_Fx, _pad; // Fourier-shifted image morphology (fft.py:399-428) on its own fast grid
+    int shifting, shift_Fy, shift_Fx, resizing; // Fourier-shifted image morphology (fft.py:399-428) on its own fast grid; dynamic box
     long long toep_off;  // offset (in vectors of length 2*Bmax-1) of this source's 8 Toeplitz vectors
     double shift_step;
     long long morph_off; // kind 0: element offset in the packed morphology arrays; kind 1: offset in pmorph

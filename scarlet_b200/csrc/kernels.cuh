@@ -1440,6 +1440,85 @@ __global__ void k_tick(int *n_active, int *n_active_next) {
 }
 
 // ======================================================================================================
+// Dynamic boxes: ImageMorphology.update's decision for one source (morphology.py:52-68 shrink_box, 132-207 update;
+// initialization.py:173-177 allowed sizes 21, 31, 41, ...).  One CTA per source; nothing is modified.
+//   shrink: d = number of complete outer rings with every pixel <= 0; new size = smallest allowed >= size - 2 d, if smaller
+//   grow  : gu = -m / sqrt(sqrt(v)) * step over pixels with v != 0; pull = gu where image > 0 else 0; if the mean pull of one
+//           of the four edges exceeds 0.1: new size = smallest allowed >= size + 1
+// The host evaluates the same rules in float64 from the same values; its edge means are pairwise sums, so a mean within 1e-9
+// (relative) of the threshold is reported as "undecided" (-1) and left to the host.
+// ======================================================================================================
+__device__ __forceinline__ int minimal_boxsize_dev(int size) {
+    int b = 21;
+    while (b < size) b += 10;
+    return b;
+}
+template <typename T>
+__global__ void __launch_bounds__(128) k_inspect(const DevSource *src, int n_src, const T *morph, const T *morph_m, const T *morph_v,
+                                                 const int *state, int *action) {
+    __shared__ int ring_ne[128];
+    __shared__ double red[40];
+    const int k = blockIdx.x;
+    if (k >= n_src) return;
+    const DevSource &d = src[k];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int act = 0;
+    const bool look = d.kind == 0 && d.resizing && !d.morph_fixed && (state[d.scene] & SB_PAUSED);
+    if (!look) {
+        if (tid == 0) action[k] = 0;
+        return;
+    }
+    if (d.By != d.Bx || d.By > 250) { // the rules are written for square boxes; anything else is the host's call
+        if (tid == 0) action[k] = -1;
+        return;
+    }
+    const int n = d.By, np = n * n;
+    const T *x = morph + d.morph_off, *m = morph_m + d.morph_off, *v = morph_v + d.morph_off;
+    for (int r = tid; r < 128; r += nt) ring_ne[r] = 0;
+    __syncthreads();
+    for (int p = tid; p < np; p += nt) {
+        const int yy = p / n, xx = p - yy * n;
+        const int r = min(min(yy, xx), min(n - 1 - yy, n - 1 - xx));
+        if (!(x[p] <= T(0))) ring_ne[r] = 1; // np.all(image <= 0) fails for this ring (a NaN fails it too)
+    }
+    __syncthreads();
+    int dist = 0;
+    while (dist < (n + 1) / 2 && !ring_ne[dist]) ++dist;
+    const int shrunk = minimal_boxsize_dev(n - 2 * dist);
+    if (shrunk < n) {
+        if (tid == 0) action[k] = shrunk;
+        return;
+    }
+    // edge pull: four edges, masked means
+    double sum[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0};
+    for (int i = tid; i < n; i += nt) {
+        const int idx[4] = {i * n, i * n + n - 1, i, (n - 1) * n + i}; // [:,0], [:,-1], [0,:], [-1,:]
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const double vv = (double)v[idx[e]];
+            if (vv != 0.0) {
+                const double gu = -(double)m[idx[e]] / sqrt(sqrt(vv)) * d.morph_step;
+                sum[e] += x[idx[e]] > T(0) ? gu : gu * 0.0;
+                cnt[e] += 1.0;
+            }
+        }
+    }
+    bool grow = false, unsure = false;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const double s_ = block_sum(sum[e], red), c_ = block_sum(cnt[e], red);
+        if (c_ > 0) {
+            const double mean = s_ / c_;
+            if (fabs(mean - 0.1) < 1e-9) unsure = true;
+            if (mean > 0.1) grow = true;
+            if (!(mean == mean)) unsure = true; // NaN: let the host see it
+        }
+    }
+    act = unsure ? -1 : (grow ? minimal_boxsize_dev(n + 1) : 0);
+    if (tid == 0) action[k] = act;
+}
+
+// ======================================================================================================
 // single-operator kernels (test / plugin entry points)
 // ======================================================================================================
 template <typename T>

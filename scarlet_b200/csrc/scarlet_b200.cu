@@ -292,6 +292,8 @@ struct sb_plan {
     virtual int run(const sb_fit_opts *o, int max_launches, int32_t *launched) = 0;
     virtual int download_loss(double *loss, int n_cols) = 0;
     virtual int upload_loss(const double *loss, int n_cols) = 0;
+    virtual int inspect(int32_t *action) = 0;
+    virtual int set_sources(const sb_batch_desc *desc) = 0;
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
@@ -425,7 +427,20 @@ template <typename T> struct PlanT : sb_plan {
         SB_CUDA(cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking));
         SB_CUDA(cudaEventCreateWithFlags(&ev_join2, cudaEventDisableTiming));
         SB_CUDA(cudaHostAlloc((void **)&h_nactive, sizeof(int), cudaHostAllocDefault));
+        SB_TRY(init_sources());
+        SB_TRY(init_observations());
+        return SB_OK;
+    }
 
+    // Everything that depends on the sources (boxes, chains, wavefront tables, parameter arrays, update-kernel groups).  Runs at
+    // plan creation and again from sb_plan_set_sources (dynamic boxes): every buffer is (re)allocated, nothing is carried over.
+    std::vector<int> psf_slot0;
+    int init_sources() {
+        n_src = desc.n_sources;
+        if (n_src < 0 || !desc.scene_src_start || (n_src && !desc.sources)) return set_err(SB_ERR_ARG, "missing source tables");
+        n_point = 0, npix_max = 0, npix_shift = 0, n_morph = 0, n_pmorph = 0, n_shift = 0, toep_len = 1;
+        monos.clear();
+        hmonos.clear();
         // ---- constraint tables
         for (int i = 0; i < desc.n_chains; ++i) SB_TRY(check_chain(desc.chains[i], desc.n_mono));
         std::vector<DevMono> hm(std::max(desc.n_mono, 1));
@@ -461,7 +476,7 @@ template <typename T> struct PlanT : sb_plan {
                 memset(&d, 0, sizeof d);
                 d.kind = in.kind, d.By = in.By, d.Bx = in.Bx, d.oy = in.oy, d.ox = in.ox, d.chain = in.chain, d.sed_chain = in.sed_chain;
                 d.sed_is_f32 = in.sed_is_f32, d.morph_fixed = in.morph_fixed, d.sed_fixed = in.sed_fixed, d.scene = s;
-                d.morph_step = in.morph_step, d.sed_step_factor = in.sed_step_factor;
+                d.morph_step = in.morph_step, d.sed_step_factor = in.sed_step_factor, d.resizing = in.kind == 0 ? in.resizing : 0;
                 memcpy(d.sed_step_min, in.sed_step_min, sizeof d.sed_step_min);
                 if (d.By <= 0 || d.Bx <= 0 || (long long)d.By * d.Bx >= 0xffff) return set_err(SB_ERR_ARG, "source %d: bad box %dx%d", k, d.By, d.Bx);
                 if (d.chain >= desc.n_chains || d.sed_chain >= desc.n_chains) return set_err(SB_ERR_ARG, "source %d: chain index out of range", k);
@@ -502,7 +517,7 @@ template <typename T> struct PlanT : sb_plan {
         }
         npix_max = (npix_max + 3) & ~3;
         // renderer parameters (psf_shift) take centre slots behind the sources': observation-major, one per scene
-        std::vector<int> psf_slot0(desc.n_obs, -1);
+        psf_slot0.assign(desc.n_obs, -1);
         for (int o = 0; o < desc.n_obs; ++o)
             if (desc.obs[o].psf_shift) {
                 psf_slot0[o] = n_point;
@@ -545,21 +560,75 @@ template <typename T> struct PlanT : sb_plan {
                 return set_err(SB_ERR_ARG, "largest box of a shifting source (%d px) does not fit in shared memory", npix_shift);
             SB_TRY(raise_smem((const void *)k_shift_apply<T>, (size_t)3 * npix_shift * sizeof(T)));
         }
-        SB_TRY(d_done.alloc(S));
-        SB_TRY(d_niter.alloc(S));
-        SB_TRY(d_status.alloc(S));
-        SB_TRY(d_it.alloc(S));
-        SB_TRY(d_state.alloc(S));
-        SB_TRY(d_limit.alloc(S));
-        SB_TRY(d_prox_iter.alloc(S));
-        SB_TRY(d_nactive.alloc(1));
-        SB_TRY(d_nactive_next.alloc(1));
-        SB_TRY(d_loss_const.alloc(S));
-        SB_TRY(d_loss_const.zero(stream));
+        if (!d_done.p) { // per-scene run state and loss constants: allocated once, they outlive a change of sources
+            SB_TRY(d_done.alloc(S));
+            SB_TRY(d_niter.alloc(S));
+            SB_TRY(d_status.alloc(S));
+            SB_TRY(d_it.alloc(S));
+            SB_TRY(d_state.alloc(S));
+            SB_TRY(d_limit.alloc(S));
+            SB_TRY(d_prox_iter.alloc(S));
+            SB_TRY(d_nactive.alloc(1));
+            SB_TRY(d_nactive_next.alloc(1));
+            SB_TRY(d_loss_const.alloc(S));
+            SB_TRY(d_loss_const.zero(stream));
+        }
         SB_TRY(ensure_loss_cap(256));
-
-        // ---- observations
+        max_src_scene = 0;
         for (int s_ = 0; s_ < S; ++s_) max_src_scene = std::max(max_src_scene, h_start[s_ + 1] - h_start[s_]);
+        // dynamic shared memory of the generic update kernel
+        const size_t smem = update_smem();
+        if (smem > 227 * 1024) return set_err(SB_ERR_ARG, "largest morphology box (%d px) does not fit in shared memory", npix_max);
+        SB_TRY(raise_smem((const void *)k_update<T>, smem));
+        return SB_OK;
+    }
+
+    size_t render_smem(const Obs &ob) const {
+        return ob.smem_row + (size_t)ob.cb * 2 * ob.npair * desc.Nx * sizeof(T) + 16 + (size_t)(max_src_scene + 1) * (sizeof(int) + sizeof(SpecCand<T>));
+    }
+
+    // sb_plan_set_sources: new boxes / chains / tables for the same scenes and observations
+    DevBuf<int> d_action;
+    int inspect(int32_t *action) override {
+        SB_CUDA(cudaSetDevice(device));
+        if (!action) return set_err(SB_ERR_ARG, "null action array");
+        if (d_action.n < (size_t)std::max(n_src, 1)) SB_TRY(d_action.alloc(std::max(n_src, 1)));
+        if (n_src) {
+            k_inspect<T><<<n_src, 128, 0, stream>>>(d_src.p, n_src, d_morph.p, d_morph_m.p, d_morph_v.p, d_state.p, d_action.p);
+            SB_CUDA(cudaGetLastError());
+            SB_CUDA(cudaMemcpyAsync(action, d_action.p, (size_t)n_src * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        }
+        SB_CUDA(cudaStreamSynchronize(stream));
+        return SB_OK;
+    }
+
+    int set_sources(const sb_batch_desc *dsc) override {
+        SB_CUDA(cudaSetDevice(device));
+        SB_CUDA(cudaStreamSynchronize(stream));
+        if (dsc->n_scenes != S || dsc->C != C || dsc->Ny != desc.Ny || dsc->Nx != desc.Nx || dsc->n_obs != desc.n_obs ||
+            dsc->precision != desc.precision || memcmp(dsc->obs, desc.obs, sizeof desc.obs) != 0)
+            return set_err(SB_ERR_ARG, "sb_plan_set_sources: scenes, frame and observations must be the plan's");
+        desc = *dsc;
+        SB_TRY(init_sources());
+        for (size_t o = 0; o < obs.size(); ++o) {
+            Obs &ob = *obs[o];
+            if (ob.psf_shift) ob.slot0 = psf_slot0[o];
+            if (ob.fused) {
+                ob.smem_render = render_smem(ob);
+                if (ob.smem_render > 227 * 1024) return set_err(SB_ERR_ARG, "observation %d: frame too wide for the fused spectral kernels", (int)o);
+                SB_TRY(raise_smem((const void *)ob.kx.render, ob.smem_render));
+            }
+        }
+        have_graph = false;
+        drop_scene_tables();
+        SB_TRY(reset_counters());
+        SB_CUDA(cudaStreamSynchronize(stream));
+        dev_bytes = total_bytes();
+        return SB_OK;
+    }
+
+    int init_observations() {
+        // ---- observations
         {
             const char *mode = getenv("SB_SPECTRAL");
             fused = !(mode && strcmp(mode, "cufft") == 0);
@@ -616,8 +685,7 @@ template <typename T> struct PlanT : sb_plan {
                 if (ob.row_threads > limit) ob.row_threads = ob.npair * ob.cb * rmax;
                 const size_t nb = (size_t)ob.npair * ob.cb;
                 ob.smem_row = (nb * ob.kx.sf + (size_t)Fx) * sizeof(cplx) + 16;
-                ob.smem_render = ob.smem_row + (size_t)ob.cb * 2 * ob.npair * desc.Nx * sizeof(T) + 16 +
-                                 (size_t)(max_src_scene + 1) * (sizeof(int) + sizeof(SpecCand<T>));
+                ob.smem_render = render_smem(ob);
                 ob.smem_col = ((size_t)ob.ky.NBcol * ob.ky.sf + (size_t)Fy) * sizeof(cplx) + 16;
                 if (ob.smem_render > 227 * 1024 || ob.smem_col > 227 * 1024)
                     return set_err(SB_ERR_ARG, "observation %d: frame too wide for the fused spectral kernels", o);
@@ -706,10 +774,6 @@ template <typename T> struct PlanT : sb_plan {
             d.data = ob.data.p, d.weights = ob.weights.p;
         }
         SB_TRY(d_stage.alloc(1));
-        // dynamic shared memory of the update kernel
-        const size_t smem = update_smem();
-        if (smem > 227 * 1024) return set_err(SB_ERR_ARG, "largest morphology box (%d px) does not fit in shared memory", npix_max);
-        SB_TRY(raise_smem((const void *)k_update<T>, smem));
         SB_TRY(reset_counters());
         SB_CUDA(cudaStreamSynchronize(stream));
         dev_bytes += total_bytes();
@@ -1803,6 +1867,11 @@ int sb_plan_scene_status(sb_plan *plan, int32_t *it_local, int32_t *loss_len, in
 int sb_plan_run(sb_plan *plan, const sb_fit_opts *opts, int max_launches, int32_t *launched) { PLAN_CALL(run(opts, max_launches, launched)) }
 int sb_plan_download_loss(sb_plan *plan, double *loss, int n_cols) { PLAN_CALL(download_loss(loss, n_cols)) }
 int sb_plan_upload_loss(sb_plan *plan, const double *loss, int n_cols) { PLAN_CALL(upload_loss(loss, n_cols)) }
+int sb_plan_inspect(sb_plan *plan, int32_t *action) { PLAN_CALL(inspect(action)) }
+int sb_plan_set_sources(sb_plan *plan, const sb_batch_desc *desc) {
+    if (!desc) return set_err(SB_ERR_ARG, "null descriptor");
+    PLAN_CALL(set_sources(desc))
+}
 int sb_fft_supported_length(int need) { return spec_supported_length(need); }
 int sb_plan_sync(sb_plan *plan) {
     if (!plan) return set_err(SB_ERR_ARG, "null plan");
