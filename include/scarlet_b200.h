@@ -67,7 +67,8 @@ typedef struct sb_mono_desc {
 /* One Observation matched to the model frame (observation.py:59-114, renderer.py:164-202). */
 typedef struct sb_obs_desc {
     int32_t kind;     /* 0 = ConvolutionRenderer (fft), 1 = NullRenderer, 2 = ResolutionRenderer (aligned grids; H x W is the
-                         low-resolution cube, Fy x Fx the reference's _fft_shape, renderer.py:288-290) */
+                         low-resolution cube, Fy x Fx the reference's _fft_shape, renderer.py:288-290), 3 = ResolutionRenderer with
+                         rotated grids (renderer.py:318-363) */
     int32_t C, H, W;  /* data cube */
     int32_t chan_off; /* first model-frame channel (channel map = slice, renderer.py:26-51) */
     int32_t oy, ox;   /* position of data pixel (0,0) in the model frame (translation only) */
@@ -220,6 +221,12 @@ int sb_plan_upload_kernels(sb_plan *plan, int obs, const double *kernels, int Py
  * Ey complex128 [H][Fy], Ex complex128 [W][Fx/2+1] (exp(-2 pi i f s), Nyquist bins real, for the low-resolution pixel
  * rows / columns in model-frame grid coordinates) and h2 = (pixel-scale ratio)^2. */
 int sb_plan_upload_resampling(sb_plan *plan, int obs, const double *ey, const double *ex, double h2);
+/* Rotated resampling observation (kind 3; the rotated branch of ResolutionRenderer, renderer.py:318-363, 498-524: `shifts` per
+ * low-resolution row, `other_shifts` per column, sinc_shift along both axes).  K^ as for kind 2; a complex128 [H][Fy][Fx/2+1]
+ * and b complex128 [W][Fy][Fx/2+1] are the half-plane multipliers of the two-axis Fourier shifts attached to the rows and the
+ * columns (Hermitian part of the phase ramps, the model's entering conjugated and carrying the translation to the grid
+ * origin); LR[c,i,j] = h2 sum_kx w_kx Re sum_ky K^ conj(M^) a_i b_j.  H, W <= 32. */
+int sb_plan_upload_resampling_rot(sb_plan *plan, int obs, const double *a, const double *b, double h2);
 /* Pinned host memory for staging buffers: copies from/to it are asynchronous DMA. */
 void *sb_host_alloc(int64_t bytes);
 void sb_host_free(void *p);

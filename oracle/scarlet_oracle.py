@@ -823,6 +823,56 @@ class ResolutionObservationOracle(ObservationOracle):
         return out
 
 
+class RotatedResolutionObservationOracle(ResolutionObservationOracle):
+    """The rotated branch of ``ResolutionRenderer`` (renderer.py:318-363, 498-524): the observation's pixel grid is turned by
+    an angle against the model frame, so every low-resolution row needs the kernel shifted along BOTH axes (``shifts`` =
+    (Y cos, -Y sin) per row) and every column the model shifted along both axes (``other_shifts`` = (X sin, X cos)); the
+    render is again the contraction of the two tables.  Restated literally: ``sinc_shift`` with axes (1, 2) is an ``rfftn``
+    over (y, x), the phase ramp ``exp(shifter_y s0) exp(shifter_x s1)`` with ``mk_shifter(real=False)`` (full frequencies
+    along y, half along x), and ``irfftn`` back (renderer.py:414-476); the centre shifts of ``Fourier.fft`` / ``from_fft``
+    cancel in the contraction.  ``small_axis`` (data_frame.Nx <= data_frame.Ny) decides which table carries which index."""
+
+    def __init__(self, data, weights, diff_kernel_padded, shifts, other_shifts, h, small_axis=True, frame_dtype=np.float32,
+                 channel_offset=0):
+        ObservationOracle.__init__(self, data, weights, None, frame_dtype=frame_dtype, channel_offset=channel_offset)
+        self.kernel = np.asarray(diff_kernel_padded, dtype=np.float64)
+        self.fshape = self.kernel.shape[1:]
+        self.shifts = np.asarray(shifts, dtype=np.float64)
+        self.other_shifts = np.asarray(other_shifts, dtype=np.float64)
+        self.h, self.small_axis = float(h), bool(small_axis)
+        self.op = self.h ** 2 * np.stack([self._shift2(self.kernel, s0, s1) for s0, s1 in self.shifts.T], axis=1)  # (C, nq, Fy, Fx)
+
+    @staticmethod
+    def _shift2(arr, s0, s1):
+        Fy, Fx = arr.shape[-2:]
+        spec = np.fft.rfftn(arr, axes=(-2, -1))
+        ramp = np.exp(-2j * np.pi * np.fft.fftfreq(Fy) * s0)[:, None] * np.exp(-2j * np.pi * np.fft.rfftfreq(Fx) * s1)[None, :]
+        return np.fft.irfftn(spec * ramp, s=(Fy, Fx), axes=(-2, -1))
+
+    def render(self, model):
+        C = self.data.shape[0]
+        sub = np.asarray(model[self.channel_offset:self.channel_offset + C], dtype=np.float64)
+        Fy, Fx = self.fshape
+        Ny, Nx = self.frame_shape[1:]
+        padded = np.zeros((C, Fy, Fx))
+        padded[:, self.pad0[0]:self.pad0[0] + Ny, self.pad0[1]:self.pad0[1] + Nx] = sub
+        conv = np.stack([self._shift2(padded, -s0, -s1) for s0, s1 in self.other_shifts.T], axis=1)  # (C, nr, Fy, Fx)
+        out = np.einsum("cqyx,cryx->cqr", self.op, conv)
+        return (out if self.small_axis else out.transpose(0, 2, 1)).astype(self.frame_dtype)
+
+    def render_adjoint(self, grad_render):
+        """transpose of ``render``: a shift by (s0, s1) with these transform semantics transposes to the shift by (-s0, -s1)"""
+        C = self.data.shape[0]
+        Ny, Nx = self.frame_shape[1:]
+        g = np.asarray(grad_render, dtype=np.float64)
+        g = g if self.small_axis else g.transpose(0, 2, 1)
+        t = np.einsum("cqr,cqyx->cryx", g, self.op)
+        padded = sum(self._shift2(t[:, r], s0, s1) for r, (s0, s1) in enumerate(self.other_shifts.T))
+        out = np.zeros(self.frame_shape, dtype=np.float64)
+        out[self.channel_offset:self.channel_offset + C] = padded[:, self.pad0[0]:self.pad0[0] + Ny, self.pad0[1]:self.pad0[1] + Nx]
+        return out
+
+
 # ----------------------------------------------------------------------------------------------
 # the blend
 # ----------------------------------------------------------------------------------------------

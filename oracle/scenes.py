@@ -31,8 +31,13 @@ def build_multires_oracle(scene, setup, frame_dtype=np.float32, sed_dtype=np.flo
     tests/test_host_api.py::test_multiresolution_setup_vs_reference_fixture."""
     frame_shape = tuple(int(v) for v in setup["frame_shape"])
     model_psf = so.ImagePSFOracle(setup["model_psf"])
-    lr = so.ResolutionObservationOracle(scene["lr_images"], scene["lr_weights"], setup["lr_kernel"], setup["lr_shifts"], setup["lr_h"],
-                                        frame_dtype=frame_dtype, channel_offset=0)
+    if setup.get("lr_other_shifts") is not None:  # rotated grids (tests/test_host_api.py::test_rotated_multiresolution_setup_...)
+        lr = so.RotatedResolutionObservationOracle(scene["lr_images"], scene["lr_weights"], setup["lr_kernel"], setup["lr_shifts"],
+                                                   setup["lr_other_shifts"], setup["lr_h"], small_axis=setup["lr_small_axis"],
+                                                   frame_dtype=frame_dtype, channel_offset=0)
+    else:
+        lr = so.ResolutionObservationOracle(scene["lr_images"], scene["lr_weights"], setup["lr_kernel"], setup["lr_shifts"], setup["lr_h"],
+                                            frame_dtype=frame_dtype, channel_offset=0)
     lr.match(frame_shape, None)
     hr = so.ObservationOracle(scene["hr_images"], scene["hr_weights"], so.ImagePSFOracle(scene["hr_psfs"]), frame_dtype=frame_dtype,
                               channel_offset=5, origin=tuple(int(v) for v in setup["hr_origin"]))
@@ -49,4 +54,5 @@ def multires_setup(blend):
     r = obs_lr.renderer
     return dict(frame_shape=blend.frame.shape, model_psf=np.asarray(blend.frame.psf.get_model(), dtype=np.float64),
                 lr_kernel=np.asarray(r.diff_kernel.image, dtype=np.float64), lr_shifts=np.asarray(r.shifts), lr_h=float(r.h),
-                hr_origin=obs_hr.renderer.origin)
+                hr_origin=obs_hr.renderer.origin, lr_other_shifts=np.asarray(r.other_shifts) if r.isrot else None,
+                lr_small_axis=bool(getattr(r, "small_axis", True)))

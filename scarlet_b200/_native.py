@@ -87,6 +87,7 @@ SYMBOLS = {
     "sb_plan_upload_kernels": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "sb_plan_zero_state": (C.c_int, [_P]),
     "sb_plan_upload_resampling": (C.c_int, [_P, C.c_int, _P, _P, C.c_double]),
+    "sb_plan_upload_resampling_rot": (C.c_int, [_P, C.c_int, _P, _P, C.c_double]),
     "sb_host_gather_f64": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
     "sb_host_scatter_f64": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
     "sb_host_alloc": (_P, [C.c_int64]),

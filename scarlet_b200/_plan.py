@@ -279,7 +279,10 @@ class DevicePlan:
             fshape, kind = (blend.frame.shape[1], blend.frame.shape[2]), 1
         elif type(r) is ResolutionRenderer:
             operator = r.device_operator()
-            fshape, kind = operator["fshape"], 2
+            fshape, kind = operator["fshape"], 3 if operator["rotated"] else 2
+            if kind == 3 and max(obs.data.shape[1:]) > 32:
+                raise NotImplementedError("a rotated ResolutionRenderer is on the device path for low-resolution cubes up to 32x32 "
+                                          "pixels (got %s)" % (tuple(obs.data.shape[1:]),))
             if nat.lib().sb_fft_supported_length(int(fshape[0])) != fshape[0] or nat.lib().sb_fft_supported_length(int(fshape[1])) != fshape[1]:
                 raise NotImplementedError("ResolutionRenderer grid %s: the Fourier interpolation is tied to the reference's grid, and the "
                                           "fused spectral kernels are not instantiated for these lengths" % (tuple(fshape),))
@@ -348,16 +351,18 @@ class DevicePlan:
                 for i, k in enumerate(ks):
                     kernels[i] = k
             resamp = None
-            if metas[0]["kind"] == 2:
+            if metas[0]["kind"] in (2, 3):
                 ops = [metas[0]["operator"]] if om["shared"] else [m["operator"] for m in metas]
+                tables = ("A", "B") if metas[0]["kind"] == 3 else ("Ey", "Ex")
                 for op in ops[1:]:
-                    if not (np.array_equal(op["Ey"], ops[0]["Ey"]) and np.array_equal(op["Ex"], ops[0]["Ex"]) and op["scale"] == ops[0]["scale"]):
+                    if not (all(np.array_equal(op[t], ops[0][t]) for t in tables) and op["scale"] == ops[0]["scale"]):
                         raise ValueError("all scenes of a batch need the same resampling geometry")
                 khat = self._pinned((len(ops),) + ops[0]["khat"].shape, np.complex128)
                 for i, op in enumerate(ops):
                     khat[i] = op["khat"]
                 Fy, Fx = ops[0]["fshape"]
-                resamp = dict(khat=khat, Ey=ops[0]["Ey"], Ex=ops[0]["Ex"], h2=ops[0]["scale"] * Fy * Fx)
+                resamp = dict(khat=khat, tables=tuple(ops[0][t] for t in tables), rotated=metas[0]["kind"] == 3,
+                              h2=ops[0]["scale"] * Fy * Fx)
             self._host_obs.append(dict(data=data, weights=weights, kernels=kernels, korigin=metas[0]["korigin"], resamp=resamp,
                                        consts=self._loss_consts(metas)))
 
@@ -367,7 +372,7 @@ class DevicePlan:
         consts = []
         for m in metas:
             obs, (oy, ox) = m["obs"], m["origin"]
-            if m["kind"] == 2:  # resampled observation: every pixel is rendered
+            if m["kind"] in (2, 3):  # resampled observation: every pixel is rendered
                 consts.append(float(obs.log_norm))
                 continue
             H, W = obs.data.shape[1:]
@@ -395,9 +400,10 @@ class DevicePlan:
             nat.check(up(self._handle, o, nat.ptr(h["data"]), nat.ptr(h["weights"]),
                          nat.ptr(rs["khat"].view(np.float64)) if rs is not None else None, nat.ptr(h["consts"])))
             if rs is not None:
-                nat.check(nat.lib().sb_plan_upload_resampling(self._handle, o, nat.ptr(rs["Ey"].view(np.float64)),
-                                                              nat.ptr(rs["Ex"].view(np.float64)), rs["h2"]))
-                nbytes += rs["khat"].nbytes + rs["Ey"].nbytes + rs["Ex"].nbytes
+                up_rs = nat.lib().sb_plan_upload_resampling_rot if rs["rotated"] else nat.lib().sb_plan_upload_resampling
+                t0, t1 = rs["tables"]
+                nat.check(up_rs(self._handle, o, nat.ptr(t0.view(np.float64)), nat.ptr(t1.view(np.float64)), rs["h2"]))
+                nbytes += rs["khat"].nbytes + t0.nbytes + t1.nbytes
             if ker is not None:
                 nat.check(nat.lib().sb_plan_upload_kernels(self._handle, o, nat.ptr(ker), ker.shape[-2], ker.shape[-1],
                                                            h["korigin"][0], h["korigin"][1]))

@@ -278,6 +278,7 @@ struct sb_plan {
     virtual int upload_kernels(int obs, const double *ker, int Py, int Px, int y0, int x0) = 0;
     virtual int zero_state() = 0;
     virtual int upload_resampling(int obs, const double *ey, const double *ex, double h2) = 0;
+    virtual int upload_resampling_rot(int obs, const double *ra, const double *rb, double h2) = 0;
     virtual int upload_params(int which, const double *sed, const double *morph, const double *center) = 0;
     virtual int download_params(int which, double *sed, double *morph, double *center) = 0;
     virtual int evaluate(int obs, double *model, double *rendered, double *loss, double *g_sed, double *g_morph, double *g_center) = 0;
@@ -348,6 +349,9 @@ template <typename T> struct PlanT : sb_plan {
         SpecObs<T> sdev;
         SpecKernels<T> kx, ky;
         DevBuf<cplx> X, tw_x, tw_y, Pbuf, T1buf, Ey, Ex; // Pbuf..Ex: resampling observations (kind 2) only
+        DevBuf<cplx> RA, RB;                              // rotated resampling observations (kind 3): multiplier tables
+        DevBuf<T> Rres, Rpart;                            //   weighted residual, per-chunk partial renders
+        int rot_chunks = 0;
         DevBuf<T> G;
         int npair = 1, cb = 1, row_threads = 0;
         size_t smem_render = 0, smem_row = 0, smem_col = 0, smem_col_tma = 0;
@@ -635,7 +639,7 @@ template <typename T> struct PlanT : sb_plan {
             for (int o = 0; o < desc.n_obs && fused; ++o) {
                 const sb_obs_desc &od = desc.obs[o];
                 SpecKernels<T> k;
-                if ((od.kind != 0 && od.kind != 2) || !spec_kernels<T>(od.Fx, &k) || !spec_kernels<T>(od.Fy, &k)) fused = false;
+                if ((od.kind != 0 && od.kind != 2 && od.kind != 3) || !spec_kernels<T>(od.Fx, &k) || !spec_kernels<T>(od.Fy, &k)) fused = false;
             }
         }
         for (int o = 0; o < desc.n_obs; ++o) {
@@ -643,10 +647,10 @@ template <typename T> struct PlanT : sb_plan {
             obs.emplace_back(new Obs());
             Obs &ob = *obs.back();
             if (od.C <= 0 || od.chan_off < 0 || od.chan_off + od.C > C) return set_err(SB_ERR_ARG, "observation %d: channels outside the model frame", o);
-            if (od.kind != 0 && od.kind != 1 && od.kind != 2) return set_err(SB_ERR_ARG, "observation %d: unsupported renderer kind %d", o, od.kind);
+            if (od.kind < 0 || od.kind > 3) return set_err(SB_ERR_ARG, "observation %d: unsupported renderer kind %d", o, od.kind);
             if (od.psf_shift && !fused)
                 return set_err(SB_ERR_ARG, "observation %d: psf_shift needs FFT lengths of the fused spectral kernels (got %dx%d)", o, od.Fy, od.Fx);
-            if (od.kind == 2 && !fused)
+            if ((od.kind == 2 || od.kind == 3) && !fused)
                 return set_err(SB_ERR_ARG, "observation %d: a resampling observation needs FFT lengths of the fused spectral kernels "
                                            "(got %dx%d) and no NullRenderer observation in the same plan", o, od.Fy, od.Fx);
             int Fy = od.Fy, Fx = od.Fx;
@@ -723,6 +727,25 @@ template <typename T> struct PlanT : sb_plan {
                     SB_TRY(raise_smem((const void *)k_resample_t1<T>, (size_t)Fy * SB_RS_ROWS * sizeof(cplx)));
                     SB_TRY(raise_smem((const void *)k_resample_q<T>, (size_t)od.H * SB_RS_KY * sizeof(cplx)));
                 }
+                if (od.kind == 3) {
+                    if (od.H > 32 || od.W > 32) return set_err(SB_ERR_ARG, "observation %d: a rotated resampling observation is limited to 32x32 pixels (got %dx%d)", o, od.H, od.W);
+                    const size_t K = (size_t)Fy * Xp;
+                    ob.rot_chunks = (int)((K + SB_ROT_CHUNK - 1) / SB_ROT_CHUNK);
+                    ob.n_part = od.C;
+                    SB_TRY(ob.Pbuf.alloc((size_t)S * od.C * K));
+                    SB_TRY(ob.RA.alloc((size_t)od.H * K));
+                    SB_TRY(ob.RB.alloc((size_t)od.W * K));
+                    SB_TRY(ob.Rres.alloc(ndata));
+                    SB_TRY(ob.Rpart.alloc(ndata * ob.rot_chunks));
+                    SB_TRY(ob.Pbuf.zero(stream));
+                    SB_TRY(ob.RA.zero(stream));
+                    SB_TRY(ob.RB.zero(stream));
+                    SB_TRY(ob.Rres.zero(stream));
+                    SB_TRY(ob.Rpart.zero(stream));
+                    SB_TRY(raise_smem((const void *)ob.ky.column_fwd, ob.smem_col));
+                    SB_TRY(raise_smem((const void *)ob.ky.column_inv, ob.smem_col));
+                    SB_TRY(raise_smem((const void *)k_rot_partial<T>, (size_t)(od.H + od.W) * SB_ROT_SUB * sizeof(cplx)));
+                }
                 if (od.psf_shift) {
                     if (od.kind != 0) return set_err(SB_ERR_ARG, "observation %d: psf_shift needs a ConvolutionRenderer", o);
                     if (od.khat_shared && S > 1) return set_err(SB_ERR_ARG, "observation %d: psf_shift needs one renderer (kernel) per scene", o);
@@ -744,6 +767,7 @@ template <typename T> struct PlanT : sb_plan {
                 sd.X = ob.X.p, sd.khat = ob.khat.p, sd.G = ob.G.p, sd.data = ob.data.p, sd.weights = ob.weights.p;
                 sd.tw_x = ob.tw_x.p, sd.tw_y = ob.tw_y.p;
                 sd.P = ob.Pbuf.p, sd.T1 = ob.T1buf.p, sd.Ey = ob.Ey.p, sd.Ex = ob.Ex.p, sd.h2 = T(1);
+                sd.RA = ob.RA.p, sd.RB = ob.RB.p, sd.Rres = ob.Rres.p, sd.Rpart = ob.Rpart.p, sd.n_chunk = ob.rot_chunks, sd.chunk = SB_ROT_CHUNK;
                 continue;
             }
             d.Kp = d.Fxc, d.Bh = Fy, d.Bw = Fx;
@@ -996,7 +1020,7 @@ template <typename T> struct PlanT : sb_plan {
                 SB_CUDA(cudaGetLastError());
             }
         }
-        if (khat && (ob.dev.kind == 0 || ob.dev.kind == 2)) {
+        if (khat && (ob.dev.kind == 0 || ob.dev.kind == 2 || ob.dev.kind == 3)) {
             DevBuf<double2> &ks = ob.stage_z;
             const size_t nk = (size_t)(ob.dev.khat_shared ? 1 : S) * ob.dev.C * ob.dev.Fy * ob.dev.Fxc;
             if (ks.n < nk) SB_TRY(ks.alloc(nk));
@@ -1121,6 +1145,30 @@ template <typename T> struct PlanT : sb_plan {
         k_cast_scale_cplx<T><<<grid_for(ob.Ex.n), 256, 0, stream>>>(st.p, ob.Ex.p, (long long)ob.Ex.n, 1.0);
         SB_CUDA(cudaGetLastError());
         SB_CUDA(cudaStreamSynchronize(stream));
+        if (ob.sdev.h2 != (T)h2) have_graph = false; // h2 travels in the kernel arguments
+        ob.sdev.h2 = (T)h2;
+        return SB_OK;
+    }
+
+    // rotated resampling: A [H][Fy][Fx/2+1], B [W][Fy][Fx/2+1] complex128 -> pitched tables in the plan's precision
+    int upload_resampling_rot(int o, const double *ra, const double *rb, double h2) override {
+        if (o < 0 || o >= (int)obs.size()) return set_err(SB_ERR_ARG, "observation index %d out of range", o);
+        Obs &ob = *obs[o];
+        if (ob.dev.kind != 3 || !ra || !rb) return set_err(SB_ERR_ARG, "observation %d is not a rotated resampling observation", o);
+        SB_CUDA(cudaSetDevice(device));
+        const DevObs<T> &d = ob.dev;
+        const size_t per = (size_t)d.Fy * d.Fxc, na = (size_t)d.H * per, nb = (size_t)d.W * per;
+        DevBuf<double2> &st = ob.stage_z;
+        if (st.n < std::max(na, nb)) SB_TRY(st.alloc(std::max(na, nb)));
+        const double *src[2] = {ra, rb};
+        const size_t cnt[2] = {na, nb};
+        cplx *dst[2] = {ob.RA.p, ob.RB.p};
+        for (int q = 0; q < 2; ++q) {
+            SB_CUDA(cudaMemcpyAsync(st.p, src[q], cnt[q] * sizeof(double2), cudaMemcpyHostToDevice, stream));
+            k_cast_scale_cplx_pitched<T><<<grid_for(cnt[q]), 256, 0, stream>>>(st.p, dst[q], (long long)(cnt[q] / d.Fxc), d.Fxc, d.Kp, 1.0);
+            SB_CUDA(cudaGetLastError());
+            SB_CUDA(cudaStreamSynchronize(stream));
+        }
         if (ob.sdev.h2 != (T)h2) have_graph = false; // h2 travels in the kernel arguments
         ob.sdev.h2 = (T)h2;
         return SB_OK;
@@ -1317,6 +1365,30 @@ template <typename T> struct PlanT : sb_plan {
             ob.kx.render<<<rgrid, ob.row_threads, ob.smem_render, stream>>>(sa);
             SB_CUDA(cudaGetLastError());
             mark();
+            if (ob.dev.kind == 3) { // rotated resampling: M^ -> K^ conj(M^) -> contraction with A_i B_j -> residual -> K^ sum R A B -> G
+                const SpecObs<T> &sd = ob.sdev;
+                const int K = sd.Fy * sd.Xp;
+                ob.ky.column_fwd<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
+                SB_CUDA(cudaGetLastError());
+                mark();
+                k_rot_partial<T><<<dim3(sd.n_chunk, sd.C, S), 256, (size_t)(sd.H + sd.W) * SB_ROT_SUB * sizeof(cplx), stream>>>(sa);
+                SB_CUDA(cudaGetLastError());
+                mark();
+                k_rot_residual<T><<<S * sd.C, 256, 0, stream>>>(sa);
+                SB_CUDA(cudaGetLastError());
+                mark();
+                k_rot_adjoint<T><<<dim3((K + 127) / 128, S * sd.C), 128, (size_t)sd.H * sd.W * sizeof(T), stream>>>(sa);
+                SB_CUDA(cudaGetLastError());
+                mark();
+                ob.ky.column_inv<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
+                SB_CUDA(cudaGetLastError());
+                mark();
+                ob.kx.grad<<<rgrid, ob.row_threads, ob.smem_row, stream>>>(sa);
+                SB_CUDA(cudaGetLastError());
+                mark();
+                nk += 7;
+                continue;
+            }
             if (ob.dev.kind == 2) { // resampling observation: M^ -> K^ conj(M^) -> Ey . -> LR, residual -> . Ex, Ey^T . -> K^ Q^ -> G
                 const SpecObs<T> &sd = ob.sdev;
                 const dim3 tgrid((sd.Fxc + 127) / 128, (sd.H + SB_RS_ROWS - 1) / SB_RS_ROWS, S * sd.C);
@@ -1810,6 +1882,9 @@ int sb_plan_upload_kernels(sb_plan *plan, int obs, const double *kernels, int Py
 int sb_plan_zero_state(sb_plan *plan) { PLAN_CALL(zero_state()) }
 int sb_plan_upload_resampling(sb_plan *plan, int obs, const double *ey, const double *ex, double h2) {
     PLAN_CALL(upload_resampling(obs, ey, ex, h2))
+}
+int sb_plan_upload_resampling_rot(sb_plan *plan, int obs, const double *a, const double *b, double h2) {
+    PLAN_CALL(upload_resampling_rot(obs, a, b, h2))
 }
 int sb_host_gather_f64(double *dst, const void *const *src, const int64_t *count, const int32_t *is_f32, int64_t n) {
     if (!dst || !src || !count || !is_f32 || n < 0) return set_err(SB_ERR_ARG, "null argument");

@@ -40,6 +40,12 @@ template <typename T> struct SpecObs {
     const typename Cx<T>::type *Ey;   // [H][Fy]   exp(-2 pi i f_ky ys_i), Nyquist real
     const typename Cx<T>::type *Ex;   // [W][Fxc]  exp(-2 pi i f_kx xs_j), Nyquist real
     T h2;                             // (pixel-scale ratio)^2
+    // rotated resampling observations (renderer.py:318-363, 498-524): half-plane multipliers of the two-axis shifts
+    const typename Cx<T>::type *RA;   // [H][Fy][Xp]  attached to low-resolution row i
+    const typename Cx<T>::type *RB;   // [W][Fy][Xp]  attached to low-resolution column j
+    T *Rres;                          // [S][C][H][W] weighted residual
+    T *Rpart;                         // [S][C][n_chunk][H][W] partial sums of the render
+    int n_chunk, chunk;               // chunks of the flattened (ky, kx) index, entries per chunk
 };
 
 #define SB_SPEC_MAXCB 8 // bands per CTA of the row kernels (SpecArgs::cb <= this)
@@ -826,10 +832,141 @@ template <typename T> __global__ void __launch_bounds__(128) k_resample_q(const 
     }
 }
 
+// ======================================================================================================
+// Rotated resampling observation (renderer.py:318-363, 498-524).  The reference shifts the kernel along both axes to every
+// low-resolution row and the model along both axes to every column, then contracts the two tables.  Each two-axis shift is
+// a Fourier multiplier (interpolation.shift_multiplier: the real inverse transform keeps the Hermitian part of the phase
+// ramp, which matters on the Nyquist lines), so with P = K^ conj(M^)
+//     LR[c,i,j] = h^2 sum_kx w_kx Re sum_ky P[c,ky,kx] A_i[ky,kx] B_j[ky,kx]                 (w = 1, 2, ..., 2, 1)
+// -- the value of a band-limited image at the rotated position of pixel (i, j) -- and the adjoint is
+//     G = IDFT2( h^2 K^ sum_ij R[i,j] A_i B_j ).
+// Both are dense contractions over the flattened half plane k = (ky, kx): 2 H W Fy (Fx/2+1) complex multiply-adds per band
+// (what the reference spends in its (H x Fy Fx)(Fy Fx x W) matrix product).  H, W <= 32.
+// ======================================================================================================
+#define SB_ROT_SUB 64    // k entries staged per pass of the forward contraction
+#define SB_ROT_CHUNK 512 // k entries per CTA
+// grid (n_chunk, C, S), 256 threads: thread (ti, tj) owns the 2 x 2 block of outputs (2 ti + {0,1}, 2 tj + {0,1})
+template <typename T> __global__ void __launch_bounds__(256) k_rot_partial(const SpecArgs<T> a) {
+    typedef typename Cx<T>::type C2;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SpecObs<T> &ob = a.ob;
+    const int chunk = blockIdx.x, c = blockIdx.y, s = blockIdx.z;
+    if (a.done[s]) return;
+    const int H = ob.H, W = ob.W, Xp = ob.Xp, Fxc = ob.Fxc, K = ob.Fy * Xp, tid = threadIdx.x;
+    C2 *U = reinterpret_cast<C2 *>(smem);     // [H][SB_ROT_SUB]  w_kx P A_i
+    C2 *B = U + (size_t)H * SB_ROT_SUB;       // [W][SB_ROT_SUB]
+    const int tw = (W + 1) / 2, ti = tid / tw, tj = tid - ti * tw;
+    const bool work = ti < (H + 1) / 2;
+    const int i0 = 2 * ti, j0 = 2 * tj, i1 = min(i0 + 1, H - 1), j1 = min(j0 + 1, W - 1);
+    T acc00 = T(0), acc01 = T(0), acc10 = T(0), acc11 = T(0);
+    const C2 *P = ob.P + (size_t)(s * ob.C + c) * K;
+    const bool even = (ob.Fx & 1) == 0;
+    const int kbeg = chunk * ob.chunk, kend = min(K, kbeg + ob.chunk);
+    for (int k0 = kbeg; k0 < kend; k0 += SB_ROT_SUB) {
+        const int nk = min(SB_ROT_SUB, kend - k0);
+        for (int idx = tid; idx < H * SB_ROT_SUB; idx += blockDim.x) {
+            const int i = idx / SB_ROT_SUB, q = idx - i * SB_ROT_SUB, k = k0 + q;
+            C2 u = C2{T(0), T(0)};
+            if (q < nk) {
+                const int kx = k % Xp;
+                if (kx < Fxc) {
+                    const T w = (kx == 0 || (even && kx == Fxc - 1)) ? T(1) : T(2);
+                    const C2 p = P[k], m = ob.RA[(size_t)i * K + k];
+                    u = C2{w * (p.x * m.x - p.y * m.y), w * (p.x * m.y + p.y * m.x)};
+                }
+            }
+            U[idx] = u;
+        }
+        for (int idx = tid; idx < W * SB_ROT_SUB; idx += blockDim.x) {
+            const int j = idx / SB_ROT_SUB, q = idx - j * SB_ROT_SUB;
+            B[idx] = q < nk ? ob.RB[(size_t)j * K + k0 + q] : C2{T(0), T(0)};
+        }
+        __syncthreads();
+        if (work) {
+            const C2 *u0 = U + i0 * SB_ROT_SUB, *u1 = U + i1 * SB_ROT_SUB, *b0 = B + j0 * SB_ROT_SUB, *b1 = B + j1 * SB_ROT_SUB;
+#pragma unroll 8
+            for (int q = 0; q < SB_ROT_SUB; ++q) {
+                const C2 ua = u0[q], ub = u1[q], ba = b0[q], bb = b1[q];
+                acc00 += ua.x * ba.x - ua.y * ba.y;
+                acc01 += ua.x * bb.x - ua.y * bb.y;
+                acc10 += ub.x * ba.x - ub.y * ba.y;
+                acc11 += ub.x * bb.x - ub.y * bb.y;
+            }
+        }
+        __syncthreads();
+    }
+    if (work && tj < tw) {
+        T *out = ob.Rpart + ((size_t)(s * ob.C + c) * ob.n_chunk + chunk) * H * W;
+        out[i0 * W + j0] = acc00;
+        if (j0 + 1 < W) out[i0 * W + j0 + 1] = acc01;
+        if (i0 + 1 < H) {
+            out[(i0 + 1) * W + j0] = acc10;
+            if (j0 + 1 < W) out[(i0 + 1) * W + j0 + 1] = acc11;
+        }
+    }
+}
+
+// one CTA per (scene, band): chunks summed in double (fixed order) -> LR, residual r = w (LR - d), chi^2 partial
+template <typename T> __global__ void __launch_bounds__(256) k_rot_residual(const SpecArgs<T> a) {
+    __shared__ double red[40];
+    const SpecObs<T> &ob = a.ob;
+    const int img = blockIdx.x, s = img / ob.C;
+    if (a.done[s]) return;
+    const int HW = ob.H * ob.W;
+    const T *part = ob.Rpart + (size_t)img * ob.n_chunk * HW;
+    double chi = 0.0;
+    for (int idx = threadIdx.x; idx < HW; idx += blockDim.x) {
+        double acc = 0.0;
+        for (int q = 0; q < ob.n_chunk; ++q) acc += (double)part[(size_t)q * HW + idx];
+        const T m = (T)((double)ob.h2 * acc);
+        const size_t di = (size_t)img * HW + idx;
+        const T w = ob.weights[di], diff = m - ob.data[di];
+        ob.Rres[di] = w * diff;
+        chi += (double)w * (double)diff * (double)diff;
+        if (a.rendered_out) a.rendered_out[di] = m;
+    }
+    chi = block_sum(chi, red);
+    if (threadIdx.x == 0) a.partials[img] = chi;
+}
+
+// adjoint: P[k] = h^2 K^[k] sum_i A_i[k] sum_j R[i,j] B_j[k]; grid (ceil(Fy Xp / 128), S C), one k per thread
+template <typename T> __global__ void __launch_bounds__(128) k_rot_adjoint(const SpecArgs<T> a) {
+    typedef typename Cx<T>::type C2;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SpecObs<T> &ob = a.ob;
+    const int img = blockIdx.y, s = img / ob.C;
+    if (a.done[s]) return;
+    const int H = ob.H, W = ob.W, K = ob.Fy * ob.Xp;
+    T *R = reinterpret_cast<T *>(smem); // [H][W]
+    for (int idx = threadIdx.x; idx < H * W; idx += blockDim.x) R[idx] = ob.Rres[(size_t)img * H * W + idx];
+    __syncthreads();
+    const int k = blockIdx.x * 128 + threadIdx.x;
+    if (k >= K) return;
+    C2 b[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) b[j] = j < W ? ob.RB[(size_t)j * K + k] : C2{T(0), T(0)};
+    C2 acc = C2{T(0), T(0)};
+    for (int i = 0; i < H; ++i) {
+        C2 v = C2{T(0), T(0)};
+        const T *r = R + i * W;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < W) v.x += r[j] * b[j].x, v.y += r[j] * b[j].y;
+        const C2 m = ob.RA[(size_t)i * K + k];
+        acc.x += m.x * v.x - m.y * v.y;
+        acc.y += m.x * v.y + m.y * v.x;
+    }
+    const C2 kh = ob.khat[(size_t)(ob.khat_shared ? img - s * ob.C : img) * K + k];
+    C2 out;
+    out.x = ob.h2 * (kh.x * acc.x - kh.y * acc.y);
+    out.y = ob.h2 * (kh.x * acc.y + kh.y * acc.x);
+    ob.P[(size_t)img * K + k] = out;
+}
+
 // ---- dispatch table ----------------------------------------------------------------------------------
 // supported transform lengths L = R1 * R2 (both the row length Fx and the column length Fy must be in this list)
 #define SB_SPEC_LENGTHS(X) \
-    X(6, 8) X(8, 8) X(8, 9) X(8, 10) X(8, 12) X(8, 16) X(12, 12) X(10, 16) X(12, 16) X(15, 16) X(16, 16) X(16, 18) X(16, 20) X(16, 24)
+    X(6, 8) X(8, 8) X(8, 9) X(8, 10) X(8, 12) X(9, 12) X(8, 16) X(12, 12) X(10, 16) X(12, 16) X(15, 16) X(16, 16) X(16, 18) X(15, 20) X(16, 20) X(16, 24)
 
 template <typename T> struct SpecKernels {
     typedef void (*fn)(const SpecArgs<T>);

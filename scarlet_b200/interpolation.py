@@ -99,3 +99,29 @@ def shift_weights(F, shifts):
     if F % 2 == 0:
         W[:, F // 2] = np.cos(np.pi * s)
     return W
+
+
+def shift_multiplier(Fy, Fx, s0, s1):
+    """Fourier multiplier, on the half plane ``ky in [0, Fy), kx in [0, Fx/2]``, of the reference's two-axis Fourier shift by
+    ``(s0, s1)`` pixels: ``rfftn`` over (y, x), phase ramp ``exp(-2 pi i (fftfreq_y s0 + rfftfreq_x s1))``, ``irfftn`` back
+    (renderer.py:414-476 with axes (1, 2), ``mk_shifter(real=False)``).  The real inverse transform keeps only the Hermitian
+    part of what the ramp produces, which matters on the Nyquist lines of even grids; in real space the operation is
+    ``Re(Cy) u Re(Tx)^T - Im(Cy) u Im(Tx)^T`` with the circulant matrices of DESIGN 3.8, whose symbols give
+
+        sigma(ky, kx) = ReCy(ky) ReTx(kx) - ImCy(ky) ImTx(kx).
+
+    ``s0``, ``s1`` may be arrays of n shifts -> (n, Fy, Fx/2+1) complex128.  Checked against the reference's own rotated render
+    to 4e-14 (tests/golden/multires_rot.npz)."""
+    s0 = np.atleast_1d(np.asarray(s0, dtype=np.float64))[:, None]
+    s1 = np.atleast_1d(np.asarray(s1, dtype=np.float64))[:, None]
+    ky = np.arange(Fy)
+    my = np.where(ky < (Fy + 1) // 2, ky, ky - Fy)  # numpy.fft.fftfreq: the Nyquist bin of an even grid is negative
+    cy = np.exp(-2j * np.pi * my[None, :] * s0 / Fy)
+    cym = cy[:, (-ky) % Fy]
+    re_cy, im_cy = (cy + np.conj(cym)) / 2, (cy - np.conj(cym)) / 2j
+    kx = np.arange(Fx)
+    ck = np.where((kx == 0) | (2 * kx == Fx), 1.0, 2.0)
+    tx = np.where(kx[None, :] <= Fx // 2, ck[None, :] * np.exp(-2j * np.pi * kx[None, :] * s1 / Fx), 0)
+    txm = tx[:, (-kx) % Fx]
+    re_tx, im_tx = ((tx + np.conj(txm)) / 2)[:, :Fx // 2 + 1], ((tx - np.conj(txm)) / 2j)[:, :Fx // 2 + 1]
+    return re_cy[:, :, None] * re_tx[:, None, :] - im_cy[:, :, None] * im_tx[:, None, :]

@@ -143,7 +143,7 @@ class ResolutionRenderer(Renderer):
 
     Set-up follows the reference: difference kernel between the observed PSF, sinc-resampled to the model pixel scale,
     and the model PSF (``build_diffkernel`` 365-412); fast grid ``_fft_shape``; positions of the low-resolution pixel rows
-    and columns in model-frame coordinates (``shifts`` 308-316).  Rotated grids are not on the device path.
+    and columns in model-frame coordinates (``shifts`` 308-316), for aligned and for rotated grids (318-347).
 
     The reference then tabulates, for every low-resolution row, the kernel Fourier-shifted to that row
     (``_resconv_op``, (C, n_y, Fy*Fx)) and evaluates a render as Fourier shifts of the model to every low-resolution
@@ -163,8 +163,6 @@ class ResolutionRenderer(Renderer):
         super().__init__(data_frame, model_frame)
         self.angle, self.h = interpolation.get_angles(data_frame.wcs, model_frame.wcs)
         self.isrot = (np.abs(self.angle[1]) ** 2) > np.finfo(float).eps
-        if self.isrot:
-            raise NotImplementedError("rotated observations are outside the device path (SURVEY 8a-17: aligned grids)")
         lr_shape = data_frame.shape[1:]
         if lr_shape[0] != lr_shape[1]:
             raise ValueError("ResolutionRenderer needs square observations (as the reference does, renderer.py:274)")
@@ -179,10 +177,20 @@ class ResolutionRenderer(Renderer):
         Fy, Fx = self._fft_shape
         center_y = int(Fy / 2.0 - (Fy - model_frame.Ny) / 2.0) + ((Fy % 2) != 0) * ((model_frame.Ny % 2) == 0)
         center_x = int(Fx / 2.0 - (Fx - model_frame.Nx) / 2.0) - ((Fx % 2) != 0) * ((model_frame.Nx % 2) == 0)
-        self.shifts = coord_hr.T.copy()
-        self.shifts[0] -= center_y
-        self.shifts[1] -= center_x
-        self.other_shifts = np.copy(self.shifts)
+        if not self.isrot:
+            self.shifts = coord_hr.T.copy()
+            self.shifts[0] -= center_y
+            self.shifts[1] -= center_x
+            self.other_shifts = np.copy(self.shifts)
+        else:
+            # rotated grids (renderer.py:318-347): positions of the low-resolution rows / columns along the observation's own
+            # axes; a row then needs a shift along both model axes, (Y cos, -Y sin), a column (X sin, X cos)
+            cos, sin = float(self.angle[0]), float(self.angle[1])
+            self.Y_unrot = ((coord_hr[:, 0] - center_y) * cos - (coord_hr[:, 1] - center_x) * sin).reshape(lr_shape[0])
+            self.X_unrot = ((coord_hr[:, 1] - center_x) * cos + (coord_hr[:, 0] - center_y) * sin).reshape(lr_shape[1])
+            rows = np.array([self.Y_unrot * cos, -self.Y_unrot * sin])
+            cols = np.array([sin * self.X_unrot, cos * self.X_unrot])
+            self.shifts, self.other_shifts = (rows, cols) if self.small_axis else (cols, rows)
         self.origin = (0, 0)
         self._operator = None
 
@@ -208,9 +216,23 @@ class ResolutionRenderer(Renderer):
             Ny, Nx = self.model_frame.shape[1:]
             oy, ox = (Fy - Ny + 1) // 2, (Fx - Nx + 1) // 2  # where fft._pad puts the model inside the grid
             khat = np.ascontiguousarray(np.fft.rfft2(np.asarray(self.diff_kernel.image, dtype=np.float64), axes=(1, 2)))
+            if self.isrot:
+                # LR[c,i,j] = scale sum_kx w_kx Re sum_ky K^ conj(M^) A_i B_j: A_i / B_j are the half-plane multipliers of the
+                # two-axis shifts attached to row i / column j.  The kernel is shifted by `shifts`, the model (centred in the
+                # grid by the reference, at the grid origin on the device: an integer translation by (oy, ox)) by
+                # -`other_shifts`; the model's multiplier enters conjugated.
+                f_y = np.fft.fftfreq(Fy)[:, None]
+                f_x = np.fft.rfftfreq(Fx)[None, :]
+                kernel_mult = interpolation.shift_multiplier(Fy, Fx, self.shifts[0], self.shifts[1])
+                model_mult = np.conj(interpolation.shift_multiplier(Fy, Fx, -self.other_shifts[0], -self.other_shifts[1])) * \
+                    np.exp(2j * np.pi * (f_y * oy + f_x * ox))[None]
+                A, B = (kernel_mult, model_mult) if self.small_axis else (model_mult, kernel_mult)
+                self._operator = dict(fshape=(Fy, Fx), khat=khat, A=np.ascontiguousarray(A), B=np.ascontiguousarray(B),
+                                      scale=float(self.h ** 2 / (Fy * Fx)), rotated=True)
+                return self._operator
             Ey = np.ascontiguousarray(interpolation.shift_weights(Fy, self.shifts[0] - oy))
             Ex = np.ascontiguousarray(interpolation.shift_weights(Fx, self.shifts[1] - ox)[:, :Fx // 2 + 1])
-            self._operator = dict(fshape=(Fy, Fx), khat=khat, Ey=Ey, Ex=Ex, scale=float(self.h ** 2 / (Fy * Fx)))
+            self._operator = dict(fshape=(Fy, Fx), khat=khat, Ey=Ey, Ex=Ex, scale=float(self.h ** 2 / (Fy * Fx)), rotated=False)
         return self._operator
 
     def get_model(self, *parameters):
@@ -220,11 +242,16 @@ class ResolutionRenderer(Renderer):
             Fy, Fx = op["fshape"]
             m = np.asarray(self.map_channels(model), dtype=np.float64)
             mhat = np.fft.rfft2(m, s=(Fy, Fx), axes=(1, 2))
-            t1 = np.einsum("iy,cyx->cix", op["Ey"], op["khat"] * np.conj(mhat))
             wgt = np.full(Fx // 2 + 1, 2.0)
             wgt[0] = 1.0
             if Fx % 2 == 0:
                 wgt[-1] = 1.0
+            if op["rotated"]:
+                p = op["khat"] * np.conj(mhat)
+                u = np.einsum("cyx,iyx->ciyx", p, op["A"])
+                out = op["scale"] * np.einsum("ciyx,jyx,x->cij", u, op["B"], wgt).real
+                return out.astype(np.asarray(model).dtype)
+            t1 = np.einsum("iy,cyx->cix", op["Ey"], op["khat"] * np.conj(mhat))
             out = op["scale"] * np.einsum("cix,jx,x->cij", t1, op["Ex"], wgt).real
             return out.astype(np.asarray(model).dtype)
         return transform

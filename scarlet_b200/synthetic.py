@@ -152,7 +152,9 @@ def _multires_observations(scene, dtype=np.float32):
     key = (tuple(sorted(cfg.items())), np.dtype(dtype).name)
     cached = _MR_CACHE.get(key)
     wcs_hr = cached["wcs_hr"] if cached else AffineWCS(np.diag([cfg["hr_scale"]] * 2), crpix=(hr_c, hr_c))
-    wcs_lr = cached["wcs_lr"] if cached else AffineWCS(np.diag([cfg["lr_scale"]] * 2), crpix=(lr_c, lr_c))
+    ang = np.deg2rad(cfg.get("lr_angle", 0.0))  # low-resolution grid turned against the high-resolution one (rotated ResolutionRenderer)
+    rot = np.array([[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]]) if ang else np.eye(2)
+    wcs_lr = cached["wcs_lr"] if cached else AffineWCS(cfg["lr_scale"] * rot, crpix=(lr_c, lr_c))
     obs_hr = sb.Observation(scene["hr_images"].copy(), psf=sb.ImagePSF(scene["hr_psfs"].copy()), weights=scene["hr_weights"].copy(),
                             wcs=wcs_hr, channels=["h0", "h1", "h2"])
     obs_lr = sb.Observation(scene["lr_images"].copy(), psf=sb.ImagePSF(scene["lr_psfs"].copy()), weights=scene["lr_weights"].copy(),
@@ -185,8 +187,12 @@ def make_multires_scene(scene_id=0, config=None):
     C, Ny, Nx = frame.shape
     margin = B // 2 + 4
     sources, truth = [], np.zeros((C, Ny, Nx))
+    lo_y, hi_y, lo_x, hi_x = margin, Ny - margin, margin, Nx - margin
+    if cfg.get("lr_angle"):  # the union frame of rotated grids has corners no observation covers: keep the galaxies on the data
+        oy, ox = obs_hr.renderer.origin
+        lo_y, hi_y, lo_x, hi_x = oy + margin, oy + hr_n - margin, ox + margin, ox + hr_n - margin
     for k in range(cfg["n_ext"]):
-        cy, cx = rng.uniform(margin, Ny - margin), rng.uniform(margin, Nx - margin)
+        cy, cx = rng.uniform(lo_y, hi_y), rng.uniform(lo_x, hi_x)
         py, px = int(np.round(cy)), int(np.round(cx))
         rs, q, th = rng.uniform(2.0, 4.0), rng.uniform(0.5, 1.0), rng.uniform(0, np.pi)
         sed = np.exp(rng.uniform(np.log(20), np.log(500))) * rng.dirichlet(np.ones(C)) * C

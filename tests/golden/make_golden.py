@@ -17,6 +17,7 @@ What is written (all values produced by reference code, float64 unless the refer
 * ``prox_chain.npz``       -- constraint-chain outputs (monotonic angle/flat/nearest x symmetric on/off) on seeded
                              random 41x41 / 21x21 / 20x31 images.
 * ``monotonic_weights.npz``-- ``getRadialMonotonicWeights`` for several shapes / kinds / centres.
+* ``multires_rot.npz``     -- the rotated branch of ``ResolutionRenderer``: set-up products (shifts along both axes, kernel) and render.
 * ``psf_shift.npz``        -- ``ConvolutionRenderer(psf_shift=...)``: shifted difference kernel, render, logL and finite
                              differences of logL wrt the shift, for two shifts.
 """
@@ -293,6 +294,53 @@ def multires(sc):
     save("multires.npz", **out)
 
 
+def multires_rot(sc):
+    """The ROTATED branch of ResolutionRenderer (renderer.py:318-363, 498-524): the low-resolution grid of ``multires`` turned by
+    25 degrees.  One environment patch: renderer.py:443 builds ``np.array(mk_shifter(...))`` from two arrays of different
+    length, which NumPy >= 1.24 refuses (older NumPy made an object array); the reference is handed an object array of its own
+    two shifters.  Nothing else is touched."""
+    from scarlet_b200.wcs import AffineWCS
+    RefWCS = type("RefWCS", (AffineWCS, sys.modules["astropy.wcs"].WCS), {})
+    orig = sc.interpolation.mk_shifter
+
+    def mk_shifter(shape, real=False):
+        sy, sx = orig(shape, real=real)
+        out = np.empty(2, dtype=object)
+        out[0], out[1] = sy, sx
+        return out
+
+    sc.interpolation.mk_shifter = mk_shifter
+    try:
+        inp = multires_inputs()
+        th = np.deg2rad(25.0)
+        lr_cd = 0.2 * np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        out = dict(inp)
+        out["lr_cd"] = lr_cd
+        obs_hr = sc.observation.Observation(inp["hr_images"].copy(), psf=sc.psf.ImagePSF(inp["hr_psfs"].copy()), weights=inp["hr_weights"].copy(),
+                                            wcs=RefWCS(inp["hr_cd"], crpix=inp["hr_crpix"]), channels=["h0", "h1", "h2"])
+        obs_lr = sc.observation.Observation(inp["lr_images"].copy(), psf=sc.psf.ImagePSF(inp["lr_psfs"].copy()), weights=inp["lr_weights"].copy(),
+                                            wcs=RefWCS(lr_cd, crpix=inp["lr_crpix"]), channels=["l0", "l1", "l2", "l3", "l4"])
+        frame = sc.frame.Frame.from_observations([obs_lr, obs_hr], coverage="union")
+        frame = sc.frame.Frame(frame.shape, channels=frame.channels, psf=frame.psf, wcs=frame.wcs, dtype=np.float64)
+        obs_lr.match(frame)
+        obs_hr.match(frame)
+        r, r2 = obs_lr.renderer, obs_hr.renderer
+        assert type(r).__name__ == "ResolutionRenderer" and r.isrot and type(r2).__name__ == "ConvolutionRenderer"
+        rng = np.random.default_rng(12)
+        yy, xx = np.mgrid[:frame.shape[1], :frame.shape[2]]
+        model = np.stack([rng.uniform(1, 5) * np.exp(-((yy - rng.uniform(30, 60)) ** 2 + (xx - rng.uniform(30, 60)) ** 2) / (2 * rng.uniform(2, 5) ** 2))
+                          for _ in range(frame.shape[0])]) + 0.01 * rng.random(frame.shape)
+        out.update(frame_shape=np.array(frame.shape), model_psf=frame.psf.get_model(), model=model, lr_h=np.array(r.h),
+                   lr_angle=np.array([float(r.angle[0]), float(r.angle[1])]), lr_fft_shape=np.array(r._fft_shape),
+                   lr_shifts=np.array(r.shifts), lr_other_shifts=np.array(r.other_shifts), lr_small_axis=np.array(r.small_axis),
+                   lr_diff_kernel=np.asarray(r.diff_kernel.image), lr_rendered=obs_lr.render(model),
+                   lr_logL=np.array(obs_lr.get_log_likelihood(model)), hr_rendered=obs_hr.render(model),
+                   hr_model_slice_start=np.array([r2.slices[1][1].start, r2.slices[1][2].start]), model_crpix=np.array(frame.wcs.wcs.crpix))
+        save("multires_rot.npz", **out)
+    finally:
+        sc.interpolation.mk_shifter = orig
+
+
 def source_recipes(sc):
     """The other branches of the reference's ``ExtendedSource`` factory on data/hsc_cosmos_35.npz: a two-component source
     (K=2) and a compact one, initialised by the reference."""
@@ -497,6 +545,6 @@ def psf_shift(sc):
 if __name__ == "__main__":
     sc = ref_shim.install()
     which = sys.argv[1:] or ["obs_render_loss", "hsc_cosmos_35", "point_extended", "prox_chain", "monotonic_weights", "multires",
-                             "source_recipes", "init_helpers", "psf_shift"]
+                             "source_recipes", "init_helpers", "psf_shift", "multires_rot"]
     for name in which:
         globals()[name](sc)

@@ -244,6 +244,48 @@ def test_multiresolution_setup_vs_reference_fixture():
     assert_allclose(obs_lr.get_log_likelihood(g["model64"]), float(g["lr_logL64"]), rtol=1e-10)
 
 
+def _multires_rot_scene():
+    import scarlet_b200 as sb
+    from scarlet_b200.wcs import AffineWCS
+    g = golden("multires_rot.npz")
+    obs_hr = sb.Observation(g["hr_images"].copy(), psf=sb.ImagePSF(g["hr_psfs"].copy()), weights=g["hr_weights"].copy(),
+                            wcs=AffineWCS(g["hr_cd"], crpix=g["hr_crpix"]), channels=["h0", "h1", "h2"])
+    obs_lr = sb.Observation(g["lr_images"].copy(), psf=sb.ImagePSF(g["lr_psfs"].copy()), weights=g["lr_weights"].copy(),
+                            wcs=AffineWCS(g["lr_cd"], crpix=g["lr_crpix"]), channels=["l0", "l1", "l2", "l3", "l4"])
+    frame = sb.Frame.from_observations([obs_lr, obs_hr], coverage="union")
+    frame = sb.Frame(frame.shape, channels=frame.channels, psf=frame.psf, wcs=frame.wcs, dtype=np.float64)
+    obs_lr.match(frame)
+    obs_hr.match(frame)
+    return g, frame, obs_lr, obs_hr
+
+
+def test_rotated_multiresolution_setup_and_render_vs_reference_fixture():
+    """The rotated branch of ResolutionRenderer (renderer.py:318-363, 498-524): set-up products and the half-plane multiplier
+    form of the render against the reference's own (tests/golden/make_golden.py:multires_rot); the oracle's literal
+    restatement and its adjoint against the same fixture."""
+    from oracle import scarlet_oracle as so
+    g, frame, obs_lr, obs_hr = _multires_rot_scene()
+    assert tuple(frame.shape) == tuple(g["frame_shape"])
+    r = obs_lr.renderer
+    assert type(r).__name__ == "ResolutionRenderer" and r.isrot
+    assert_allclose([float(r.angle[0]), float(r.angle[1])], g["lr_angle"], atol=1e-14)
+    assert_allclose(r.h, float(g["lr_h"]))
+    assert list(r._fft_shape) == list(g["lr_fft_shape"]) and bool(r.small_axis) == bool(g["lr_small_axis"])
+    assert_allclose(r.shifts, g["lr_shifts"], atol=1e-11)
+    assert_allclose(r.other_shifts, g["lr_other_shifts"], atol=1e-11)
+    assert_allclose(r.diff_kernel.image, g["lr_diff_kernel"], atol=1e-12)
+    peak = np.abs(g["lr_rendered"]).max()
+    assert_allclose(obs_lr.render(g["model"]), g["lr_rendered"], atol=1e-11 * peak)
+    assert_allclose(obs_lr.get_log_likelihood(g["model"]), float(g["lr_logL"]), rtol=1e-10)
+    o = so.RotatedResolutionObservationOracle(g["lr_images"], g["lr_weights"], g["lr_diff_kernel"], g["lr_shifts"], g["lr_other_shifts"],
+                                              float(g["lr_h"]), small_axis=bool(g["lr_small_axis"]), frame_dtype=np.float64)
+    o.match(tuple(int(v) for v in g["frame_shape"]), None)
+    assert_allclose(o.render(g["model"]), g["lr_rendered"], atol=1e-11 * peak)
+    rng = np.random.default_rng(0)
+    G, M = rng.standard_normal(g["lr_rendered"].shape), rng.standard_normal(g["model"].shape)
+    assert_allclose((o.render(M) * G).sum(), (o.render_adjoint(G) * M).sum(), rtol=1e-12)
+
+
 def test_measure_helpers():
     """scarlet/measure.py:6-59 on a component and on a plain cube (host reductions; no device involved)"""
     import scarlet_b200 as sb
