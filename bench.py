@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="cfg3", choices=["cfg2", "cfg3", "cfg4", "cfg5", "tiny"])
+    ap.add_argument("--config", default="cfg3", choices=["cfg2", "cfg3", "cfg4", "cfg4_rot", "cfg5", "tiny"])
     ap.add_argument("--scenes", type=int, default=0, help="scenes per GPU (default per config)")
     ap.add_argument("--iters", type=int, default=0, help="iterations per step (default per config)")
     ap.add_argument("--unique", type=int, default=16, help="distinct synthetic scenes generated per rank (then cycled)")
@@ -51,8 +51,9 @@ def parse():
     return ap.parse_args()
 
 
-DEFAULT_SCENES = {"cfg2": 256, "cfg3": 192, "cfg4": 64, "cfg5": 512, "tiny": 64}
-DEFAULT_ITERS = {"cfg2": 50, "cfg3": 50, "cfg4": 50, "cfg5": 50, "tiny": 20}
+DEFAULT_SCENES = {"cfg2": 256, "cfg3": 192, "cfg4": 64, "cfg4_rot": 64, "cfg5": 512, "tiny": 64}
+DEFAULT_ITERS = {"cfg2": 50, "cfg3": 50, "cfg4": 50, "cfg4_rot": 50, "cfg5": 50, "tiny": 20}
+MULTIRES = ("cfg4", "cfg4_rot")  # cfg4_rot: cfg4 with the low-resolution grid turned by 25 degrees (rotated ResolutionRenderer)
 
 
 def peaks():
@@ -112,22 +113,26 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 def _make_scene(config, scene_id):
     from scarlet_b200 import synthetic
+    if config == "cfg4_rot":
+        return synthetic.make_multires_scene(scene_id, dict(synthetic.CFG4, lr_angle=25.0, config_id=41))
     return synthetic.make_multires_scene(scene_id) if config == "cfg4" else synthetic.make_scene(config, scene_id)
 
 
 def _make_blend(config, scene, precision=32, device=None):
     from scarlet_b200 import synthetic
-    if config == "cfg4":
+    if config in MULTIRES:
         return synthetic.make_multires_blend(scene, precision=precision, device=device)
     return synthetic.make_blend(scene, precision=precision, device=device)
 
 
 def _config_dict(config):
     from scarlet_b200 import synthetic
-    if config == "cfg4":
+    if config in MULTIRES:
         c = synthetic.CFG4
-        return dict(C=8, N=228, n_ext=c["n_ext"], n_pt=0, psf="gaussian-image", P=c["hr_P"], B=c["B"], symmetric=True,
-                    note="5 bands 30x30 at 0.2 arcsec/px (ResolutionRenderer) + 3 bands 200x200 at 0.03 arcsec/px (ConvolutionRenderer)")
+        rot = config == "cfg4_rot"
+        return dict(C=8, N=284 if rot else 228, n_ext=c["n_ext"], n_pt=0, psf="gaussian-image", P=c["hr_P"], B=c["B"], symmetric=True,
+                    note="5 bands 30x30 at 0.2 arcsec/px (ResolutionRenderer%s) + 3 bands 200x200 at 0.03 arcsec/px (ConvolutionRenderer)"
+                         % (", grid rotated by 25 deg" if rot else ""))
     return synthetic.CONFIGS[config]
 
 
@@ -135,7 +140,7 @@ def _ref_worker(job):
     config, scene_id, iters = job
     from oracle import scenes
     scene = _make_scene(config, scene_id)
-    if config == "cfg4":  # the set-up products of the low-resolution renderer come from the host objects (no GPU involved)
+    if config in MULTIRES:  # the set-up products of the low-resolution renderer come from the host objects (no GPU involved)
         o = scenes.build_multires_oracle(scene, scenes.multires_setup(_make_blend(config, scene)))
     else:
         o = scenes.build_oracle(scene)
@@ -145,7 +150,7 @@ def _ref_worker(job):
 
 
 def cpu_iters_for(config):
-    return {"cfg2": 20, "cfg3": 6, "cfg4": 4, "cfg5": 12, "tiny": 30}[config]
+    return {"cfg2": 20, "cfg3": 6, "cfg4": 4, "cfg4_rot": 3, "cfg5": 12, "tiny": 30}[config]
 
 
 def run_reference(args):
@@ -357,6 +362,9 @@ def measure(env, args, config, S, iters, steps, warmup, headline):
         if fused:  # the same marks carry the fused kernels (csrc/scarlet_b200.cu: enqueue_iteration)
             relabel = {"fft_fwd_model": "spec_render", "kmul": "spec_column", "residual_loss": "spec_residual",
                        "kmul_conj": "spec_column_adj", "fft_inv_grad": "spec_grad"}
+            # a rotated resampling observation has two more kernels on the marks the cuFFT pipeline uses for its transforms
+            extra = {"fft_inv_model": "rot_contract", "fft_fwd_resid": "rot_adjoint"}
+            relabel.update({k: v for k, v in extra.items() if stages.get(k, 0) > 0})
             stages = {relabel.get(k, k): v for k, v in stages.items() if k in relabel or k in ("source_update", "advance")}
         peak, peak_src = peaks()
         C, N, B = cfg["C"], cfg["N"], cfg["B"]
@@ -385,11 +393,11 @@ def measure(env, args, config, S, iters, steps, warmup, headline):
             "advance": 16,
         }
         stage_bytes.update(fused_bytes)
-        if config == "cfg4":  # two observations on different grids: only the per-source kernel has a closed-form byte count here
+        if config in MULTIRES:  # two observations on different grids: only the per-source kernel has a closed-form byte count here
             for k in list(stage_bytes):
                 if k not in ("source_update", "advance"):
                     stage_bytes[k] = 0
-            alg_iter = synthetic.algorithmic_bytes_multires(cfg, eb)
+            alg_iter = synthetic.algorithmic_bytes_multires(cfg, eb, frame=tuple(plan.frame_shape), fft_shape=tuple(fshape))
         else:
             alg_iter = synthetic.algorithmic_bytes(cfg, fshape, eb)
         own = {k: v for k, v in stages.items() if not k.startswith("fft_") and stage_bytes.get(k, 0) > 0}
@@ -422,6 +430,16 @@ def measure(env, args, config, S, iters, steps, warmup, headline):
                     "stages_gbs": {k: (stage_bytes[k] * S / (v / 1e3) / 1e9 if v > 0 and stage_bytes.get(k, 0) > 0 else None)
                                    for k, v in stages.items()}}
 
+        if "rot_contract" in stages:  # dense FP32 contraction over the half plane (not tensor-core work: float32 parity)
+            H, W = plan.obs_meta[0]["metas"][0]["shape"][1:]
+            Kh, lrC = Fy * (Fx // 2 + 1), plan.obs_meta[0]["metas"][0]["shape"][0]
+            flop = {"rot_contract": lrC * Kh * (4 * H * W + 6 * H), "rot_adjoint": lrC * Kh * (4 * H * W + 8 * H + 6)}
+            mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+            fp32_peak = 148 * 128 * 2 * mhz * 1e6 / 1e12
+            roofline["fp32_contraction"] = {k: {"flop_per_scene": v, "ms": stages[k], "achieved_tflops": v * S / (stages[k] / 1e3) / 1e12,
+                                                "frac_of_fp32_peak": v * S / (stages[k] / 1e3) / 1e12 / fp32_peak} for k, v in flop.items()}
+            roofline["fp32_contraction"]["fp32_peak_tflops"] = fp32_peak
+
         # single-scene latency (the 200 it/s target of the north star is a per-scene figure)
         single = None
         if headline and not args.no_single:
@@ -443,7 +461,7 @@ def measure(env, args, config, S, iters, steps, warmup, headline):
                    "spectral": "fused row/column kernels" if fused else "cuFFT",
                    "cufft_execs_per_iteration": 0 if fused else 4 * len(plan.obs_meta),
                    "kernels_per_iteration": launches // max(steps * iters, 1), "precision": args.precision,
-                   "per_scene_psf": config != "cfg4",
+                   "per_scene_psf": config not in MULTIRES,
                    "value_includes": "the proximal-gradient loop (CUDA events) + the final NCCL gather of fitted parameters (N > 1)"}
         if cfg.get("note"):
             details["observations"] = cfg["note"]
@@ -506,13 +524,14 @@ def run_b200(args):
     # the other BASELINE configurations, a few steps each, as sub-records of the same line (device value, e2e, roofline)
     others = {}
     if args.config == "cfg3" and not args.only_headline:
-        for c in ("cfg5", "cfg2", "cfg4"):
+        for c in ("cfg5", "cfg2", "cfg4", "cfg4_rot"):
             rec = measure(env, args, c, DEFAULT_SCENES[c], DEFAULT_ITERS[c], min(args.steps, 5), 3, headline=False)
             if rec is not None:
                 others[c] = {"value": rec["value"], "unit": rec["unit"], "ms_per_step": rec["ms_per_step"], "steps": rec["steps"],
                              "config": rec["config"], "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"],
                              "roofline": {"iteration": rec["roofline"]["iteration"], "kernel": rec["roofline"]["kernel"],
-                                          "frac": rec["roofline"]["frac"], "stages_ms": rec["roofline"]["stages_ms"]},
+                                          "frac": rec["roofline"]["frac"], "stages_ms": rec["roofline"]["stages_ms"],
+                                          "fp32_contraction": rec["roofline"].get("fp32_contraction")},
                              "fft_grid": rec["details"]["fft_grid"], "device_bytes_per_gpu": rec["details"]["device_bytes_per_gpu"]}
     if args.config == "cfg3" and not args.only_headline:
         dyn = measure_dynamic(env, args)  # boxes too small at the start: every source resizes in the first rounds (worst case)

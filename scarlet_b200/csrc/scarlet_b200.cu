@@ -351,7 +351,8 @@ template <typename T> struct PlanT : sb_plan {
         DevBuf<cplx> X, tw_x, tw_y, Pbuf, T1buf, Ey, Ex; // Pbuf..Ex: resampling observations (kind 2) only
         DevBuf<cplx> RA, RB;                              // rotated resampling observations (kind 3): multiplier tables
         DevBuf<T> Rres, Rpart;                            //   weighted residual, per-chunk partial renders
-        int rot_chunks = 0;
+        int rot_chunks = 0, rot_chunk = 0, rot_cb = 1;
+        size_t rot_smem = 0;
         DevBuf<T> G;
         int npair = 1, cb = 1, row_threads = 0;
         size_t smem_render = 0, smem_row = 0, smem_col = 0, smem_col_tma = 0;
@@ -730,7 +731,15 @@ template <typename T> struct PlanT : sb_plan {
                 if (od.kind == 3) {
                     if (od.H > 32 || od.W > 32) return set_err(SB_ERR_ARG, "observation %d: a rotated resampling observation is limited to 32x32 pixels (got %dx%d)", o, od.H, od.W);
                     const size_t K = (size_t)Fy * Xp;
-                    ob.rot_chunks = (int)((K + SB_ROT_CHUNK - 1) / SB_ROT_CHUNK);
+                    // k range per CTA: at least two CTAs per SM in flight when the batch is small, 2048 entries at most
+                    ob.rot_cb = SB_ROT_MAXB;
+                    const int groups = (od.C + ob.rot_cb - 1) / ob.rot_cb;
+                    long long want = (2 * 148 + (long long)S * groups - 1) / ((long long)S * groups);
+                    want = std::max<long long>(want, (long long)(K + 2047) / 2048);
+                    want = std::min<long long>(want, (long long)(K + 255) / 256);
+                    ob.rot_chunk = (int)(((K + want - 1) / want + SB_ROT_SUB - 1) / SB_ROT_SUB) * SB_ROT_SUB;
+                    ob.rot_chunks = (int)((K + ob.rot_chunk - 1) / ob.rot_chunk);
+                    ob.rot_smem = (size_t)(2 + 2 * ob.rot_cb) * SB_ROT_SUB * SB_ROT_LD * sizeof(T) + (size_t)2 * ob.rot_cb * SB_ROT_SUB * sizeof(cplx);
                     ob.n_part = od.C;
                     SB_TRY(ob.Pbuf.alloc((size_t)S * od.C * K));
                     SB_TRY(ob.RA.alloc((size_t)od.H * K));
@@ -744,7 +753,7 @@ template <typename T> struct PlanT : sb_plan {
                     SB_TRY(ob.Rpart.zero(stream));
                     SB_TRY(raise_smem((const void *)ob.ky.column_fwd, ob.smem_col));
                     SB_TRY(raise_smem((const void *)ob.ky.column_inv, ob.smem_col));
-                    SB_TRY(raise_smem((const void *)k_rot_partial<T>, (size_t)(od.H + od.W) * SB_ROT_SUB * sizeof(cplx)));
+                    SB_TRY(raise_smem((const void *)k_rot_partial<T>, ob.rot_smem));
                 }
                 if (od.psf_shift) {
                     if (od.kind != 0) return set_err(SB_ERR_ARG, "observation %d: psf_shift needs a ConvolutionRenderer", o);
@@ -767,7 +776,7 @@ template <typename T> struct PlanT : sb_plan {
                 sd.X = ob.X.p, sd.khat = ob.khat.p, sd.G = ob.G.p, sd.data = ob.data.p, sd.weights = ob.weights.p;
                 sd.tw_x = ob.tw_x.p, sd.tw_y = ob.tw_y.p;
                 sd.P = ob.Pbuf.p, sd.T1 = ob.T1buf.p, sd.Ey = ob.Ey.p, sd.Ex = ob.Ex.p, sd.h2 = T(1);
-                sd.RA = ob.RA.p, sd.RB = ob.RB.p, sd.Rres = ob.Rres.p, sd.Rpart = ob.Rpart.p, sd.n_chunk = ob.rot_chunks, sd.chunk = SB_ROT_CHUNK;
+                sd.RA = ob.RA.p, sd.RB = ob.RB.p, sd.Rres = ob.Rres.p, sd.Rpart = ob.Rpart.p, sd.n_chunk = ob.rot_chunks, sd.chunk = ob.rot_chunk;
                 continue;
             }
             d.Kp = d.Fxc, d.Bh = Fy, d.Bw = Fx;
@@ -1371,13 +1380,13 @@ template <typename T> struct PlanT : sb_plan {
                 ob.ky.column_fwd<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
                 SB_CUDA(cudaGetLastError());
                 mark();
-                k_rot_partial<T><<<dim3(sd.n_chunk, sd.C, S), 256, (size_t)(sd.H + sd.W) * SB_ROT_SUB * sizeof(cplx), stream>>>(sa);
+                k_rot_partial<T><<<dim3(sd.n_chunk, (sd.C + ob.rot_cb - 1) / ob.rot_cb, S), 32 * ob.rot_cb, ob.rot_smem, stream>>>(sa);
                 SB_CUDA(cudaGetLastError());
                 mark();
                 k_rot_residual<T><<<S * sd.C, 256, 0, stream>>>(sa);
                 SB_CUDA(cudaGetLastError());
                 mark();
-                k_rot_adjoint<T><<<dim3((K + 127) / 128, S * sd.C), 128, (size_t)sd.H * sd.W * sizeof(T), stream>>>(sa);
+                k_rot_adjoint<T><<<dim3((K + 127) / 128, S * sd.C), 128, (size_t)sd.H * 32 * sizeof(T), stream>>>(sa);
                 SB_CUDA(cudaGetLastError());
                 mark();
                 ob.ky.column_inv<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);

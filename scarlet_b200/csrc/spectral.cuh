@@ -45,7 +45,7 @@ template <typename T> struct SpecObs {
     const typename Cx<T>::type *RB;   // [W][Fy][Xp]  attached to low-resolution column j
     T *Rres;                          // [S][C][H][W] weighted residual
     T *Rpart;                         // [S][C][n_chunk][H][W] partial sums of the render
-    int n_chunk, chunk;               // chunks of the flattened (ky, kx) index, entries per chunk
+    int n_chunk, chunk;               // chunks of the flattened (ky, kx) index, entries per chunk (multiple of SB_ROT_SUB)
 };
 
 #define SB_SPEC_MAXCB 8 // bands per CTA of the row kernels (SpecArgs::cb <= this)
@@ -843,66 +843,131 @@ template <typename T> __global__ void __launch_bounds__(128) k_resample_q(const 
 // Both are dense contractions over the flattened half plane k = (ky, kx): 2 H W Fy (Fx/2+1) complex multiply-adds per band
 // (what the reference spends in its (H x Fy Fx)(Fy Fx x W) matrix product).  H, W <= 32.
 // ======================================================================================================
-#define SB_ROT_SUB 64    // k entries staged per pass of the forward contraction
-#define SB_ROT_CHUNK 512 // k entries per CTA
-// grid (n_chunk, C, S), 256 threads: thread (ti, tj) owns the 2 x 2 block of outputs (2 ti + {0,1}, 2 tj + {0,1})
-template <typename T> __global__ void __launch_bounds__(256) k_rot_partial(const SpecArgs<T> a) {
+#define SB_ROT_SUB 32    // k entries staged per pass of the forward contraction
+#define SB_ROT_LD 40     // row pitch of the staged planes: 32 outputs + 8, so that (4 k) x (8 rows) stores hit 32 banks
+#define SB_ROT_MAXB 5    // bands per CTA of the forward contraction (one warp each)
+template <typename T> __device__ __forceinline__ void cp_async_c2(typename Cx<T>::type *dst, const typename Cx<T>::type *src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+    else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <typename T> struct RotVec;
+template <> struct RotVec<float> {
+    static __device__ __forceinline__ void load4(const float *p, float (&v)[4]) {
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+    }
+};
+template <> struct RotVec<double> {
+    static __device__ __forceinline__ void load4(const double *p, double (&v)[4]) {
+        const double2 t0 = *reinterpret_cast<const double2 *>(p), t1 = *reinterpret_cast<const double2 *>(p + 2);
+        v[0] = t0.x, v[1] = t0.y, v[2] = t1.x, v[3] = t1.y;
+    }
+};
+// grid (n_chunk, ceil(C / SB_ROT_MAXB), S), 32 SB_ROT_MAXB threads.  Warp b owns band c0 + b and the whole H x W output of it over this CTA's k
+// range: lane (ti, tj) = (lane / 8, lane % 8) accumulates the 8 x 4 block of rows 8 ti.. and columns 4 tj.. in registers.  The
+// operands are staged per 32 k as planar real / imaginary [k][32] tiles -- the column table B_j once for all bands, and
+// U = w_kx P A_i per band -- so one k costs a lane six 128-bit shared loads for 64 fused multiply-adds.
+template <typename T> __global__ void __launch_bounds__(32 * SB_ROT_MAXB) k_rot_partial(const SpecArgs<T> a) {
     typedef typename Cx<T>::type C2;
     extern __shared__ __align__(16) unsigned char smem[];
     const SpecObs<T> &ob = a.ob;
-    const int chunk = blockIdx.x, c = blockIdx.y, s = blockIdx.z;
+    constexpr int cb = SB_ROT_MAXB;
+    const int chunk = blockIdx.x, s = blockIdx.z, c0 = blockIdx.y * cb, nb = min(cb, ob.C - c0);
     if (a.done[s]) return;
-    const int H = ob.H, W = ob.W, Xp = ob.Xp, Fxc = ob.Fxc, K = ob.Fy * Xp, tid = threadIdx.x;
-    C2 *U = reinterpret_cast<C2 *>(smem);     // [H][SB_ROT_SUB]  w_kx P A_i
-    C2 *B = U + (size_t)H * SB_ROT_SUB;       // [W][SB_ROT_SUB]
-    const int tw = (W + 1) / 2, ti = tid / tw, tj = tid - ti * tw;
-    const bool work = ti < (H + 1) / 2;
-    const int i0 = 2 * ti, j0 = 2 * tj, i1 = min(i0 + 1, H - 1), j1 = min(j0 + 1, W - 1);
-    T acc00 = T(0), acc01 = T(0), acc10 = T(0), acc11 = T(0);
-    const C2 *P = ob.P + (size_t)(s * ob.C + c) * K;
+    const int H = ob.H, W = ob.W, Xp = ob.Xp, Fxc = ob.Fxc, K = ob.Fy * Xp, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int PLANE = SB_ROT_SUB * SB_ROT_LD;
+    T *Br = reinterpret_cast<T *>(smem), *Bi = Br + PLANE, *Ur = Bi + PLANE, *Ui = Ur + (size_t)cb * PLANE;
+    const int ti = lane >> 3, tj = lane & 7;
+    T acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[r][q] = T(0);
+    const C2 *P = ob.P + (size_t)(s * ob.C + c0) * K;
+    C2 *Praw = reinterpret_cast<C2 *>(Ui + (size_t)cb * PLANE); // [2][cb][SB_ROT_SUB] spectra of the next / current pass
     const bool even = (ob.Fx & 1) == 0;
     const int kbeg = chunk * ob.chunk, kend = min(K, kbeg + ob.chunk);
-    for (int k0 = kbeg; k0 < kend; k0 += SB_ROT_SUB) {
-        const int nk = min(SB_ROT_SUB, kend - k0);
-        for (int idx = tid; idx < H * SB_ROT_SUB; idx += blockDim.x) {
-            const int i = idx / SB_ROT_SUB, q = idx - i * SB_ROT_SUB, k = k0 + q;
-            C2 u = C2{T(0), T(0)};
-            if (q < nk) {
-                const int kx = k % Xp;
-                if (kx < Fxc) {
-                    const T w = (kx == 0 || (even && kx == Fxc - 1)) ? T(1) : T(2);
-                    const C2 p = P[k], m = ob.RA[(size_t)i * K + k];
-                    u = C2{w * (p.x * m.x - p.y * m.y), w * (p.x * m.y + p.y * m.x)};
+    // A thread stages elements e = tid + n blockDim of the (32 k) x (32 rows) tile, e = [q_hi:3][row_hi:2][row_lo:3][q_lo:2]: a
+    // warp covers 8 table rows x 4 consecutive k (eight full 32-byte sectors) and its stores hit 32 distinct banks.  The
+    // table entries of the NEXT pass are fetched into registers (and its spectra by cp.async) before the products of the
+    // current one, so the loads fly under the arithmetic.
+    constexpr int NT = 32 * SB_ROT_MAXB, NE = (SB_ROT_SUB * 32 + NT - 1) / NT; // elements per thread
+    C2 av[NE], bv[NE];
+    auto fetch = [&](int k0, int buf) {
+#pragma unroll
+        for (int n = 0; n < NE; ++n) {
+            const int e = tid + n * NT;
+            av[n] = bv[n] = C2{T(0), T(0)};
+            if (e < SB_ROT_SUB * 32) {
+                const int q = (e & 3) | ((e >> 7) << 2), row = ((e >> 2) & 7) | (((e >> 5) & 3) << 3), k = k0 + q;
+                if (k < kend && row < W) bv[n] = ob.RB[(size_t)row * K + k];
+                if (k < kend && row < H) av[n] = ob.RA[(size_t)row * K + k];
+            }
+        }
+        for (int e = tid; e < nb * SB_ROT_SUB; e += NT) {
+            const int b = e / SB_ROT_SUB, q = e - b * SB_ROT_SUB;
+            if (k0 + q < kend) cp_async_c2<T>(Praw + (buf * cb + b) * SB_ROT_SUB + q, P + (size_t)b * K + k0 + q);
+            else Praw[(buf * cb + b) * SB_ROT_SUB + q] = C2{T(0), T(0)};
+        }
+        cp_async_commit();
+    };
+    fetch(kbeg, 0);
+    int buf = 0;
+    for (int k0 = kbeg; k0 < kend; k0 += SB_ROT_SUB, buf ^= 1) {
+        cp_async_wait_all();
+        __syncthreads(); // spectra of this pass landed; every warp is done with the planes of the previous pass
+#pragma unroll
+        for (int n = 0; n < NE; ++n) {
+            const int e = tid + n * NT;
+            if (e < SB_ROT_SUB * 32) {
+                const int q = (e & 3) | ((e >> 7) << 2), row = ((e >> 2) & 7) | (((e >> 5) & 3) << 3), kx = (k0 + q) % Xp;
+                const T w = kx >= Fxc ? T(0) : ((kx == 0 || (even && kx == Fxc - 1)) ? T(1) : T(2));
+                Br[q * SB_ROT_LD + row] = bv[n].x, Bi[q * SB_ROT_LD + row] = bv[n].y;
+                const C2 m = C2{w * av[n].x, w * av[n].y};
+                for (int b = 0; b < nb; ++b) {
+                    const C2 p = Praw[(buf * cb + b) * SB_ROT_SUB + q];
+                    Ur[b * PLANE + q * SB_ROT_LD + row] = p.x * m.x - p.y * m.y;
+                    Ui[b * PLANE + q * SB_ROT_LD + row] = p.x * m.y + p.y * m.x;
                 }
             }
-            U[idx] = u;
-        }
-        for (int idx = tid; idx < W * SB_ROT_SUB; idx += blockDim.x) {
-            const int j = idx / SB_ROT_SUB, q = idx - j * SB_ROT_SUB;
-            B[idx] = q < nk ? ob.RB[(size_t)j * K + k0 + q] : C2{T(0), T(0)};
         }
         __syncthreads();
-        if (work) {
-            const C2 *u0 = U + i0 * SB_ROT_SUB, *u1 = U + i1 * SB_ROT_SUB, *b0 = B + j0 * SB_ROT_SUB, *b1 = B + j1 * SB_ROT_SUB;
-#pragma unroll 8
+        if (k0 + SB_ROT_SUB < kend) fetch(k0 + SB_ROT_SUB, buf ^ 1);
+        if (warp < nb) {
+            const T *ur = Ur + warp * PLANE + 8 * ti, *ui = Ui + warp * PLANE + 8 * ti, *br = Br + 4 * tj, *bi = Bi + 4 * tj;
+#pragma unroll 4
             for (int q = 0; q < SB_ROT_SUB; ++q) {
-                const C2 ua = u0[q], ub = u1[q], ba = b0[q], bb = b1[q];
-                acc00 += ua.x * ba.x - ua.y * ba.y;
-                acc01 += ua.x * bb.x - ua.y * bb.y;
-                acc10 += ub.x * ba.x - ub.y * ba.y;
-                acc11 += ub.x * bb.x - ub.y * bb.y;
+                T u0[4], u1[4], v0[4], v1[4], x[4], y[4];
+                RotVec<T>::load4(ur + q * SB_ROT_LD, u0);
+                RotVec<T>::load4(ur + q * SB_ROT_LD + 4, u1);
+                RotVec<T>::load4(ui + q * SB_ROT_LD, v0);
+                RotVec<T>::load4(ui + q * SB_ROT_LD + 4, v1);
+                RotVec<T>::load4(br + q * SB_ROT_LD, x);
+                RotVec<T>::load4(bi + q * SB_ROT_LD, y);
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        acc[r][m] += u0[r] * x[m];
+                        acc[r][m] -= v0[r] * y[m];
+                        acc[r + 4][m] += u1[r] * x[m];
+                        acc[r + 4][m] -= v1[r] * y[m];
+                    }
             }
         }
-        __syncthreads();
     }
-    if (work && tj < tw) {
-        T *out = ob.Rpart + ((size_t)(s * ob.C + c) * ob.n_chunk + chunk) * H * W;
-        out[i0 * W + j0] = acc00;
-        if (j0 + 1 < W) out[i0 * W + j0 + 1] = acc01;
-        if (i0 + 1 < H) {
-            out[(i0 + 1) * W + j0] = acc10;
-            if (j0 + 1 < W) out[(i0 + 1) * W + j0 + 1] = acc11;
-        }
+    if (warp < nb) {
+        T *out = ob.Rpart + ((size_t)(s * ob.C + c0 + warp) * ob.n_chunk + chunk) * H * W;
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int i = 8 * ti + r, j = 4 * tj + m;
+                if (i < H && j < W) out[i * W + j] = acc[r][m];
+            }
     }
 }
 
@@ -937,8 +1002,11 @@ template <typename T> __global__ void __launch_bounds__(128) k_rot_adjoint(const
     const int img = blockIdx.y, s = img / ob.C;
     if (a.done[s]) return;
     const int H = ob.H, W = ob.W, K = ob.Fy * ob.Xp;
-    T *R = reinterpret_cast<T *>(smem); // [H][W]
-    for (int idx = threadIdx.x; idx < H * W; idx += blockDim.x) R[idx] = ob.Rres[(size_t)img * H * W + idx];
+    T *R = reinterpret_cast<T *>(smem); // [H][32], columns beyond W zero: rows are read four entries per shared load
+    for (int idx = threadIdx.x; idx < H * 32; idx += blockDim.x) {
+        const int i = idx >> 5, j = idx & 31;
+        R[idx] = j < W ? ob.Rres[(size_t)img * H * W + i * W + j] : T(0);
+    }
     __syncthreads();
     const int k = blockIdx.x * 128 + threadIdx.x;
     if (k >= K) return;
@@ -948,10 +1016,13 @@ template <typename T> __global__ void __launch_bounds__(128) k_rot_adjoint(const
     C2 acc = C2{T(0), T(0)};
     for (int i = 0; i < H; ++i) {
         C2 v = C2{T(0), T(0)};
-        const T *r = R + i * W;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < W) v.x += r[j] * b[j].x, v.y += r[j] * b[j].y;
+        for (int j = 0; j < 32; j += 4) {
+            T r[4];
+            RotVec<T>::load4(R + i * 32 + j, r);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) v.x += r[m] * b[j + m].x, v.y += r[m] * b[j + m].y;
+        }
         const C2 m = ob.RA[(size_t)i * K + k];
         acc.x += m.x * v.x - m.y * v.y;
         acc.y += m.x * v.y + m.y * v.x;

@@ -61,8 +61,22 @@ def sinc_interp(images, coord_hr, coord_lr, angle=None, padding=3):
     shifted = fft.Fourier.from_fft(res_fft, fshape, shape, [2, 3]).image
     shy = np.sinc((y_lr[np.newaxis, :] + x_hr[:, np.newaxis] * sin) / hy)
     shx = np.sinc((x_lr[np.newaxis, :] - x_hr[:, np.newaxis] * cos) / hx)
-    res_y = (shifted[:, :, np.newaxis, :, :] * shy[np.newaxis, np.newaxis, :, :, np.newaxis]).sum(axis=-2)
-    return (res_y * shx[np.newaxis, np.newaxis, :, :]).sum(axis=-1)
+    # out[c, i, a] = sum_x (sum_y shifted[c, i, y, x] shy[a, y]) shx[a, x].  The y sum runs row by row in index order -- the
+    # order of the reference's reduction over that axis; the deconvolved difference kernel amplifies a different summation
+    # order (a matrix product) to 1e-10 -- without materialising the (C, n_y_hr, n_x_hr, Ny, Nx) product.
+    # Blocks of output rows keep the accumulator in cache.
+    n_c, n_i, n_y, n_x = shifted.shape
+    out = np.empty((n_c, n_i, shy.shape[0]), dtype=np.result_type(shifted, shy))
+    rows = max(1, (1 << 18) // max(1, n_c * shy.shape[0] * n_x))
+    for i0 in range(0, n_i, rows):
+        blk = shifted[:, i0:i0 + rows]
+        acc = np.zeros((n_c, blk.shape[1], shy.shape[0], n_x), dtype=out.dtype)
+        tmp = np.empty_like(acc)
+        for y in range(n_y):
+            np.multiply(blk[:, :, np.newaxis, y, :], shy[np.newaxis, np.newaxis, :, y, np.newaxis], out=tmp)
+            acc += tmp
+        out[:, i0:i0 + rows] = (acc * shx[np.newaxis, np.newaxis, :, :]).sum(axis=-1)
+    return out
 
 
 def sinc_interp_inplace(image, h_image, h_target, angle, pad_shape=None):

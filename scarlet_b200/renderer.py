@@ -247,9 +247,10 @@ class ResolutionRenderer(Renderer):
             if Fx % 2 == 0:
                 wgt[-1] = 1.0
             if op["rotated"]:
-                p = op["khat"] * np.conj(mhat)
-                u = np.einsum("cyx,iyx->ciyx", p, op["A"])
-                out = op["scale"] * np.einsum("ciyx,jyx,x->cij", u, op["B"], wgt).real
+                p = op["khat"] * np.conj(mhat) * wgt
+                nc, ni, nj = p.shape[0], op["A"].shape[0], op["B"].shape[0]
+                u = (p[:, None] * op["A"][None]).reshape(nc * ni, -1)  # one (C H) x (Fy Fx/2+1) by (Fy Fx/2+1) x W product
+                out = op["scale"] * (u @ op["B"].reshape(nj, -1).T).real.reshape(nc, ni, nj)
                 return out.astype(np.asarray(model).dtype)
             t1 = np.einsum("iy,cyx->cix", op["Ey"], op["khat"] * np.conj(mhat))
             out = op["scale"] * np.einsum("cix,jx,x->cij", t1, op["Ex"], wgt).real
