@@ -364,7 +364,8 @@ def measure(env, args, config, S, iters, steps, warmup, headline):
                        "kmul_conj": "spec_column_adj", "fft_inv_grad": "spec_grad"}
             # a rotated resampling observation has two more kernels on the marks the cuFFT pipeline uses for its transforms
             extra = {"fft_inv_model": "rot_contract", "fft_fwd_resid": "rot_adjoint"}
-            relabel.update({k: v for k, v in extra.items() if stages.get(k, 0) > 0})
+            if any(om["metas"][0]["kind"] == 3 for om in plan.obs_meta):
+                relabel.update(extra)
             stages = {relabel.get(k, k): v for k, v in stages.items() if k in relabel or k in ("source_update", "advance")}
         peak, peak_src = peaks()
         C, N, B = cfg["C"], cfg["N"], cfg["B"]

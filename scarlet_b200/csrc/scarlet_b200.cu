@@ -349,6 +349,8 @@ template <typename T> struct PlanT : sb_plan {
         SpecObs<T> sdev;
         SpecKernels<T> kx, ky;
         DevBuf<cplx> X, tw_x, tw_y, Pbuf, T1buf, Ey, Ex; // Pbuf..Ex: resampling observations (kind 2) only
+        DevBuf<int> cand_start, cand;                     // render kernel: sources per (scene, row block)
+        int max_cand = 0;
         DevBuf<cplx> RA, RB;                              // rotated resampling observations (kind 3): multiplier tables
         DevBuf<T> Rres, Rpart;                            //   weighted residual, per-chunk partial renders
         int rot_chunks = 0, rot_chunk = 0, rot_cb = 1;
@@ -589,7 +591,30 @@ template <typename T> struct PlanT : sb_plan {
     }
 
     size_t render_smem(const Obs &ob) const {
-        return ob.smem_row + (size_t)ob.cb * 2 * ob.npair * desc.Nx * sizeof(T) + 16 + (size_t)(max_src_scene + 1) * (sizeof(int) + sizeof(SpecCand<T>));
+        return ob.smem_row + (size_t)ob.cb * 2 * ob.npair * desc.Nx * sizeof(T) + 16 + (size_t)(ob.max_cand + 1) * sizeof(SpecCand<T>);
+    }
+    // Render kernel: per (scene, block of 2 npair frame rows) the sources whose boxes touch the rows, in scene order.  Boxes are
+    // fixed for the life of the source tables (sb_plan_set_sources rebuilds the lists).
+    int build_candidates(Obs &ob) {
+        const int rows = 2 * ob.npair, nblk = (desc.Ny + rows - 1) / rows;
+        std::vector<int> start((size_t)S * nblk + 1, 0), list;
+        ob.max_cand = 0;
+        for (int s = 0; s < S; ++s)
+            for (int b = 0; b < nblk; ++b) {
+                const int y0 = b * rows;
+                start[(size_t)s * nblk + b] = (int)list.size();
+                for (int k = h_start[s]; k < h_start[s + 1]; ++k)
+                    if (h_src[k].oy < y0 + rows && h_src[k].oy + h_src[k].By > y0) list.push_back(k);
+                ob.max_cand = std::max(ob.max_cand, (int)list.size() - start[(size_t)s * nblk + b]);
+            }
+        start[(size_t)S * nblk] = (int)list.size();
+        if (ob.cand_start.n < start.size()) SB_TRY(ob.cand_start.alloc(start.size()));
+        if (ob.cand.n < std::max<size_t>(list.size(), 1)) SB_TRY(ob.cand.alloc(std::max<size_t>(list.size(), 1) * 5 / 4 + 16));
+        SB_CUDA(cudaMemcpyAsync(ob.cand_start.p, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        if (!list.empty()) SB_CUDA(cudaMemcpyAsync(ob.cand.p, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        SB_CUDA(cudaStreamSynchronize(stream)); // the host vectors go out of scope
+        ob.sdev.cand_start = ob.cand_start.p, ob.sdev.cand = ob.cand.p;
+        return SB_OK;
     }
 
     // sb_plan_set_sources: new boxes / chains / tables for the same scenes and observations
@@ -619,6 +644,7 @@ template <typename T> struct PlanT : sb_plan {
             Obs &ob = *obs[o];
             if (ob.psf_shift) ob.slot0 = psf_slot0[o];
             if (ob.fused) {
+                SB_TRY(build_candidates(ob));
                 ob.smem_render = render_smem(ob);
                 if (ob.smem_render > 227 * 1024) return set_err(SB_ERR_ARG, "observation %d: frame too wide for the fused spectral kernels", (int)o);
                 SB_TRY(raise_smem((const void *)ob.kx.render, ob.smem_render));
@@ -690,6 +716,7 @@ template <typename T> struct PlanT : sb_plan {
                 if (ob.row_threads > limit) ob.row_threads = ob.npair * ob.cb * rmax;
                 const size_t nb = (size_t)ob.npair * ob.cb;
                 ob.smem_row = (nb * ob.kx.sf + (size_t)Fx) * sizeof(cplx) + 16;
+                SB_TRY(build_candidates(ob));
                 ob.smem_render = render_smem(ob);
                 ob.smem_col = ((size_t)ob.ky.NBcol * ob.ky.sf + (size_t)Fy) * sizeof(cplx) + 16;
                 if (ob.smem_render > 227 * 1024 || ob.smem_col > 227 * 1024)
@@ -777,6 +804,7 @@ template <typename T> struct PlanT : sb_plan {
                 sd.tw_x = ob.tw_x.p, sd.tw_y = ob.tw_y.p;
                 sd.P = ob.Pbuf.p, sd.T1 = ob.T1buf.p, sd.Ey = ob.Ey.p, sd.Ex = ob.Ex.p, sd.h2 = T(1);
                 sd.RA = ob.RA.p, sd.RB = ob.RB.p, sd.Rres = ob.Rres.p, sd.Rpart = ob.Rpart.p, sd.n_chunk = ob.rot_chunks, sd.chunk = ob.rot_chunk;
+                sd.cand_start = ob.cand_start.p, sd.cand = ob.cand.p;
                 continue;
             }
             d.Kp = d.Fxc, d.Bh = Fy, d.Bw = Fx;
@@ -1366,7 +1394,7 @@ template <typename T> struct PlanT : sb_plan {
             sa.smorph = d_smorph.p;
             sa.model_out = ob.psf_shift ? d_model.p : model_out, sa.partials = ob.partials.p;
             sa.resid_out = ob.psf_shift ? ob.resid.p : nullptr;
-            sa.magic_nx = 0xffffffffu / (unsigned)desc.Nx + 1u, sa.max_cand = max_src_scene + 1;
+            sa.magic_nx = 0xffffffffu / (unsigned)desc.Nx + 1u;
             sa.rendered_out = ((int)o == rendered_obs) ? rendered_out : nullptr;
             const dim3 rgrid((desc.Ny + 2 * ob.npair - 1) / (2 * ob.npair), S, (ob.sdev.C + ob.cb - 1) / ob.cb);
             const dim3 cgrid((ob.sdev.Fxc + ob.ky.NBcol - 1) / ob.ky.NBcol, S * ob.sdev.C);

@@ -45,6 +45,7 @@ template <typename T> struct SpecObs {
     const typename Cx<T>::type *RB;   // [W][Fy][Xp]  attached to low-resolution column j
     T *Rres;                          // [S][C][H][W] weighted residual
     T *Rpart;                         // [S][C][n_chunk][H][W] partial sums of the render
+    const int *cand_start, *cand;     // render kernel: per (scene, block of 2 npair rows) the sources whose boxes touch the rows
     int n_chunk, chunk;               // chunks of the flattened (ky, kx) index, entries per chunk (multiple of SB_ROT_SUB)
 };
 
@@ -68,7 +69,6 @@ template <typename T> struct SpecArgs {
     T *resid_out;     // optional [S][C][Ny][Nx]: w (rendered - data) in the model frame (psf_shift gradient)
     int conj;         // column kernel: multiply by conj(K^)
     unsigned magic_nx; // 2^32 / Nx + 1: idx / Nx == umulhi(idx, magic_nx)
-    int max_cand;      // capacity of the render kernel's candidate list (largest number of sources in a scene)
 };
 
 // what the render kernel needs to know about one source whose box intersects the CTA's rows
@@ -189,7 +189,6 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
     typedef typename Cx<T>::type C2;
     typedef sbfft::Plan2<R1, R2> P;
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_ncand;
     const int s = blockIdx.y;
     if (a.done[s]) return;
     const SpecObs<T> &ob = a.ob;
@@ -202,90 +201,57 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
     SpecCand<T> *recs = reinterpret_cast<SpecCand<T> *>(
         (reinterpret_cast<uintptr_t>(tile + (size_t)a.cb * rows * Nx) + 15) & ~(uintptr_t)15);
     stage_twiddles<T, R1, R2>(tw, ob.tw_x);
-    // Sources whose boxes intersect these rows, in scene order (deterministic accumulation order).  The first warp tests 32
-    // sources per trip and each lane with a hit writes its own compact record (everything the pixel loop needs) to shared
-    // memory: one pass over the source table, one barrier.
-    const int k0 = a.scene_src_start[s], k1 = a.scene_src_start[s + 1];
-    if (tid < 32) {
-        int cnt = 0;
-        for (int base = k0; base < k1; base += 32) {
-            const int k = base + tid;
-            bool ok = false;
-            if (k < k1) {
-                const DevSource &d = a.src[k];
-                ok = d.oy < y0 + rows && d.oy + d.By > y0;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-                const DevSource &d = a.src[k];
-                SpecCand<T> rc;
-                rc.oy = d.oy, rc.ox = d.ox, rc.By = d.By, rc.Bx = d.Bx;
-                const int plane = d.kind == 0 ? 0 : d.By * d.Bx;
-                rc.plane = plane;
-                rc.mp = (d.kind == 0 ? (d.shifting ? a.smorph : a.morph) : a.pmorph + (size_t)(ob.chan_off + c0) * plane) + d.morph_off;
-                const double *sed = a.sed + (size_t)k * a.Cm + ob.chan_off + c0;
+    // Sources whose boxes intersect these rows: a list made once per plan (boxes do not move inside a plan; ob.cand_start /
+    // ob.cand, scene order = the accumulation order of blend.py:17-27).  Thread j turns entry j into a compact record while
+    // the others clear the tile; then the sources are added one after the other, a thread per covered pixel -- the work is
+    // the covered area, not (pixels of the rows) x (sources).
+    const int blk = s * gridDim.x + blockIdx.x, l0 = ob.cand_start[blk], ncand = ob.cand_start[blk + 1] - l0;
+    for (int j = tid; j < ncand; j += nt) {
+        const int k = ob.cand[l0 + j];
+        const DevSource &d = a.src[k];
+        SpecCand<T> rc;
+        rc.oy = d.oy, rc.ox = d.ox, rc.By = d.By, rc.Bx = d.Bx;
+        const int plane = d.kind == 0 ? 0 : d.By * d.Bx;
+        rc.plane = plane, rc.pad = 0;
+        rc.mp = (d.kind == 0 ? (d.shifting ? a.smorph : a.morph) : a.pmorph + (size_t)(ob.chan_off + c0) * plane) + d.morph_off;
+        const double *sed = a.sed + (size_t)k * a.Cm + ob.chan_off + c0;
 #pragma unroll
-                for (int c = 0; c < SB_SPEC_MAXCB; ++c) rc.sed[c] = c < Cb ? (T)sed[c] : T(0);
-                recs[cnt + __popc(m & ((1u << tid) - 1u))] = rc;
-            }
-            cnt += __popc(m);
-        }
-        if (tid == 0) s_ncand = cnt;
+        for (int c = 0; c < SB_SPEC_MAXCB; ++c) rc.sed[c] = c < Cb ? (T)sed[c] : T(0);
+        recs[j] = rc;
     }
+    for (int idx = tid; idx < Cb * rows * Nx; idx += nt) tile[idx] = T(0);
     __syncthreads();
-    const int ncand = s_ncand;
 #pragma unroll 1
-    for (int idx = tid; idx < rows * Nx; idx += nt) {
-        const int r = (int)__umulhi((unsigned)idx, a.magic_nx), x = idx - r * Nx, y = y0 + r;
-        T acc[SB_SPEC_MAXCB];
+    for (int i = 0; i < ncand; ++i) {
+        const SpecCand<T> &rc = recs[i];
+        const int ry0 = max(y0, rc.oy), ry1 = min(min(y0 + rows, Ny), rc.oy + rc.By); // rows of the box inside this CTA's rows
+        const int bx0 = max(0, -rc.ox), bx1 = min(rc.Bx, Nx - rc.ox), wx = bx1 - bx0;  // columns of the box inside the frame
+        const int npx = wx > 0 ? (ry1 - ry0) * wx : 0;
+        const unsigned magic_w = wx > 0 ? 0xffffffffu / (unsigned)wx + 1u : 0u;
+        const int plane = rc.plane;
+        for (int idx = tid; idx < npx; idx += nt) {
+            const int rr = (int)__umulhi((unsigned)idx, magic_w), bx = bx0 + idx - rr * wx, y = ry0 + rr;
+            const T *pm = rc.mp + (y - rc.oy) * rc.Bx + bx;
+            T *t = tile + (size_t)(y - y0) * Nx + rc.ox + bx;
+            if (plane == 0) {
+                const T v = pm[0];
 #pragma unroll
-        for (int c = 0; c < SB_SPEC_MAXCB; ++c) acc[c] = T(0);
-        if (y < Ny) {
-            // candidates four at a time: the morphology values of a chunk are fetched back to back, then accumulated in
-            // candidate order (one memory round trip per chunk instead of one per overlapping source)
-#pragma unroll 1
-            for (int i0 = 0; i0 < ncand; i0 += 4) {
-                const T *pm[4];
-                T v[4];
+                for (int c = 0; c < SB_SPEC_MAXCB; ++c)
+                    if (c < Cb) t[(size_t)c * rows * Nx] += rc.sed[c] * v;
+            } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    pm[j] = nullptr;
-                    v[j] = T(0);
-                    if (i0 + j < ncand) {
-                        const SpecCand<T> &rc = recs[i0 + j];
-                        const int by = y - rc.oy, bx = x - rc.ox;
-                        if ((unsigned)by < (unsigned)rc.By && (unsigned)bx < (unsigned)rc.Bx) {
-                            pm[j] = rc.mp + by * rc.Bx + bx;
-                            v[j] = pm[j][0];
-                        }
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (pm[j]) {
-                        const SpecCand<T> &rc = recs[i0 + j];
-                        const int plane = rc.plane; // 0: one morphology image for all bands; else per-band planes (point sources)
-                        if (plane == 0) {
-#pragma unroll
-                            for (int c = 0; c < SB_SPEC_MAXCB; ++c)
-                                if (c < Cb) acc[c] += rc.sed[c] * v[j];
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < SB_SPEC_MAXCB; ++c)
-                                if (c < Cb) acc[c] += rc.sed[c] * pm[j][c * plane];
-                        }
-                    }
-                }
+                for (int c = 0; c < SB_SPEC_MAXCB; ++c)
+                    if (c < Cb) t[(size_t)c * rows * Nx] += rc.sed[c] * pm[c * plane];
             }
         }
-#pragma unroll
-        for (int c = 0; c < SB_SPEC_MAXCB; ++c)
-            if (c < Cb) {
-                tile[((size_t)c * rows + r) * Nx + x] = acc[c];
-                if (a.model_out && y < Ny) a.model_out[(((size_t)s * a.Cm + ob.chan_off + c0 + c) * Ny + y) * Nx + x] = acc[c];
-            }
+        __syncthreads(); // the next source may cover the same pixels from other threads
     }
-    __syncthreads();
+    if (a.model_out) {
+        for (int idx = tid; idx < Cb * rows * Nx; idx += nt) {
+            const int cr = (int)__umulhi((unsigned)idx, a.magic_nx), x = idx - cr * Nx, c = cr / rows, y = y0 + cr - c * rows;
+            if (y < Ny) a.model_out[(((size_t)s * a.Cm + ob.chan_off + c0 + c) * Ny + y) * Nx + x] = tile[idx];
+        }
+    }
     C2 a_[R1];
     {
         const int f = tid / R2, n2 = tid - f * R2;
