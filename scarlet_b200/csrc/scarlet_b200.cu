@@ -324,7 +324,9 @@ template <typename T> struct PlanT : sb_plan {
     // warp-per-source kernel (update_warp.cuh)
     static constexpr int WARP_NPT = 56, WARP_MAXT = sizeof(T) == 4 ? 448 : 256;
     static constexpr size_t WARP_RING = XpRing<T>::BYTES;
-    DevBuf<int> d_warp_groups;
+    DevBuf<int> d_warp_groups, d_warp_ctr;
+    DevBuf<int4> d_warp_segs;
+    int n_warp_chains = 0;
     DevBuf<XP<T>> d_xp;
     int n_warp_cta = 0, warp_G = 0, warp_npix = 0, warp_cap = 0;
     size_t warp_smem = 0;
@@ -946,16 +948,37 @@ template <typename T> struct PlanT : sb_plan {
         {
             size_t n_warp = 0;
             for (auto &kv : warp_chain) n_warp += kv.second.size();
-            warp_G = pick_G(n_warp, WARP_MAXT / 32, [&](int G) { return warp_smem_bytes(G, warp_npix, warp_cap); });
+            // Persistent warps: one CTA per SM (fewer when the batch is small), G warps each; the CTAs are dealt to the chains in
+            // proportion to their source counts and the warps of a chain's CTAs claim its sources from one counter.
+            {
+                const int gmax = WARP_MAXT / 32;
+                int G = n_warp ? (int)std::min<size_t>(gmax, (n_warp + sms - 1) / sms) : 0;
+                while (G > 1 && warp_smem_bytes(G, warp_npix, warp_cap) > (size_t)220 * 1024) --G;
+                if (G && warp_smem_bytes(G, warp_npix, warp_cap) > (size_t)220 * 1024) G = 0;
+                warp_G = G;
+            }
             std::vector<int> groups;
-            if (warp_G)
-                make_groups(warp_chain, warp_G, groups);
-            else
+            std::vector<int4> segs;
+            n_warp_chains = 0;
+            if (warp_G) {
+                const size_t n_cta_target = std::min<size_t>(sms, (n_warp + warp_G - 1) / warp_G);
+                for (auto &kv : warp_chain) {
+                    const std::vector<int> &v = kv.second;
+                    const size_t ctas = std::max<size_t>(1, std::min<size_t>((v.size() + warp_G - 1) / warp_G,
+                                                                             (n_cta_target * v.size() + n_warp / 2) / n_warp));
+                    for (size_t c = 0; c < ctas; ++c) segs.push_back(make_int4((int)groups.size(), (int)v.size(), n_warp_chains, 0));
+                    groups.insert(groups.end(), v.begin(), v.end());
+                    ++n_warp_chains;
+                }
+            } else
                 for (auto &kv : warp_chain) by_chain[kv.first].insert(by_chain[kv.first].end(), kv.second.begin(), kv.second.end());
-            n_warp_cta = warp_G ? (int)(groups.size() / warp_G) : 0;
+            n_warp_cta = (int)segs.size();
             warp_smem = warp_G ? warp_smem_bytes(warp_G, warp_npix, warp_cap) : 0;
             SB_TRY(d_warp_groups.alloc(std::max<size_t>(groups.size(), 1)));
+            SB_TRY(d_warp_segs.alloc(std::max<size_t>(segs.size(), 1)));
+            SB_TRY(d_warp_ctr.alloc(std::max(n_warp_chains, 1)));
             if (!groups.empty()) SB_CUDA(cudaMemcpy(d_warp_groups.p, groups.data(), groups.size() * sizeof(int), cudaMemcpyHostToDevice));
+            if (!segs.empty()) SB_CUDA(cudaMemcpy(d_warp_segs.p, segs.data(), segs.size() * sizeof(int4), cudaMemcpyHostToDevice));
             if (n_warp_cta) {
                 SB_TRY(d_xp.alloc((size_t)n_warp_cta * warp_G * (32 * WARP_NPT))); // one padded, 16-byte aligned slot per warp
                 SB_TRY(raise_smem((const void *)k_update_warp<T, WARP_NPT, WARP_MAXT>, warp_smem));
@@ -1534,6 +1557,8 @@ template <typename T> struct PlanT : sb_plan {
                 if (n_warp_cta) {
                     WarpArgs<T> wa;
                     wa.groups = d_warp_groups.p, wa.G = warp_G, wa.npix = warp_npix, wa.table_cap = warp_cap, wa.xp = d_xp.p;
+                    wa.segs = d_warp_segs.p, wa.counters = d_warp_ctr.p;
+                    SB_CUDA(cudaMemsetAsync(d_warp_ctr.p, 0, (size_t)std::max(n_warp_chains, 1) * sizeof(int), stream));
                     wa.use_ring = getenv("SB_NO_XP_RING") == nullptr;
                     wa.bulk_table = getenv("SB_NO_BULK_TABLE") == nullptr;
                     k_update_warp<T, WARP_NPT, WARP_MAXT><<<n_warp_cta, 32 * warp_G, warp_smem, stream>>>(ua, wa);

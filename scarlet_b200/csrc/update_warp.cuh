@@ -62,8 +62,10 @@ template <typename T> struct XpRing {
 };
 
 template <typename T> struct WarpArgs {
-    const int *groups;   // [n_cta][G] source index or -1
-    int G;               // warps (= sources) per CTA
+    const int *groups;   // source lists of the chains, back to back
+    const int4 *segs;    // [n_cta] {offset of the CTA's chain list in groups, its length, index of the chain's counter, -}
+    int *counters;       // [n_chains] next unclaimed entry of each list (zeroed before every launch)
+    int G;               // warps per CTA
     int npix;            // shared-memory image length per warp (largest box + spare cell, padded)
     int table_cap;       // task capacity of the shared-memory table
     XP<T> *xp;           // one padded slot of 32 NPT entries per warp
@@ -152,7 +154,13 @@ template <typename T> __device__ __forceinline__ void warp_sweep(unsigned zb, co
 template <typename T, int NPT, int MAXT> __global__ void __launch_bounds__(MAXT, 1) k_update_warp(const UpdateArgs<T> a, const WarpArgs<T> wa) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int G = wa.G, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int *mine = wa.groups + (size_t)blockIdx.x * G;
+    // The CTA serves one constraint chain (one operator table); its warps claim sources of that chain one at a time from a
+    // counter shared by all CTAs of the chain, so a warp whose source converged after two proximal sub-iterations moves on
+    // while its neighbour runs all ten: the kernel ends when the work is done, not when the unluckiest CTA is.
+    const int4 seg = wa.segs[blockIdx.x];
+    const int *list = wa.groups + seg.x;
+    const int n_list = seg.y;
+    int *counter = wa.counters + seg.z;
     // ---- shared memory: table by trips (W4 | uint2 | u16 pix, table_cap entries each), barriers, then per warp: spectrum
     // gradient, image, x/psi ring
     typedef XpRing<T> Ring;
@@ -165,13 +173,7 @@ template <typename T, int NPT, int MAXT> __global__ void __launch_bounds__(MAXT,
     T *s_img = reinterpret_cast<T *>(s_gsum + (size_t)G * SB_FAST_MAXC);
     unsigned char *s_ring = reinterpret_cast<unsigned char *>(s_img + (size_t)G * wa.npix);
 
-    int k0 = -1;
-    for (int i = 0; i < G; ++i)
-        if (mine[i] >= 0) {
-            k0 = mine[i];
-            break;
-        }
-    const DevChain &ch = a.chains[a.src[k0].chain];
+    const DevChain &ch = a.chains[a.src[list[0]].chain];
     const DevMono &mo = a.monos[ch.ops[0].iarg]; // host: the chain starts with the monotonic operator (fused pattern)
     // The CTA's operator table: three bulk asynchronous copies issued by one thread, complete on s_bar[0]; every warp waits for
     // them only right before its first sweep, i.e. the copy runs under the gradient gather of phase 1.
@@ -181,10 +183,10 @@ template <typename T, int NPT, int MAXT> __global__ void __launch_bounds__(MAXT,
         for (int i = 0; i < G * Ring::STAGES; ++i) mbar_init(bar_tab + 8u * (unsigned)(1 + i), 1);
         mbar_fence_init();
     }
-    // every warp looks at its own source (one dependent chain per warp, all in parallel); barrier + OR
-    const int k_mine = wid < G ? mine[wid] : -1;
-    const bool live_mine = k_mine >= 0 && !a.done[a.src[k_mine].scene];
-    if (!__syncthreads_or(live_mine ? 1 : 0)) return; // every scene of this CTA has stopped: nothing is copied
+    // is any source of the list still running?  (threads look at different entries; barrier + OR)
+    int live_any = 0;
+    for (int i = threadIdx.x; i < n_list; i += blockDim.x) live_any |= !a.done[a.src[list[i]].scene];
+    if (!__syncthreads_or(live_any)) return; // every scene of this chain has stopped: nothing is copied
     if (wa.bulk_table) {
         if (threadIdx.x == 0) {
             const unsigned n = (unsigned)mo.w_cap;
@@ -205,17 +207,21 @@ template <typename T, int NPT, int MAXT> __global__ void __launch_bounds__(MAXT,
         __syncthreads();
         if (threadIdx.x == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tab) : "memory");
     }
-    // (a warp without work still waits for the table copies: shared memory must not be released under them)
-    const int k = k_mine;
-    if (!live_mine) {
-        mbar_wait(bar_tab, 0u);
-        return;
-    }
-    const DevSource &d = a.src[k];
-    const int s = d.scene;
-
     WarpTable<T> tab;
     tab.nbr = smem_u32(s_nbr + lane), tab.w = smem_u32(s_w + lane), tab.pix = smem_u32(s_pix + lane), tab.n_trips = mo.w_trips;
+    // ring state of this warp, carried from source to source (every source leaves the ring drained)
+    int iss_stage = 0, use_stage = 0, n_flight = 0;
+    unsigned use_parity = 0u;
+#pragma unroll 1
+    for (;;) {
+    int claim = 0;
+    if (lane == 0) claim = atomicAdd(counter, 1);
+    claim = __shfl_sync(0xffffffffu, claim, 0);
+    if (claim >= n_list) break;
+    const int k = list[claim];
+    const DevSource &d = a.src[k];
+    const int s = d.scene;
+    if (a.done[s]) continue;
     const int it = a.it_ptr[s], C = a.C, n = d.By * d.Bx, Bx = d.Bx;
     const unsigned magic = 0xffffffffu / (unsigned)Bx + 1u; // p / Bx == umulhi(p, magic) for p, Bx < 65536
     T *zn = s_img + (size_t)wid * wa.npix;
@@ -316,11 +322,9 @@ template <typename T, int NPT, int MAXT> __global__ void __launch_bounds__(MAXT,
         const int nch = (((n + 31) >> 5) + Ring::TRIPS - 1) / Ring::TRIPS; // chunks per pass
         const int g_end = nch * (prox_max - 1);                            // chunks of the whole stream
         const unsigned ring = smem_u32(s_ring + (size_t)wid * Ring::BYTES), bar_ring = bar_tab + 8u * (unsigned)(1 + wid * Ring::STAGES);
-        // producer side (lane 0 issues; every lane keeps the same counters): stage, chunk within the pass, chunks left to request
-        int iss_stage = 0, iss_chunk = 0, iss_left = g_end > 0 ? g_end : 0;
-        // consumer side: stage, its phase parity, requested-but-unconsumed chunks
-        int use_stage = 0, n_flight = 0;
-        unsigned use_parity = 0u;
+        // producer side (lane 0 issues; every lane keeps the same counters): stage, chunk within the pass, chunks left to request;
+        // consumer side: stage, its phase parity, requested-but-unconsumed chunks (iss_stage, use_stage, use_parity, n_flight)
+        int iss_chunk = 0, iss_left = g_end > 0 ? g_end : 0;
         auto issue = [&]() {
             if (lane == 0) {
                 mbar_expect_tx(bar_ring + 8u * (unsigned)iss_stage, (unsigned)Ring::CHUNK);
@@ -462,8 +466,10 @@ template <typename T, int NPT, int MAXT> __global__ void __launch_bounds__(MAXT,
         chk = warp_sum_all_t(chk);
         if (lane == 0 && !isfinite((double)chk)) atomicExch(a.status + s, SB_ERR_NONFINITE);
     }
-    if (!upd) mbar_wait(bar_tab, 0u); // nobody leaves while the table copies are in flight
     if (lane == 0 && !d.sed_fixed) sed_update<T>(a, d, k, gsum, it);
+    __syncwarp(); // the image and the spectrum sums of this source are dead: the next one may overwrite them
+    }
+    mbar_wait(bar_tab, 0u); // nobody leaves while the table copies are in flight
 }
 
 } // namespace sb
