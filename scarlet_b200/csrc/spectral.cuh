@@ -203,8 +203,8 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
     stage_twiddles<T, R1, R2>(tw, ob.tw_x);
     // Sources whose boxes intersect these rows: a list made once per plan (boxes do not move inside a plan; ob.cand_start /
     // ob.cand, scene order = the accumulation order of blend.py:17-27).  Thread j turns entry j into a compact record while
-    // the others clear the tile; then the sources are added one after the other, a thread per covered pixel -- the work is
-    // the covered area, not (pixels of the rows) x (sources).
+    // the others clear the tile; then the sources are added in list order, a thread per covered pixel -- the work is the
+    // covered area, not (pixels of the rows) x (sources).
     const int blk = s * gridDim.x + blockIdx.x, l0 = ob.cand_start[blk], ncand = ob.cand_start[blk + 1] - l0;
     for (int j = tid; j < ncand; j += nt) {
         const int k = ob.cand[l0 + j];
@@ -221,30 +221,71 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
     }
     for (int idx = tid; idx < Cb * rows * Nx; idx += nt) tile[idx] = T(0);
     __syncthreads();
+    // Sources four at a time: every thread first requests its pixel of each of the four (one memory round trip for the
+    // chunk), then the four are added in list order, a barrier after each (the next source may cover the same pixels from
+    // other threads).  Boxes with more pixels in these rows than the CTA has threads, and point sources (one morphology
+    // plane per band), take the plain loop.
 #pragma unroll 1
-    for (int i = 0; i < ncand; ++i) {
-        const SpecCand<T> &rc = recs[i];
-        const int ry0 = max(y0, rc.oy), ry1 = min(min(y0 + rows, Ny), rc.oy + rc.By); // rows of the box inside this CTA's rows
-        const int bx0 = max(0, -rc.ox), bx1 = min(rc.Bx, Nx - rc.ox), wx = bx1 - bx0;  // columns of the box inside the frame
-        const int npx = wx > 0 ? (ry1 - ry0) * wx : 0;
-        const unsigned magic_w = wx > 0 ? 0xffffffffu / (unsigned)wx + 1u : 0u;
-        const int plane = rc.plane;
-        for (int idx = tid; idx < npx; idx += nt) {
-            const int rr = (int)__umulhi((unsigned)idx, magic_w), bx = bx0 + idx - rr * wx, y = ry0 + rr;
-            const T *pm = rc.mp + (y - rc.oy) * rc.Bx + bx;
-            T *t = tile + (size_t)(y - y0) * Nx + rc.ox + bx;
-            if (plane == 0) {
-                const T v = pm[0];
+    for (int i0 = 0; i0 < ncand; i0 += 4) {
+        T v[4];
+        T *tp[4];
+        bool plain = false;
 #pragma unroll
-                for (int c = 0; c < SB_SPEC_MAXCB; ++c)
-                    if (c < Cb) t[(size_t)c * rows * Nx] += rc.sed[c] * v;
-            } else {
-#pragma unroll
-                for (int c = 0; c < SB_SPEC_MAXCB; ++c)
-                    if (c < Cb) t[(size_t)c * rows * Nx] += rc.sed[c] * pm[c * plane];
+        for (int j = 0; j < 4; ++j) {
+            v[j] = T(0), tp[j] = nullptr;
+            if (i0 + j < ncand) {
+                const SpecCand<T> &rc = recs[i0 + j];
+                const int ry0 = max(y0, rc.oy), ry1 = min(min(y0 + rows, Ny), rc.oy + rc.By); // rows of the box inside this CTA's rows
+                const int bx0 = max(0, -rc.ox), bx1 = min(rc.Bx, Nx - rc.ox), wx = bx1 - bx0;  // columns of the box inside the frame
+                const int npx = wx > 0 ? (ry1 - ry0) * wx : 0;
+                if (npx > nt || rc.plane != 0) plain = true;
+                else if (tid < npx) {
+                    const int rr = (int)__umulhi((unsigned)tid, 0xffffffffu / (unsigned)wx + 1u), bx = bx0 + tid - rr * wx, y = ry0 + rr;
+                    v[j] = rc.mp[(y - rc.oy) * rc.Bx + bx];
+                    tp[j] = tile + (size_t)(y - y0) * Nx + rc.ox + bx;
+                }
             }
         }
-        __syncthreads(); // the next source may cover the same pixels from other threads
+        if (!plain) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (i0 + j < ncand) { // CTA-uniform
+                    if (tp[j]) {
+                        const SpecCand<T> &rc = recs[i0 + j];
+#pragma unroll
+                        for (int c = 0; c < SB_SPEC_MAXCB; ++c)
+                            if (c < Cb) tp[j][(size_t)c * rows * Nx] += rc.sed[c] * v[j];
+                    }
+                    __syncthreads();
+                }
+            }
+            continue;
+        }
+#pragma unroll 1
+        for (int i = i0; i < min(i0 + 4, ncand); ++i) {
+            const SpecCand<T> &rc = recs[i];
+            const int ry0 = max(y0, rc.oy), ry1 = min(min(y0 + rows, Ny), rc.oy + rc.By);
+            const int bx0 = max(0, -rc.ox), bx1 = min(rc.Bx, Nx - rc.ox), wx = bx1 - bx0;
+            const int npx = wx > 0 ? (ry1 - ry0) * wx : 0;
+            const unsigned magic_w = wx > 0 ? 0xffffffffu / (unsigned)wx + 1u : 0u;
+            const int plane = rc.plane;
+            for (int idx = tid; idx < npx; idx += nt) {
+                const int rr = (int)__umulhi((unsigned)idx, magic_w), bx = bx0 + idx - rr * wx, y = ry0 + rr;
+                const T *pm = rc.mp + (y - rc.oy) * rc.Bx + bx;
+                T *t = tile + (size_t)(y - y0) * Nx + rc.ox + bx;
+                if (plane == 0) {
+                    const T v1 = pm[0];
+#pragma unroll
+                    for (int c = 0; c < SB_SPEC_MAXCB; ++c)
+                        if (c < Cb) t[(size_t)c * rows * Nx] += rc.sed[c] * v1;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < SB_SPEC_MAXCB; ++c)
+                        if (c < Cb) t[(size_t)c * rows * Nx] += rc.sed[c] * pm[c * plane];
+                }
+            }
+            __syncthreads();
+        }
     }
     if (a.model_out) {
         for (int idx = tid; idx < Cb * rows * Nx; idx += nt) {
