@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--only-headline", action="store_true", help="skip the sub-records of the other BASELINE configurations")
     ap.add_argument("--e2e-mode", default="pipeline", choices=["pipeline", "batch"],
                     help="end-to-end leg: a stream of batches through BatchPipeline (default) or one BlendBatch.fit per step")
+    ap.add_argument("--e2e-batches", type=int, default=2, help="--e2e-mode pipeline: BlendBatch objects that take turns (= pipeline depth)")
     ap.add_argument("--e2e-streams", type=int, default=3, help="--e2e-mode batch: plans/streams of the BlendBatch (copy/compute overlap)")
     return ap.parse_args()
 
@@ -297,12 +298,14 @@ def measure(env, args, config, S, iters, steps, warmup, headline):
     # kernel images and parameters in.  Every step's H2D and D2H copies are inside the timed region.
     # (--e2e-mode batch: one BlendBatch.fit per step, split over --e2e-streams plans.)
     h2d = d2h = 0
+    pipe_stats = {}
     pipelined = args.e2e_mode == "pipeline"
-    batch_b = None
+    extra_batches = []
     if pipelined:
-        blends_b = [_make_blend(config, base[i % uniq], precision=args.precision, device=local) for i in range(S)]
-        batch_b = BlendBatch(blends_b, precision=args.precision, device=local)
-        turn_batches = [batch, batch_b]
+        for _ in range(max(1, args.e2e_batches - 1)):
+            blends_b = [_make_blend(config, base[i % uniq], precision=args.precision, device=local) for i in range(S)]
+            extra_batches.append(BlendBatch(blends_b, precision=args.precision, device=local))
+        turn_batches = [batch] + extra_batches
         batch_e2e = batch
     else:
         batch_e2e = BlendBatch(blends, precision=args.precision, device=local, n_streams=args.e2e_streams) if args.e2e_streams > 1 else batch
@@ -335,9 +338,14 @@ def measure(env, args, config, S, iters, steps, warmup, headline):
             restart(k, b)                      # later uses restart inside the pipeline (prepare), overlapped with the other loop
         barrier()
         t0 = time.perf_counter()
-        BatchPipeline(depth=2).run([turn_batches[k % 2] for k in range(n)], max_iter=iters, e_rel=1e-3, fixed_iterations=True,
-                                   check_every=10 ** 6, upload_observations=True,
-                                   prepare=lambda k, b: restart(k, b) if k >= len(turn_batches) else None)
+        pipe = BatchPipeline(depth=len(turn_batches))
+        pipe.run([turn_batches[k % len(turn_batches)] for k in range(n)], max_iter=iters, e_rel=1e-3, fixed_iterations=True,
+                 check_every=10 ** 6, upload_observations=True,
+                 prepare=lambda k, b: restart(k, b) if k >= len(turn_batches) else None)
+        starts = sorted(t["loop"][0] for t in pipe.timings)
+        if len(starts) > 2:  # period between the starts of consecutive device loops = a step without the pipeline's fill and drain
+            pipe_stats["period_ms"] = 1e3 * float(np.median(np.diff(starts)))
+            pipe_stats["fill_ms"] = 1e3 * (starts[0] - t0)
         for _ in range(n):
             gather_results()
         barrier()
@@ -345,7 +353,7 @@ def measure(env, args, config, S, iters, steps, warmup, headline):
         h2d, d2h = batch.last_transfer_bytes
         return dt
 
-    e2e_steps(2 if pipelined else 1)
+    e2e_steps(len(turn_batches) if pipelined else 1)
     e2e_total = env.max_over_ranks(float(e2e_steps(steps)))
     e2e_value = world * S * iters * steps / e2e_total
     clocks = sampler.stop() if sampler else None
@@ -455,7 +463,8 @@ def measure(env, args, config, S, iters, steps, warmup, headline):
             single = 200 / (ms1 / 1e3)
             one.plan.close()
 
-        details = {"e2e": ("BatchPipeline(depth=2): two BlendBatch objects take turns, the copies of one overlap the loop of the other"
+        details = {"e2e": ("BatchPipeline(depth=%d): %d BlendBatch objects take turns, the copies of one overlap the loop of another"
+                           % (len(turn_batches), len(turn_batches))
                            if pipelined else "one BlendBatch.fit per step over %d plans/streams" % len(batch_e2e.plans)),
                    "fft_grid": list(fshape), "unique_scenes_per_gpu": uniq, "device_bytes_per_gpu": plan.device_bytes,
                    "single_scene_iterations_per_sec": single,
@@ -464,6 +473,11 @@ def measure(env, args, config, S, iters, steps, warmup, headline):
                    "kernels_per_iteration": launches // max(steps * iters, 1), "precision": args.precision,
                    "per_scene_psf": config not in MULTIRES,
                    "value_includes": "the proximal-gradient loop (CUDA events) + the final NCCL gather of fitted parameters (N > 1)"}
+        if pipe_stats.get("period_ms"):
+            details["e2e_pipeline"] = {"steady_state_ms_per_step": pipe_stats["period_ms"], "fill_ms": pipe_stats["fill_ms"],
+                                       "steady_state_value": world * S * iters / (pipe_stats["period_ms"] / 1e3),
+                                       "note": "e2e.value times exactly K steps, i.e. it carries the first copy-in and the last copy-out "
+                                               "un-overlapped; the period between consecutive loop starts is what a long stream sees"}
         if cfg.get("note"):
             details["observations"] = cfg["note"]
         rec = {"value": value, "unit": "scene-iterations/s", "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,
@@ -474,8 +488,8 @@ def measure(env, args, config, S, iters, steps, warmup, headline):
     barrier()
     if batch_e2e is not batch:
         batch_e2e.close()
-    if batch_b is not None:
-        batch_b.close()
+    for b in extra_batches:
+        b.close()
     plan.close()
     return rec
 

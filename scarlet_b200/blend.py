@@ -395,7 +395,9 @@ class BatchPipeline:
     def run(self, batches, max_iter=200, e_rel=1e-3, min_iter=1, noise_factor=0, upload_observations=True, prepare=None,
             **alg_kwargs):
         import threading
+        import time
         from concurrent.futures import ThreadPoolExecutor
+        self.timings = []  # per batch: wall-clock intervals (time.perf_counter) of its three stages
         check_every = int(alg_kwargs.pop("check_every", 10))
         opts = _fit_options(max_iter, e_rel, min_iter, noise_factor, alg_kwargs, check_every)
         batches = list(batches)
@@ -424,19 +426,25 @@ class BatchPipeline:
                         return None
                     own[id(b)].acquire()  # inside the turn: an earlier use of the same batch object finishes first
                     held = True
+                    t0 = time.perf_counter()
                     if prepare is not None:
                         prepare(k, b)
                     h2d = [b._copy_in(i, upload_observations) for i in idx]
+                    t1 = time.perf_counter()
                 finally:
                     give("in")
                 take("loop", k)
                 try:
                     if failed:
                         return None
+                    t2 = time.perf_counter()
                     outs = b._each(lambda i: b.plans[i].fit(opts))
+                    t3 = time.perf_counter()
                 finally:
                     give("loop")
-                return b._finish([outs[i] + (h2d[i], b._copy_out(i, outs[i])) for i in idx])
+                res = b._finish([outs[i] + (h2d[i], b._copy_out(i, outs[i])) for i in idx])
+                self.timings.append(dict(k=k, copy_in=(t0, t1), loop=(t2, t3), copy_out=(t3, time.perf_counter())))
+                return res
             except BaseException as e:  # let the other workers drain instead of waiting for this turn forever
                 with cond:
                     failed.append(e)
@@ -446,5 +454,13 @@ class BatchPipeline:
                 if held:
                     own[id(b)].release()
 
-        with ThreadPoolExecutor(self.depth) as pool:
-            return list(pool.map(work, range(len(batches))))
+        # The worker whose turn it is to start the next device loop must not wait for the interpreter lock behind another
+        # worker's Python bookkeeping (CPython hands the lock over every 5 ms by default; the GPU idles meanwhile).
+        import sys
+        interval = sys.getswitchinterval()
+        sys.setswitchinterval(min(interval, 2e-4))
+        try:
+            with ThreadPoolExecutor(self.depth) as pool:
+                return list(pool.map(work, range(len(batches))))
+        finally:
+            sys.setswitchinterval(interval)
