@@ -52,7 +52,7 @@ def parse():
     return ap.parse_args()
 
 
-DEFAULT_SCENES = {"cfg2": 256, "cfg3": 192, "cfg4": 64, "cfg4_rot": 64, "cfg5": 512, "tiny": 64}
+DEFAULT_SCENES = {"cfg2": 256, "cfg3": 192, "cfg4": 256, "cfg4_rot": 128, "cfg5": 512, "tiny": 64}
 DEFAULT_ITERS = {"cfg2": 50, "cfg3": 50, "cfg4": 50, "cfg4_rot": 50, "cfg5": 50, "tiny": 20}
 MULTIRES = ("cfg4", "cfg4_rot")  # cfg4_rot: cfg4 with the low-resolution grid turned by 25 degrees (rotated ResolutionRenderer)
 
