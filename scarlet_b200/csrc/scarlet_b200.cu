@@ -351,9 +351,6 @@ template <typename T> struct PlanT : sb_plan {
         SpecObs<T> sdev;
         SpecKernels<T> kx, ky;
         DevBuf<cplx> X, tw_x, tw_y, Pbuf, T1buf, Ey, Ex; // Pbuf..Ex: resampling observations (kind 2) only
-        bool grad_persist = false;
-        size_t smem_grad_p = 0;
-        int grad_ctas = 148;
         DevBuf<int> cand_start, cand;                     // render kernel: sources per (scene, row block)
         int max_cand = 0;
         DevBuf<cplx> RA, RB;                              // rotated resampling observations (kind 3): multiplier tables
@@ -730,16 +727,6 @@ template <typename T> struct PlanT : sb_plan {
                 SB_TRY(raise_smem((const void *)ob.kx.residual, ob.smem_row));
                 SB_TRY(raise_smem((const void *)ob.kx.residual_r, ob.smem_row));
                 SB_TRY(raise_smem((const void *)ob.kx.grad, ob.smem_row));
-                {   // persistent gradient kernel: staged rows of one item + exchange buffer + twiddles + barrier
-                    ob.smem_grad_p = 128 + ((size_t)ob.cb * 2 * ob.npair * Xp + nb * ob.kx.sf + (size_t)Fx + 1) * sizeof(cplx) + 16;
-                    ob.grad_persist = getenv("SB_GRAD_PERSIST") != nullptr && ob.smem_grad_p <= 227 * 1024;
-                    if (ob.grad_persist) {
-                        SB_TRY(raise_smem((const void *)ob.kx.grad_p, ob.smem_grad_p));
-                        int per_sm = 1;
-                        SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)ob.kx.grad_p, ob.row_threads, ob.smem_grad_p));
-                        ob.grad_ctas = 148 * std::max(per_sm, 1);
-                    }
-                }
                 SB_TRY(raise_smem((const void *)ob.ky.column, ob.smem_col));
                 if (sizeof(T) == 4 && od.kind == 0 && ob.ky.column_tma && desc.Ny <= 256 && Fy % 2 == 0 && Fy / 2 <= 256 &&
                     getenv("SB_NO_TMA") == nullptr) {
@@ -1435,13 +1422,6 @@ template <typename T> struct PlanT : sb_plan {
             const dim3 rgrid((desc.Ny + 2 * ob.npair - 1) / (2 * ob.npair), S, (ob.sdev.C + ob.cb - 1) / ob.cb);
             const dim3 cgrid((ob.sdev.Fxc + ob.ky.NBcol - 1) / ob.ky.NBcol, S * ob.sdev.C);
             const int cthreads = ob.ky.NBcol * std::max(ob.ky.R1, ob.ky.R2);
-            auto launch_grad = [&]() {
-                if (ob.grad_persist) {
-                    const int nblk = (int)rgrid.x, nz = (int)rgrid.z, n_items = nblk * nz * S;
-                    ob.kx.grad_p<<<std::min(n_items, ob.grad_ctas), ob.row_threads, ob.smem_grad_p, stream>>>(sa, n_items, nblk, nz);
-                } else
-                    ob.kx.grad<<<rgrid, ob.row_threads, ob.smem_row, stream>>>(sa);
-            };
             ob.kx.render<<<rgrid, ob.row_threads, ob.smem_render, stream>>>(sa);
             SB_CUDA(cudaGetLastError());
             mark();
@@ -1463,7 +1443,7 @@ template <typename T> struct PlanT : sb_plan {
                 ob.ky.column_inv<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
                 SB_CUDA(cudaGetLastError());
                 mark();
-                launch_grad();
+                ob.kx.grad<<<rgrid, ob.row_threads, ob.smem_row, stream>>>(sa);
                 SB_CUDA(cudaGetLastError());
                 mark();
                 nk += 7;
@@ -1485,7 +1465,7 @@ template <typename T> struct PlanT : sb_plan {
                 ob.ky.column_inv<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
                 SB_CUDA(cudaGetLastError());
                 mark();
-                launch_grad();
+                ob.kx.grad<<<rgrid, ob.row_threads, ob.smem_row, stream>>>(sa);
                 SB_CUDA(cudaGetLastError());
                 mark();
                 nk += 7;
@@ -1508,7 +1488,7 @@ template <typename T> struct PlanT : sb_plan {
                 ob.ky.column<<<cgrid, cthreads, ob.smem_col, stream>>>(sa);
             SB_CUDA(cudaGetLastError());
             mark();
-            launch_grad();
+            ob.kx.grad<<<rgrid, ob.row_threads, ob.smem_row, stream>>>(sa);
             SB_CUDA(cudaGetLastError());
             mark();
             nk += 5;

@@ -840,109 +840,6 @@ template <typename T> __global__ void __launch_bounds__(128) k_resample_q(const 
 }
 
 // ======================================================================================================
-// Persistent form of the gradient row kernel: a CTA walks over (scene, band group, row block) items with a stride of the grid,
-// and the half spectra of its NEXT item arrive by bulk asynchronous copies (cp.async.bulk, one contiguous run of rows per
-// band, completion on an mbarrier) while the current item is transformed and stored -- the loads of an item are never waited
-// for at the top of a CTA's life, and twiddles / barrier set-up are paid once per CTA instead of once per item.
-// ======================================================================================================
-namespace tma {
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
-                 "r"(bar)
-                 : "memory");
-}
-} // namespace tma
-
-// staged half spectra of rows y, y+1 (shared memory, [Cb][rows][Xp]) -> natural-order full spectrum of the packed pair in fbuf
-template <typename T, int R1, int R2>
-__device__ __forceinline__ void merge_staged(const typename Cx<T>::type *stage, typename Cx<T>::type *fbuf, int NB, int Cb, int rows, int Xp,
-                                             int nr) {
-    typedef typename Cx<T>::type C2;
-    typedef sbfft::Plan2<R1, R2> P;
-    constexpr int Fx = R1 * R2, Fxc = Fx / 2 + 1;
-    const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int f = threadIdx.x >> 5; f < NB; f += nw) {
-        const int p = f / Cb, c = f - p * Cb, r = 2 * p;
-        C2 *z0 = fbuf + f * P::SF;
-        const bool one = r < nr, two = r + 1 < nr;
-        const C2 *row = stage + ((size_t)c * rows + (one ? r : 0)) * Xp;
-        for (int k = lane; k < Fxc; k += 32) {
-            const C2 A = one ? row[k] : C2{T(0), T(0)}, B = two ? row[Xp + k] : C2{T(0), T(0)};
-            z0[k] = C2{A.x - B.y, A.y + B.x};
-            if (k > 0 && 2 * k < Fx) z0[Fx - k] = C2{A.x + B.y, B.x - A.y};
-        }
-    }
-}
-
-template <typename T, int R1, int R2>
-__global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) k_spec_grad_p(const SpecArgs<T> a, int n_items, int nblk, int nz) {
-    typedef typename Cx<T>::type C2;
-    typedef sbfft::Plan2<R1, R2> P;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const SpecObs<T> &ob = a.ob;
-    const int Co = ob.C, Nx = a.Nx, Ny = a.Ny, rows = 2 * a.npair, Xp = ob.Xp, tid = threadIdx.x;
-    unsigned char *smem = smem_raw + ((128u - (tma::smem_addr(smem_raw) & 127u)) & 127u);
-    C2 *stage = reinterpret_cast<C2 *>(smem);                 // [cb][rows][Xp] (16-byte aligned rows: Xp is a multiple of 2)
-    C2 *fbuf = stage + (size_t)a.cb * rows * Xp;              // [npair cb][SF]
-    C2 *tw = fbuf + (size_t)a.npair * a.cb * P::SF;
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(tw + R1 * R2 + ((R1 * R2) & 1));
-    const unsigned bar_a = tma::smem_addr(bar);
-    if (tid == 0) {
-        tma::mbar_init(bar_a, 1);
-        tma::fence_barrier_init();
-    }
-    stage_twiddles<T, R1, R2>(tw, ob.tw_x);
-    // item -> (scene, band group, row block); items of stopped scenes are skipped by everybody alike
-    auto live_from = [&](int item) {
-        while (item < n_items && a.done[item / (nblk * nz)]) item += gridDim.x;
-        return item;
-    };
-    auto issue = [&](int item) { // one thread: the rows of every band of the item, one contiguous run per band
-        const int bx = item % nblk, rest = item / nblk, z = rest % nz, s = rest / nz;
-        const int c0 = z * a.cb, Cb = min(a.cb, Co - c0), y0 = bx * rows, nr = min(rows, Ny - y0);
-        const unsigned bytes = (unsigned)((size_t)nr * Xp * sizeof(C2));
-        tma::expect_tx(bar_a, bytes * (unsigned)Cb);
-        for (int c = 0; c < Cb; ++c)
-            tma::bulk_g2s(tma::smem_addr(stage + (size_t)c * rows * Xp), ob.X + ((size_t)(s * Co + c0 + c) * Ny + y0) * Xp, bytes, bar_a);
-    };
-    __syncthreads(); // barrier initialised, twiddles staged
-    int item = live_from(blockIdx.x);
-    if (tid == 0 && item < n_items) issue(item);
-    unsigned parity = 0u;
-    while (item < n_items) {
-        const int next = live_from(item + gridDim.x);
-        const int bx = item % nblk, rest = item / nblk, z = rest % nz, s = rest / nz;
-        const int c0 = z * a.cb, Cb = min(a.cb, Co - c0), NB = a.npair * Cb, y0 = bx * rows, nr = min(rows, Ny - y0);
-        tma::wait(bar_a, parity);
-        parity ^= 1u;
-        merge_staged<T, R1, R2>(stage, fbuf, NB, Cb, rows, Xp, nr);
-        tma::fence_proxy_async_smem(); // the staged rows have been read: the copy engine may overwrite them
-        __syncthreads();
-        if (tid == 0 && next < n_items) issue(next);
-        C2 a_[R1];
-        rows_inverse<T, R1, R2>(a_, fbuf, tw, NB);
-        const int f = tid / R2, n2 = tid - f * R2;
-        if (tid < NB * R2) {
-            const int p = f / Cb, c = c0 + f - p * Cb, y = y0 + 2 * p;
-            if (y < Ny) {
-                T *g0 = ob.G + ((size_t)(s * Co + c) * Ny + y) * Nx;
-                const bool row1 = y + 1 < Ny;
-                sbfft::static_for<0, R1>([&](auto i) {
-                    constexpr int n1 = decltype(i)::value;
-                    const int x = n1 * R2 + n2;
-                    if (x < Nx) {
-                        g0[x] = a_[n1].x;
-                        if (row1) g0[Nx + x] = a_[n1].y;
-                    }
-                });
-            }
-        }
-        __syncthreads(); // the exchange buffer is free for the next item's merge
-        item = next;
-    }
-}
-
-// ======================================================================================================
 // Rotated resampling observation (renderer.py:318-363, 498-524).  The reference shifts the kernel along both axes to every
 // low-resolution row and the model along both axes to every column, then contracts the two tables.  Each two-axis shift is
 // a Fourier multiplier (interpolation.shift_multiplier: the real inverse transform keeps the Hermitian part of the phase
@@ -1153,8 +1050,6 @@ template <typename T> struct SpecKernels {
     typedef void (*fn)(const SpecArgs<T>);
     int R1 = 0, R2 = 0, NBcol = 0;
     typedef void (*fn_tma)(const SpecArgs<T>, const CUtensorMap, const CUtensorMap);
-    typedef void (*fn_items)(const SpecArgs<T>, int, int, int);
-    fn_items grad_p = nullptr; // persistent gradient row kernel
     fn render = nullptr, residual = nullptr, residual_r = nullptr, grad = nullptr, column = nullptr, column_fwd = nullptr, column_inv = nullptr;
     fn_tma column_tma = nullptr; // float only
     size_t sf = 0; // Plan2::SF

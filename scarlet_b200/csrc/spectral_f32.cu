@@ -11,7 +11,6 @@ bool spec_kernels_f32(int L, SpecKernels<float> *out) {
         out->residual = k_spec_residual<float, A, B>;                                 \
         out->residual_r = k_spec_residual<float, A, B, true>;                             \
         out->grad = k_spec_grad<float, A, B>;                                     \
-        out->grad_p = k_spec_grad_p<float, A, B>;                                     \
         out->column = k_spec_column<float, A, B, SpecColNB<float>::value>;        \
         out->column_tma = k_spec_column_tma<float, A, B, SpecColNB<float>::value>; \
         out->column_fwd = k_spec_column_fwd<float, A, B, SpecColNB<float>::value>; \

@@ -11,7 +11,6 @@ bool spec_kernels_f64(int L, SpecKernels<double> *out) {
         out->residual = k_spec_residual<double, A, B>;                                 \
         out->residual_r = k_spec_residual<double, A, B, true>;                             \
         out->grad = k_spec_grad<double, A, B>;                                     \
-        out->grad_p = k_spec_grad_p<double, A, B>;                                     \
         out->column = k_spec_column<double, A, B, SpecColNB<double>::value>;        \
         out->column_fwd = k_spec_column_fwd<double, A, B, SpecColNB<double>::value>; \
         out->column_inv = k_spec_column_inv<double, A, B, SpecColNB<double>::value>; \
