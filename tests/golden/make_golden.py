@@ -291,6 +291,25 @@ def multires(sc):
                     "hr_logL" + tag: np.array(obs_hr.get_log_likelihood(model)),
                     "hr_model_slice_start" + tag: np.array([r2.slices[1][1].start, r2.slices[1][2].start]),
                     "model_crpix" + tag: np.array(frame.wcs.wcs.crpix)})
+    # coverage="intersection" with the high-resolution observation named as the reference (obs_id=1), float64 frame: compact products
+    obs_hr = sc.observation.Observation(inp["hr_images"].copy(), psf=sc.psf.ImagePSF(inp["hr_psfs"].copy()), weights=inp["hr_weights"].copy(),
+                                        wcs=RefWCS(inp["hr_cd"], crpix=inp["hr_crpix"]), channels=["h0", "h1", "h2"])
+    obs_lr = sc.observation.Observation(inp["lr_images"].copy(), psf=sc.psf.ImagePSF(inp["lr_psfs"].copy()), weights=inp["lr_weights"].copy(),
+                                        wcs=RefWCS(inp["lr_cd"], crpix=inp["lr_crpix"]), channels=["l0", "l1", "l2", "l3", "l4"])
+    frame = sc.frame.Frame.from_observations([obs_lr, obs_hr], obs_id=1, coverage="intersection")
+    frame = sc.frame.Frame(frame.shape, channels=frame.channels, psf=frame.psf, wcs=frame.wcs, dtype=np.float64)
+    obs_lr.match(frame)
+    obs_hr.match(frame)
+    r, r2 = obs_lr.renderer, obs_hr.renderer
+    rng = np.random.default_rng(21)
+    yy, xx = np.mgrid[:frame.shape[1], :frame.shape[2]]
+    model = np.stack([rng.uniform(1, 5) * np.exp(-((yy - rng.uniform(10, 30)) ** 2 + (xx - rng.uniform(10, 30)) ** 2) / (2 * rng.uniform(2, 5) ** 2))
+                      for _ in range(frame.shape[0])]) + 0.01 * rng.random(frame.shape)
+    out.update(isect_frame_shape=np.array(frame.shape), isect_model_crpix=np.array(frame.wcs.wcs.crpix), isect_model=model,
+               isect_lr_renderer=np.array(type(r).__name__), isect_hr_renderer=np.array(type(r2).__name__),
+               isect_lr_h=np.array(r.h), isect_lr_fft_shape=np.array(r._fft_shape), isect_lr_shifts=np.array(r.shifts),
+               isect_lr_rendered=obs_lr.render(model), isect_lr_logL=np.array(obs_lr.get_log_likelihood(model)),
+               isect_hr_rendered=obs_hr.render(model), isect_hr_logL=np.array(obs_hr.get_log_likelihood(model)))
     save("multires.npz", **out)
 
 

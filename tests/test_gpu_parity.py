@@ -511,6 +511,25 @@ def test_multiresolution_fit_matches_oracle(precision, tol, rotated):
     assert rel_peak(blend.get_model(), o.get_model()) < tol
 
 
+def test_intersection_frame_convolution_render():
+    """coverage="intersection" model frame (frame.py:200-312): the high-resolution observation overhangs the frame; its
+    ConvolutionRenderer render and logL against the reference's own (tests/golden/make_golden.py:multires, isect_*)"""
+    import scarlet_b200 as sb
+    from scarlet_b200.wcs import AffineWCS
+    g = golden("multires.npz")
+    obs_hr = sb.Observation(g["hr_images"].copy(), psf=sb.ImagePSF(g["hr_psfs"].copy()), weights=g["hr_weights"].copy(),
+                            wcs=AffineWCS(g["hr_cd"], crpix=g["hr_crpix"]), channels=["h0", "h1", "h2"])
+    obs_lr = sb.Observation(g["lr_images"].copy(), psf=sb.ImagePSF(g["lr_psfs"].copy()), weights=g["lr_weights"].copy(),
+                            wcs=AffineWCS(g["lr_cd"], crpix=g["lr_crpix"]), channels=["l0", "l1", "l2", "l3", "l4"])
+    frame = sb.Frame.from_observations([obs_lr, obs_hr], obs_id=1, coverage="intersection")
+    frame = sb.Frame(frame.shape, channels=frame.channels, psf=frame.psf, wcs=frame.wcs, dtype=np.float64)
+    obs_lr.match(frame)
+    obs_hr.match(frame)
+    model = g["isect_model"]
+    assert rel_peak(obs_hr.render(model), g["isect_hr_rendered"]) < 1e-9
+    assert_allclose(obs_hr.get_log_likelihood(model), float(g["isect_hr_logL"]), rtol=1e-8)
+
+
 def test_multiresolution_cfg4_full_size():
     """BASELINE config 4 shape: 5 bands 30x30 at 0.2"/px + 3 bands 200x200 at 0.03"/px, model frame (8,228,228), grid 240^2,
     8 ExtendedSource: 5 iterations against the oracle.  Model pixels and SEDs at 1e-5 of their peaks; morphologies at

@@ -244,6 +244,33 @@ def test_multiresolution_setup_vs_reference_fixture():
     assert_allclose(obs_lr.get_log_likelihood(g["model64"]), float(g["lr_logL64"]), rtol=1e-10)
 
 
+def test_multiresolution_intersection_coverage_vs_reference_fixture():
+    """Frame.from_observations(obs_id=1, coverage="intersection") (frame.py:200-312) and both renderers on that frame against
+    the reference's own products (tests/golden/make_golden.py:multires, keys isect_*)."""
+    import scarlet_b200 as sb
+    from scarlet_b200.wcs import AffineWCS
+    g = golden("multires.npz")
+    obs_hr = sb.Observation(g["hr_images"].copy(), psf=sb.ImagePSF(g["hr_psfs"].copy()), weights=g["hr_weights"].copy(),
+                            wcs=AffineWCS(g["hr_cd"], crpix=g["hr_crpix"]), channels=["h0", "h1", "h2"])
+    obs_lr = sb.Observation(g["lr_images"].copy(), psf=sb.ImagePSF(g["lr_psfs"].copy()), weights=g["lr_weights"].copy(),
+                            wcs=AffineWCS(g["lr_cd"], crpix=g["lr_crpix"]), channels=["l0", "l1", "l2", "l3", "l4"])
+    frame = sb.Frame.from_observations([obs_lr, obs_hr], obs_id=1, coverage="intersection")
+    assert tuple(frame.shape) == tuple(g["isect_frame_shape"])
+    assert_allclose(frame.wcs.wcs.crpix, g["isect_model_crpix"], atol=1e-12)
+    frame = sb.Frame(frame.shape, channels=frame.channels, psf=frame.psf, wcs=frame.wcs, dtype=np.float64)
+    obs_lr.match(frame)
+    obs_hr.match(frame)
+    r = obs_lr.renderer
+    assert type(r).__name__ == str(g["isect_lr_renderer"]) and type(obs_hr.renderer).__name__ == str(g["isect_hr_renderer"])
+    assert_allclose(r.h, float(g["isect_lr_h"]))
+    assert list(r._fft_shape) == list(g["isect_lr_fft_shape"])
+    assert_allclose(r.shifts, g["isect_lr_shifts"], atol=1e-11)
+    model = g["isect_model"]
+    assert_allclose(obs_lr.render(model), g["isect_lr_rendered"], atol=1e-11 * np.abs(g["isect_lr_rendered"]).max())
+    assert_allclose(obs_lr.get_log_likelihood(model), float(g["isect_lr_logL"]), rtol=1e-10)
+    # (the high-resolution render runs on the device: tests/test_gpu_parity.py::test_intersection_frame_convolution_render)
+
+
 def _multires_rot_scene():
     import scarlet_b200 as sb
     from scarlet_b200.wcs import AffineWCS
