@@ -34,12 +34,19 @@ static const char *kStageNames[SB_N_STAGES] = {"render",       "fft_fwd_model", 
 
 template <typename T> struct DevBuf {
     T *p = nullptr;
-    size_t n = 0;
+    size_t n = 0, cap = 0;
+    // (contents are unspecified after alloc; an allocation that is large enough is kept -- cudaFree synchronises the device,
+    // and a batch with dynamic boxes re-sizes its source-side buffers at every re-plan)
     int alloc(size_t count) {
+        if (p && cap >= count && count > 0) {
+            n = count;
+            return SB_OK;
+        }
         release();
         n = count;
         if (count == 0) return SB_OK;
         SB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+        cap = count;
         return SB_OK;
     }
     int zero(cudaStream_t st) {
@@ -49,10 +56,10 @@ template <typename T> struct DevBuf {
     void release() {
         if (p) cudaFree(p);
         p = nullptr;
-        n = 0;
+        n = 0, cap = 0;
     }
     ~DevBuf() { release(); }
-    size_t bytes() const { return n * sizeof(T); }
+    size_t bytes() const { return (cap > n ? cap : n) * sizeof(T); }
 };
 
 // ---- wavefront tables ---------------------------------------------------------------------------
