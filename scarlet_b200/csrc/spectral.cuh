@@ -16,6 +16,11 @@
 //   k_spec_column    (adjoint)
 //   k_spec_grad      inverse row FFTs -> gradient of the loss wrt the model, rows [0,Ny) x [0,Nx)   [writes G]
 //
+//   k_spec_column_tma              the column pass with its tiles moved by the Tensor Memory Accelerator (float)
+//   k_spec_column_fwd / _inv       the two halves of the column pass for observations on another pixel grid
+//   k_resample_t1 / _lr / _q       ResolutionRenderer, aligned grids: separable Fourier resampling (renderer.py:262-547)
+//   k_rot_partial / _residual / _adjoint   ResolutionRenderer, rotated grids: dense half-plane contraction (renderer.py:318-363)
+//
 // X: [S][C][Ny][Xp] complex, G: [S][C][Ny][Nx] real.  All transforms are unnormalised; 1/(Fy Fx) is folded into K^.
 #pragma once
 #include <cuda.h> // CUtensorMap
