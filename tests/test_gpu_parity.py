@@ -682,6 +682,52 @@ def test_batch_equals_individual_fits():
             assert_array_equal(np.asarray(p1), np.asarray(p2))
 
 
+def test_batch_of_rotated_multiresolution_scenes_equals_individual_fits():
+    """three scenes on the rotated two-grid geometry (shared resampling tables, per-scene data and sources): a batch gives the
+    single fits bit for bit"""
+    import scarlet_b200 as sb
+    from multires_scene import product_scene
+    rng = np.random.default_rng(3)
+    singles, batch = [], []
+    for k in range(3):
+        scale, noise = rng.uniform(0.7, 1.4), rng.standard_normal((5, 8, 8)).astype(np.float32)
+        for out in (singles, batch):
+            _, blend, obs_lr, obs_hr = product_scene(32, rotated=True)
+            obs_lr.data[...] = obs_lr.data * scale + 0.3 * noise
+            for src in blend.sources:
+                src.parameters[0][...] = np.asarray(src.parameters[0]) * scale
+            out.append(blend)
+    for b in singles:
+        b.fit(max_iter=12, e_rel=1e-4)
+    res = sb.BlendBatch(batch).fit(max_iter=12, e_rel=1e-4)
+    for b1, b2, r in zip(singles, batch, res):
+        assert r[0] == len(b1.loss)
+        assert_array_equal(np.array(b1.loss), np.array(b2.loss))
+        for p1, p2 in zip(b1.parameters, b2.parameters):
+            assert_array_equal(np.asarray(p1), np.asarray(p2))
+    assert len({tuple(b.loss) for b in singles}) == 3  # the scenes do differ
+
+
+def test_batch_with_fitted_psf_offsets_equals_individual_fits():
+    """two scenes whose ConvolutionRenderers carry their own fitted psf_shift: the batch keeps one kernel per scene"""
+    import scarlet_b200 as sb
+    g = golden("psf_shift.npz")
+    shifts = ([0.12, -0.2], [-0.3, 0.25])
+    singles = [_psf_shift_blend(g, sh, 32, fit_sources=True)[0] for sh in shifts]
+    batch = [_psf_shift_blend(g, sh, 32, fit_sources=True)[0] for sh in shifts]
+    for b in singles:
+        b.fit(max_iter=8, e_rel=1e-5)
+    res = sb.BlendBatch(batch).fit(max_iter=8, e_rel=1e-5)
+    for b1, b2, r in zip(singles, batch, res):
+        assert r[0] == len(b1.loss)
+        assert_array_equal(np.array(b1.loss), np.array(b2.loss))
+        for p1, p2 in zip(b1.parameters, b2.parameters):
+            assert_array_equal(np.asarray(p1), np.asarray(p2))
+        assert_array_equal(np.asarray(b1.observations[0].renderer.parameters[0]), np.asarray(b2.observations[0].renderer.parameters[0]))
+    fitted = [np.asarray(b.observations[0].renderer.parameters[0]) for b in batch]
+    assert not np.array_equal(fitted[0], fitted[1]) and all(np.abs(f - sh).max() > 0 for f, sh in zip(fitted, shifts))
+
+
 def _resizing_scene():
     """a wide and a compact galaxy in 31x31 boxes that are too small for what the data pull in: the boxes grow several
     times within 45 iterations (dynamic boxes on, morphology.py:132-207)"""
