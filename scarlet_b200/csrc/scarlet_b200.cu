@@ -366,6 +366,7 @@ template <typename T> struct PlanT : sb_plan {
         size_t rot_smem = 0;
         DevBuf<T> G;
         int npair = 1, cb = 1, row_threads = 0;
+        bool render_two = false;
         size_t smem_render = 0, smem_row = 0, smem_col = 0, smem_col_tma = 0;
         bool use_tma = false; // column pass through the Tensor Memory Accelerator (float, Ny <= 256)
         CUtensorMap tmX, tmK;
@@ -608,15 +609,31 @@ template <typename T> struct PlanT : sb_plan {
         const int rows = 2 * ob.npair, nblk = (desc.Ny + rows - 1) / rows;
         std::vector<int> start((size_t)S * nblk + 1, 0), list;
         ob.max_cand = 0;
+        int max_npx = 0; // most pixels of one source inside one row block
         for (int s = 0; s < S; ++s)
             for (int b = 0; b < nblk; ++b) {
                 const int y0 = b * rows;
                 start[(size_t)s * nblk + b] = (int)list.size();
+                // bit 31 of an entry: the source's columns overlap those of an earlier source added since the last barrier --
+                // the kernel then waits before adding it; sources side by side need no barrier between them
+                std::vector<std::pair<int, int>> group;
                 for (int k = h_start[s]; k < h_start[s + 1]; ++k)
-                    if (h_src[k].oy < y0 + rows && h_src[k].oy + h_src[k].By > y0) list.push_back(k);
+                    if (h_src[k].oy < y0 + rows && h_src[k].oy + h_src[k].By > y0) {
+                        const int x0 = h_src[k].ox, x1 = h_src[k].ox + h_src[k].Bx;
+                        const int nr = std::min(std::min(y0 + rows, desc.Ny), h_src[k].oy + h_src[k].By) - std::max(y0, h_src[k].oy);
+                        max_npx = std::max(max_npx, nr * (std::min(x1, desc.Nx) - std::max(x0, 0)));
+                        bool hit = false;
+                        for (auto &g : group) hit = hit || (x0 < g.second && g.first < x1);
+                        if (hit) group.clear();
+                        group.emplace_back(x0, x1);
+                        list.push_back(k | (hit ? (int)0x80000000u : 0));
+                    }
                 ob.max_cand = std::max(ob.max_cand, (int)list.size() - start[(size_t)s * nblk + b]);
             }
         start[(size_t)S * nblk] = (int)list.size();
+        // the render kernel adds a source with one thread per covered pixel and requests the pixels of four sources ahead: where
+        // a box has more pixels in a row block than the CTA has threads, the two-pixels-per-thread instantiation is used
+        ob.render_two = max_npx > ob.row_threads && max_npx <= 2 * ob.row_threads;
         if (ob.cand_start.n < start.size()) SB_TRY(ob.cand_start.alloc(start.size()));
         if (ob.cand.n < std::max<size_t>(list.size(), 1)) SB_TRY(ob.cand.alloc(std::max<size_t>(list.size(), 1) * 5 / 4 + 16));
         SB_CUDA(cudaMemcpyAsync(ob.cand_start.p, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -657,6 +674,7 @@ template <typename T> struct PlanT : sb_plan {
                 ob.smem_render = render_smem(ob);
                 if (ob.smem_render > 227 * 1024) return set_err(SB_ERR_ARG, "observation %d: frame too wide for the fused spectral kernels", (int)o);
                 SB_TRY(raise_smem((const void *)ob.kx.render, ob.smem_render));
+                SB_TRY(raise_smem((const void *)ob.kx.render2, ob.smem_render));
             }
         }
         have_graph = false;
@@ -731,6 +749,7 @@ template <typename T> struct PlanT : sb_plan {
                 if (ob.smem_render > 227 * 1024 || ob.smem_col > 227 * 1024)
                     return set_err(SB_ERR_ARG, "observation %d: frame too wide for the fused spectral kernels", o);
                 SB_TRY(raise_smem((const void *)ob.kx.render, ob.smem_render));
+                SB_TRY(raise_smem((const void *)ob.kx.render2, ob.smem_render));
                 SB_TRY(raise_smem((const void *)ob.kx.residual, ob.smem_row));
                 SB_TRY(raise_smem((const void *)ob.kx.residual_r, ob.smem_row));
                 SB_TRY(raise_smem((const void *)ob.kx.grad, ob.smem_row));
@@ -1429,7 +1448,7 @@ template <typename T> struct PlanT : sb_plan {
             const dim3 rgrid((desc.Ny + 2 * ob.npair - 1) / (2 * ob.npair), S, (ob.sdev.C + ob.cb - 1) / ob.cb);
             const dim3 cgrid((ob.sdev.Fxc + ob.ky.NBcol - 1) / ob.ky.NBcol, S * ob.sdev.C);
             const int cthreads = ob.ky.NBcol * std::max(ob.ky.R1, ob.ky.R2);
-            ob.kx.render<<<rgrid, ob.row_threads, ob.smem_render, stream>>>(sa);
+            (ob.render_two ? ob.kx.render2 : ob.kx.render)<<<rgrid, ob.row_threads, ob.smem_render, stream>>>(sa);
             SB_CUDA(cudaGetLastError());
             mark();
             if (ob.dev.kind == 3) { // rotated resampling: M^ -> K^ conj(M^) -> contraction with A_i B_j -> residual -> K^ sum R A B -> G

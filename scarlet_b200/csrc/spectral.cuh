@@ -80,7 +80,8 @@ template <typename T> struct SpecArgs {
 template <typename T> struct __align__(16) SpecCand {
     int oy, ox, By, Bx;
     const T *mp; // morphology image (or first per-band plane of a point source)
-    int plane, pad;
+    int plane;
+    int sync_before; // 1: a barrier before this source is added (its columns overlap an earlier source of the same barrier group)
     T sed[SB_SPEC_MAXCB];
 };
 
@@ -190,7 +191,9 @@ __device__ __forceinline__ void rows_forward(typename Cx<T>::type (&a_)[R1], typ
 // ======================================================================================================
 // render + forward row FFT
 // ======================================================================================================
-template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) k_spec_render(const SpecArgs<T> a) {
+// E: pixels of one source a thread can hold ahead of the additions (2 where a typical box has more pixels in a row block than
+// the CTA has threads; the one-pixel form is leaner where it suffices)
+template <typename T, int R1, int R2, int E = 1> __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) k_spec_render(const SpecArgs<T> a) {
     typedef typename Cx<T>::type C2;
     typedef sbfft::Plan2<R1, R2> P;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -212,12 +215,12 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
     // covered area, not (pixels of the rows) x (sources).
     const int blk = s * gridDim.x + blockIdx.x, l0 = ob.cand_start[blk], ncand = ob.cand_start[blk + 1] - l0;
     for (int j = tid; j < ncand; j += nt) {
-        const int k = ob.cand[l0 + j];
+        const int entry = ob.cand[l0 + j], k = entry & 0x7fffffff; // bit 31: barrier before this source
         const DevSource &d = a.src[k];
         SpecCand<T> rc;
         rc.oy = d.oy, rc.ox = d.ox, rc.By = d.By, rc.Bx = d.Bx;
         const int plane = d.kind == 0 ? 0 : d.By * d.Bx;
-        rc.plane = plane, rc.pad = 0;
+        rc.plane = plane, rc.sync_before = (int)((unsigned)entry >> 31);
         rc.mp = (d.kind == 0 ? (d.shifting ? a.smorph : a.morph) : a.pmorph + (size_t)(ob.chan_off + c0) * plane) + d.morph_off;
         const double *sed = a.sed + (size_t)k * a.Cm + ob.chan_off + c0;
 #pragma unroll
@@ -227,48 +230,56 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
     for (int idx = tid; idx < Cb * rows * Nx; idx += nt) tile[idx] = T(0);
     __syncthreads();
     // Sources four at a time: every thread first requests its pixel of each of the four (one memory round trip for the
-    // chunk), then the four are added in list order, a barrier after each (the next source may cover the same pixels from
-    // other threads).  Boxes with more pixels in these rows than the CTA has threads, and point sources (one morphology
-    // plane per band), take the plain loop.
+    // chunk), then the four are added in list order.  A barrier separates two sources only where the host found that their
+    // columns overlap inside these rows (SpecCand::sync_before): sources side by side are added without waiting for each
+    // other.  Boxes with more pixels in these rows than the CTA has threads, and point sources (one morphology plane per
+    // band), load and add in one go when their turn comes.
 #pragma unroll 1
     for (int i0 = 0; i0 < ncand; i0 += 4) {
-        T v[4];
-        T *tp[4];
-        bool plain = false;
+        T v[4][E];
+        int tp[4][E]; // tile offsets, -1: none
+        bool plain[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            v[j] = T(0), tp[j] = nullptr;
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[j][e] = T(0), tp[j][e] = -1;
+            plain[j] = false;
             if (i0 + j < ncand) {
                 const SpecCand<T> &rc = recs[i0 + j];
                 const int ry0 = max(y0, rc.oy), ry1 = min(min(y0 + rows, Ny), rc.oy + rc.By); // rows of the box inside this CTA's rows
                 const int bx0 = max(0, -rc.ox), bx1 = min(rc.Bx, Nx - rc.ox), wx = bx1 - bx0;  // columns of the box inside the frame
                 const int npx = wx > 0 ? (ry1 - ry0) * wx : 0;
-                if (npx > nt || rc.plane != 0) plain = true;
-                else if (tid < npx) {
-                    const int rr = (int)__umulhi((unsigned)tid, 0xffffffffu / (unsigned)wx + 1u), bx = bx0 + tid - rr * wx, y = ry0 + rr;
-                    v[j] = rc.mp[(y - rc.oy) * rc.Bx + bx];
-                    tp[j] = tile + (size_t)(y - y0) * Nx + rc.ox + bx;
+                plain[j] = npx > E * nt || rc.plane != 0;
+                if (!plain[j]) {
+                    const unsigned magic_w = wx > 0 ? 0xffffffffu / (unsigned)wx + 1u : 0u;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const int idx = tid + e * nt;
+                        if (idx < npx) {
+                            const int rr = (int)__umulhi((unsigned)idx, magic_w), bx = bx0 + idx - rr * wx, y = ry0 + rr;
+                            v[j][e] = rc.mp[(y - rc.oy) * rc.Bx + bx];
+                            tp[j][e] = (y - y0) * Nx + rc.ox + bx;
+                        }
+                    }
                 }
             }
         }
-        if (!plain) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (i0 + j < ncand) { // CTA-uniform
-                    if (tp[j]) {
-                        const SpecCand<T> &rc = recs[i0 + j];
+        for (int j = 0; j < 4; ++j) {
+            if (i0 + j >= ncand) break; // CTA-uniform
+            const SpecCand<T> &rc = recs[i0 + j];
+            if (rc.sync_before) __syncthreads();
+            if (!plain[j]) {
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (tp[j][e] >= 0) {
+                        T *t = tile + tp[j][e];
 #pragma unroll
                         for (int c = 0; c < SB_SPEC_MAXCB; ++c)
-                            if (c < Cb) tp[j][(size_t)c * rows * Nx] += rc.sed[c] * v[j];
+                            if (c < Cb) t[(size_t)c * rows * Nx] += rc.sed[c] * v[j][e];
                     }
-                    __syncthreads();
-                }
+                continue;
             }
-            continue;
-        }
-#pragma unroll 1
-        for (int i = i0; i < min(i0 + 4, ncand); ++i) {
-            const SpecCand<T> &rc = recs[i];
             const int ry0 = max(y0, rc.oy), ry1 = min(min(y0 + rows, Ny), rc.oy + rc.By);
             const int bx0 = max(0, -rc.ox), bx1 = min(rc.Bx, Nx - rc.ox), wx = bx1 - bx0;
             const int npx = wx > 0 ? (ry1 - ry0) * wx : 0;
@@ -289,9 +300,9 @@ template <typename T, int R1, int R2> __global__ void __launch_bounds__(sizeof(T
                         if (c < Cb) t[(size_t)c * rows * Nx] += rc.sed[c] * pm[c * plane];
                 }
             }
-            __syncthreads();
         }
     }
+    __syncthreads(); // the tile is complete
     if (a.model_out) {
         for (int idx = tid; idx < Cb * rows * Nx; idx += nt) {
             const int cr = (int)__umulhi((unsigned)idx, a.magic_nx), x = idx - cr * Nx, c = cr / rows, y = y0 + cr - c * rows;
@@ -1055,6 +1066,7 @@ template <typename T> struct SpecKernels {
     typedef void (*fn)(const SpecArgs<T>);
     int R1 = 0, R2 = 0, NBcol = 0;
     typedef void (*fn_tma)(const SpecArgs<T>, const CUtensorMap, const CUtensorMap);
+    fn render2 = nullptr; // render with two pixels per source and thread held ahead
     fn render = nullptr, residual = nullptr, residual_r = nullptr, grad = nullptr, column = nullptr, column_fwd = nullptr, column_inv = nullptr;
     fn_tma column_tma = nullptr; // float only
     size_t sf = 0; // Plan2::SF

@@ -8,6 +8,7 @@ bool spec_kernels_f32(int L, SpecKernels<float> *out) {
     if (L == (A) * (B)) {                                                         \
         out->R1 = A, out->R2 = B, out->NBcol = SpecColNB<float>::value;           \
         out->render = k_spec_render<float, A, B>;                                 \
+        out->render2 = k_spec_render<float, A, B, 2>; \
         out->residual = k_spec_residual<float, A, B>;                                 \
         out->residual_r = k_spec_residual<float, A, B, true>;                             \
         out->grad = k_spec_grad<float, A, B>;                                     \

@@ -8,6 +8,7 @@ bool spec_kernels_f64(int L, SpecKernels<double> *out) {
     if (L == (A) * (B)) {                                                         \
         out->R1 = A, out->R2 = B, out->NBcol = SpecColNB<double>::value;           \
         out->render = k_spec_render<double, A, B>;                                 \
+        out->render2 = k_spec_render<double, A, B, 2>; \
         out->residual = k_spec_residual<double, A, B>;                                 \
         out->residual_r = k_spec_residual<double, A, B, true>;                             \
         out->grad = k_spec_grad<double, A, B>;                                     \
