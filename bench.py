@@ -518,13 +518,15 @@ def measure_dynamic(env, args, S=64, iters=50, start_box=31):
         return out
 
     run()
-    dt, n_it, replans, (h2d, d2h), sizes = run()
+    runs = sorted((run() for _ in range(3)), key=lambda r: r[0])  # host-driven and short: the median of three fits
+    dt, n_it, replans, (h2d, d2h), sizes = runs[1]
+    spread = [runs[0][0], runs[2][0]]
     dt = env.max_over_ranks(dt)
     return {"value": None, "unit": "scene-iterations/s",
             "config": workload_config("cfg2 with dynamic boxes (resizing=True, start %dx%d)" % (start_box, start_box), cfg, S, iters),
             "e2e": {"value": env.world * n_it / dt, "unit": "scene-iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * dt},
-            "replans": replans, "final_box_sizes": sizes,
+            "replans": replans, "final_box_sizes": sizes, "fit_seconds_min_max": spread,
             "note": "host-driven inspection + re-plan; no device-resident figure"}
 
 
