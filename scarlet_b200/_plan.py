@@ -37,14 +37,16 @@ def leaf_components(sources):
     return out
 
 
-_REUSE_STEPS = [False]
+import threading  # noqa: E402
+
+_REUSE_STEPS = threading.local()  # .on: inside replace_sources of this thread
 
 
 def _step_of_spectrum(p, C):
     """-> (factor, min_step[C]); factor < 0 encodes a constant scalar step."""
     st = p.step
     # inside one fit (re-plans of dynamic boxes) the descriptor of an unchanged step object is reused; a new fit reads it afresh
-    cached = p.__dict__.get("_sb_step") if (_REUSE_STEPS[0] and hasattr(p, "__dict__")) else None
+    cached = p.__dict__.get("_sb_step") if (getattr(_REUSE_STEPS, "on", False) and hasattr(p, "__dict__")) else None
     if cached is not None and cached[0] is st and cached[1] == C:
         return cached[2], cached[3].copy()
     out = _step_of_spectrum_uncached(p, st, C)
@@ -149,11 +151,11 @@ class DevicePlan:
         for p in getattr(self, "_store_ptrs", []):  # back to the pool (still owned by the plan, freed in close())
             self._pinned_pool.append((p, self._pinned_sizes[p]))
         self._store_ptrs = []
-        _REUSE_STEPS[0] = True
+        _REUSE_STEPS.on = True
         try:
             self._describe_sources(self._desc)
         finally:
-            _REUSE_STEPS[0] = False
+            _REUSE_STEPS.on = False
         nat.check(nat.lib().sb_plan_set_sources(self._handle, ctypes.byref(self._desc)))
         self._replanning = True
         try:
