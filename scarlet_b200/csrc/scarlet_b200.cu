@@ -600,6 +600,9 @@ template <typename T> struct PlanT : sb_plan {
         return SB_OK;
     }
 
+    static size_t resample_lr_smem(int H, int W, int Fxc) { // spectra [H][Fxc], shift table [W][Fxc], residual [H][W]
+        return (size_t)(H + W) * Fxc * sizeof(cplx) + (size_t)H * W * sizeof(T);
+    }
     size_t render_smem(const Obs &ob) const {
         return ob.smem_row + (size_t)ob.cb * 2 * ob.npair * desc.Nx * sizeof(T) + 16 + (size_t)(ob.max_cand + 1) * sizeof(SpecCand<T>);
     }
@@ -774,10 +777,10 @@ template <typename T> struct PlanT : sb_plan {
                     SB_TRY(ob.T1buf.zero(stream));
                     SB_TRY(ob.Ey.zero(stream));
                     SB_TRY(ob.Ex.zero(stream));
-                    if ((size_t)od.H * od.W * sizeof(T) > 200 * 1024) return set_err(SB_ERR_ARG, "observation %d: resampled image too large", o);
+                    if (resample_lr_smem(od.H, od.W, d.Fxc) > 200 * 1024) return set_err(SB_ERR_ARG, "observation %d: resampled image too large", o);
                     SB_TRY(raise_smem((const void *)ob.ky.column_fwd, ob.smem_col));
                     SB_TRY(raise_smem((const void *)ob.ky.column_inv, ob.smem_col));
-                    SB_TRY(raise_smem((const void *)k_resample_lr<T>, (size_t)od.H * od.W * sizeof(T)));
+                    SB_TRY(raise_smem((const void *)k_resample_lr<T>, resample_lr_smem(od.H, od.W, d.Fxc)));
                     if ((size_t)Fy * SB_RS_ROWS * sizeof(cplx) > 200 * 1024 || (size_t)od.H * SB_RS_KY * sizeof(cplx) > 200 * 1024)
                         return set_err(SB_ERR_ARG, "observation %d: resampling geometry too large", o);
                     SB_TRY(raise_smem((const void *)k_resample_t1<T>, (size_t)Fy * SB_RS_ROWS * sizeof(cplx)));
@@ -1484,7 +1487,7 @@ template <typename T> struct PlanT : sb_plan {
                 k_resample_t1<T><<<tgrid, 128, t1_smem, stream>>>(sa);
                 SB_CUDA(cudaGetLastError());
                 mark(), mark();
-                k_resample_lr<T><<<S * sd.C, 256, (size_t)sd.H * sd.W * sizeof(T), stream>>>(sa);
+                k_resample_lr<T><<<S * sd.C, 256, resample_lr_smem(sd.H, sd.W, sd.Fxc), stream>>>(sa);
                 SB_CUDA(cudaGetLastError());
                 mark(), mark();
                 k_resample_q<T><<<qgrid, 128, q_smem, stream>>>(sa);

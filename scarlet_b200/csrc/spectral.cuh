@@ -732,6 +732,20 @@ template <typename T, int R1, int R2, int NB> __global__ void __launch_bounds__(
 
 // T1[img][i][kx] = sum_ky Ey[i][ky] P[img][ky][kx];  grid (ceil(Fxc/128), ceil(H/16), S*C), 128 threads: one kx per thread,
 // 16 low-resolution rows per CTA whose Ey rows are staged in shared memory (P is read ceil(H/16) times in total)
+// four consecutive reals by 128-bit shared / global loads
+template <typename T> struct RotVec;
+template <> struct RotVec<float> {
+    static __device__ __forceinline__ void load4(const float *p, float (&v)[4]) {
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+    }
+};
+template <> struct RotVec<double> {
+    static __device__ __forceinline__ void load4(const double *p, double (&v)[4]) {
+        const double2 t0 = *reinterpret_cast<const double2 *>(p), t1 = *reinterpret_cast<const double2 *>(p + 2);
+        v[0] = t0.x, v[1] = t0.y, v[2] = t1.x, v[3] = t1.y;
+    }
+};
 #define SB_RS_ROWS 16
 template <typename T> __global__ void __launch_bounds__(128) k_resample_t1(const SpecArgs<T> a) {
     typedef typename Cx<T>::type C2;
@@ -751,13 +765,28 @@ template <typename T> __global__ void __launch_bounds__(128) k_resample_t1(const
 #pragma unroll
     for (int q = 0; q < SB_RS_ROWS; ++q) acc[q] = C2{T(0), T(0)};
     const C2 *Pc = ob.P + (size_t)img * ob.Fy * ob.Xp + kx;
-    for (int ky = 0; ky < ob.Fy; ++ky) {
-        const C2 p = Pc[(size_t)ky * ob.Xp];
-        const C2 *e = ey + ky * SB_RS_ROWS;
+    // four spectrum rows per trip, requested before they are used (rolled, every trip waited for its own L2 round trip);
+    // the shift rows are read two complex entries per shared load
+    constexpr int UN = 4;
+#pragma unroll 1
+    for (int ky = 0; ky < ob.Fy; ky += UN) {
+        C2 p[UN];
 #pragma unroll
-        for (int q = 0; q < SB_RS_ROWS; ++q) {
-            acc[q].x += e[q].x * p.x - e[q].y * p.y;
-            acc[q].y += e[q].x * p.y + e[q].y * p.x;
+        for (int u = 0; u < UN; ++u) p[u] = ky + u < ob.Fy ? Pc[(size_t)(ky + u) * ob.Xp] : C2{T(0), T(0)};
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            if (ky + u < ob.Fy) { // CTA-uniform
+                const T *e = reinterpret_cast<const T *>(ey + (ky + u) * SB_RS_ROWS);
+#pragma unroll
+                for (int q = 0; q < SB_RS_ROWS; q += 2) {
+                    T ev[4];
+                    RotVec<T>::load4(e + 2 * q, ev);
+                    acc[q].x += ev[0] * p[u].x - ev[1] * p[u].y;
+                    acc[q].y += ev[0] * p[u].y + ev[1] * p[u].x;
+                    acc[q + 1].x += ev[2] * p[u].x - ev[3] * p[u].y;
+                    acc[q + 1].y += ev[2] * p[u].y + ev[3] * p[u].x;
+                }
+            }
         }
     }
 #pragma unroll
@@ -774,19 +803,33 @@ template <typename T> __global__ void __launch_bounds__(256) k_resample_lr(const
     const int img = blockIdx.x, s = img / ob.C;
     if (a.done[s]) return;
     const int H = ob.H, W = ob.W, Fxc = ob.Fxc, tid = threadIdx.x, nt = blockDim.x;
-    T *r = reinterpret_cast<T *>(smem); // [H][W]
+    // shared memory: the row-resampled spectra of this image [H][Fxc], the column shift table [W][Fxc], the residual [H][W]
+    C2 *sT = reinterpret_cast<C2 *>(smem);
+    C2 *sE = sT + (size_t)H * Fxc;
+    T *r = reinterpret_cast<T *>(sE + (size_t)W * Fxc);
     C2 *T1 = ob.T1 + (size_t)img * H * ob.Xp;
+    for (int idx = tid; idx < H * Fxc; idx += nt) {
+        const int i = idx / Fxc, kx = idx - i * Fxc;
+        sT[idx] = T1[(size_t)i * ob.Xp + kx];
+    }
+    for (int idx = tid; idx < W * Fxc; idx += nt) sE[idx] = ob.Ex[idx];
+    __syncthreads();
     const bool even = (ob.Fx & 1) == 0;
     double part = 0.0;
     for (int idx = tid; idx < H * W; idx += nt) {
         const int i = idx / W, j = idx - i * W;
-        const C2 *t = T1 + (size_t)i * ob.Xp, *e = ob.Ex + (size_t)j * Fxc;
-        T acc = T(0);
-        for (int kx = 0; kx < Fxc; ++kx) {
-            const T re = e[kx].x * t[kx].x - e[kx].y * t[kx].y;
-            acc += (kx == 0 || (even && kx == Fxc - 1)) ? re : T(2) * re;
+        const C2 *t = sT + (size_t)i * Fxc, *e = sE + (size_t)j * Fxc;
+        // sum_kx c_kx Re(e t) with c = 1, 2, ..., 2, (1): twice the plain sum minus the end terms
+        T acc0 = T(0), acc1 = T(0);
+        int kx = 0;
+        for (; kx + 1 < Fxc; kx += 2) {
+            acc0 += e[kx].x * t[kx].x - e[kx].y * t[kx].y;
+            acc1 += e[kx + 1].x * t[kx + 1].x - e[kx + 1].y * t[kx + 1].y;
         }
-        const T m = ob.h2 * acc;
+        if (kx < Fxc) acc0 += e[kx].x * t[kx].x - e[kx].y * t[kx].y;
+        const T first = e[0].x * t[0].x - e[0].y * t[0].y;
+        const T last = even ? e[Fxc - 1].x * t[Fxc - 1].x - e[Fxc - 1].y * t[Fxc - 1].y : T(0);
+        const T m = ob.h2 * (T(2) * (acc0 + acc1) - first - last);
         const size_t di = (size_t)img * H * W + idx;
         const T w = ob.weights[di], diff = m - ob.data[di];
         r[idx] = w * diff;
@@ -798,7 +841,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_resample_lr(const
         const int i = idx / Fxc, kx = idx - i * Fxc;
         C2 acc = C2{T(0), T(0)};
         for (int j = 0; j < W; ++j) {
-            const C2 e = ob.Ex[(size_t)j * Fxc + kx];
+            const C2 e = sE[(size_t)j * Fxc + kx];
             const T rv = r[i * W + j];
             acc.x += rv * e.x, acc.y += rv * e.y;
         }
@@ -809,8 +852,11 @@ template <typename T> __global__ void __launch_bounds__(256) k_resample_lr(const
 }
 
 // P[img][ky][kx] = h^2 K^[ky][kx] sum_i Ey[i][ky] U[img][i][kx];  grid (ceil(Fxc/128), ceil(Fy/64), S*C), 128 threads: one kx
-// per thread, 64 ky per CTA; the U column of a thread is held in registers 16 rows at a time, Ey in shared memory
+// per thread, 64 ky per CTA.  The U column of a thread is held in registers 32 rows at a time (a low-resolution cube of up to
+// 32 rows goes in one pass: P is written once, never read back), Ey in shared memory, four ky per trip: two 128-bit shared
+// loads serve four outputs (eight independent accumulation chains) and the four K^ entries are requested ahead of the products.
 #define SB_RS_KY 64
+#define SB_RS_QROWS 32
 template <typename T> __global__ void __launch_bounds__(128) k_resample_q(const SpecArgs<T> a) {
     typedef typename Cx<T>::type C2;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -828,29 +874,44 @@ template <typename T> __global__ void __launch_bounds__(128) k_resample_q(const 
     const C2 *U = ob.T1 + (size_t)img * ob.H * ob.Xp + kx;
     const C2 *K = ob.khat + ((size_t)(ob.khat_shared ? img - s * ob.C : img) * ob.Fy + ky0) * ob.Xp + kx;
     C2 *Pout = ob.P + ((size_t)img * ob.Fy + ky0) * ob.Xp + kx;
-    for (int ib = 0; ib < ob.H; ib += SB_RS_ROWS) {
-        C2 u[SB_RS_ROWS];
+    for (int ib = 0; ib < ob.H; ib += SB_RS_QROWS) {
+        C2 u[SB_RS_QROWS];
 #pragma unroll
-        for (int q = 0; q < SB_RS_ROWS; ++q) u[q] = ib + q < ob.H ? U[(size_t)(ib + q) * ob.Xp] : C2{T(0), T(0)};
-        for (int q = 0; q < nky; ++q) {
-            C2 acc = C2{T(0), T(0)};
+        for (int r = 0; r < SB_RS_QROWS; ++r) u[r] = ib + r < ob.H ? U[(size_t)(ib + r) * ob.Xp] : C2{T(0), T(0)};
+        const int nr = min(SB_RS_QROWS, ob.H - ib);
+#pragma unroll 1
+        for (int q = 0; q < nky; q += 4) { // (SB_RS_KY is a multiple of 4; entries beyond nky are zero-filled in ey and not stored)
+            C2 k[4], acc[4];
 #pragma unroll
-            for (int r = 0; r < SB_RS_ROWS; ++r) {
-                if (ib + r < ob.H) {
-                    const C2 e = ey[(ib + r) * SB_RS_KY + q];
-                    acc.x += e.x * u[r].x - e.y * u[r].y;
-                    acc.y += e.x * u[r].y + e.y * u[r].x;
+            for (int m = 0; m < 4; ++m) {
+                k[m] = q + m < nky ? K[(size_t)(q + m) * ob.Xp] : C2{T(0), T(0)};
+                acc[m] = C2{T(0), T(0)};
+            }
+#pragma unroll
+            for (int r = 0; r < SB_RS_QROWS; ++r) {
+                if (r < nr) { // CTA-uniform
+                    T e0[4], e1[4];
+                    const T *e = reinterpret_cast<const T *>(ey + (ib + r) * SB_RS_KY + q);
+                    RotVec<T>::load4(e, e0);
+                    RotVec<T>::load4(e + 4, e1);
+                    acc[0].x += e0[0] * u[r].x - e0[1] * u[r].y, acc[0].y += e0[0] * u[r].y + e0[1] * u[r].x;
+                    acc[1].x += e0[2] * u[r].x - e0[3] * u[r].y, acc[1].y += e0[2] * u[r].y + e0[3] * u[r].x;
+                    acc[2].x += e1[0] * u[r].x - e1[1] * u[r].y, acc[2].y += e1[0] * u[r].y + e1[1] * u[r].x;
+                    acc[3].x += e1[2] * u[r].x - e1[3] * u[r].y, acc[3].y += e1[2] * u[r].y + e1[3] * u[r].x;
                 }
             }
-            const C2 k = K[(size_t)q * ob.Xp];
-            C2 out;
-            out.x = ob.h2 * (k.x * acc.x - k.y * acc.y);
-            out.y = ob.h2 * (k.x * acc.y + k.y * acc.x);
-            C2 *dst = Pout + (size_t)q * ob.Xp;
-            if (ib == 0)
-                *dst = out;
-            else
-                dst->x += out.x, dst->y += out.y;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                if (q + m < nky) {
+                    C2 o;
+                    o.x = ob.h2 * (k[m].x * acc[m].x - k[m].y * acc[m].y), o.y = ob.h2 * (k[m].x * acc[m].y + k[m].y * acc[m].x);
+                    C2 *d = Pout + (size_t)(q + m) * ob.Xp;
+                    if (ib == 0)
+                        *d = o;
+                    else
+                        d->x += o.x, d->y += o.y;
+                }
+            }
         }
     }
 }
@@ -876,19 +937,6 @@ template <typename T> __device__ __forceinline__ void cp_async_c2(typename Cx<T>
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-template <typename T> struct RotVec;
-template <> struct RotVec<float> {
-    static __device__ __forceinline__ void load4(const float *p, float (&v)[4]) {
-        const float4 t = *reinterpret_cast<const float4 *>(p);
-        v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
-    }
-};
-template <> struct RotVec<double> {
-    static __device__ __forceinline__ void load4(const double *p, double (&v)[4]) {
-        const double2 t0 = *reinterpret_cast<const double2 *>(p), t1 = *reinterpret_cast<const double2 *>(p + 2);
-        v[0] = t0.x, v[1] = t0.y, v[2] = t1.x, v[3] = t1.y;
-    }
-};
 // grid (n_chunk, ceil(C / SB_ROT_MAXB), S), 32 SB_ROT_MAXB threads.  Warp b owns band c0 + b and the whole H x W output of it over this CTA's k
 // range: lane (ti, tj) = (lane / 8, lane % 8) accumulates the 8 x 4 block of rows 8 ti.. and columns 4 tj.. in registers.  The
 // operands are staged per 32 k as planar real / imaginary [k][32] tiles -- the column table B_j once for all bands, and
