@@ -99,7 +99,6 @@ class ImageMorphology(Morphology):
 
     def update(self):
         """Dynamic box: shrink / grow and raise ``UpdateException`` when the box changed (morphology.py:132-207)."""
-        import numpy.ma as ma
         image = self._parameters[0]
         if not self.resizing or image.fixed:
             return
@@ -113,18 +112,35 @@ class ImageMorphology(Morphology):
             raise UpdateException
         elif image.m is not None:
             # next gradient update, in units of the peak (= 1 at the centre): does the optimiser pull flux to an edge?
-            gu = -image.m / np.sqrt(np.sqrt(ma.masked_equal(image.v, 0))) * image.step
-            gu_pull = gu * (image._data > 0)
-            edge_pull = np.array((gu_pull[:, 0].mean(), gu_pull[:, -1].mean(), gu_pull[0, :].mean(), gu_pull[-1, :].mean()))
+            # (the reference forms the masked quotient over the whole image, morphology.py:165-170; only the four edges enter,
+            # evaluated here with the same operations in the same order: pixels with v == 0 are left out of the mean)
+            edge_pull = np.array([_edge_pull(image.m[sl], image.v[sl], image._data[sl], image.step)
+                                  for sl in ((slice(None), 0), (slice(None), -1), (0, slice(None)), (-1, slice(None)))])
             if np.any(edge_pull > 0.1):
                 size = max(bbox.shape)
                 newsize = get_minimal_boxsize(size + 1)
                 pad = (newsize - size) // 2
-                def grown(a):
-                    return None if a is None else np.pad(a, pad, mode="constant")
+                def grown(a):  # zero padding (numpy.pad(mode="constant") without its generic machinery)
+                    if a is None:
+                        return None
+                    out = np.zeros(tuple(n + 2 * pad for n in a.shape), dtype=a.dtype)
+                    out[(slice(pad, -pad),) * a.ndim] = a
+                    return out
                 self._replace_image(image, np.pad(image._data, pad, mode="linear_ramp"), grown(image.m), grown(image.v), grown(image.vhat))
                 self.bbox = Box((newsize, newsize), origin=tuple(o - pad for o in self.bbox.origin))
                 raise UpdateException
+
+
+def _edge_pull(m, v, data, step):
+    """mean over one edge of the next gradient update ``-m / sqrt(sqrt(v)) * step`` where the image is positive, pixels with
+    ``v == 0`` masked out -- what ``numpy.ma`` gives for the reference's expression (nan when every pixel is masked)"""
+    ok = v != 0
+    n = int(np.count_nonzero(ok))
+    if n == 0:
+        return np.nan
+    gu = np.zeros(m.shape, dtype=np.result_type(m, v, np.float64))
+    gu[ok] = (-m[ok] / np.sqrt(np.sqrt(v[ok])) * step) * (data[ok] > 0)
+    return gu.sum() / n
 
 
 class PointSourceMorphology(Morphology):
