@@ -399,6 +399,34 @@ __device__ __forceinline__ void grad_bands(const UpdateArgs<T> &a, int s, int C,
     }
 }
 
+// The same for several observations: per observation the band loads are issued back to back, the sums over the observations
+// that see a band are formed in double in observation order (exactly grad_at's arithmetic, one memory round trip per
+// observation instead of one per band).
+template <typename T, int CMAX>
+__device__ __forceinline__ void grad_bands_multi(const UpdateArgs<T> &a, int s, int C, int y, int x, T (&v)[CMAX]) {
+    double acc[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) acc[c] = 0.0;
+    for (int o = 0; o < a.n_obs; ++o) {
+        const DevObs<T> &ob = a.obs[o];
+        const size_t plane = (size_t)ob.Bh * ob.Bw;
+        const T *b = ob.B + ((size_t)s * ob.C * ob.Bh + y) * ob.Bw + x;
+        T t[CMAX];
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+            const int co = c - ob.chan_off;
+            t[c] = (c < C && co >= 0 && co < ob.C) ? b[(size_t)co * plane] : T(0);
+        }
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+            const int co = c - ob.chan_off;
+            if (c < C && co >= 0 && co < ob.C) acc[c] += (double)t[c];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) v[c] = (T)acc[c];
+}
+
 template <typename T> __device__ __forceinline__ int prox_max_iter_of(const UpdateArgs<T> &a, int scene) {
     return a.prox_iter ? a.prox_iter[scene] : a.fs.prox_max_iter;
 }

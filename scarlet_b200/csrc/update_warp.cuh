@@ -261,9 +261,7 @@ template <typename T, int NPT, int MAXT> __global__ void __launch_bounds__(MAXT,
                     if (a.n_obs == 1) {
                         grad_bands<T, SB_FAST_MAXC>(a, s, C, y, x, gv[i]);
                     } else {
-#pragma unroll
-                        for (int c = 0; c < SB_FAST_MAXC; ++c)
-                            if (c < C) gv[i][c] = (T)grad_at<T>(a, s, c, y, x);
+                        grad_bands_multi<T, SB_FAST_MAXC>(a, s, C, y, x, gv[i]);
                     }
                 }
             }
