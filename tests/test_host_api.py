@@ -313,6 +313,30 @@ def test_rotated_multiresolution_setup_and_render_vs_reference_fixture():
     assert_allclose((o.render(M) * G).sum(), (o.render_adjoint(G) * M).sum(), rtol=1e-12)
 
 
+def test_edge_pull_equals_the_masked_array_expression():
+    """ImageMorphology.update's grow rule (morphology.py:165-177) is evaluated on the four edges only: bit-identical to the
+    reference's masked-array expression over the whole image, zeros of v masked, fully masked edges -> nan"""
+    import warnings
+    import numpy.ma as ma
+    from scarlet_b200.morphology import _edge_pull
+    rng = np.random.default_rng(0)
+    edges = ((slice(None), 0), (slice(None), -1), (0, slice(None)), (-1, slice(None)))
+    for t in range(60):
+        B = int(rng.choice([15, 21, 31, 41, 51]))
+        m, v = rng.standard_normal((B, B)), rng.uniform(0, 1, (B, B)) ** 4
+        v[rng.uniform(size=(B, B)) < rng.choice([0, 0.1, 0.9])] = 0
+        if t % 7 == 0:
+            v[:, 0] = 0
+        data = (rng.uniform(size=(B, B)) * (rng.uniform(size=(B, B)) > 0.3)).astype(np.float32)
+        step = 0.01 / 2 ** int(rng.integers(0, 3))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gp = (-m / np.sqrt(np.sqrt(ma.masked_equal(v, 0))) * step) * (data > 0)
+            ref = np.array((gp[:, 0].mean(), gp[:, -1].mean(), gp[0, :].mean(), gp[-1, :].mean()))
+        new = np.array([_edge_pull(m[sl], v[sl], data[sl], step) for sl in edges])
+        assert np.array_equal(ref, new, equal_nan=True)
+
+
 def test_measure_helpers():
     """scarlet/measure.py:6-59 on a component and on a plain cube (host reductions; no device involved)"""
     import scarlet_b200 as sb
@@ -380,8 +404,16 @@ def test_batch_pipeline_orders_stages_and_overlaps_copies():
 
     a, b = FakeBatch("a"), FakeBatch("b")
     prepared = []
-    res = BatchPipeline(depth=2).run([a, b, a, b, a], max_iter=3, prepare=lambda k, batch: prepared.append((k, batch.name)))
+    pipe = BatchPipeline(depth=2)
+    res = pipe.run([a, b, a, b, a], max_iter=3, prepare=lambda k, batch: prepared.append((k, batch.name)))
     assert res == [("a", 1, 7, 5), ("b", 1, 7, 5), ("a", 2, 7, 5), ("b", 2, 7, 5), ("a", 3, 7, 5)]
+    # the stage intervals the pipeline records (bench.py derives the steady-state step period from them)
+    tm = sorted(pipe.timings, key=lambda t: t["k"])
+    assert [t["k"] for t in tm] == [0, 1, 2, 3, 4]
+    for t in tm:
+        assert t["copy_in"][0] <= t["copy_in"][1] <= t["loop"][0] <= t["loop"][1] <= t["copy_out"][1]
+    assert all(t2["loop"][0] >= t1["loop"][1] for t1, t2 in zip(tm, tm[1:]))  # one loop at a time
+    assert tm[1]["copy_in"][0] < tm[0]["loop"][1]                             # copies overlap the neighbour's loop
     assert prepared == [(0, "a"), (1, "b"), (2, "a"), (3, "b"), (4, "a")]
     order = [e[1] for e in log if e[0] == "loop+"]
     assert order == ["a", "b", "a", "b", "a"]
