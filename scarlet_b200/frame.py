@@ -72,59 +72,52 @@ class Frame:
 
     @staticmethod
     def from_observations(observations, model_psf=None, model_wcs=None, obs_id=None, coverage="union"):
-        """Common model frame of several observations: highest resolution, smallest PSF, union / intersection of the
-        footprints padded by the widest PSF; matches every observation to it (frame.py:155-287)."""
+        """Common model frame of several observations (frame.py:155-287): the pixel grid of the finest observation (or of
+        ``obs_id``), the narrowest PSF among the eligible bands as model PSF, the union / intersection of the footprints grown
+        by half the widest PSF; every observation is matched to the result."""
         assert coverage in ["union", "intersection"]
-        if not hasattr(observations, "__iter__"):
-            observations = (observations,)
-        pix_tab, channels = [], []
-        fat_psf_size = small_psf_size = None
-        model_psf_temp, psf_h = None, None
-        for c, obs in enumerate(observations):
-            channels = channels + list(obs.channels)
-            h_temp = interpolation.get_pixel_size(np.asarray(interpolation.get_affine(obs.wcs)))
-            pix_tab.append(h_temp)
-            for psf in obs.psf.get_model():
-                psf_size = interpolation.get_psf_size(psf) * h_temp
-                if fat_psf_size is None or psf_size > fat_psf_size:
-                    fat_psf_size = psf_size
-                if obs_id is None or c == obs_id:
-                    if model_psf is None and (small_psf_size is None or psf_size < small_psf_size):
-                        small_psf_size = psf_size
-                        model_psf_temp = ImagePSF(psf[np.newaxis, :, :])
-                        psf_h = h_temp
-        obs_ref = observations[int(np.where(np.array(pix_tab) == np.min(pix_tab))[0][0])] if obs_id is None else observations[obs_id]
+        observations = tuple(observations) if hasattr(observations, "__iter__") else (observations,)
+        scales = [interpolation.get_pixel_size(np.asarray(interpolation.get_affine(o.wcs))) for o in observations]
+        channels = [ch for o in observations for ch in o.channels]
+
+        # PSF widths of all bands in sky units: the widest pads the frame, the narrowest eligible one becomes the model PSF
+        widths = [(interpolation.get_psf_size(img) * scales[k], k, img) for k, o in enumerate(observations) for img in o.psf.get_model()]
+        widest = max(w for w, _, _ in widths)
+        reference = observations[int(np.argmin(scales))] if obs_id is None else observations[obs_id]  # first finest grid
         if model_wcs is None:
-            model_wcs = obs_ref.wcs
+            model_wcs = reference.wcs
         h = interpolation.get_pixel_size(np.asarray(interpolation.get_affine(model_wcs)))
         if model_psf is None:
-            if psf_h > h:
-                angle, h = interpolation.get_angles(model_wcs, obs.wcs)
-                model_psf = ImagePSF(interpolation.sinc_interp_inplace(model_psf_temp.get_model(), psf_h, h, angle))
+            eligible = [t for t in widths if obs_id is None or t[1] == obs_id]
+            _, k_narrow, img = eligible[int(np.argmin([t[0] for t in eligible]))]  # first of the narrowest
+            model_psf = ImagePSF(img[np.newaxis, :, :])
+            if scales[k_narrow] > h:  # tabulated on a coarser grid than the model's: resample it
+                # (sic: the reference measures the rotation against the LAST observation's grid, frame.py:229)
+                angle, h = interpolation.get_angles(model_wcs, observations[-1].wcs)
+                model_psf = ImagePSF(interpolation.sinc_interp_inplace(model_psf.get_model(), scales[k_narrow], h, angle))
+
+        # footprints in the pixel grid of the model
+        grid = Frame((len(channels), 0, 0), channels=channels, psf=model_psf, wcs=model_wcs)
+        area = None
+        for o in observations:
+            if grid.wcs is o.wcs:
+                foot = reference.bbox[-2:]
             else:
-                model_psf = model_psf_temp
-        model_frame = Frame((len(channels), 0, 0), channels=channels, psf=model_psf, wcs=model_wcs)
-        model_box = None
-        for c, obs in enumerate(observations):
-            if model_frame.wcs is obs.wcs:
-                this_box = obs_ref.bbox[-2:]
-            else:
-                coord = obs.convert_pixel_to(model_frame)
-                y_min, x_min = int(np.floor(np.min(coord[:, 0]))), int(np.floor(np.min(coord[:, 1])))
-                y_max, x_max = int(np.ceil(np.max(coord[:, 0]))), int(np.ceil(np.max(coord[:, 1])))
-                this_box = Box.from_bounds((y_min, y_max + 1), (x_min, x_max + 1))
-            if c == 0:
-                model_box = this_box
+                yx = o.convert_pixel_to(grid)
+                lo, hi = np.floor(yx.min(axis=0)).astype(int), np.ceil(yx.max(axis=0)).astype(int)
+                foot = Box.from_bounds((int(lo[0]), int(hi[0]) + 1), (int(lo[1]), int(hi[1]) + 1))
+            if area is None:
+                area = foot
             elif coverage == "union":
-                model_box |= this_box
+                area |= foot
             else:
-                model_box &= this_box
-        pad = int(np.round(fat_psf_size / h / 2))
-        model_box = Box(tuple(s + 2 * pad for s in model_box.shape), origin=tuple(o - pad for o in model_box.origin))
+                area &= foot
+        margin = int(np.round(widest / h / 2))
+        area = Box(tuple(n + 2 * margin for n in area.shape), origin=tuple(o - margin for o in area.origin))
         model_wcs = model_wcs.deepcopy()
-        model_wcs.wcs.crpix -= model_box.origin  # sic: (y, x) origin subtracted from the (x, y) reference pixel (frame.py:274)
-        model_wcs.array_shape = model_box.shape
-        model_frame = Frame((len(channels),) + tuple(model_box.shape), channels=channels, psf=model_psf, wcs=model_wcs)
-        for obs in observations:
-            obs.match(model_frame)
+        model_wcs.wcs.crpix -= area.origin  # sic: (y, x) origin subtracted from the (x, y) reference pixel (frame.py:274)
+        model_wcs.array_shape = area.shape
+        model_frame = Frame((len(channels),) + tuple(area.shape), channels=channels, psf=model_psf, wcs=model_wcs)
+        for o in observations:
+            o.match(model_frame)
         return model_frame
