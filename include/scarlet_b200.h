@@ -166,7 +166,7 @@ int64_t sb_plan_device_bytes(const sb_plan *plan);
 /* 1: the convolutions of this plan run in the fused row/column spectral kernels; 0: cuFFT + separate kernels
  * (grids with unsupported lengths, NullRenderer observations, or SB_SPECTRAL=cufft in the environment). */
 int sb_plan_spectral_mode(const sb_plan *plan);
-/* Diagnostic: histogram of the proximal sub-iterations (1..prox_max_iter, blend.py:145) the grouped update kernel ran
+/* Diagnostic: histogram of the proximal sub-iterations (1..prox_max_iter, blend.py:145) the warp and grouped update kernels ran
  * per source since the last call.  enable=1 starts (or continues) counting and zeroes the counters after reading;
  * enable=0 reads and switches the counters off.  out16 may be NULL. */
 int sb_plan_prox_histogram(sb_plan *plan, int enable, int64_t *out16);
@@ -185,7 +185,6 @@ int sb_plan_scene_control(sb_plan *plan, const int32_t *it_local, const int32_t 
                           const int32_t *active, const int32_t *prox_iter);
 int sb_plan_scene_status(sb_plan *plan, int32_t *it_local, int32_t *loss_len, int32_t *state);
 int sb_plan_run(sb_plan *plan, const sb_fit_opts *opts, int max_launches, int32_t *launched);
-/* loss histories [n_scenes][n_cols] (n_cols <= the capacity set by the largest max_iter seen so far) */
 /* Dynamic boxes: for every source of a PAUSED scene that is marked `resizing`, evaluate ImageMorphology.update's rules on the
  * device (morphology.py:52-68, 132-207): action[k] = new box size (shrink: outer rings entirely <= 0; grow: the next gradient
  * update pulls more than 0.1 of the peak towards an edge), 0 = keep, -1 = too close to a threshold to call (the host decides).
@@ -195,6 +194,7 @@ int sb_plan_inspect(sb_plan *plan, int32_t *action);
  * observation side -- data, weights, K^, spectral buffers, tensor maps -- stays where it is.  Parameters and optimiser state
  * are NOT carried over: upload them afterwards.  desc->obs must equal the plan's. */
 int sb_plan_set_sources(sb_plan *plan, const sb_batch_desc *desc);
+/* loss histories [n_scenes][n_cols] (n_cols <= the capacity set by the largest max_iter seen so far) */
 int sb_plan_download_loss(sb_plan *plan, double *loss, int n_cols);
 /* ... and back (a re-planned batch continues its histories: the stop rule compares with the previous entry) */
 int sb_plan_upload_loss(sb_plan *plan, const double *loss, int n_cols);
