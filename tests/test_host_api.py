@@ -313,6 +313,28 @@ def test_rotated_multiresolution_setup_and_render_vs_reference_fixture():
     assert_allclose((o.render(M) * G).sum(), (o.render_adjoint(G) * M).sum(), rtol=1e-12)
 
 
+def test_plan_classifies_renderers_without_a_device():
+    """host half of the plan (no GPU): which device observation kind a matched renderer maps to, and what is refused"""
+    import scarlet_b200 as sb
+    from multires_scene import product_scene
+    from scarlet_b200._plan import DevicePlan
+    for rotated, kind, tables in ((False, 2, ("Ey", "Ex")), (True, 3, ("A", "B"))):
+        _, blend, obs_lr, obs_hr = product_scene(32, rotated)
+        m_lr, m_hr = DevicePlan._obs_meta(blend, 0), DevicePlan._obs_meta(blend, 1)
+        assert (m_lr["kind"], m_hr["kind"]) == (kind, 0)
+        assert all(t in m_lr["operator"] for t in tables) and m_lr["operator"]["rotated"] == rotated
+        Fy, Fx = m_lr["fshape"]
+        assert m_lr["operator"]["khat"].shape == (5, Fy, Fx // 2 + 1)
+        if rotated:  # half-plane multiplier tables, one per low-resolution row / column
+            assert m_lr["operator"]["A"].shape == (8, Fy, Fx // 2 + 1) and m_lr["operator"]["B"].shape == (8, Fy, Fx // 2 + 1)
+    # a renderer the device path does not know
+    class Other(sb.renderer.Renderer):
+        pass
+    obs_hr.renderer = object.__new__(Other)
+    with pytest.raises(TypeError):
+        DevicePlan._obs_meta(blend, 1)
+
+
 def test_edge_pull_equals_the_masked_array_expression():
     """ImageMorphology.update's grow rule (morphology.py:165-177) is evaluated on the four edges only: bit-identical to the
     reference's masked-array expression over the whole image, zeros of v masked, fully masked edges -> nan"""
