@@ -328,9 +328,9 @@ def test_plan_classifies_renderers_without_a_device():
         if rotated:  # half-plane multiplier tables, one per low-resolution row / column
             assert m_lr["operator"]["A"].shape == (8, Fy, Fx // 2 + 1) and m_lr["operator"]["B"].shape == (8, Fy, Fx // 2 + 1)
     # a renderer the device path does not know
-    class Other(sb.renderer.Renderer):
+    class Other:  # (stands for any user-written Renderer subclass)
         pass
-    obs_hr.renderer = object.__new__(Other)
+    obs_hr.renderer = Other()
     with pytest.raises(TypeError):
         DevicePlan._obs_meta(blend, 1)
 
