@@ -151,7 +151,12 @@ def _ref_worker(job):
 
 
 def cpu_iters_for(config):
-    return {"cfg2": 20, "cfg3": 6, "cfg4": 4, "cfg4_rot": 3, "cfg5": 12, "tiny": 30}[config]
+    # iterations of one scene per step of the reference arm (about a second per step and core on the GPU box's host); the
+    # one-core cpu_baseline of the default arm runs CPU_BASELINE_FACTOR times as many (about ten seconds)
+    return {"cfg2": 120, "cfg3": 40, "cfg4": 4, "cfg4_rot": 3, "cfg5": 100, "tiny": 200}[config]
+
+
+CPU_BASELINE_FACTOR = 8
 
 
 def run_reference(args):
@@ -571,7 +576,7 @@ def run_b200(args):
         if env.world == 1 and not args.no_cpu_baseline:
             from oracle import monotonic_c
             monotonic_c._load()
-            n_cpu = cpu_iters_for(args.config)
+            n_cpu = CPU_BASELINE_FACTOR * cpu_iters_for(args.config)
             _ref_worker((args.config, 0, 2))
             dt = _ref_worker((args.config, 0, n_cpu))
             cpu = {"value": n_cpu / dt, "unit": "scene-iterations/s", "cores": 1, "kind": "port",
